@@ -1,0 +1,439 @@
+/*
+ * pdae_oracle.c -- CPU restatement of Point-DAE's point-cloud geometry hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA kernels in
+ * point-dae_b200/csrc.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it; the product path never does.
+ *
+ * Every function restates (does not copy) the algorithm of the reference file:line it cites
+ * (paths relative to the upstream YBZh/Point-DAE tree).  fp32 arithmetic is written with
+ * explicit fmaf()/single-rounded operations in exactly the order nvcc 12.9 emits for the
+ * reference kernels on sm_100a (checked with cuobjdump -sass on the rebuilt reference,
+ * see DESIGN.md "rounding orders"), and the file is compiled with -ffp-contract=off so the
+ * host compiler cannot add or remove a fusion.
+ *
+ * Pinning: the reference's own tests hold no golden vector for any op on this path
+ * (SURVEY.md section 4).  The pins are outputs of the reference's own CUDA kernels, rebuilt
+ * unmodified for sm_100a (oracle/build_ref.py) and run on a B200 by tests/golden/make_golden.py;
+ * they are committed under tests/golden/ and this oracle is checked against them by
+ * tests/test_oracle_golden.py.  knn (KNN_CUDA 0.2) is an un-vendored dependency: its oracle is
+ * pinned only against the published algorithm -> "parity unpinned" for that one op.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__x86_64__)
+#define TGT_FMA __attribute__((target("fma")))
+#else
+#define TGT_FMA
+#endif
+
+/* --------------------------------------------------------------------------------------------
+ * rounding helpers.  Two instantiations of each hot loop: one compiled with hardware FMA, one
+ * that calls libm's (correctly rounded) fmaf; chosen at run time so the .so is safe anywhere.
+ * ------------------------------------------------------------------------------------------ */
+static int have_fma(void) {
+#if defined(__x86_64__)
+  static int v = -1;
+  if (v < 0) v = __builtin_cpu_supports("fma") ? 1 : 0;
+  return v;
+#else
+  return 0;
+#endif
+}
+
+/* chamfer.cu:42-45 and sampling_gpu.cu:106-107: nvcc contracts a*a + b*b + c*c to
+ * fma(c,c, fma(a,a, rn(b*b))) */
+#define DIST3_XYZ(dx, dy, dz) fmaf((dz), (dz), fmaf((dx), (dx), (dy) * (dy)))
+
+int pdae_oracle_version(void) { return 1; }
+
+/* reference: extensions/pointnet2/_ext_src/include/cuda_utils.h:15-21 (opt_n_threads) */
+int pdae_oracle_fps_block_size(int n) {
+  if (n <= 0) return 1;
+  const int pow_2 = (int)(log((double)n) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
+
+/* ============================================================================================
+ * FPS.  reference: extensions/pointnet2/_ext_src/src/sampling_gpu.cu:72-176 (kernel),
+ * sampling.cpp:67-88 (temp = 1e10, idx zeros), cuda_utils.h:15-21 (block size).
+ * Literal simulation of the block: `bs` thread slots, strided point ownership, per-thread
+ * first-strict-max, then the shared-memory tree in which ties keep the lower slot.
+ * ========================================================================================== */
+#define FPS_BODY                                                                                \
+  const int bs = pdae_oracle_fps_block_size(n);                                                 \
+  float *temp = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));                       \
+  float *dists = (float *)malloc(sizeof(float) * (size_t)bs);                                   \
+  int *dists_i = (int *)malloc(sizeof(int) * (size_t)bs);                                       \
+  for (int bi = 0; bi < b; ++bi) {                                                              \
+    const float *P = xyz + (size_t)bi * n * 3;                                                  \
+    int *out = idx + (size_t)bi * m;                                                            \
+    for (int k = 0; k < n; ++k) temp[k] = 1e10f;                                                \
+    for (int j = 0; j < m; ++j) out[j] = 0; /* sampling.cpp:71 zeros */                         \
+    if (m <= 0 || n <= 0) continue;                                                             \
+    int old = 0;                                                                                \
+    out[0] = 0;                                                                                 \
+    for (int j = 1; j < m; ++j) {                                                               \
+      const float x1 = P[old * 3 + 0], y1 = P[old * 3 + 1], z1 = P[old * 3 + 2];                \
+      for (int tid = 0; tid < bs; ++tid) {                                                      \
+        int besti = 0;                                                                          \
+        float best = -1.0f;                                                                     \
+        for (int k = tid; k < n; k += bs) {                                                     \
+          const float x2 = P[k * 3 + 0], y2 = P[k * 3 + 1], z2 = P[k * 3 + 2];                  \
+          const float mag = DIST3_XYZ(x2, y2, z2);                                              \
+          if ((double)mag <= 1e-3) continue; /* :103-104, compared in double */                 \
+          const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;                                 \
+          const float d = DIST3_XYZ(dx, dy, dz);                                                \
+          const float d2 = fminf(d, temp[k]);                                                   \
+          temp[k] = d2;                                                                         \
+          besti = d2 > best ? k : besti;                                                        \
+          best = d2 > best ? d2 : best;                                                         \
+        }                                                                                       \
+        dists[tid] = best;                                                                      \
+        dists_i[tid] = besti;                                                                   \
+      }                                                                                         \
+      for (int s = bs >> 1; s >= 1; s >>= 1) { /* :118-171, __update :62-68 */                  \
+        for (int t = 0; t < s; ++t) {                                                           \
+          const float v1 = dists[t], v2 = dists[t + s];                                         \
+          const int i1 = dists_i[t], i2 = dists_i[t + s];                                       \
+          dists[t] = fmaxf(v1, v2);                                                             \
+          dists_i[t] = v2 > v1 ? i2 : i1;                                                       \
+        }                                                                                       \
+      }                                                                                         \
+      old = dists_i[0];                                                                         \
+      out[j] = old;                                                                             \
+    }                                                                                           \
+  }                                                                                             \
+  free(temp);                                                                                   \
+  free(dists);                                                                                  \
+  free(dists_i);
+
+TGT_FMA static void fps_hw(const float *xyz, int b, int n, int m, int *idx) { FPS_BODY }
+static void fps_sw(const float *xyz, int b, int n, int m, int *idx) { FPS_BODY }
+
+void pdae_oracle_fps(const float *xyz, int b, int n, int m, int *idx) {
+  if (have_fma()) fps_hw(xyz, b, n, m, idx);
+  else fps_sw(xyz, b, n, m, idx);
+}
+
+/* ============================================================================================
+ * gather / gather_grad.  reference: sampling_gpu.cu:11-23 and :37-50.
+ * grad accumulates in double and rounds once (the reference's float atomics are order-free).
+ * ========================================================================================== */
+void pdae_oracle_gather(const float *feat, const int *idx, int b, int c, int n, int m, float *out) {
+  for (int i = 0; i < b; ++i)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < m; ++j)
+        out[((size_t)i * c + l) * m + j] = feat[((size_t)i * c + l) * n + idx[(size_t)i * m + j]];
+}
+
+void pdae_oracle_gather_grad(const float *gout, const int *idx, int b, int c, int n, int m, float *gfeat) {
+  double *acc = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+  for (int i = 0; i < b; ++i)
+    for (int l = 0; l < c; ++l) {
+      memset(acc, 0, sizeof(double) * (size_t)n);
+      for (int j = 0; j < m; ++j) acc[idx[(size_t)i * m + j]] += (double)gout[((size_t)i * c + l) * m + j];
+      for (int a = 0; a < n; ++a) gfeat[((size_t)i * c + l) * n + a] = (float)acc[a];
+    }
+  free(acc);
+}
+
+/* ============================================================================================
+ * kNN (knn_cuda.KNN).  KNN_CUDA 0.2 is NOT vendored in the reference tree; this restates its
+ * published algorithm (Garcia et al. kNN-CUDA as packaged by KNN_CUDA: full squared-distance
+ * matrix with `ssd += tmp*tmp` over dims in order, per-query insertion sort with strict `<`,
+ * sqrt of the kept rows, 1-based indices shifted to 0-based).  Anchored on the reference call
+ * sites models/PointCAE_transformer.py:59,76 and models/MaskSurf_v2.py:79,124.
+ * Canonical order = ascending (d, index): an equal distance never displaces an earlier one.
+ * ref (b,r,dim), query (b,q,dim) row-major; dist (b,q,k) = sqrt(d), idx (b,q,k) int64.
+ * If k > r the tail is filled with (inf, -1) (cannot occur through the Python facade).
+ * ========================================================================================== */
+#define KNN_BODY                                                                                \
+  _Pragma("omp parallel for schedule(dynamic, 4)") for (long long bq = 0; bq < (long long)b * q; ++bq) { \
+    const int bi = (int)(bq / q);                                                               \
+    const float *Q = query + (size_t)bq * dim;                                                  \
+    const float *R = ref + (size_t)bi * r * dim;                                                \
+    float *D = dist + (size_t)bq * k;                                                           \
+    int64_t *I = idx + (size_t)bq * k;                                                          \
+    int cnt = 0;                                                                                \
+    for (int j = 0; j < r; ++j) {                                                               \
+      float ssd = 0.0f;                                                                         \
+      for (int c = 0; c < dim; ++c) {                                                           \
+        const float t = R[(size_t)j * dim + c] - Q[c];                                          \
+        ssd = fmaf(t, t, ssd);                                                                  \
+      }                                                                                         \
+      if (cnt == k && !(ssd < D[k - 1])) continue;                                              \
+      int p = cnt < k ? cnt : k - 1;                                                            \
+      while (p > 0 && ssd < D[p - 1]) {                                                         \
+        D[p] = D[p - 1];                                                                        \
+        I[p] = I[p - 1];                                                                        \
+        --p;                                                                                    \
+      }                                                                                         \
+      D[p] = ssd;                                                                               \
+      I[p] = j;                                                                                 \
+      if (cnt < k) ++cnt;                                                                       \
+    }                                                                                           \
+    for (int p = 0; p < k; ++p) {                                                               \
+      if (p < cnt) D[p] = sqrtf(D[p]);                                                          \
+      else { D[p] = INFINITY; I[p] = -1; }                                                      \
+    }                                                                                           \
+  }
+
+TGT_FMA static void knn_hw(const float *ref, const float *query, int b, int r, int q, int dim, int k,
+                           float *dist, int64_t *idx) { KNN_BODY }
+static void knn_sw(const float *ref, const float *query, int b, int r, int q, int dim, int k,
+                   float *dist, int64_t *idx) { KNN_BODY }
+
+void pdae_oracle_knn(const float *ref, const float *query, int b, int r, int q, int dim, int k,
+                     float *dist, int64_t *idx) {
+  if (k <= 0) return;
+  if (have_fma()) knn_hw(ref, query, b, r, q, dim, k, dist, idx);
+  else knn_sw(ref, query, b, r, q, dim, k, dist, idx);
+}
+
+/* ============================================================================================
+ * Group patchifier.  reference: models/PointCAE_transformer.py:61-86 (Group.forward) over
+ * utils/misc.py:13-20 (fps).  xyz (b,n,3) -> center (b,g,3), idx (b,g,m) int64,
+ * neighborhood (b,g,m,3) = xyz[idx] - center.
+ * ========================================================================================== */
+void pdae_oracle_group(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center,
+                       int64_t *idx, float *neighborhood) {
+  pdae_oracle_fps(xyz, b, n, g, fps_idx);
+  for (int bi = 0; bi < b; ++bi)
+    for (int j = 0; j < g; ++j)
+      for (int c = 0; c < 3; ++c)
+        center[((size_t)bi * g + j) * 3 + c] = xyz[((size_t)bi * n + fps_idx[(size_t)bi * g + j]) * 3 + c];
+  float *d = (float *)malloc(sizeof(float) * (size_t)b * g * m);
+  pdae_oracle_knn(xyz, center, b, n, g, 3, m, d, idx);
+  free(d);
+  for (int bi = 0; bi < b; ++bi)
+    for (int j = 0; j < g; ++j)
+      for (int p = 0; p < m; ++p) {
+        const int64_t a = idx[((size_t)bi * g + j) * m + p];
+        for (int c = 0; c < 3; ++c)
+          neighborhood[(((size_t)bi * g + j) * m + p) * 3 + c] =
+              xyz[((size_t)bi * n + a) * 3 + c] - center[((size_t)bi * g + j) * 3 + c];
+      }
+}
+
+/* ============================================================================================
+ * Chamfer forward.  reference: extensions/chamfer_dist/chamfer.cu:15-145 (one direction),
+ * :147-171 (both directions, outputs zero-initialised).  dx = b - a; lowest index wins ties
+ * (strict `<` inside a tile :47-79, strict `>` across tiles :137).
+ * ========================================================================================== */
+#define CHAMFER_DIR_BODY                                                                        \
+  _Pragma("omp parallel for schedule(static)") for (long long ij = 0; ij < (long long)b * n; ++ij) { \
+    const int i = (int)(ij / n);                                                                \
+    const float x1 = xyz1[ij * 3 + 0], y1 = xyz1[ij * 3 + 1], z1 = xyz1[ij * 3 + 2];            \
+    const float *B = xyz2 + (size_t)i * m * 3;                                                  \
+    float best = 0.0f;                                                                          \
+    int besti = 0;                                                                              \
+    for (int k = 0; k < m; ++k) {                                                               \
+      const float dx = B[k * 3 + 0] - x1, dy = B[k * 3 + 1] - y1, dz = B[k * 3 + 2] - z1;       \
+      const float d = DIST3_XYZ(dx, dy, dz);                                                    \
+      if (k == 0 || d < best) { best = d; besti = k; }                                          \
+    }                                                                                           \
+    dist[ij] = best;                                                                            \
+    indexes[ij] = besti;                                                                        \
+  }
+
+TGT_FMA static void chamfer_dir_hw(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist,
+                                   int *indexes) { CHAMFER_DIR_BODY }
+static void chamfer_dir_sw(int b, int n, const float *xyz1, int m, const float *xyz2, float *dist,
+                           int *indexes) { CHAMFER_DIR_BODY }
+
+void pdae_oracle_chamfer_fwd(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1,
+                             float *dist2, int *idx1, int *idx2) {
+  if (have_fma()) {
+    chamfer_dir_hw(b, n, xyz1, m, xyz2, dist1, idx1);
+    chamfer_dir_hw(b, m, xyz2, n, xyz1, dist2, idx2);
+  } else {
+    chamfer_dir_sw(b, n, xyz1, m, xyz2, dist1, idx1);
+    chamfer_dir_sw(b, m, xyz2, n, xyz1, dist2, idx2);
+  }
+}
+
+/* ============================================================================================
+ * Chamfer backward.  reference: chamfer.cu:173-201 (kernel), :203-229 (two launches).
+ * Each term is formed in fp32 exactly as the kernel does (g = 2*gd, v = g*(a-b)); the
+ * accumulation, order-free in the reference (float atomics), is done in double here and
+ * rounded once, so callers compare with a tolerance (1e-5 rel per north_star).
+ * ========================================================================================== */
+static void chamfer_grad_dir(int b, int n, const float *xyz1, int m, const float *xyz2, const float *gd1,
+                             const int *idx1, double *g1, double *g2) {
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < n; ++j) {
+      const size_t a = ((size_t)i * n + j);
+      const int j2 = idx1[a];
+      const size_t q = ((size_t)i * m + j2);
+      const float g = gd1[a] * 2.0f;
+      for (int c = 0; c < 3; ++c) {
+        const float diff = xyz1[a * 3 + c] - xyz2[q * 3 + c];
+        const float v = g * diff;
+        g1[a * 3 + c] += (double)v;
+        g2[q * 3 + c] += (double)(-v);
+      }
+    }
+}
+
+void pdae_oracle_chamfer_bwd(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2,
+                             const float *gd1, const float *gd2, int b, int n, int m, float *gx1, float *gx2) {
+  const size_t s1 = (size_t)b * n * 3, s2 = (size_t)b * m * 3;
+  double *a1 = (double *)calloc(s1 ? s1 : 1, sizeof(double));
+  double *a2 = (double *)calloc(s2 ? s2 : 1, sizeof(double));
+  chamfer_grad_dir(b, n, xyz1, m, xyz2, gd1, idx1, a1, a2);
+  chamfer_grad_dir(b, m, xyz2, n, xyz1, gd2, idx2, a2, a1);
+  for (size_t t = 0; t < s1; ++t) gx1[t] = (float)a1[t];
+  for (size_t t = 0; t < s2; ++t) gx2[t] = (float)a2[t];
+  free(a1);
+  free(a2);
+}
+
+/* ============================================================================================
+ * DGCNN knn, canonical (direct-form) definition.  reference: models/dgcnn_util.py:7-12 computes
+ * topk of the *expanded* form through cuBLAS (rounding and tie order unspecified); this repo
+ * defines the neighbour list on sum_c (x_j - x_i)^2 accumulated in channel order with
+ * ties -> lower index.  x (b,c,n) -> idx (b,n,k) int64 nearest first.
+ * ========================================================================================== */
+#define FEATKNN_BODY                                                                            \
+  _Pragma("omp parallel for schedule(dynamic, 8)") for (long long bi_i = 0; bi_i < (long long)b * n; ++bi_i) { \
+    const int bi = (int)(bi_i / n), i = (int)(bi_i % n);                                        \
+    const float *X = x + (size_t)bi * c * n;                                                    \
+    int64_t *I = idx + (size_t)bi_i * k;                                                        \
+    float *D = dist + (size_t)bi_i * k;                                                         \
+    int cnt = 0;                                                                                \
+    for (int j = 0; j < n; ++j) {                                                               \
+      float ssd = 0.0f;                                                                         \
+      for (int ch = 0; ch < c; ++ch) {                                                          \
+        const float t = X[(size_t)ch * n + j] - X[(size_t)ch * n + i];                          \
+        ssd = fmaf(t, t, ssd);                                                                  \
+      }                                                                                         \
+      if (cnt == k && !(ssd < D[k - 1])) continue;                                              \
+      int p = cnt < k ? cnt : k - 1;                                                            \
+      while (p > 0 && ssd < D[p - 1]) { D[p] = D[p - 1]; I[p] = I[p - 1]; --p; }                \
+      D[p] = ssd;                                                                               \
+      I[p] = j;                                                                                 \
+      if (cnt < k) ++cnt;                                                                       \
+    }                                                                                           \
+    for (int p = cnt; p < k; ++p) { D[p] = INFINITY; I[p] = -1; }                               \
+  }
+
+TGT_FMA static void featknn_hw(const float *x, int b, int c, int n, int k, float *dist, int64_t *idx) { FEATKNN_BODY }
+static void featknn_sw(const float *x, int b, int c, int n, int k, float *dist, int64_t *idx) { FEATKNN_BODY }
+
+/* dist (b,n,k) receives the *squared* direct-form distances (used by tests to measure gaps). */
+void pdae_oracle_feat_knn(const float *x, int b, int c, int n, int k, float *dist, int64_t *idx) {
+  if (k <= 0) return;
+  if (have_fma()) featknn_hw(x, b, c, n, k, dist, idx);
+  else featknn_sw(x, b, c, n, k, dist, idx);
+}
+
+/* ============================================================================================
+ * get_graph_feature.  reference: models/dgcnn_util.py:15-36.  x (b,c,n), idx (b,n,k) int64
+ * (per-cloud indices, i.e. before the reference's in-place `idx += idx_base`).
+ * out physical layout (b,n,k,2c): [.., 0:c] = x[:, idx] - x_i ; [.., c:2c] = x_i.
+ * ========================================================================================== */
+void pdae_oracle_graph_feature(const float *x, const int64_t *idx, int b, int c, int n, int k, float *out) {
+#pragma omp parallel for schedule(static)
+  for (long long bi_i = 0; bi_i < (long long)b * n; ++bi_i) {
+    const int bi = (int)(bi_i / n), i = (int)(bi_i % n);
+    const float *X = x + (size_t)bi * c * n;
+    for (int p = 0; p < k; ++p) {
+      const int64_t j = idx[(size_t)bi_i * k + p];
+      float *O = out + ((size_t)bi_i * k + p) * 2 * c;
+      for (int ch = 0; ch < c; ++ch) {
+        const float xi = X[(size_t)ch * n + i];
+        O[ch] = X[(size_t)ch * n + j] - xi;
+        O[c + ch] = xi;
+      }
+    }
+  }
+}
+
+/* backward of the above w.r.t. x.  gout physical (b,n,k,2c) -> gx (b,c,n); double accumulate. */
+void pdae_oracle_graph_feature_grad(const float *gout, const int64_t *idx, int b, int c, int n, int k, float *gx) {
+  double *acc = (double *)malloc(sizeof(double) * (size_t)c * n);
+  for (int bi = 0; bi < b; ++bi) {
+    memset(acc, 0, sizeof(double) * (size_t)c * n);
+    for (int i = 0; i < n; ++i)
+      for (int p = 0; p < k; ++p) {
+        const int64_t j = idx[((size_t)bi * n + i) * k + p];
+        const float *G = gout + (((size_t)bi * n + i) * k + p) * 2 * c;
+        for (int ch = 0; ch < c; ++ch) {
+          acc[(size_t)ch * n + j] += (double)G[ch];
+          acc[(size_t)ch * n + i] += (double)G[c + ch] - (double)G[ch];
+        }
+      }
+    for (size_t t = 0; t < (size_t)c * n; ++t) gx[(size_t)bi * c * n + t] = (float)acc[t];
+  }
+  free(acc);
+}
+
+/* ============================================================================================
+ * "next" rows: ball_query and group_points.
+ * reference: extensions/pointnet2/_ext_src/src/ball_query_gpu.cu:12-47,
+ *            group_points_gpu.cu:11-31 (fwd) and :46-67 (grad).
+ * ========================================================================================== */
+#define BALLQ_BODY                                                                              \
+  const float radius2 = radius * radius;                                                        \
+  for (int bi = 0; bi < b; ++bi)                                                                \
+    for (int j = 0; j < m; ++j) {                                                               \
+      const float *Q = new_xyz + ((size_t)bi * m + j) * 3;                                      \
+      int *I = idx + ((size_t)bi * m + j) * nsample;                                            \
+      for (int l = 0; l < nsample; ++l) I[l] = 0; /* ball_query.cpp: zeros */                   \
+      int cnt = 0;                                                                              \
+      for (int k = 0; k < n && cnt < nsample; ++k) {                                            \
+        const float *P = xyz + ((size_t)bi * n + k) * 3;                                        \
+        const float dx = Q[0] - P[0], dy = Q[1] - P[1], dz = Q[2] - P[2];                       \
+        const float d2 = DIST3_XYZ(dx, dy, dz);                                                 \
+        if (d2 < radius2) {                                                                     \
+          if (cnt == 0)                                                                         \
+            for (int l = 0; l < nsample; ++l) I[l] = k;                                         \
+          I[cnt] = k;                                                                           \
+          ++cnt;                                                                                \
+        }                                                                                       \
+      }                                                                                         \
+    }
+
+TGT_FMA static void ballq_hw(const float *new_xyz, const float *xyz, int b, int n, int m, float radius,
+                             int nsample, int *idx) { BALLQ_BODY }
+static void ballq_sw(const float *new_xyz, const float *xyz, int b, int n, int m, float radius, int nsample,
+                     int *idx) { BALLQ_BODY }
+
+void pdae_oracle_ball_query(const float *new_xyz, const float *xyz, int b, int n, int m, float radius,
+                            int nsample, int *idx) {
+  if (have_fma()) ballq_hw(new_xyz, xyz, b, n, m, radius, nsample, idx);
+  else ballq_sw(new_xyz, xyz, b, n, m, radius, nsample, idx);
+}
+
+/* points (b,c,n), idx (b,npoints,nsample) int32 -> out (b,c,npoints,nsample) */
+void pdae_oracle_group_points(const float *points, const int *idx, int b, int c, int n, int npoints,
+                              int nsample, float *out) {
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l)
+      for (int j = 0; j < npoints; ++j)
+        for (int k = 0; k < nsample; ++k)
+          out[(((size_t)bi * c + l) * npoints + j) * nsample + k] =
+              points[((size_t)bi * c + l) * n + idx[((size_t)bi * npoints + j) * nsample + k]];
+}
+
+void pdae_oracle_group_points_grad(const float *gout, const int *idx, int b, int c, int n, int npoints,
+                                   int nsample, float *gpoints) {
+  double *acc = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l) {
+      memset(acc, 0, sizeof(double) * (size_t)n);
+      for (int j = 0; j < npoints; ++j)
+        for (int k = 0; k < nsample; ++k)
+          acc[idx[((size_t)bi * npoints + j) * nsample + k]] +=
+              (double)gout[(((size_t)bi * c + l) * npoints + j) * nsample + k];
+      for (int a = 0; a < n; ++a) gpoints[((size_t)bi * c + l) * n + a] = (float)acc[a];
+    }
+  free(acc);
+}
