@@ -1,0 +1,130 @@
+/*
+ * pointdae_b200.h -- C ABI of libpointdae_b200.so: Point-DAE's point-cloud geometry hot path
+ * (FPS + gather, kNN + Group, DGCNN kNN / graph feature, Chamfer fwd/bwd) as sm_100a CUDA.
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers, sizes as int; no torch / C++ types.  fp32 data, int32 indices for
+ *     FPS / gather / Chamfer / ball-query, int64 for kNN (they feed `idx + idx_base`).
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated inside.
+ *   - work is enqueued on `stream` (a cudaStream_t / CUstream) of the CURRENT device and the
+ *     call returns without synchronising: safe under CUDA-graph capture, re-entrant, and
+ *     callable from several host threads (one per device) at once.
+ *   - return value: 0 on success, a positive cudaError_t when the CUDA runtime refused a
+ *     launch, a negative PDAE_E_* for an invalid argument.  Never exit(), never print and
+ *     continue (the reference does both: cuda_utils.h:32-41, chamfer.cu:166-169).
+ *
+ * "replaces" cites the reference (YBZh/Point-DAE) interface each symbol stands in for.
+ */
+#ifndef POINTDAE_B200_H
+#define POINTDAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDAE_ABI_VERSION 1
+
+#define PDAE_E_INVALID (-1)     /* bad size / null pointer */
+#define PDAE_E_UNSUPPORTED (-2) /* shape outside what the kernels implement (message via pdae_strerror) */
+#define PDAE_E_WORKSPACE (-3)   /* workspace too small */
+
+typedef void *pdae_stream_t; /* cudaStream_t */
+
+int pdae_abi_version(void);
+/* human-readable text for a code returned by any entry point (cudaGetErrorString for >0). */
+const char *pdae_strerror(int code);
+
+/* ---- FPS ------------------------------------------------------------------------------------
+ * replaces: pointnet2_ops / extensions/pointnet2 `furthest_point_sampling(points, nsamples)`
+ *           _ext_src/src/sampling.cpp:67-88 -> sampling_gpu.cu:72-176 (bindings.cpp:12).
+ * xyz (b,n,3) dense; idx (b,m) int32.  Bit-exact with the reference including the
+ * |p|^2 <= 1e-3 skip and the bit-reversed-slot tie rule (block size from pdae_fps_block_size).
+ * Needs no workspace for n <= 12288 (state lives in registers / shared memory); larger n uses
+ * `workspace` (pdae_fps_workspace_bytes, may be 0) for the running min-distances.            */
+int pdae_fps_block_size(int n); /* replaces opt_n_threads, cuda_utils.h:15-21 */
+size_t pdae_fps_workspace_bytes(int b, int n, int m);
+int pdae_fps_f32(const float *xyz, int b, int n, int m, int *idx, void *workspace, size_t workspace_bytes,
+                 pdae_stream_t stream);
+
+/* fused utils/misc.py:13-20 `fps(data, number)`: data (b,n,c) with c >= 3 (xyz first),
+ * idx (b,m) int32, centers (b,m,c) = data[idx] -- one launch instead of FPS + 2 transposes +
+ * gather + transpose.                                                                         */
+int pdae_fps_gather_f32(const float *data, int b, int n, int c, int m, int *idx, float *centers, void *workspace,
+                        size_t workspace_bytes, pdae_stream_t stream);
+
+/* ---- gather ---------------------------------------------------------------------------------
+ * replaces: `gather_points` sampling.cpp:17-40 / sampling_gpu.cu:11-33 and `gather_points_grad`
+ *           sampling.cpp:42-66 / sampling_gpu.cu:37-60 (bindings.cpp:10-11).
+ * feat (b,c,n), idx (b,m) int32 -> out (b,c,m).  grad: gout (b,c,m) -> gfeat (b,c,n),
+ * overwritten (zero-filled inside, then scatter-added).                                       */
+int pdae_gather_f32(const float *feat, const int *idx, int b, int c, int n, int m, float *out, pdae_stream_t stream);
+int pdae_gather_grad_f32(const float *gout, const int *idx, int b, int c, int n, int m, float *gfeat,
+                         pdae_stream_t stream);
+
+/* ---- kNN ------------------------------------------------------------------------------------
+ * replaces: knn_cuda.KNN(k, transpose_mode).forward(ref, query) (KNN_CUDA 0.2, un-vendored;
+ *           call sites models/PointCAE_transformer.py:59,76, models/MaskSurf_v2.py:79,124).
+ * ref (b,r,dim), query (b,q,dim) row-major (the facade transposes for transpose_mode=False).
+ * Outputs ascending by (distance, index): dist = sqrt(squared distance) or NULL,
+ * idx int64.  out_kq = 0: (b,q,k) layout; 1: (b,k,q) layout (transpose_mode=False).
+ * Requires 1 <= k <= min(r, 128).                                                             */
+int pdae_knn_f32(const float *ref, const float *query, int b, int r, int q, int dim, int k, int out_kq, float *dist,
+                 int64_t *idx, pdae_stream_t stream);
+
+/* fused Group.forward tail, models/PointCAE_transformer.py:76-85: kNN of `center` (b,g,3) in
+ * xyz (b,n,3) + gather + centre-subtract.  idx (b,g,m) int64 (may be NULL),
+ * neighborhood (b,g,m,3).                                                                     */
+int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
+                   float *neighborhood, pdae_stream_t stream);
+
+/* ---- DGCNN kNN + graph feature --------------------------------------------------------------
+ * replaces: models/dgcnn_util.py:7-12 `knn(x, k)` and :15-36 `get_graph_feature`.
+ * x (b,c,n) channel-major.  idx (b,n,k) int64 nearest-first, self included, direct-form
+ * distance accumulated in channel order, ties -> lower index.
+ * graph_feature: out physical (b,n,k,2c): [0:c] = x[:,idx]-x_i, [c:2c] = x_i (the reference's
+ * permuted view).  grad: gout same layout -> gx (b,c,n) overwritten.                          */
+int pdae_feat_knn_f32(const float *x, int b, int c, int n, int k, int64_t *idx, pdae_stream_t stream);
+/* workspace for graph_feature / _grad: one (b,n,c) fp32 transposed copy. */
+size_t pdae_graph_feature_workspace_bytes(int b, int c, int n);
+int pdae_graph_feature_f32(const float *x, const int64_t *idx, int b, int c, int n, int k, float *out,
+                           void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+int pdae_graph_feature_grad_f32(const float *gout, const int64_t *idx, int b, int c, int n, int k, float *gx,
+                                void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+
+/* ---- Chamfer --------------------------------------------------------------------------------
+ * replaces: `chamfer.forward(xyz1, xyz2)` chamfer_cuda.cpp:22-25 -> chamfer.cu:147-171 and
+ *           `chamfer.backward(...)` chamfer_cuda.cpp:27-34 -> chamfer.cu:203-229.
+ * xyz1 (b,n,3), xyz2 (b,m,3) read as dense storage exactly like the reference's raw data_ptr
+ * access.  dist1 (b,n), dist2 (b,m) squared distances; idx1, idx2 int32, lowest index on ties.
+ * backward: gx1 (b,n,3), gx2 (b,m,3) overwritten.                                             */
+int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
+                         int *idx1, int *idx2, pdae_stream_t stream);
+int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2, const float *gd1,
+                         const float *gd2, int b, int n, int m, float *gx1, float *gx2, pdae_stream_t stream);
+
+/* reference-set sharding (scene-scale clouds; new, no reference counterpart):
+ * one direction, queries (b,nq,3) against the local slice refs (b,nr,3) whose first point has
+ * global index `ref_offset`; emits keys[b,nq] = (float_bits(min d) << 32) | global argmin, an
+ * order-preserving packing so a uint64/int64 MIN all-reduce across ranks yields the global
+ * (min, lowest argmin).  pdae_chamfer_unpack_keys splits reduced keys into dist / idx.        */
+int pdae_chamfer_min_keys_u64(const float *queries, const float *refs, int b, int nq, int nr, int ref_offset,
+                              uint64_t *keys, pdae_stream_t stream);
+int pdae_chamfer_unpack_keys(const uint64_t *keys, long long count, float *dist, int *idx, pdae_stream_t stream);
+
+/* ---- "next" rows: ball query + grouping (3DETR / PointNet++ configs) ------------------------
+ * replaces: `ball_query` ball_query_gpu.cu:12-57, `group_points` / `_grad`
+ *           group_points_gpu.cu:11-78 (bindings.cpp:18-21).                                    */
+int pdae_ball_query_f32(const float *new_xyz, const float *xyz, int b, int n, int m, float radius, int nsample,
+                        int *idx, pdae_stream_t stream);
+int pdae_group_points_f32(const float *points, const int *idx, int b, int c, int n, int npoints, int nsample,
+                          float *out, pdae_stream_t stream);
+int pdae_group_points_grad_f32(const float *gout, const int *idx, int b, int c, int n, int npoints, int nsample,
+                               float *gpoints, pdae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTDAE_B200_H */

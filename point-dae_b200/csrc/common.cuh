@@ -1,0 +1,84 @@
+// common.cuh -- shared device helpers for the sm_100a geometry kernels.
+//
+// Rounding contract: every distance is formed with explicitly rounded single operations in
+// the order nvcc emits for the reference kernels (chamfer.cu:42-45, sampling_gpu.cu:106-107:
+// fma(dz,dz, fma(dx,dx, rn(dy*dy)))), so results are bit-identical with the reference on any
+// input.  Blackwell's packed fp32 ops (FADD2/FMUL2/FFMA2, PTX *.f32x2) are IEEE-exact per half
+// and are used to halve the issue slots of the FMA-pipe-bound inner loops.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pointdae_b200.h"
+
+namespace pdae {
+
+__device__ __forceinline__ uint64_t f2_as_u64(float2 v) { return *reinterpret_cast<uint64_t *>(&v); }
+__device__ __forceinline__ float2 u64_as_f2(uint64_t v) { return *reinterpret_cast<float2 *>(&v); }
+
+// packed fp32x2 (sm_100+): one issue slot, two IEEE fp32 results.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
+  return u64_as_f2(r);
+}
+// 3-input min (FMNMX3, sm_100+); NaN operands are ignored like fminf.
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// squared distance, chamfer / FPS / ball-query rounding order (y product first, then x, then z).
+__device__ __forceinline__ float dist_yxz(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+__device__ __forceinline__ float2 dist_yxz2(float2 dx, float2 dy, float2 dz) {
+  return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+}
+// squared distance, kNN rounding order (sequential fma over dims 0,1,2 from +0).
+__device__ __forceinline__ float dist_seq3(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ascending-order key of a (non-negative distance, index) pair: a plain unsigned compare orders
+// by distance first and by index on ties.
+__device__ __forceinline__ uint64_t pack_key(float d, uint32_t i) {
+  return (static_cast<uint64_t>(__float_as_uint(d)) << 32) | i;
+}
+
+static inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// cross-file internals
+// knn.cu: planar-input, any-channel-count DGCNN kNN (warp-select kernel); used directly for small c.
+int feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *idx, cudaStream_t st);
+
+}  // namespace pdae
+
+// host-side launch check: returns the cudaError_t (positive) to the caller, never prints/exits.
+#define PDAE_RETURN_IF_LAUNCH_FAILED()          \
+  do {                                          \
+    cudaError_t e__ = cudaPeekAtLastError();    \
+    if (e__ != cudaSuccess) {                   \
+      (void)cudaGetLastError();                 \
+      return static_cast<int>(e__);             \
+    }                                           \
+  } while (0)
+
+#define PDAE_CUDA_TRY(expr)                                  \
+  do {                                                       \
+    cudaError_t e__ = (expr);                                \
+    if (e__ != cudaSuccess) return static_cast<int>(e__);    \
+  } while (0)

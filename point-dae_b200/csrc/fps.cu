@@ -1,0 +1,307 @@
+// fps.cu -- furthest point sampling (+ fused centre gather) and gather / gather_grad.
+//
+// Semantics follow extensions/pointnet2/_ext_src/src/sampling_gpu.cu:72-176 of the reference
+// (identical in pointnet2_ops): idx[0] = 0; every later sample maximises the running minimum
+// squared distance over the points with (double)|p|^2 > 1e-3; ties are resolved the way the
+// reference's block does it -- thread slot `k mod bs` in bit-reversed order first (its shared
+// memory tree keeps the lower slot), then the smaller k (its per-thread strict `>`), with
+// bs = opt_n_threads(n) (cuda_utils.h:15-21).  That order is encoded as a 32-bit rank so the
+// arg-max becomes two warp-wide integer reductions (max of the value bits, then min of the rank
+// among the lanes holding that value) instead of a 9-level shared-memory tree with 10 barriers.
+//
+// Design (latency bound: npoint-1 strictly sequential iterations, one CTA per cloud):
+//   * every thread keeps its P points (x, y, z, running min) in registers for the whole call;
+//     the cloud is also staged once in shared memory (float4 per point) so the coordinates of
+//     the point just selected are one broadcast LDS.128 away;
+//   * skipped points and padding carry min = -2, which no update can raise above the -1 a
+//     thread starts from, so the inner loop is branch-free;
+//   * one __syncthreads per iteration (double-buffered per-warp slots), REDUX for both levels.
+//   * clouds too large for one CTA's registers fall back to a variant that keeps the running
+//     minima in a global workspace (same arithmetic, same tie rule).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pdae {
+
+// value -> monotone unsigned: -1 ("no valid point", the reference's initial best) -> 0,
+// v >= 0 -> bits + 1.  Values are never NaN (fminf drops NaN distances) and never exceed 1e10.
+__device__ __forceinline__ unsigned fps_val_bits(float v) { return v < 0.0f ? 0u : __float_as_uint(v) + 1u; }
+
+// tie rank of point k: smaller wins.  (bit-reversed slot, k / bs) lexicographic.
+__device__ __forceinline__ unsigned fps_rank(int k, int lg_bs) {
+  const unsigned slot = static_cast<unsigned>(k) & ((1u << lg_bs) - 1u);
+  const unsigned rev = lg_bs ? (__brev(slot) >> (32 - lg_bs)) : 0u;
+  return (rev << 22) | (static_cast<unsigned>(k) >> lg_bs);
+}
+__device__ __forceinline__ int fps_unrank(unsigned r, int lg_bs) {
+  const unsigned rev = r >> 22, hi = r & 0x3fffffu;
+  const unsigned slot = lg_bs ? (__brev(rev) >> (32 - lg_bs)) : 0u;
+  return static_cast<int>((hi << lg_bs) | slot);
+}
+
+// block-wide arg-max of (value bits, rank): returns the winning rank in every thread.
+template <int T>
+__device__ __forceinline__ unsigned fps_block_argmax(unsigned vb, unsigned rank, uint2 *slots /*[2][32]*/, int it) {
+  constexpr int W = T / 32;
+  const unsigned full = 0xffffffffu;
+  unsigned m = __reduce_max_sync(full, vb);
+  unsigned r = __reduce_min_sync(full, vb == m ? rank : 0xffffffffu);
+  if (W == 1) return r;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2 *buf = slots + (it & 1) * 32;
+  if (lane == 0) buf[warp] = make_uint2(m, r);
+  __syncthreads();
+  const uint2 v = lane < W ? buf[lane] : make_uint2(0u, 0xffffffffu);
+  m = __reduce_max_sync(full, v.x);
+  r = __reduce_min_sync(full, v.x == m ? v.y : 0xffffffffu);
+  return r;
+}
+
+// ---- register-resident variant: n <= T*P -----------------------------------------------------
+template <int T, int P>
+__global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ data, int n, int c, int m, int lg_bs,
+                                                    int *__restrict__ idx, float *__restrict__ centers) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *sp = reinterpret_cast<float4 *>(smem_raw);            // [n] staged cloud
+  uint2 *slots = reinterpret_cast<uint2 *>(sp + n);             // [2][32]
+  const int tid = threadIdx.x;
+  const float *__restrict__ cloud = data + static_cast<size_t>(blockIdx.x) * n * c;
+  int *__restrict__ out = idx + static_cast<size_t>(blockIdx.x) * m;
+
+  float px[P], py[P], pz[P], pt[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int k = tid + p * T;
+    float x = 0.f, y = 0.f, z = 0.f, t = -2.0f;
+    if (k < n) {
+      x = __ldg(cloud + static_cast<size_t>(k) * c);
+      y = __ldg(cloud + static_cast<size_t>(k) * c + 1);
+      z = __ldg(cloud + static_cast<size_t>(k) * c + 2);
+      const float mag = dist_yxz(x, y, z);
+      t = (static_cast<double>(mag) <= 1e-3) ? -2.0f : 1e10f;  // sampling_gpu.cu:103-104
+      sp[k] = make_float4(x, y, z, 0.f);
+    }
+    px[p] = x; py[p] = y; pz[p] = z; pt[p] = t;
+  }
+  if (tid == 0) out[0] = 0;
+  __syncthreads();
+
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    const float4 o = sp[old];
+    float best = -1.0f;
+    int bestp = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float d = dist_yxz(__fsub_rn(px[p], o.x), __fsub_rn(py[p], o.y), __fsub_rn(pz[p], o.z));
+      const float d2 = fminf(d, pt[p]);
+      pt[p] = d2;
+      const bool take = d2 > best;
+      bestp = take ? p : bestp;
+      best = take ? d2 : best;
+    }
+    // a thread with no valid point reports (value -1, index 0) like the reference (:93-94)
+    const int bk = best < 0.0f ? 0 : tid + bestp * T;
+    const unsigned r = fps_block_argmax<T>(fps_val_bits(best), fps_rank(bk, lg_bs), slots, j);
+    old = fps_unrank(r, lg_bs);
+    if (tid == 0) out[j] = old;
+  }
+
+  if (centers != nullptr) {  // fused utils/misc.py:18-19 gather of the sampled rows
+    __syncthreads();
+    float *__restrict__ cen = centers + static_cast<size_t>(blockIdx.x) * m * c;
+    for (int e = tid; e < m * c; e += T) {
+      const int j = e / c, ch = e - j * c;
+      cen[e] = __ldg(cloud + static_cast<size_t>(out[j]) * c + ch);
+    }
+  }
+}
+
+// ---- large-cloud fallback: running minima in a global workspace -------------------------------
+template <int T>
+__global__ void __launch_bounds__(T) fps_global_kernel(const float *__restrict__ data, int n, int c, int m, int lg_bs,
+                                                       int *__restrict__ idx, float *__restrict__ centers,
+                                                       float *__restrict__ temp_ws) {
+  __shared__ uint2 slots[2 * 32];
+  const int tid = threadIdx.x;
+  const float *__restrict__ cloud = data + static_cast<size_t>(blockIdx.x) * n * c;
+  float *__restrict__ temp = temp_ws + static_cast<size_t>(blockIdx.x) * n;
+  int *__restrict__ out = idx + static_cast<size_t>(blockIdx.x) * m;
+  for (int k = tid; k < n; k += T) {
+    const float x = cloud[static_cast<size_t>(k) * c], y = cloud[static_cast<size_t>(k) * c + 1],
+                z = cloud[static_cast<size_t>(k) * c + 2];
+    temp[k] = (static_cast<double>(dist_yxz(x, y, z)) <= 1e-3) ? -2.0f : 1e10f;
+  }
+  if (tid == 0) out[0] = 0;
+  __syncthreads();
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    const float ox = cloud[static_cast<size_t>(old) * c], oy = cloud[static_cast<size_t>(old) * c + 1],
+                oz = cloud[static_cast<size_t>(old) * c + 2];
+    float best = -1.0f;
+    int bk = 0;
+    // T is a multiple of bs, so a thread's points share one slot and ascending k is rank order
+    for (int k = tid; k < n; k += T) {
+      const float x = cloud[static_cast<size_t>(k) * c], y = cloud[static_cast<size_t>(k) * c + 1],
+                  z = cloud[static_cast<size_t>(k) * c + 2];
+      const float d = dist_yxz(__fsub_rn(x, ox), __fsub_rn(y, oy), __fsub_rn(z, oz));
+      const float d2 = fminf(d, temp[k]);
+      temp[k] = d2;
+      const bool take = d2 > best;
+      bk = take ? k : bk;
+      best = take ? d2 : best;
+    }
+    if (best < 0.0f) bk = 0;
+    const unsigned r = fps_block_argmax<T>(fps_val_bits(best), fps_rank(bk, lg_bs), slots, j);
+    old = fps_unrank(r, lg_bs);
+    if (tid == 0) out[j] = old;
+  }
+  if (centers != nullptr) {
+    __syncthreads();
+    float *__restrict__ cen = centers + static_cast<size_t>(blockIdx.x) * m * c;
+    for (int e = tid; e < m * c; e += T) {
+      const int j = e / c, ch = e - j * c;
+      cen[e] = cloud[static_cast<size_t>(out[j]) * c + ch];
+    }
+  }
+}
+
+// ---- gather ------------------------------------------------------------------------------------
+// reference: sampling_gpu.cu:11-23.  One thread per output element, idx read once per (b, j).
+__global__ void __launch_bounds__(256) gather_kernel(const float *__restrict__ feat, const int *__restrict__ idx, int c,
+                                                     int n, int m, long long total, float *__restrict__ out) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int j = static_cast<int>(e % m);
+  const long long bc = e / m;  // b*c + l
+  const long long bi = bc / c;
+  out[e] = __ldg(feat + bc * n + __ldg(idx + bi * m + j));
+}
+
+// reference: sampling_gpu.cu:37-50 (atomicAdd scatter into zeros).
+__global__ void __launch_bounds__(256) gather_grad_kernel(const float *__restrict__ gout, const int *__restrict__ idx,
+                                                          int c, int n, int m, long long total,
+                                                          float *__restrict__ gfeat) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int j = static_cast<int>(e % m);
+  const long long bc = e / m;
+  const long long bi = bc / c;
+  atomicAdd(gfeat + bc * n + __ldg(idx + bi * m + j), __ldg(gout + e));
+}
+
+static int ilog2_floor(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+
+template <int T, int P>
+static int launch_fps_reg(const float *data, int b, int n, int c, int m, int lg_bs, int *idx, float *centers,
+                          cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(n) * sizeof(float4) + 2 * 32 * sizeof(uint2);
+  if (smem > 48 * 1024) {
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(fps_reg_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  }
+  fps_reg_kernel<T, P><<<b, T, smem, st>>>(data, n, c, m, lg_bs, idx, centers);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+constexpr int FPS_REG_MAX_N = 12288;
+
+static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx, float *centers, void *ws,
+                        size_t ws_bytes, cudaStream_t st) {
+  if (b < 0 || n < 0 || m < 0 || c < 3) return PDAE_E_INVALID;
+  if (b == 0 || m == 0) return 0;
+  if (!idx) return PDAE_E_INVALID;
+  if (n == 0) {  // reference kernel would read out of bounds; define as all-zero indices
+    PDAE_CUDA_TRY(cudaMemsetAsync(idx, 0, static_cast<size_t>(b) * m * sizeof(int), st));
+    return 0;
+  }
+  if (!data) return PDAE_E_INVALID;
+  const int bs = pdae_fps_block_size(n);
+  const int lg_bs = ilog2_floor(bs);
+  // thread count must be a multiple of bs so that ascending k inside a thread is rank order
+  if (n <= 128) return launch_fps_reg<128, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 256) return launch_fps_reg<256, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 512) return launch_fps_reg<512, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 1024) return launch_fps_reg<512, 2>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 2048) return launch_fps_reg<512, 4>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 4096) return launch_fps_reg<1024, 4>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 8192) return launch_fps_reg<1024, 8>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= FPS_REG_MAX_N) return launch_fps_reg<512, 24>(data, b, n, c, m, lg_bs, idx, centers, st);
+  const size_t need = static_cast<size_t>(b) * n * sizeof(float);
+  if (!ws || ws_bytes < need) return PDAE_E_WORKSPACE;
+  fps_global_kernel<1024><<<b, 1024, 0, st>>>(data, n, c, m, lg_bs, idx, centers, static_cast<float *>(ws));
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+}  // namespace pdae
+
+using namespace pdae;
+
+// reference: cuda_utils.h:15-21.  Evaluated with the same double log() expression so the tie
+// rule can never disagree with the reference about the block size.
+extern "C" int pdae_fps_block_size(int n) {
+  if (n <= 0) return 1;
+  const int pow_2 = static_cast<int>(log(static_cast<double>(n)) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
+
+extern "C" size_t pdae_fps_workspace_bytes(int b, int n, int m) {
+  (void)m;
+  if (b <= 0 || n <= FPS_REG_MAX_N) return 0;
+  return static_cast<size_t>(b) * n * sizeof(float);
+}
+
+extern "C" int pdae_fps_f32(const float *xyz, int b, int n, int m, int *idx, void *workspace, size_t workspace_bytes,
+                            pdae_stream_t stream) {
+  return fps_dispatch(xyz, b, n, 3, m, idx, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pdae_fps_gather_f32(const float *data, int b, int n, int c, int m, int *idx, float *centers,
+                                   void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
+  if (b > 0 && m > 0 && !centers) return PDAE_E_INVALID;
+  if (n == 0 && b > 0 && m > 0) return PDAE_E_INVALID;
+  return fps_dispatch(data, b, n, c, m, idx, centers, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pdae_gather_f32(const float *feat, const int *idx, int b, int c, int n, int m, float *out,
+                               pdae_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0) return PDAE_E_INVALID;
+  const long long total = static_cast<long long>(b) * c * m;
+  if (total == 0) return 0;
+  if (!feat || !idx || !out || n == 0) return PDAE_E_INVALID;
+  const long long grid = (total + 255) / 256;
+  if (grid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  gather_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, idx, c, n, m, total,
+                                                                                           out);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+extern "C" int pdae_gather_grad_f32(const float *gout, const int *idx, int b, int c, int n, int m, float *gfeat,
+                                    pdae_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0) return PDAE_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t gsz = static_cast<size_t>(b) * c * n;
+  if (gsz) {
+    if (!gfeat) return PDAE_E_INVALID;
+    PDAE_CUDA_TRY(cudaMemsetAsync(gfeat, 0, gsz * sizeof(float), st));
+  }
+  const long long total = static_cast<long long>(b) * c * m;
+  if (total == 0 || gsz == 0) return 0;
+  if (!gout || !idx) return PDAE_E_INVALID;
+  const long long grid = (total + 255) / 256;
+  if (grid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  gather_grad_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(gout, idx, c, n, m, total, gfeat);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}

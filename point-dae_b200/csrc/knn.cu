@@ -1,0 +1,286 @@
+// knn.cu -- brute-force k nearest neighbours (knn_cuda.KNN), the fused Group tail
+// (kNN + gather + centre-subtract) and the low-dimensional DGCNN kNN.
+//
+// Semantics: KNN_CUDA 0.2 (un-vendored dependency of the reference; algorithm restated in
+// oracle/pdae_oracle.c): squared distance accumulated as sequential fma over the dims in order,
+// the k smallest kept in ascending order with strict `<` insertion, i.e. ascending by
+// (distance, index); Euclidean (sqrt) distances and 0-based int64 indices are returned.
+// Call sites: models/PointCAE_transformer.py:59,76 (transpose_mode=True, k=32, dim 3),
+// models/MaskSurf_v2.py:79,124 (transpose_mode=False).  DGCNN kNN: models/dgcnn_util.py:7-12.
+//
+// Design: the reference launches ~12 kernels per cloud from a Python loop; here the whole batch
+// is one launch.  A CTA stages a tile of the reference cloud in shared memory as planes and each
+// warp owns one query at a time: every lane evaluates one reference point per step, candidates
+// below the running k-th key are appended to a per-warp queue with a ballot, and a full queue
+// (32 entries) is bitonic-sorted and merged into the warp-resident sorted list (one key per lane
+// per 32 of k).  Keys are (float bits << 32 | index), so the unsigned order *is* the
+// (distance, lower index first) order and the selection is exact and deterministic.
+#include "common.cuh"
+
+namespace pdae {
+
+constexpr int KNN_WARPS = 8;
+constexpr int KNN_THREADS = KNN_WARPS * 32;
+constexpr int KNN_MAX_K = 128;
+constexpr uint64_t KEY_INF = 0xffffffffffffffffull;
+
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) {
+  const unsigned lo = __shfl_xor_sync(0xffffffffu, static_cast<unsigned>(v), m);
+  const unsigned hi = __shfl_xor_sync(0xffffffffu, static_cast<unsigned>(v >> 32), m);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(v), src);
+  const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(v >> 32), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a < b ? b : a; }
+
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = shfl_xor64(v, j);
+      const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+      v = keep_min ? umin64(v, o) : umax64(v, o);
+    }
+  }
+  return v;
+}
+// lanes hold a bitonic sequence -> ascending
+__device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t v, int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint64_t o = shfl_xor64(v, j);
+    v = (lane & j) == 0 ? umin64(v, o) : umax64(v, o);
+  }
+  return v;
+}
+
+// merge 32 ascending candidates `c` into the ascending list L[0..NS) (32 keys per slot),
+// keeping the 32*NS smallest.
+template <int NS>
+__device__ __forceinline__ void warp_merge(uint64_t (&L)[NS], uint64_t c, int lane) {
+  uint64_t mcur = warp_bitonic_merge32(umin64(L[NS - 1], shfl64(c, 31 - lane)), lane);
+#pragma unroll
+  for (int s = NS - 2; s >= 0; --s) {
+    const uint64_t r = shfl64(mcur, 31 - lane);
+    const uint64_t lo = umin64(L[s], r), hi = umax64(L[s], r);
+    L[s + 1] = warp_bitonic_merge32(hi, lane);
+    mcur = warp_bitonic_merge32(lo, lane);
+  }
+  L[0] = mcur;
+}
+
+struct KnnArgs {
+  const float *ref;    // PLANAR ? (b, dim, r) : (b, r, dim)
+  const float *query;  // PLANAR ? unused (queries are the reference points) : (b, q, dim)
+  float *dist;         // optional, Euclidean
+  int64_t *idx;        // optional
+  float *group;        // optional (b, q, k, 3): ref[idx] - query   (dim == 3, !PLANAR)
+  int r, q, dim, k;
+  int tile;            // reference points per shared-memory tile (multiple of 32)
+  int qpw;             // queries per warp (1 when the cloud spans several tiles)
+  int out_kq;          // 1: outputs laid out (b, k, q)
+};
+
+template <int D /*0 = runtime*/, bool PLANAR, int NS>
+__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t *queue_all = reinterpret_cast<uint64_t *>(smem_raw);              // [KNN_WARPS][64]
+  float *planes = reinterpret_cast<float *>(queue_all + KNN_WARPS * 64);     // [dim][tile]
+  const int dim = D ? D : a.dim;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cloud = blockIdx.y;
+  const int r = a.r, q = a.q, k = a.k, tile = a.tile;
+  const float *__restrict__ R = a.ref + static_cast<size_t>(cloud) * r * dim;
+  const float *__restrict__ Qp = PLANAR ? R : a.query + static_cast<size_t>(cloud) * q * dim;
+  uint64_t *queue = queue_all + warp * 64;
+  const int ntiles = (r + tile - 1) / tile;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int kslot = (k - 1) >> 5, klane = (k - 1) & 31;
+
+  for (int qi = 0; qi < a.qpw; ++qi) {
+    const int qidx = (blockIdx.x * KNN_WARPS + warp) * a.qpw + qi;
+    const bool qvalid = qidx < q;
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+    if (D == 3 && qvalid) {
+      if (PLANAR) {
+        q0 = __ldg(Qp + qidx); q1 = __ldg(Qp + r + qidx); q2 = __ldg(Qp + 2 * r + qidx);
+      } else {
+        q0 = __ldg(Qp + 3 * qidx); q1 = __ldg(Qp + 3 * qidx + 1); q2 = __ldg(Qp + 3 * qidx + 2);
+      }
+    }
+    uint64_t L[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) L[s] = KEY_INF;
+    uint64_t tau = KEY_INF;
+    int qn = 0;
+
+    for (int tl = 0; tl < ntiles; ++tl) {
+      const int tbase = tl * tile;
+      const int tn = (r - tbase) < tile ? (r - tbase) : tile;
+      if (ntiles > 1 || qi == 0) {
+        __syncthreads();  // previous tile fully consumed
+        if (PLANAR) {
+          for (int c = 0; c < dim; ++c)
+            for (int p = tid; p < tn; p += KNN_THREADS) planes[c * tile + p] = __ldg(R + static_cast<size_t>(c) * r + tbase + p);
+        } else {
+          const float *src = R + static_cast<size_t>(tbase) * dim;
+          for (int f = tid; f < tn * dim; f += KNN_THREADS) {
+            const int p = f / dim, c = f - p * dim;
+            planes[c * tile + p] = __ldg(src + f);
+          }
+        }
+        __syncthreads();
+      }
+      if (!qvalid) continue;
+      for (int j0 = 0; j0 < tn; j0 += 32) {
+        const int j = j0 + lane;
+        const bool in = j < tn;
+        float d = 0.f;
+        if (in) {
+          if (D == 3) {
+            d = dist_seq3(__fsub_rn(planes[j], q0), __fsub_rn(planes[tile + j], q1), __fsub_rn(planes[2 * tile + j], q2));
+          } else {
+            for (int c = 0; c < dim; ++c) {
+              const float qc = PLANAR ? __ldg(Qp + static_cast<size_t>(c) * r + qidx) : __ldg(Qp + static_cast<size_t>(qidx) * dim + c);
+              const float t = __fsub_rn(planes[c * tile + j], qc);
+              d = __fmaf_rn(t, t, d);
+            }
+          }
+        }
+        const uint64_t key = pack_key(d, static_cast<uint32_t>(tbase + j));
+        const bool pass = in && key < tau;
+        const unsigned mk = __ballot_sync(0xffffffffu, pass);
+        if (mk) {
+          if (pass) queue[qn + __popc(mk & lt_mask)] = key;
+          qn += __popc(mk);
+          __syncwarp();
+          if (qn >= 32) {
+            qn -= 32;
+            uint64_t c = queue[qn + lane];
+            __syncwarp();
+            c = warp_sort32(c, lane);
+            warp_merge<NS>(L, c, lane);
+            uint64_t lk = L[0];
+#pragma unroll
+            for (int s = 1; s < NS; ++s) lk = (s == kslot) ? L[s] : lk;
+            tau = shfl64(lk, klane);
+          }
+        }
+      }
+    }
+    if (!qvalid) continue;
+    if (qn > 0) {
+      uint64_t c = lane < qn ? queue[lane] : KEY_INF;
+      __syncwarp();
+      c = warp_sort32(c, lane);
+      warp_merge<NS>(L, c, lane);
+    }
+    // ---- epilogue: ascending list -> outputs -------------------------------------------------
+    const size_t bq = static_cast<size_t>(cloud) * q + qidx;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int p = s * 32 + lane;
+      if (p < k) {
+        const uint64_t key = L[s];
+        const uint32_t ji = static_cast<uint32_t>(key);
+        const size_t o = a.out_kq ? (static_cast<size_t>(cloud) * k + p) * q + qidx : bq * k + p;
+        if (a.idx) a.idx[o] = static_cast<int64_t>(ji);
+        if (a.dist) a.dist[o] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(key >> 32)));
+        if (D == 3 && !PLANAR && a.group) {
+          float *g = a.group + (bq * k + p) * 3;
+          g[0] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji)), q0);
+          g[1] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji) + 1), q1);
+          g[2] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji) + 2), q2);
+        }
+      }
+    }
+  }
+}
+
+template <int D, bool PLANAR>
+static int launch_knn(const KnnArgs &a, int b, cudaStream_t st) {
+  const int ns = (a.k + 31) / 32;
+  const size_t smem = static_cast<size_t>(KNN_WARPS) * 64 * sizeof(uint64_t) + static_cast<size_t>(a.dim) * a.tile * sizeof(float);
+  const dim3 grid(ceil_div(a.q, KNN_WARPS * a.qpw), b);
+  if (b > 65535) return PDAE_E_UNSUPPORTED;
+#define PDAE_KNN_LAUNCH(NS)                                                                              \
+  do {                                                                                                   \
+    if (smem > 48 * 1024)                                                                                \
+      PDAE_CUDA_TRY(cudaFuncSetAttribute(knn_kernel<D, PLANAR, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         static_cast<int>(smem)));                                      \
+    knn_kernel<D, PLANAR, NS><<<grid, KNN_THREADS, smem, st>>>(a);                                       \
+  } while (0)
+  if (ns == 1) PDAE_KNN_LAUNCH(1);
+  else if (ns == 2) PDAE_KNN_LAUNCH(2);
+  else PDAE_KNN_LAUNCH(4);
+#undef PDAE_KNN_LAUNCH
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+static int knn_plan(KnnArgs &a, int b) {
+  // tile: whole cloud when it fits in ~96 KB of planes, else 2048-point tiles (dim <= 11) or less
+  const int dim = a.dim;
+  const int budget_floats = (96 * 1024) / 4;
+  int tile_cap = (budget_floats / dim) & ~31;
+  if (tile_cap < 32) return PDAE_E_UNSUPPORTED;  // dim > 768
+  const int r32 = (a.r + 31) & ~31;
+  if (r32 <= tile_cap) {
+    a.tile = r32;
+    long long per = (static_cast<long long>(b) * a.q) / (148LL * KNN_WARPS * 3);
+    a.qpw = per < 1 ? 1 : (per > 8 ? 8 : static_cast<int>(per));
+  } else {
+    a.tile = tile_cap > 2048 ? 2048 : tile_cap;
+    a.qpw = 1;
+  }
+  return 0;
+}
+
+}  // namespace pdae
+
+using namespace pdae;
+
+extern "C" int pdae_knn_f32(const float *ref, const float *query, int b, int r, int q, int dim, int k, int out_kq,
+                            float *dist, int64_t *idx, pdae_stream_t stream) {
+  if (b < 0 || r < 0 || q < 0 || dim <= 0 || k <= 0) return PDAE_E_INVALID;
+  if (b == 0 || q == 0) return 0;
+  if (k > r || k > KNN_MAX_K) return PDAE_E_INVALID;
+  if (!ref || !query || (!dist && !idx)) return PDAE_E_INVALID;
+  KnnArgs a{ref, query, dist, idx, nullptr, r, q, dim, k, 0, 1, out_kq ? 1 : 0};
+  const int rc = knn_plan(a, b);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dim == 3 ? launch_knn<3, false>(a, b, st) : launch_knn<0, false>(a, b, st);
+}
+
+extern "C" int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
+                              float *neighborhood, pdae_stream_t stream) {
+  if (b < 0 || n < 0 || g < 0 || m <= 0) return PDAE_E_INVALID;
+  if (b == 0 || g == 0) return 0;
+  if (m > n || m > KNN_MAX_K) return PDAE_E_INVALID;
+  if (!xyz || !center || !neighborhood) return PDAE_E_INVALID;
+  KnnArgs a{xyz, center, nullptr, idx, neighborhood, n, g, 3, m, 0, 1, 0};
+  const int rc = knn_plan(a, b);
+  if (rc) return rc;
+  return launch_knn<3, false>(a, b, static_cast<cudaStream_t>(stream));
+}
+
+// DGCNN kNN: x (b, c, n) channel-major, every point is a query.  Low channel counts (the first
+// EdgeConv layer, c = 3) use the planar variant of the kernel above; wide feature layers are
+// served by featknn.cu.
+int pdae::feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *idx, cudaStream_t st) {
+  if (b < 0 || c <= 0 || n < 0 || k <= 0) return PDAE_E_INVALID;
+  if (b == 0 || n == 0) return 0;
+  if (k > n || k > KNN_MAX_K) return PDAE_E_INVALID;
+  if (!x || !idx) return PDAE_E_INVALID;
+  KnnArgs a{x, nullptr, nullptr, idx, nullptr, n, n, c, k, 0, 1, 0};
+  const int rc = knn_plan(a, b);
+  if (rc) return rc;
+  return c == 3 ? launch_knn<3, true>(a, b, st) : launch_knn<0, true>(a, b, st);
+}

@@ -1,0 +1,31 @@
+"""Drop-in for the two hot functions of `models/dgcnn_util.py` of the reference: `knn` (:7-12) and
+`get_graph_feature` (:15-36), same signatures.  `install()` rebinds them inside the reference's
+models.dgcnn_util / models.PointCAE_DGCNN / segmentation.models.dgcnn_util.
+"""
+import torch
+
+from . import ops
+
+
+def knn(x, k):
+    """x (B,C,N) -> idx (B,N,k) int64, nearest first, self included.  The reference ranks by the
+    expanded form through cuBLAS (tie order unspecified); this ranks by the direct-form squared
+    distance with ties -> lower index, and never materialises the B x N x N matrix."""
+    return ops.feat_knn(x, k)
+
+
+def get_graph_feature(x, k=20, idx=None, extra_dim=False):
+    batch_size, num_dims, num_points = x.size()
+    x = x.view(batch_size, -1, num_points)
+    caller_idx = idx
+    if idx is None:
+        idx = knn(x, k=k) if extra_dim is False else knn(x[:, 6:], k=k)
+    if idx.dtype != torch.int64 or not idx.is_contiguous():
+        idx = idx.long().contiguous()
+    k = idx.size(2)
+    feature = ops.GraphFeatureFunction.apply(x.float(), idx)
+    if caller_idx is not None and caller_idx.dtype == torch.int64:
+        # the reference offsets a caller-supplied idx in place (dgcnn_util.py:27); keep that visible effect
+        idx_base = torch.arange(0, batch_size, device=caller_idx.device).view(-1, 1, 1) * num_points
+        caller_idx += idx_base
+    return feature  # (batch_size, 2 * num_dims, num_points, k)

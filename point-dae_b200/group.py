@@ -1,0 +1,29 @@
+"""Drop-in for the Point-MAE-style patchifier `Group(num_group, group_size)`
+(models/PointCAE_transformer.py:54-86, byte-identical copies in models/Point_MAE.py:51-83 etc.)
+and for `utils/misc.py:13-20 fps`.  Two launches (FPS+centre gather, kNN+gather+centre-subtract)
+replace the reference's ~1500."""
+import torch.nn as nn
+
+from . import ops
+from .knn_cuda import KNN
+
+
+def fps(data, number):
+    """utils/misc.py:13-20.  data (B,N,3|6) -> (fps_idx (B,G) int32, fps_data (B,G,3|6))."""
+    return ops.fps_gather(data, number)
+
+
+class Group(nn.Module):  # FPS + KNN
+    def __init__(self, num_group, group_size):
+        super().__init__()
+        self.num_group = num_group
+        self.group_size = group_size
+        self.knn = KNN(k=self.group_size, transpose_mode=True)  # kept for attribute parity
+
+    def forward(self, xyz):
+        """input: B N 3  ->  neighborhood: B G M 3 (centre-subtracted), center: B G 3"""
+        batch_size, num_points, _ = xyz.shape
+        xyz = xyz.float().contiguous()
+        _, center = fps(xyz, self.num_group)  # B G 3
+        neighborhood, _ = ops.group_points_knn(xyz.detach(), center, self.group_size, want_idx=False)
+        return neighborhood, center

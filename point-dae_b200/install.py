@@ -1,0 +1,67 @@
+"""`install()` makes the reference's imports resolve to this package, so Point-DAE's models/ and
+main.py run unchanged:
+
+    import pointdae_b200; pointdae_b200.install()
+    # now: from pointnet2_ops import pointnet2_utils ; from knn_cuda import KNN ; import chamfer ;
+    #      import pointnet2._ext  -> all served by the sm_100a kernels
+
+Only the *compiled / third-party* modules are replaced (the reference's own Python, e.g.
+extensions/chamfer_dist/__init__.py, keeps running on top).  `patch_models()` additionally rebinds
+the pure-torch hot functions that live inside the reference's packages (dgcnn knn / get_graph_feature,
+misc.fps, Group) once those packages are importable.
+"""
+import importlib
+import sys
+import types
+
+
+def install():
+    from . import chamfer, knn_cuda, pointnet2_ext, pointnet2_utils
+
+    pkg = types.ModuleType("pointnet2_ops")
+    pkg.__path__ = []  # mark as package
+    pkg.pointnet2_utils = pointnet2_utils
+    pkg.__version__ = "3.0.0"
+    sys.modules["pointnet2_ops"] = pkg
+    sys.modules["pointnet2_ops.pointnet2_utils"] = pointnet2_utils
+
+    sys.modules["knn_cuda"] = knn_cuda
+    sys.modules["chamfer"] = chamfer
+
+    # `import pointnet2._ext as _ext` (extensions/pointnet2/pointnet2_utils.py:23-24)
+    p2 = sys.modules.get("pointnet2")
+    if p2 is None:
+        p2 = types.ModuleType("pointnet2")
+        p2.__path__ = []
+        sys.modules["pointnet2"] = p2
+    p2._ext = pointnet2_ext
+    sys.modules["pointnet2._ext"] = pointnet2_ext
+    return True
+
+
+def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentation.models.dgcnn_util")):
+    """Rebind knn / get_graph_feature in the reference's already-importable modules, misc.fps, and Group."""
+    from . import dgcnn_util, group
+
+    patched = []
+    for name in names:
+        try:
+            mod = importlib.import_module(name)
+        except Exception:
+            continue
+        for fn in ("knn", "get_graph_feature"):
+            if hasattr(mod, fn):
+                setattr(mod, fn, getattr(dgcnn_util, fn))
+                patched.append(name + "." + fn)
+    try:
+        misc = importlib.import_module("utils.misc")
+        misc.fps = group.fps
+        patched.append("utils.misc.fps")
+    except Exception:
+        pass
+    for name in ("models.PointCAE_transformer", "models.Point_MAE", "models.Point_MlMAE"):
+        mod = sys.modules.get(name)
+        if mod is not None and hasattr(mod, "Group"):
+            mod.Group = group.Group
+            patched.append(name + ".Group")
+    return patched

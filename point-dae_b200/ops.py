@@ -1,0 +1,349 @@
+"""Torch-tensor host layer over the C ABI: allocates outputs, picks device / stream, raises on error.
+
+PyTorch is plumbing here (device memory, streams, autograd glue); every computation is a
+hand-written sm_100a kernel in csrc/.  No function in this module has a CPU or torch fallback:
+a CPU tensor raises, a missing library raises.
+"""
+import torch
+
+from . import _native
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("%s: CPU not supported" % name)  # sampling.cpp:36,84 of the reference
+
+
+def _require_f32_contig(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be a float tensor" % name)  # utils.h CHECK_IS_FLOAT
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be a contiguous tensor" % name)  # utils.h CHECK_CONTIGUOUS
+
+
+def _require_i32_contig(t, name):
+    if t.dtype != torch.int32:
+        raise RuntimeError("%s must be an int tensor" % name)  # utils.h CHECK_IS_INT
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be a contiguous tensor" % name)
+
+
+def _dense_storage(t):
+    """True when t's elements occupy exactly numel contiguous storage slots (any permutation)."""
+    if t.numel() == 0 or t.is_contiguous():
+        return True
+    dims = sorted(((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1))
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+# ------------------------------------------------------------------------------------------ FPS
+def fps_block_size(n):
+    return int(_native.lib().pdae_fps_block_size(int(n)))
+
+
+def furthest_point_sample(xyz, npoint):
+    """pointnet2_utils.furthest_point_sample: xyz (B,N,3) f32 contiguous CUDA -> (B,npoint) int32."""
+    _require_f32_contig(xyz, "xyz")
+    _require_cuda(xyz, "furthest_point_sampling")
+    if xyz.dim() != 3 or xyz.size(2) != 3:
+        raise RuntimeError("xyz must have shape (B, N, 3)")
+    b, n, _ = xyz.shape
+    npoint = int(npoint)
+    L = _native.lib()
+    with torch.cuda.device(xyz.device):
+        idx = torch.empty((b, npoint), dtype=torch.int32, device=xyz.device)
+        nbytes = L.pdae_fps_workspace_bytes(b, n, npoint)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device) if nbytes else None
+        rc = L.pdae_fps_f32(xyz.data_ptr(), b, n, npoint, idx.data_ptr(), ws.data_ptr() if nbytes else None, nbytes,
+                            _stream())
+    _native.check(rc, "pdae_fps_f32")
+    return idx
+
+
+def fps_gather(data, number):
+    """Fused utils/misc.py:13-20 `fps`: data (B,N,C>=3) -> (fps_idx (B,G) int32, fps_data (B,G,C))."""
+    _require_cuda(data, "fps")
+    if data.dim() != 3 or data.size(2) < 3:
+        raise RuntimeError("data must have shape (B, N, C>=3)")
+    src = data.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    b, n, c = src.shape
+    number = int(number)
+    L = _native.lib()
+    with torch.cuda.device(src.device):
+        idx = torch.empty((b, number), dtype=torch.int32, device=src.device)
+        centers = torch.empty((b, number, c), dtype=torch.float32, device=src.device)
+        nbytes = L.pdae_fps_workspace_bytes(b, n, number)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device) if nbytes else None
+        rc = L.pdae_fps_gather_f32(src.data_ptr(), b, n, c, number, idx.data_ptr(), centers.data_ptr(),
+                                   ws.data_ptr() if nbytes else None, nbytes, _stream())
+    _native.check(rc, "pdae_fps_gather_f32")
+    return idx, centers
+
+
+# --------------------------------------------------------------------------------------- gather
+def gather_points(features, idx):
+    _require_f32_contig(features, "features")
+    _require_i32_contig(idx, "idx")
+    _require_cuda(features, "gather_points")
+    _require_cuda(idx, "gather_points")
+    b, c, n = features.shape
+    m = idx.size(1)
+    with torch.cuda.device(features.device):
+        out = torch.empty((b, c, m), dtype=torch.float32, device=features.device)
+        rc = _native.lib().pdae_gather_f32(features.data_ptr(), idx.data_ptr(), b, c, n, m, out.data_ptr(), _stream())
+    _native.check(rc, "pdae_gather_f32")
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    _require_f32_contig(grad_out, "grad_out")
+    _require_i32_contig(idx, "idx")
+    _require_cuda(grad_out, "gather_points_grad")
+    _require_cuda(idx, "gather_points_grad")
+    b, c, m = grad_out.shape
+    with torch.cuda.device(grad_out.device):
+        out = torch.empty((b, c, int(n)), dtype=torch.float32, device=grad_out.device)
+        rc = _native.lib().pdae_gather_grad_f32(grad_out.data_ptr(), idx.data_ptr(), b, c, int(n), m, out.data_ptr(),
+                                                _stream())
+    _native.check(rc, "pdae_gather_grad_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ kNN
+def knn_points(ref, query, k, out_kq=False, want_dist=True):
+    """ref (B,R,D), query (B,Q,D) f32 contiguous -> (dist (B,Q,k)|(B,k,Q) f32 or None, idx int64)."""
+    _require_cuda(ref, "knn")
+    _require_cuda(query, "knn")
+    b, r, d = ref.shape
+    q = query.size(1)
+    k = int(k)
+    if query.size(0) != b or query.size(2) != d:
+        raise RuntimeError("ref.shape=%s != query.shape=%s" % (tuple(ref.shape), tuple(query.shape)))
+    if not (1 <= k <= r):
+        raise RuntimeError("k=%d must satisfy 1 <= k <= %d reference points" % (k, r))
+    shape = (b, k, q) if out_kq else (b, q, k)
+    with torch.cuda.device(ref.device):
+        idx = torch.empty(shape, dtype=torch.int64, device=ref.device)
+        dist = torch.empty(shape, dtype=torch.float32, device=ref.device) if want_dist else None
+        rc = _native.lib().pdae_knn_f32(ref.data_ptr(), query.data_ptr(), b, r, q, d, k, 1 if out_kq else 0,
+                                        dist.data_ptr() if want_dist else None, idx.data_ptr(), _stream())
+    _native.check(rc, "pdae_knn_f32")
+    return dist, idx
+
+
+def group_points_knn(xyz, center, group_size, want_idx=True):
+    """Fused Group tail: xyz (B,N,3), center (B,G,3) -> (neighborhood (B,G,M,3), idx (B,G,M) int64|None)."""
+    _require_cuda(xyz, "group")
+    _require_f32_contig(xyz, "xyz")
+    _require_f32_contig(center, "center")
+    b, n, _ = xyz.shape
+    g = center.size(1)
+    m = int(group_size)
+    if not (1 <= m <= n):
+        raise RuntimeError("group_size=%d must satisfy 1 <= group_size <= %d points" % (m, n))
+    with torch.cuda.device(xyz.device):
+        nb = torch.empty((b, g, m, 3), dtype=torch.float32, device=xyz.device)
+        idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
+        rc = _native.lib().pdae_group_f32(xyz.data_ptr(), center.data_ptr(), b, n, g, m,
+                                          idx.data_ptr() if want_idx else None, nb.data_ptr(), _stream())
+    _native.check(rc, "pdae_group_f32")
+    return nb, idx
+
+
+# -------------------------------------------------------------------------------------- Chamfer
+def chamfer_forward(xyz1, xyz2):
+    """chamfer.forward: returns [dist1 (B,N), dist2 (B,M), idx1 int32, idx2 int32].
+
+    Reference-faithful storage semantics (chamfer.cu:159-164 reads raw data_ptr): a tensor whose
+    elements densely fill their storage is read in *storage order* as [B][size(1)][3], even when it
+    is a transposed view -- exactly what the reference computes for
+    models/PointCAE_transformer.py:1059-1066.  Anything else (gaps, overlaps, wrong dtype) raises
+    instead of reading out of bounds like the reference would.
+    """
+    for t, name in ((xyz1, "xyz1"), (xyz2, "xyz2")):
+        _require_cuda(t, "chamfer.forward")
+        if t.dtype != torch.float32:
+            raise RuntimeError("%s must be a float tensor" % name)
+        if t.dim() != 3 or t.size(2) != 3:
+            raise RuntimeError("%s must have shape (B, N, 3)" % name)
+        if not _dense_storage(t):
+            raise RuntimeError("%s must densely fill its storage (the reference reads raw memory)" % name)
+    b, n, _ = xyz1.shape
+    m = xyz2.size(1)
+    if xyz2.size(0) != b:
+        raise RuntimeError("batch sizes differ: %d vs %d" % (b, xyz2.size(0)))
+    dev = xyz1.device
+    with torch.cuda.device(dev):
+        dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+        dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+        idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        rc = _native.lib().pdae_chamfer_fwd_f32(xyz1.data_ptr(), xyz2.data_ptr(), b, n, m, dist1.data_ptr(),
+                                                dist2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), _stream())
+    _native.check(rc, "pdae_chamfer_fwd_f32")
+    return [dist1, dist2, idx1, idx2]
+
+
+def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
+    """chamfer.backward: returns [grad_xyz1, grad_xyz2], allocated like the reference's
+    zeros_like (strides of the inputs preserved, chamfer.cu:212-213) and written in storage order."""
+    b, n, _ = xyz1.shape
+    m = xyz2.size(1)
+    dev = xyz1.device
+    grad_dist1 = grad_dist1.contiguous().float()
+    grad_dist2 = grad_dist2.contiguous().float()
+    with torch.cuda.device(dev):
+        gx1 = torch.empty_like(xyz1)  # preserve_format: dense inputs keep their strides
+        gx2 = torch.empty_like(xyz2)
+        rc = _native.lib().pdae_chamfer_bwd_f32(xyz1.data_ptr(), xyz2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
+                                                grad_dist1.data_ptr(), grad_dist2.data_ptr(), b, n, m, gx1.data_ptr(),
+                                                gx2.data_ptr(), _stream())
+    _native.check(rc, "pdae_chamfer_bwd_f32")
+    return [gx1, gx2]
+
+
+def chamfer_min_keys(queries, refs, ref_offset):
+    """One Chamfer direction against a local slice of the reference set -> packed int64 keys (B,Nq)."""
+    _require_f32_contig(queries, "queries")
+    _require_f32_contig(refs, "refs")
+    _require_cuda(queries, "chamfer_min_keys")
+    b, nq, _ = queries.shape
+    nr = refs.size(1)
+    with torch.cuda.device(queries.device):
+        keys = torch.empty((b, nq), dtype=torch.int64, device=queries.device)
+        rc = _native.lib().pdae_chamfer_min_keys_u64(queries.data_ptr(), refs.data_ptr(), b, nq, nr, int(ref_offset),
+                                                     keys.data_ptr(), _stream())
+    _native.check(rc, "pdae_chamfer_min_keys_u64")
+    return keys
+
+
+def chamfer_unpack_keys(keys):
+    keys = keys.contiguous()
+    with torch.cuda.device(keys.device):
+        dist = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+        idx = torch.empty(keys.shape, dtype=torch.int32, device=keys.device)
+        rc = _native.lib().pdae_chamfer_unpack_keys(keys.data_ptr(), keys.numel(), dist.data_ptr(), idx.data_ptr(),
+                                                    _stream())
+    _native.check(rc, "pdae_chamfer_unpack_keys")
+    return dist, idx
+
+
+# ---------------------------------------------------------------------------------------- DGCNN
+def feat_knn(x, k):
+    """models/dgcnn_util.py:7-12 `knn`: x (B,C,N) -> idx (B,N,k) int64."""
+    _require_cuda(x, "knn")
+    xc = x.detach()
+    if xc.dtype != torch.float32 or not xc.is_contiguous():
+        xc = xc.float().contiguous()
+    b, c, n = xc.shape
+    k = int(k)
+    if not (1 <= k <= n):
+        raise RuntimeError("selected index k out of range")  # torch.topk's message
+    with torch.cuda.device(xc.device):
+        idx = torch.empty((b, n, k), dtype=torch.int64, device=xc.device)
+        rc = _native.lib().pdae_feat_knn_f32(xc.data_ptr(), b, c, n, k, idx.data_ptr(), _stream())
+    _native.check(rc, "pdae_feat_knn_f32")
+    return idx
+
+
+def _graph_feature_fwd(x, idx):
+    b, c, n = x.shape
+    k = idx.size(2)
+    L = _native.lib()
+    with torch.cuda.device(x.device):
+        out = torch.empty((b, n, k, 2 * c), dtype=torch.float32, device=x.device)
+        nbytes = L.pdae_graph_feature_workspace_bytes(b, c, n)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+        rc = L.pdae_graph_feature_f32(x.data_ptr(), idx.data_ptr(), b, c, n, k, out.data_ptr(), ws.data_ptr(), nbytes,
+                                      _stream())
+    _native.check(rc, "pdae_graph_feature_f32")
+    return out
+
+
+def _graph_feature_bwd(gout_phys, idx, c, n):
+    b = gout_phys.size(0)
+    k = idx.size(2)
+    L = _native.lib()
+    with torch.cuda.device(gout_phys.device):
+        gx = torch.empty((b, c, n), dtype=torch.float32, device=gout_phys.device)
+        nbytes = L.pdae_graph_feature_workspace_bytes(b, c, n)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=gout_phys.device)
+        rc = L.pdae_graph_feature_grad_f32(gout_phys.data_ptr(), idx.data_ptr(), b, c, n, k, gx.data_ptr(),
+                                           ws.data_ptr(), nbytes, _stream())
+    _native.check(rc, "pdae_graph_feature_grad_f32")
+    return gx
+
+
+class GraphFeatureFunction(torch.autograd.Function):
+    """x (B,C,N) f32, idx (B,N,k) int64 per-cloud -> (B,2C,N,k) view of a (B,N,k,2C) tensor."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        xc = x.contiguous()
+        ctx.save_for_backward(idx)
+        ctx.cn = (xc.size(1), xc.size(2))
+        return _graph_feature_fwd(xc, idx).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        c, n = ctx.cn
+        g = grad.permute(0, 2, 3, 1).contiguous().float()
+        return _graph_feature_bwd(g, idx, c, n), None
+
+
+# ---------------------------------------------------------------------------- ball query / group
+def ball_query(new_xyz, xyz, radius, nsample):
+    """pointnet2._ext.ball_query(new_xyz (B,M,3), xyz (B,N,3), radius, nsample) -> (B,M,nsample) int32."""
+    _require_f32_contig(new_xyz, "new_xyz")
+    _require_f32_contig(xyz, "xyz")
+    _require_cuda(new_xyz, "ball_query")
+    _require_cuda(xyz, "ball_query")
+    b, m, _ = new_xyz.shape
+    n = xyz.size(1)
+    with torch.cuda.device(xyz.device):
+        idx = torch.empty((b, m, int(nsample)), dtype=torch.int32, device=xyz.device)
+        rc = _native.lib().pdae_ball_query_f32(new_xyz.data_ptr(), xyz.data_ptr(), b, n, m, float(radius),
+                                               int(nsample), idx.data_ptr(), _stream())
+    _native.check(rc, "pdae_ball_query_f32")
+    return idx
+
+
+def group_points(points, idx):
+    """pointnet2._ext.group_points(points (B,C,N), idx (B,P,S) int32) -> (B,C,P,S)."""
+    _require_f32_contig(points, "points")
+    _require_i32_contig(idx, "idx")
+    _require_cuda(points, "group_points")
+    _require_cuda(idx, "group_points")
+    b, c, n = points.shape
+    _, p, s = idx.shape
+    with torch.cuda.device(points.device):
+        out = torch.empty((b, c, p, s), dtype=torch.float32, device=points.device)
+        rc = _native.lib().pdae_group_points_f32(points.data_ptr(), idx.data_ptr(), b, c, n, p, s, out.data_ptr(),
+                                                 _stream())
+    _native.check(rc, "pdae_group_points_f32")
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    _require_f32_contig(grad_out, "grad_out")
+    _require_i32_contig(idx, "idx")
+    _require_cuda(grad_out, "group_points_grad")
+    b, c, p, s = grad_out.shape
+    with torch.cuda.device(grad_out.device):
+        out = torch.empty((b, c, int(n)), dtype=torch.float32, device=grad_out.device)
+        rc = _native.lib().pdae_group_points_grad_f32(grad_out.data_ptr(), idx.data_ptr(), b, c, int(n), p, s,
+                                                      out.data_ptr(), _stream())
+    _native.check(rc, "pdae_group_points_grad_f32")
+    return out
