@@ -1,0 +1,62 @@
+"""The C-ABI shared library loads and exports every symbol include/pointdae_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pointdae_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pointdae_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pdae_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    syms = declared_symbols()
+    for need in ("pdae_fps_f32", "pdae_gather_f32", "pdae_gather_grad_f32", "pdae_knn_f32", "pdae_group_f32",
+                 "pdae_feat_knn_f32", "pdae_graph_feature_f32", "pdae_graph_feature_grad_f32", "pdae_chamfer_fwd_f32",
+                 "pdae_chamfer_bwd_f32", "pdae_chamfer_min_keys_u64"):
+        assert need in syms
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_native.LIB_PATH):
+        _native.build()
+    handle = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(handle, name), "libpointdae_b200.so does not export %s" % name
+
+
+def test_python_binding_covers_the_header():
+    assert sorted(_native.SIGNATURES) == declared_symbols()
+
+
+def test_host_only_entry_points():
+    L = _native.lib()
+    assert L.pdae_abi_version() == 1
+    assert L.pdae_strerror(0) == b"success"
+    assert b"invalid" in L.pdae_strerror(-1)
+    assert L.pdae_fps_workspace_bytes(4, 2048, 64) == 0
+    assert L.pdae_fps_workspace_bytes(2, 100000, 64) == 2 * 100000 * 4
+    assert L.pdae_graph_feature_workspace_bytes(2, 64, 1024) == 2 * 64 * 1024 * 4
+
+
+def test_argument_validation_needs_no_gpu():
+    L = _native.lib()
+    # negative sizes / null pointers are rejected before any CUDA call
+    assert L.pdae_chamfer_fwd_f32(None, None, -1, 4, 4, None, None, None, None, None) == -1
+    assert L.pdae_chamfer_fwd_f32(None, None, 2, 4, 4, None, None, None, None, None) == -1
+    assert L.pdae_knn_f32(None, None, 1, 8, 4, 3, 0, 0, None, None, None) == -1
+    assert L.pdae_fps_f32(None, 0, 16, 4, None, None, 0, None) == 0  # empty batch is a no-op
+
+
+def test_source_is_sm100a_only():
+    sh = open(os.path.join(ROOT, "point-dae_b200", "csrc", "build.sh")).read()
+    assert "arch=compute_100a,code=sm_100a" in sh and "-lineinfo" in sh

@@ -1,0 +1,95 @@
+"""Host-side logic that needs no GPU: block-size rule, drop-in import surface, error behaviour on
+CPU tensors, storage-density rule of the Chamfer facade, shard partitioning."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import pointdae_b200
+from oracle import cpu as oracle
+from pointdae_b200 import _native, chamfer_dist, dgcnn_util, group, knn_cuda, ops, pointnet2_utils, sharded
+
+
+def test_fps_block_size_matches_reference_rule():
+    L = _native.lib()
+    for n in list(range(1, 3000)) + [4095, 4096, 4097, 8191, 8192, 65535, 65536, 100000, 1 << 20, (1 << 29) - 1, 1 << 29]:
+        want = oracle.fps_block_size(n)
+        assert L.pdae_fps_block_size(n) == want
+        # cuda_utils.h:15-21: largest power of two <= n, capped at 512
+        p = 1
+        while p * 2 <= n:
+            p *= 2
+        assert want == min(p, 512), n
+
+
+def test_install_makes_reference_imports_resolve():
+    pointdae_b200.install()
+    from pointnet2_ops import pointnet2_utils as p2u
+    from knn_cuda import KNN
+    import chamfer
+    import pointnet2._ext as ext
+    assert p2u.furthest_point_sample is pointnet2_utils.furthest_point_sample
+    assert p2u.gather_operation is pointnet2_utils.gather_operation
+    assert KNN is knn_cuda.KNN
+    assert callable(chamfer.forward) and callable(chamfer.backward)
+    for name in ("furthest_point_sampling", "gather_points", "gather_points_grad", "ball_query", "group_points",
+                 "group_points_grad", "three_nn", "three_interpolate", "three_interpolate_grad"):
+        assert callable(getattr(ext, name))  # bindings.cpp:9-22
+    with pytest.raises(NotImplementedError):
+        ext.three_nn(None, None)
+
+
+def test_modules_construct_without_cuda():
+    # datasets/corrupt_util_tensor.py:591 builds KNN at import time; build_loss_func builds the losses
+    k = knn_cuda.KNN(k=32, transpose_mode=True)
+    assert k.k == 32 and k._t is True
+    g = group.Group(64, 32)
+    assert g.num_group == 64 and g.group_size == 32 and isinstance(g.knn, knn_cuda.KNN)
+    chamfer_dist.ChamferDistanceL1()
+    chamfer_dist.ChamferDistanceL2(ignore_zeros=True)
+    assert len(list(g.parameters())) == 0
+
+
+def test_cpu_tensors_raise_like_the_reference():
+    x = torch.zeros(2, 16, 3)
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        pointnet2_utils.furthest_point_sample(x, 4)
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        pointnet2_utils.gather_operation(torch.zeros(2, 3, 16), torch.zeros(2, 4, dtype=torch.int32))
+    with pytest.raises(RuntimeError):
+        chamfer_dist.ChamferDistanceL2()(x, x)
+    with pytest.raises(RuntimeError):
+        knn_cuda.KNN(4, True)(x, x)
+    with pytest.raises(RuntimeError):
+        dgcnn_util.get_graph_feature(torch.zeros(2, 3, 16), k=4)
+    with pytest.raises(AssertionError):
+        knn_cuda.KNN(4, True)(torch.zeros(2, 16, 3), torch.zeros(3, 4, 3))  # batch sizes must agree
+
+
+def test_dense_storage_rule():
+    a = torch.zeros(4, 3, 36)
+    assert ops._dense_storage(a) and ops._dense_storage(a.transpose(1, 2)) and ops._dense_storage(a.permute(2, 0, 1))
+    assert not ops._dense_storage(torch.zeros(4, 36, 6)[:, :, :3])
+    assert not ops._dense_storage(torch.zeros(4, 36, 3)[:, ::2])
+    assert not ops._dense_storage(torch.zeros(1, 36, 3).expand(4, -1, -1))
+    assert ops._dense_storage(torch.zeros(0, 5, 3))
+
+
+@pytest.mark.parametrize("n,world", [(128, 8), (100000, 8), (10, 3), (3, 8), (0, 4), (2049, 2)])
+def test_shard_bounds_partition(n, world):
+    spans = [sharded.shard_bounds(n, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a, b), (c, d) in zip(spans[:-1], spans[1:]):
+        assert b == c and a <= b
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_key_packing_orders_by_distance_then_index():
+    d = np.array([0.0, 1e-30, 0.5, 0.5, 3.0, np.inf], dtype=np.float32)
+    i = np.array([7, 3, 9, 2, 0, 1], dtype=np.uint64)
+    keys = (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | i
+    order = np.argsort(keys.view(np.int64), kind="stable")
+    assert list(order) == [0, 1, 3, 2, 4, 5]
+    assert (keys < np.uint64(0x7fffffffffffffff)).all()  # identity of the MIN all-reduce stays on top
