@@ -100,8 +100,13 @@ int pdae_graph_feature_grad_f32(const float *gout, const int64_t *idx, int b, in
  * xyz1 (b,n,3), xyz2 (b,m,3) read as dense storage exactly like the reference's raw data_ptr
  * access.  dist1 (b,n), dist2 (b,m) squared distances; idx1, idx2 int32, lowest index on ties.
  * backward: gx1 (b,n,3), gx2 (b,m,3) overwritten.                                             */
+/* Optional workspace (pdae_chamfer_fwd_workspace_bytes, 8 bytes per point of the smaller cloud): when given,
+ * every point pair is evaluated ONCE and feeds both directions (the squared distance is symmetric bit for
+ * bit), halving the arithmetic; with workspace == NULL each direction is scanned separately.  Results are
+ * identical either way.                                                                          */
+size_t pdae_chamfer_fwd_workspace_bytes(int b, int n, int m);
 int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
-                         int *idx1, int *idx2, pdae_stream_t stream);
+                         int *idx1, int *idx2, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
 int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2, const float *gd1,
                          const float *gd2, int b, int n, int m, float *gx1, float *gx2, pdae_stream_t stream);
 

@@ -32,7 +32,8 @@ SIGNATURES = {
     "pdae_graph_feature_workspace_bytes": (_sz, [_i, _i, _i]),
     "pdae_graph_feature_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pdae_graph_feature_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
-    "pdae_chamfer_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdae_chamfer_fwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pdae_chamfer_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_chamfer_min_keys_u64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_chamfer_unpack_keys": (_i, [_vp, _ll, _vp, _vp, _vp]),

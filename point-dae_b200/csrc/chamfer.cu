@@ -11,16 +11,20 @@
 //     64-bit register pair) and streams the other cloud through shared memory in planar
 //     (SoA) tiles, so one LDS.128 feeds two packed FADD2/FMUL2/FFMA2 evaluations per query;
 //   * the inner loop carries no index: the running minimum is updated with one FMNMX3 per two
-//     pairs; the only bookkeeping is "which 32-point chunk last lowered the minimum";
-//   * after the scan each warp re-evaluates, cooperatively and coalesced, the single 32-point
-//     chunk recorded for each of its queries and takes the first lane whose distance equals
-//     the minimum bit-for-bit -> the lowest index, as the reference's strict `<` does.
+//     pairs; the only bookkeeping is "which group of 16 reference points last lowered the
+//     minimum" (one FSETP + SEL per sixteen pairs).  Every instruction that is not FMA-pipe work
+//     costs a dispatch slot the FMA pipe could have used (packed ops take two), so the loop is
+//     built to minimise them: 6 FMA-pipe slots + ~1.06 other slots per point pair;
+//   * after the scan every thread re-evaluates the single 16-point group recorded for each of
+//     its queries and takes the first point whose distance equals the minimum bit-for-bit ->
+//     the lowest index, as the reference's strict `<` does.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pdae {
 
-constexpr int CH_TILE = 512;  // reference points per shared-memory tile (3 planes x 2 KB)
-constexpr int CH_CHUNK = 32;  // argmin bookkeeping granularity == one warp-wide rescan
+constexpr int CH_GROUP = 16;  // argmin bookkeeping granularity: four LDS.128 steps = 16 reference points
 
 struct ChamferDir {
   const float *q;   // (b, nq, 3) query cloud
@@ -28,19 +32,28 @@ struct ChamferDir {
   float *dist;      // (b, nq) or null
   int *idx;         // (b, nq) or null
   uint64_t *keys;   // (b, nq) packed output (sharded mode) or null
+  uint64_t *colkeys;  // (b, nr) symmetric mode: (min over the queries, 32*QT-query group id), RED.MIN target
   int nq, nr;
   int qtiles;       // CTAs per cloud for this direction (0 = direction absent)
   int ref_offset;   // global index of r[0] (sharded mode)
 };
 
-template <int QT, int THREADS>
-__global__ void __launch_bounds__(THREADS) chamfer_min_kernel(const ChamferDir d0, const ChamferDir d1) {
+// SYM: the squared distance is symmetric bit for bit (the operands of every product only change
+// sign), so one evaluation of pair (a_i, b_j) serves both directions: besides the per-query running
+// minimum the kernel reduces, for every reference point, the minimum over the warp's 32*QT queries
+// (FMNMX3 across the thread's queries, one REDUX.MIN across the lanes) and posts
+// (min bits << 32 | query-group id) with a 64-bit RED.MIN per CTA; chamfer_col_recover_kernel then
+// finds the lowest query index inside the winning group.  Halves the FMA-pipe work of the forward.
+template <int QT, int THREADS, int MINB, bool SYM, int CH_TILE = 512 /* reference points per shared-memory tile */>
+__global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const ChamferDir d0, const ChamferDir d1) {
   constexpr int QPW = 32 * QT;                  // queries per warp
+  constexpr int W = THREADS / 32;
   constexpr int LD = 3 * CH_TILE / THREADS;     // floats staged per thread per tile
   static_assert(3 * CH_TILE % THREADS == 0, "tile must split evenly over the CTA");
-  static_assert(QT * THREADS * 20 <= 2 * 3 * CH_TILE * 4, "rescan records must fit in the tile buffers");
+  static_assert(CH_TILE % CH_GROUP == 0, "tile must hold whole bookkeeping groups");
 
   __shared__ __align__(16) float tile[2][3][CH_TILE];
+  __shared__ __align__(16) unsigned colmin[SYM ? 2 : 1][SYM ? W : 1][SYM ? CH_TILE : 4];
 
   const int per_cloud = d0.qtiles + d1.qtiles;
   const int cloud = blockIdx.x / per_cloud;
@@ -57,7 +70,7 @@ __global__ void __launch_bounds__(THREADS) chamfer_min_kernel(const ChamferDir d
 
   float2 qx[QT], qy[QT], qz[QT];
   float best[QT];
-  int bchunk[QT];
+  int bgrp[QT];
 #pragma unroll
   for (int s = 0; s < QT; ++s) {
     int q = qbase + s * 32 + lane;
@@ -67,7 +80,7 @@ __global__ void __launch_bounds__(THREADS) chamfer_min_kernel(const ChamferDir d
     qy[s] = make_float2(y, y);
     qz[s] = make_float2(z, z);
     best[s] = __int_as_float(0x7f800000);
-    bchunk[s] = 0;
+    bgrp[s] = 0;
   }
 
   float pre[LD];
@@ -90,6 +103,25 @@ __global__ void __launch_bounds__(THREADS) chamfer_min_kernel(const ChamferDir d
     }
   };
 
+  // SYM: post the per-warp column minima of tile `tp` (complete since the last barrier)
+  auto flush_cols = [&](int tp) {
+    if (!SYM) return;
+    uint64_t *ck = d0.colkeys + static_cast<size_t>(cloud) * nr;
+    const int tb = tp * CH_TILE;
+    for (int j = tid; j < CH_TILE && tb + j < nr; j += THREADS) {
+      unsigned v = colmin[tp & 1][0][j];
+      int wm = 0;
+#pragma unroll
+      for (int w = 1; w < W; ++w) {
+        const unsigned u = colmin[tp & 1][w][j];
+        wm = u < v ? w : wm;
+        v = u < v ? u : v;
+      }
+      atomicMin(reinterpret_cast<unsigned long long *>(ck + tb + j),
+                (static_cast<unsigned long long>(v) << 32) | static_cast<unsigned>(t * W + wm));
+    }
+  };
+
   const int ntiles = (nr + CH_TILE - 1) / CH_TILE;
   fetch(0);
   stash(0);
@@ -97,65 +129,112 @@ __global__ void __launch_bounds__(THREADS) chamfer_min_kernel(const ChamferDir d
   for (int tl = 0; tl < ntiles; ++tl) {
     const bool more = tl + 1 < ntiles;
     if (more) fetch((tl + 1) * CH_TILE);
+    if (tl > 0) flush_cols(tl - 1);
     const float *sx = tile[tl & 1][0], *sy = tile[tl & 1][1], *sz = tile[tl & 1][2];
+    unsigned pend[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    int pend_off = -1;
     const int left = nr - tl * CH_TILE;
-    const int nchunks = ((left < CH_TILE ? left : CH_TILE) + CH_CHUNK - 1) / CH_CHUNK;
-    const int chunk_base = tl * (CH_TILE / CH_CHUNK);
-    for (int c = 0; c < nchunks; ++c) {
-      float prev[QT];
+    const int ngroups = ((left < CH_TILE ? left : CH_TILE) + CH_GROUP - 1) / CH_GROUP;
+    const int group_base = tl * (CH_TILE / CH_GROUP);
+#pragma unroll 2
+    for (int g = 0; g < ngroups; ++g) {
+      const int gid = group_base + g;
+      float cur[QT];
 #pragma unroll
-      for (int s = 0; s < QT; ++s) prev[s] = best[s];
+      for (int s = 0; s < QT; ++s) cur[s] = best[s];
 #pragma unroll
-      for (int j = 0; j < CH_CHUNK; j += 4) {
-        const float4 X = *reinterpret_cast<const float4 *>(sx + c * CH_CHUNK + j);
-        const float4 Y = *reinterpret_cast<const float4 *>(sy + c * CH_CHUNK + j);
-        const float4 Z = *reinterpret_cast<const float4 *>(sz + c * CH_CHUNK + j);
-        const float2 x01 = make_float2(X.x, X.y), x23 = make_float2(X.z, X.w);
-        const float2 y01 = make_float2(Y.x, Y.y), y23 = make_float2(Y.z, Y.w);
-        const float2 z01 = make_float2(Z.x, Z.y), z23 = make_float2(Z.z, Z.w);
+      for (int h = 0; h < CH_GROUP; h += 8) {
+        const float4 X0 = *reinterpret_cast<const float4 *>(sx + g * CH_GROUP + h);
+        const float4 Y0 = *reinterpret_cast<const float4 *>(sy + g * CH_GROUP + h);
+        const float4 Z0 = *reinterpret_cast<const float4 *>(sz + g * CH_GROUP + h);
+        const float4 X1 = *reinterpret_cast<const float4 *>(sx + g * CH_GROUP + h + 4);
+        const float4 Y1 = *reinterpret_cast<const float4 *>(sy + g * CH_GROUP + h + 4);
+        const float4 Z1 = *reinterpret_cast<const float4 *>(sz + g * CH_GROUP + h + 4);
+        float2 dd[QT][4];
 #pragma unroll
         for (int s = 0; s < QT; ++s) {
-          const float2 da = dist_yxz2(sub2(x01, qx[s]), sub2(y01, qy[s]), sub2(z01, qz[s]));
-          const float2 db = dist_yxz2(sub2(x23, qx[s]), sub2(y23, qy[s]), sub2(z23, qz[s]));
-          const float tm = min3(da.x, da.y, db.x);
-          best[s] = min3(best[s], tm, db.y);
+          dd[s][0] = dist_yxz2(sub2(make_float2(X0.x, X0.y), qx[s]), sub2(make_float2(Y0.x, Y0.y), qy[s]),
+                               sub2(make_float2(Z0.x, Z0.y), qz[s]));
+          dd[s][1] = dist_yxz2(sub2(make_float2(X0.z, X0.w), qx[s]), sub2(make_float2(Y0.z, Y0.w), qy[s]),
+                               sub2(make_float2(Z0.z, Z0.w), qz[s]));
+          dd[s][2] = dist_yxz2(sub2(make_float2(X1.x, X1.y), qx[s]), sub2(make_float2(Y1.x, Y1.y), qy[s]),
+                               sub2(make_float2(Z1.x, Z1.y), qz[s]));
+          dd[s][3] = dist_yxz2(sub2(make_float2(X1.z, X1.w), qx[s]), sub2(make_float2(Y1.z, Y1.w), qy[s]),
+                               sub2(make_float2(Z1.z, Z1.w), qz[s]));
+          const float t0 = min3(dd[s][0].x, dd[s][0].y, dd[s][1].x);
+          const float t1 = min3(dd[s][1].y, dd[s][2].x, dd[s][2].y);
+          const float t2 = min3(dd[s][3].x, dd[s][3].y, t0);
+          cur[s] = min3(cur[s], t1, t2);
+        }
+        if (SYM) {  // column minima over this warp's 32*QT queries for the 8 reference points of the step
+          // the REDUX results of the previous step are stored only now, a full step of FMA work later, so
+          // their latency never stalls the warp
+          if (pend_off >= 0 && lane == 0) {
+            uint4 *dst = reinterpret_cast<uint4 *>(&colmin[tl & 1][warp][pend_off]);
+            dst[0] = make_uint4(pend[0], pend[1], pend[2], pend[3]);
+            dst[1] = make_uint4(pend[4], pend[5], pend[6], pend[7]);
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            float c = (r & 1) ? dd[0][r >> 1].y : dd[0][r >> 1].x;
+#pragma unroll
+            for (int s = 1; s + 1 < QT; s += 2)
+              c = min3(c, (r & 1) ? dd[s][r >> 1].y : dd[s][r >> 1].x, (r & 1) ? dd[s + 1][r >> 1].y : dd[s + 1][r >> 1].x);
+            if ((QT & 1) == 0) c = fminf(c, (r & 1) ? dd[QT - 1][r >> 1].y : dd[QT - 1][r >> 1].x);
+            pend[r] = __reduce_min_sync(0xffffffffu, __float_as_uint(c));
+          }
+          pend_off = g * CH_GROUP + h;
         }
       }
 #pragma unroll
-      for (int s = 0; s < QT; ++s) bchunk[s] = best[s] < prev[s] ? chunk_base + c : bchunk[s];
+      for (int s = 0; s < QT; ++s) {
+        bgrp[s] = cur[s] < best[s] ? gid : bgrp[s];
+        best[s] = cur[s];
+      }
+    }
+    if (SYM && pend_off >= 0 && lane == 0) {
+      uint4 *dst = reinterpret_cast<uint4 *>(&colmin[tl & 1][warp][pend_off]);
+      dst[0] = make_uint4(pend[0], pend[1], pend[2], pend[3]);
+      dst[1] = make_uint4(pend[4], pend[5], pend[6], pend[7]);
     }
     if (more) stash((tl + 1) & 1);
     __syncthreads();
   }
+  flush_cols(ntiles - 1);
 
-  // ---- index recovery: one coalesced 32-point rescan per query, warp-cooperative -------------
-  float4 *rec = reinterpret_cast<float4 *>(&tile[0][0][0]);
-  int *recc = reinterpret_cast<int *>(rec + QT * THREADS);
-#pragma unroll
-  for (int s = 0; s < QT; ++s) {
-    rec[warp * QPW + s * 32 + lane] = make_float4(qx[s].x, qy[s].x, qz[s].x, best[s]);
-    recc[warp * QPW + s * 32 + lane] = bchunk[s];
-  }
-  __syncwarp();
+  // ---- index recovery: each thread rescans the one 16-point group recorded per query ----------
+  // (scanned back to front so the lowest matching index is the one kept)
   int myidx[QT];
+  const bool vec_ok = (nr & 3) == 0;  // every cloud then starts 16-byte aligned
 #pragma unroll
   for (int s = 0; s < QT; ++s) {
-    myidx[s] = 0;
-#pragma unroll 4
-    for (int ii = 0; ii < 32; ++ii) {
-      const float4 rq = rec[warp * QPW + s * 32 + ii];
-      const int ch = recc[warp * QPW + s * 32 + ii];
-      const int j = ch * CH_CHUNK + lane;
-      const bool ok = j < nr;
-      float d = 0.0f;
-      if (ok) {
-        const float bx = __ldg(R + 3 * j), by = __ldg(R + 3 * j + 1), bz = __ldg(R + 3 * j + 2);
-        d = dist_yxz(__fsub_rn(bx, rq.x), __fsub_rn(by, rq.y), __fsub_rn(bz, rq.z));
+    const int base = bgrp[s] * CH_GROUP;
+    int found = 0;
+    if (vec_ok && base + CH_GROUP <= nr) {
+      const float4 *p4 = reinterpret_cast<const float4 *>(R + 3 * static_cast<size_t>(base));
+      float v[3 * CH_GROUP];
+#pragma unroll
+      for (int t = 0; t < 3 * CH_GROUP / 4; ++t) {
+        const float4 w = __ldg(p4 + t);
+        v[4 * t] = w.x; v[4 * t + 1] = w.y; v[4 * t + 2] = w.z; v[4 * t + 3] = w.w;
       }
-      const unsigned mk = __ballot_sync(0xffffffffu, ok && d == rq.w);
-      const int first = mk ? ch * CH_CHUNK + __ffs(mk) - 1 : 0;
-      if (ii == lane) myidx[s] = first;
+#pragma unroll
+      for (int t = CH_GROUP - 1; t >= 0; --t) {
+        const float d = dist_yxz(__fsub_rn(v[3 * t], qx[s].x), __fsub_rn(v[3 * t + 1], qy[s].x), __fsub_rn(v[3 * t + 2], qz[s].x));
+        found = (d == best[s]) ? base + t : found;
+      }
+    } else {
+#pragma unroll
+      for (int t = CH_GROUP - 1; t >= 0; --t) {
+        const int j = base + t;
+        if (j < nr) {
+          const float bx = __ldg(R + 3 * j), by = __ldg(R + 3 * j + 1), bz = __ldg(R + 3 * j + 2);
+          const float d = dist_yxz(__fsub_rn(bx, qx[s].x), __fsub_rn(by, qy[s].x), __fsub_rn(bz, qz[s].x));
+          found = (d == best[s]) ? j : found;
+        }
+      }
     }
+    myidx[s] = found;
   }
 
   float *dist = second ? d1.dist : d0.dist;
@@ -225,22 +304,22 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) chamfer_small_kernel(const f
 __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                                           const int *__restrict__ idx1, const int *__restrict__ idx2,
                                                           const float *__restrict__ gd1, const float *__restrict__ gd2,
-                                                          int n, int m, long long total1, long long total2,
-                                                          float *__restrict__ gx1, float *__restrict__ gx2) {
-  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+                                                          int n, int m, float *__restrict__ gx1, float *__restrict__ gx2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // point of cloud 1 (i < n) or of cloud 2 (i - n < m)
+  const size_t cloud = blockIdx.y;
   const float *A, *Bp, *gd;
   const int *idx;
   float *ga, *gb;
-  int na, nb;
-  if (i < total1) {
-    A = xyz1; Bp = xyz2; gd = gd1; idx = idx1; ga = gx1; gb = gx2; na = n; nb = m;
+  if (i < n) {
+    A = xyz1 + cloud * n * 3; Bp = xyz2 + cloud * m * 3; gd = gd1 + cloud * n; idx = idx1 + cloud * n;
+    ga = gx1 + cloud * n * 3; gb = gx2 + cloud * m * 3;
   } else {
-    i -= total1;
-    if (i >= total2) return;
-    A = xyz2; Bp = xyz1; gd = gd2; idx = idx2; ga = gx2; gb = gx1; na = m; nb = n;
+    i -= n;
+    if (i >= m) return;
+    A = xyz2 + cloud * m * 3; Bp = xyz1 + cloud * n * 3; gd = gd2 + cloud * m; idx = idx2 + cloud * m;
+    ga = gx2 + cloud * m * 3; gb = gx1 + cloud * n * 3;
   }
-  const long long cloud = i / na;
-  const long long j2 = cloud * nb + __ldg(idx + i);
+  const int j2 = __ldg(idx + i);
   const float g = __fmul_rn(__ldg(gd + i), 2.0f);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -248,15 +327,6 @@ __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float *__restric
     atomicAdd(ga + 3 * i + c, v);
     atomicAdd(gb + 3 * j2 + c, -v);
   }
-}
-
-// identity of the MIN reduction: larger than every real key both as uint64 and as int64 (torch /
-// NCCL reduce the keys as signed 64-bit; real keys have a clear top bit because d >= 0).
-constexpr uint64_t CHAMFER_KEY_IDENTITY = 0x7fffffffffffffffull;
-
-__global__ void __launch_bounds__(256) fill_keys_kernel(uint64_t *__restrict__ keys, long long count) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < count) keys[i] = CHAMFER_KEY_IDENTITY;
 }
 
 __global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t *__restrict__ keys, long long count,
@@ -268,27 +338,123 @@ __global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t *__rest
   idx[i] = static_cast<int>(static_cast<uint32_t>(k));
 }
 
+// tuning hook: PDAE_CHAMFER_CFG selects the CTA shape of the large-cloud kernel
+static int chamfer_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("PDAE_CHAMFER_CFG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+// queries per CTA of the kernel launch_min / launch_sym will pick (the callers size `qtiles` with it)
+static int chamfer_qpc(int nq_max, bool sym) {
+  if (!sym && nq_max <= 256) return 128;
+  switch (chamfer_variant() % 10) {
+    case 3: return 512;   // <2,256>
+    case 4: return 256;   // <2,128>
+    case 5: case 6: case 7: return 256;   // <4,64>
+    default: return 512;  // <4,128>
+  }
+}
+
+template <bool SYM>
 static int launch_min(const ChamferDir &d0, const ChamferDir &d1, int b, cudaStream_t st) {
   const long long per_cloud = static_cast<long long>(d0.qtiles) + d1.qtiles;
   const long long grid = per_cloud * b;
   if (grid <= 0) return 0;
   if (grid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  const unsigned g = static_cast<unsigned>(grid);
   const int nq_max = d0.nq > d1.nq ? d0.nq : d1.nq;
-  if (nq_max > 256) {
-    chamfer_min_kernel<4, 128><<<static_cast<unsigned>(grid), 128, 0, st>>>(d0, d1);
+  if (!SYM && nq_max <= 256) {
+    chamfer_min_kernel<1, 128, 1, false><<<g, 128, 0, st>>>(d0, d1);
   } else {
-    chamfer_min_kernel<1, 128><<<static_cast<unsigned>(grid), 128, 0, st>>>(d0, d1);
+    switch (chamfer_variant() % 10) {
+      case 1: chamfer_min_kernel<4, 128, 4, SYM><<<g, 128, 0, st>>>(d0, d1); break;
+      case 2: chamfer_min_kernel<4, 128, 3, SYM><<<g, 128, 0, st>>>(d0, d1); break;
+      case 3: chamfer_min_kernel<2, 256, 3, SYM><<<g, 256, 0, st>>>(d0, d1); break;
+      case 4: chamfer_min_kernel<2, 128, 6, SYM><<<g, 128, 0, st>>>(d0, d1); break;
+      case 5: chamfer_min_kernel<4, 64, 4, SYM, 256><<<g, 64, 0, st>>>(d0, d1); break;
+      case 6: chamfer_min_kernel<4, 64, 8, SYM, 256><<<g, 64, 0, st>>>(d0, d1); break;
+      case 7: chamfer_min_kernel<4, 64, 6, SYM, 256><<<g, 64, 0, st>>>(d0, d1); break;
+      default: chamfer_min_kernel<4, 128, 1, SYM><<<g, 128, 0, st>>>(d0, d1); break;
+    }
   }
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
+}
+
+// identity of the MIN reduction over packed keys: larger than every real key both as uint64 and as
+// int64 (torch / NCCL reduce the keys as signed 64-bit; real keys have a clear top bit because d >= 0).
+constexpr uint64_t CHAMFER_KEY_IDENTITY = 0x7fffffffffffffffull;
+
+__global__ void __launch_bounds__(256) fill_keys_kernel(uint64_t *__restrict__ keys, long long count) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) keys[i] = CHAMFER_KEY_IDENTITY;
+}
+
+// symmetric mode, second half: one warp per column point b_j.  colkeys[j] = (min_i d(a_i, b_j), id of the
+// QPG-query group holding a minimiser; lowest such group).  Scanning that group in index order and taking
+// the first query whose distance equals the minimum bit for bit yields the lowest index overall.
+// QPG = queries per group (32 * QT of the main kernel).  A group's queries are contiguous, so each lane
+// takes QPG/32 consecutive ones (float4 loads when the cloud base is 16-byte aligned) and the whole group
+// is examined in one step; lanes are in index order, hence ballot + ffs gives the lowest index.
+template <int QPG>
+__global__ void __launch_bounds__(256) chamfer_col_recover_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
+                                                                  const uint64_t *__restrict__ colkeys, int n_rows,
+                                                                  int n_cols,
+                                                                  float *__restrict__ dist, int *__restrict__ idx) {
+  constexpr int PER = QPG / 32;  // consecutive queries per lane
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // column point within the cloud
+  if (j >= n_cols) return;
+  const int lane = threadIdx.x & 31;
+  const size_t cloud = blockIdx.y;
+  const size_t gw = cloud * n_cols + j;
+  const uint64_t key = colkeys[gw];
+  const float v = __uint_as_float(static_cast<uint32_t>(key >> 32));
+  const int base = static_cast<int>(static_cast<uint32_t>(key)) * QPG + lane * PER;
+  const float bx = __ldg(cols + 3 * gw), by = __ldg(cols + 3 * gw + 1), bz = __ldg(cols + 3 * gw + 2);
+  const float *__restrict__ A = rows + cloud * n_rows * 3;
+  float c[3 * PER];
+  if ((n_rows & 3) == 0 && PER == 4 && base + PER <= n_rows) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(A + 3 * static_cast<size_t>(base));
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const float4 w = __ldg(p4 + t);
+      c[4 * t] = w.x; c[4 * t + 1] = w.y; c[4 * t + 2] = w.z; c[4 * t + 3] = w.w;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 3 * PER; ++t) c[t] = (base + t / 3 < n_rows) ? __ldg(A + 3 * static_cast<size_t>(base) + t) : __int_as_float(0x7fc00000);
+  }
+  int first = PER;  // first matching query of this lane
+#pragma unroll
+  for (int t = PER - 1; t >= 0; --t) {
+    const float d = dist_yxz(__fsub_rn(bx, c[3 * t]), __fsub_rn(by, c[3 * t + 1]), __fsub_rn(bz, c[3 * t + 2]));
+    first = (d == v) ? t : first;  // NaN padding never matches
+  }
+  const unsigned mk = __ballot_sync(0xffffffffu, first < PER);
+  const int src = mk ? __ffs(mk) - 1 : 0;
+  const int found = __shfl_sync(0xffffffffu, base + first, src);
+  if (lane == 0) {
+    dist[gw] = v;
+    idx[gw] = mk ? found : 0;
+  }
 }
 
 }  // namespace pdae
 
 using namespace pdae;
 
+extern "C" size_t pdae_chamfer_fwd_workspace_bytes(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0) return 0;
+  if (n <= SMALL_MAX && m <= SMALL_MAX) return 0;
+  return static_cast<size_t>(b) * (n < m ? n : m) * sizeof(uint64_t);
+}
+
 extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1,
-                                    float *dist2, int *idx1, int *idx2, pdae_stream_t stream) {
+                                    float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
+                                    pdae_stream_t stream) {
   if (b < 0 || n < 0 || m < 0) return PDAE_E_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t bn = static_cast<size_t>(b) * n, bm = static_cast<size_t>(b) * m;
@@ -315,10 +481,38 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
     return 0;
   }
   const int nq_max = n > m ? n : m;
-  const int qpc = nq_max > 256 ? 512 : 128;
-  ChamferDir d0{xyz1, xyz2, dist1, idx1, nullptr, n, m, ceil_div(n, qpc), 0};
-  ChamferDir d1{xyz2, xyz1, dist2, idx2, nullptr, m, n, ceil_div(m, qpc), 0};
-  return launch_min(d0, d1, b, st);
+  const size_t need = pdae_chamfer_fwd_workspace_bytes(b, n, m);
+  const bool sym = workspace != nullptr && workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 10;
+  if (sym) {
+    // rows (register-resident queries) = the larger cloud, columns = the smaller one
+    const bool swap = m > n;
+    const float *rows = swap ? xyz2 : xyz1, *cols = swap ? xyz1 : xyz2;
+    const int nr_rows = swap ? m : n, nr_cols = swap ? n : m;
+    float *drow = swap ? dist2 : dist1, *dcol = swap ? dist1 : dist2;
+    int *irow = swap ? idx2 : idx1, *icol = swap ? idx1 : idx2;
+    uint64_t *ck = static_cast<uint64_t *>(workspace);
+    const long long ncol = static_cast<long long>(b) * nr_cols;
+    if (b > 65535) return PDAE_E_UNSUPPORTED;
+    fill_keys_kernel<<<static_cast<unsigned>((ncol + 255) / 256), 256, 0, st>>>(ck, ncol);
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+    const int qpc = chamfer_qpc(nr_rows, true);
+    ChamferDir d0{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, ceil_div(nr_rows, qpc), 0};
+    ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+    const int rc = launch_min<true>(d0, d1, b, st);
+    if (rc) return rc;
+    const int v = chamfer_variant() % 10;
+    const dim3 rgrid(static_cast<unsigned>((static_cast<long long>(nr_cols) * 32 + 255) / 256), b);
+    if (v == 3 || v == 4)  // queries per warp = 32 * QT of the variant launched
+      chamfer_col_recover_kernel<64><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
+    else
+      chamfer_col_recover_kernel<128><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+  }
+  const int qpc = chamfer_qpc(nq_max, false);
+  ChamferDir d0{xyz1, xyz2, dist1, idx1, nullptr, nullptr, n, m, ceil_div(n, qpc), 0};
+  ChamferDir d1{xyz2, xyz1, dist2, idx2, nullptr, nullptr, m, n, ceil_div(m, qpc), 0};
+  return launch_min<false>(d0, d1, b, st);
 }
 
 extern "C" int pdae_chamfer_min_keys_u64(const float *queries, const float *refs, int b, int nq, int nr,
@@ -333,10 +527,10 @@ extern "C" int pdae_chamfer_min_keys_u64(const float *queries, const float *refs
     PDAE_RETURN_IF_LAUNCH_FAILED();
     return 0;
   }
-  const int qpc = nq > 256 ? 512 : 128;
-  ChamferDir d0{queries, refs, nullptr, nullptr, keys, nq, nr, ceil_div(nq, qpc), ref_offset};
-  ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
-  return launch_min(d0, d1, b, st);
+  const int qpc = chamfer_qpc(nq, false);
+  ChamferDir d0{queries, refs, nullptr, nullptr, keys, nullptr, nq, nr, ceil_div(nq, qpc), ref_offset};
+  ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+  return launch_min<false>(d0, d1, b, st);
 }
 
 extern "C" int pdae_chamfer_unpack_keys(const uint64_t *keys, long long count, float *dist, int *idx,
@@ -362,10 +556,9 @@ extern "C" int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const 
   if (t2) PDAE_CUDA_TRY(cudaMemsetAsync(gx2, 0, static_cast<size_t>(t2) * 3 * sizeof(float), st));
   if (n == 0 || m == 0 || b == 0) return 0;  // reference: the loops never execute, grads stay zero
   if (!idx1 || !idx2 || !gd1 || !gd2) return PDAE_E_INVALID;
-  const long long grid = (t1 + t2 + 255) / 256;
-  if (grid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
-  chamfer_bwd_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(xyz1, xyz2, idx1, idx2, gd1, gd2, n, m, t1, t2, gx1,
-                                                                 gx2);
+  if (b > 65535) return PDAE_E_UNSUPPORTED;
+  const dim3 grid(static_cast<unsigned>((static_cast<long long>(n) + m + 255) / 256), b);
+  chamfer_bwd_kernel<<<grid, 256, 0, st>>>(xyz1, xyz2, idx1, idx2, gd1, gd2, n, m, gx1, gx2);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }

@@ -19,6 +19,8 @@
 //   * clouds too large for one CTA's registers fall back to a variant that keeps the running
 //     minima in a global workspace (same arithmetic, same tie rule).
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -90,17 +92,28 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ da
   int old = 0;
   for (int j = 1; j < m; ++j) {
     const float4 o = sp[old];
-    float best = -1.0f;
-    int bestp = 0;
+    float v[P];
+    int vi[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const float d = dist_yxz(__fsub_rn(px[p], o.x), __fsub_rn(py[p], o.y), __fsub_rn(pz[p], o.z));
-      const float d2 = fminf(d, pt[p]);
-      pt[p] = d2;
-      const bool take = d2 > best;
-      bestp = take ? p : bestp;
-      best = take ? d2 : best;
+      pt[p] = fminf(d, pt[p]);
+      v[p] = pt[p];
+      vi[p] = p;
     }
+    // first-maximum tournament (strict `>` keeps the lower p on ties, like the reference's serial scan)
+#pragma unroll
+    for (int stride = 1; stride < P; stride *= 2) {
+#pragma unroll
+      for (int i = 0; i + stride < P; i += 2 * stride) {
+        const bool take = v[i + stride] > v[i];
+        v[i] = take ? v[i + stride] : v[i];
+        vi[i] = take ? vi[i + stride] : vi[i];
+      }
+    }
+    const bool any = v[0] > -1.0f;
+    const float best = any ? v[0] : -1.0f;
+    const int bestp = any ? vi[0] : 0;
     // a thread with no valid point reports (value -1, index 0) like the reference (:93-94)
     const int bk = best < 0.0f ? 0 : tid + bestp * T;
     const unsigned r = fps_block_argmax<T>(fps_val_bits(best), fps_rank(bk, lg_bs), slots, j);
@@ -225,6 +238,19 @@ static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx,
   const int bs = pdae_fps_block_size(n);
   const int lg_bs = ilog2_floor(bs);
   // thread count must be a multiple of bs so that ascending k inside a thread is rank order
+  // (bs <= 512 and bs <= n, so every configuration below satisfies T % bs == 0 or is rejected).
+#define PDAE_FPS_TRY(T, P)                                                                   \
+  if (want_t == (T) && want_p == (P) && n <= (T) * (P) && (T) % bs == 0)                      \
+    return launch_fps_reg<T, P>(data, b, n, c, m, lg_bs, idx, centers, st);
+  int want_t = 0, want_p = 0;
+  if (const char *e = getenv("PDAE_FPS_CFG")) {  // tuning hook: "T,P"
+    if (sscanf(e, "%d,%d", &want_t, &want_p) == 2) {
+      PDAE_FPS_TRY(128, 8) PDAE_FPS_TRY(128, 16) PDAE_FPS_TRY(128, 32) PDAE_FPS_TRY(256, 4) PDAE_FPS_TRY(256, 8)
+      PDAE_FPS_TRY(256, 16) PDAE_FPS_TRY(512, 2) PDAE_FPS_TRY(512, 4) PDAE_FPS_TRY(512, 8) PDAE_FPS_TRY(512, 16)
+      PDAE_FPS_TRY(1024, 1) PDAE_FPS_TRY(1024, 2) PDAE_FPS_TRY(1024, 4) PDAE_FPS_TRY(1024, 8)
+    }
+  }
+#undef PDAE_FPS_TRY
   if (n <= 128) return launch_fps_reg<128, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= 256) return launch_fps_reg<256, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= 512) return launch_fps_reg<512, 1>(data, b, n, c, m, lg_bs, idx, centers, st);

@@ -15,65 +15,9 @@
 // (32 entries) is bitonic-sorted and merged into the warp-resident sorted list (one key per lane
 // per 32 of k).  Keys are (float bits << 32 | index), so the unsigned order *is* the
 // (distance, lower index first) order and the selection is exact and deterministic.
-#include "common.cuh"
+#include "knn_select.cuh"
 
 namespace pdae {
-
-constexpr int KNN_WARPS = 8;
-constexpr int KNN_THREADS = KNN_WARPS * 32;
-constexpr int KNN_MAX_K = 128;
-constexpr uint64_t KEY_INF = 0xffffffffffffffffull;
-
-__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) {
-  const unsigned lo = __shfl_xor_sync(0xffffffffu, static_cast<unsigned>(v), m);
-  const unsigned hi = __shfl_xor_sync(0xffffffffu, static_cast<unsigned>(v >> 32), m);
-  return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-  const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(v), src);
-  const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(v >> 32), src);
-  return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
-__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a < b ? b : a; }
-
-// ascending bitonic sort of one key per lane
-__device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const uint64_t o = shfl_xor64(v, j);
-      const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
-      v = keep_min ? umin64(v, o) : umax64(v, o);
-    }
-  }
-  return v;
-}
-// lanes hold a bitonic sequence -> ascending
-__device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t v, int lane) {
-#pragma unroll
-  for (int j = 16; j > 0; j >>= 1) {
-    const uint64_t o = shfl_xor64(v, j);
-    v = (lane & j) == 0 ? umin64(v, o) : umax64(v, o);
-  }
-  return v;
-}
-
-// merge 32 ascending candidates `c` into the ascending list L[0..NS) (32 keys per slot),
-// keeping the 32*NS smallest.
-template <int NS>
-__device__ __forceinline__ void warp_merge(uint64_t (&L)[NS], uint64_t c, int lane) {
-  uint64_t mcur = warp_bitonic_merge32(umin64(L[NS - 1], shfl64(c, 31 - lane)), lane);
-#pragma unroll
-  for (int s = NS - 2; s >= 0; --s) {
-    const uint64_t r = shfl64(mcur, 31 - lane);
-    const uint64_t lo = umin64(L[s], r), hi = umax64(L[s], r);
-    L[s + 1] = warp_bitonic_merge32(hi, lane);
-    mcur = warp_bitonic_merge32(lo, lane);
-  }
-  L[0] = mcur;
-}
 
 struct KnnArgs {
   const float *ref;    // PLANAR ? (b, dim, r) : (b, r, dim)
@@ -100,7 +44,6 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnArgs a) {
   const float *__restrict__ Qp = PLANAR ? R : a.query + static_cast<size_t>(cloud) * q * dim;
   uint64_t *queue = queue_all + warp * 64;
   const int ntiles = (r + tile - 1) / tile;
-  const unsigned lt_mask = (1u << lane) - 1u;
   const int kslot = (k - 1) >> 5, klane = (k - 1) & 31;
 
   for (int qi = 0; qi < a.qpw; ++qi) {
@@ -114,11 +57,8 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnArgs a) {
         q0 = __ldg(Qp + 3 * qidx); q1 = __ldg(Qp + 3 * qidx + 1); q2 = __ldg(Qp + 3 * qidx + 2);
       }
     }
-    uint64_t L[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) L[s] = KEY_INF;
-    uint64_t tau = KEY_INF;
-    int qn = 0;
+    WarpSelect<NS> sel;
+    sel.init();
 
     for (int tl = 0; tl < ntiles; ++tl) {
       const int tbase = tl * tile;
@@ -154,40 +94,18 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnArgs a) {
           }
         }
         const uint64_t key = pack_key(d, static_cast<uint32_t>(tbase + j));
-        const bool pass = in && key < tau;
-        const unsigned mk = __ballot_sync(0xffffffffu, pass);
-        if (mk) {
-          if (pass) queue[qn + __popc(mk & lt_mask)] = key;
-          qn += __popc(mk);
-          __syncwarp();
-          if (qn >= 32) {
-            qn -= 32;
-            uint64_t c = queue[qn + lane];
-            __syncwarp();
-            c = warp_sort32(c, lane);
-            warp_merge<NS>(L, c, lane);
-            uint64_t lk = L[0];
-#pragma unroll
-            for (int s = 1; s < NS; ++s) lk = (s == kslot) ? L[s] : lk;
-            tau = shfl64(lk, klane);
-          }
-        }
+        sel.offer(in && key < sel.tau, key, queue, lane, kslot, klane);
       }
     }
     if (!qvalid) continue;
-    if (qn > 0) {
-      uint64_t c = lane < qn ? queue[lane] : KEY_INF;
-      __syncwarp();
-      c = warp_sort32(c, lane);
-      warp_merge<NS>(L, c, lane);
-    }
+    sel.finish(queue, lane);
     // ---- epilogue: ascending list -> outputs -------------------------------------------------
     const size_t bq = static_cast<size_t>(cloud) * q + qidx;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       const int p = s * 32 + lane;
       if (p < k) {
-        const uint64_t key = L[s];
+        const uint64_t key = sel.L[s];
         const uint32_t ji = static_cast<uint32_t>(key);
         const size_t o = a.out_kq ? (static_cast<size_t>(cloud) * k + p) * q + qidx : bq * k + p;
         if (a.idx) a.idx[o] = static_cast<int64_t>(ji);
@@ -252,10 +170,11 @@ extern "C" int pdae_knn_f32(const float *ref, const float *query, int b, int r, 
   if (b == 0 || q == 0) return 0;
   if (k > r || k > KNN_MAX_K) return PDAE_E_INVALID;
   if (!ref || !query || (!dist && !idx)) return PDAE_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dim == 3 && k <= 64) return knn3_points(ref, query, b, r, q, k, out_kq ? 1 : 0, dist, idx, nullptr, st);
   KnnArgs a{ref, query, dist, idx, nullptr, r, q, dim, k, 0, 1, out_kq ? 1 : 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   return dim == 3 ? launch_knn<3, false>(a, b, st) : launch_knn<0, false>(a, b, st);
 }
 
@@ -265,6 +184,7 @@ extern "C" int pdae_group_f32(const float *xyz, const float *center, int b, int 
   if (b == 0 || g == 0) return 0;
   if (m > n || m > KNN_MAX_K) return PDAE_E_INVALID;
   if (!xyz || !center || !neighborhood) return PDAE_E_INVALID;
+  if (m <= 64) return knn3_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, static_cast<cudaStream_t>(stream));
   KnnArgs a{xyz, center, nullptr, idx, neighborhood, n, g, 3, m, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
@@ -279,6 +199,7 @@ int pdae::feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *
   if (b == 0 || n == 0) return 0;
   if (k > n || k > KNN_MAX_K) return PDAE_E_INVALID;
   if (!x || !idx) return PDAE_E_INVALID;
+  if (c == 3 && k <= 64) return knn3_planar(x, b, n, k, idx, st);
   KnnArgs a{x, nullptr, nullptr, idx, nullptr, n, n, c, k, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;

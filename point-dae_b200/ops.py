@@ -162,7 +162,7 @@ def group_points_knn(xyz, center, group_size, want_idx=True):
 
 
 # -------------------------------------------------------------------------------------- Chamfer
-def chamfer_forward(xyz1, xyz2):
+def chamfer_forward(xyz1, xyz2, symmetric=True):
     """chamfer.forward: returns [dist1 (B,N), dist2 (B,M), idx1 int32, idx2 int32].
 
     Reference-faithful storage semantics (chamfer.cu:159-164 reads raw data_ptr): a tensor whose
@@ -189,8 +189,14 @@ def chamfer_forward(xyz1, xyz2):
         dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
         idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
         idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
-        rc = _native.lib().pdae_chamfer_fwd_f32(xyz1.data_ptr(), xyz2.data_ptr(), b, n, m, dist1.data_ptr(),
-                                                dist2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), _stream())
+        L = _native.lib()
+        # with the workspace every pair is evaluated once for both directions; without it (symmetric=False)
+        # each direction is scanned separately -- same results, twice the arithmetic
+        nbytes = L.pdae_chamfer_fwd_workspace_bytes(b, n, m) if symmetric else 0
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
+        rc = L.pdae_chamfer_fwd_f32(xyz1.data_ptr(), xyz2.data_ptr(), b, n, m, dist1.data_ptr(), dist2.data_ptr(),
+                                    idx1.data_ptr(), idx2.data_ptr(), ws.data_ptr() if nbytes else None, nbytes,
+                                    _stream())
     _native.check(rc, "pdae_chamfer_fwd_f32")
     return [dist1, dist2, idx1, idx2]
 

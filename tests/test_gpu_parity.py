@@ -211,6 +211,22 @@ def test_chamfer_matches_reference_cuda(b, n, m):
     assert_grad_close(gx2.cpu().numpy(), rg2.cpu().numpy())
 
 
+@pytest.mark.parametrize("b,n,m", [(2, 2048, 2048), (3, 700, 1300), (2, 1300, 700), (1, 5000, 300), (2, 300, 5000), (4, 513, 257)])
+def test_chamfer_symmetric_and_two_pass_kernels_agree(b, n, m):
+    """The single-evaluation (workspace) path and the two-scan path must give identical bits."""
+    x1 = cu(synth.adversarial(synth.clouds(b, n, seed=700 + n), seed=n, n_small=0, n_dup=n // 8))
+    x2 = cu(synth.adversarial(synth.clouds(b, m, seed=800 + m), seed=m, n_small=0, n_dup=m // 8))
+    x2[:, : min(n, m) // 2] = x1[:, : min(n, m) // 2]  # exact zero distances and cross-cloud ties
+    a = ops.chamfer_forward(x1, x2, symmetric=True)
+    c = ops.chamfer_forward(x1, x2, symmetric=False)
+    for u, v in zip(a, c):
+        assert torch.equal(u, v)
+    wd1, wd2, wi1, wi2 = oracle.chamfer_fwd(x1.cpu().numpy(), x2.cpu().numpy())
+    np.testing.assert_array_equal(a[2].cpu().numpy(), wi1)
+    np.testing.assert_array_equal(a[3].cpu().numpy(), wi2)
+    np.testing.assert_array_equal(a[1].cpu().numpy(), wd2)
+
+
 def test_chamfer_transposed_input_reference_faithful():
     """models/PointCAE_transformer.py:1059-1066 passes a transposed view; the reference reads raw storage."""
     conv_out = cu(synth.clouds(8, 36, seed=33)).transpose(1, 2).contiguous()  # (8,3,36)
