@@ -42,6 +42,21 @@ __device__ __forceinline__ int fps_unrank(unsigned r, int lg_bs) {
   return static_cast<int>((hi << lg_bs) | slot);
 }
 
+// register i of a thread  ->  which of the thread's points (k = tid + p*T) it holds
+template <int S, int PG>
+__host__ __device__ constexpr int fps_point_of_reg(int i) {
+  int sub = i / PG, rev = 0;
+  for (int b = 0; b < S; ++b) rev |= ((sub >> b) & 1) << (S - 1 - b);
+  return rev + ((i % PG) << S);
+}
+template <int S, int PG>
+__device__ __forceinline__ int fps_point_of_reg_rt(int i) {
+  if (S == 0) return i;
+  const int sub = i / PG;
+  const int rev = static_cast<int>(__brev(static_cast<unsigned>(sub)) >> (32 - S));
+  return rev + ((i % PG) << S);
+}
+
 // block-wide arg-max of (value bits, rank): returns the winning rank in every thread.
 template <int T>
 __device__ __forceinline__ unsigned fps_block_argmax(unsigned vb, unsigned rank, uint2 *slots /*[2][32]*/, int it) {
@@ -61,7 +76,10 @@ __device__ __forceinline__ unsigned fps_block_argmax(unsigned vb, unsigned rank,
 }
 
 // ---- register-resident variant: n <= T*P -----------------------------------------------------
-template <int T, int P>
+// S = log2(bs / T) when the CTA is narrower than the reference's block (T < bs = 512): a thread then owns
+// 2^S different reference slots, and its registers are laid out in tie-rank order (slot sub-index
+// bit-reversed first, then k / bs) so that the in-thread first-maximum scan still reproduces the rule.
+template <int T, int P, int S>
 __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ data, int n, int c, int m, int lg_bs,
                                                     int *__restrict__ idx, float *__restrict__ centers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,10 +89,12 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ da
   const float *__restrict__ cloud = data + static_cast<size_t>(blockIdx.x) * n * c;
   int *__restrict__ out = idx + static_cast<size_t>(blockIdx.x) * m;
 
+  static_assert(P % (1 << S) == 0, "points per thread must cover whole slot groups");
+  constexpr int PG = P >> S;  // points per slot sub-index
   float px[P], py[P], pz[P], pt[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) {
-    const int k = tid + p * T;
+    const int k = tid + fps_point_of_reg<S, PG>(p) * T;
     float x = 0.f, y = 0.f, z = 0.f, t = -2.0f;
     if (k < n) {
       x = __ldg(cloud + static_cast<size_t>(k) * c);
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ da
     const float best = any ? v[0] : -1.0f;
     const int bestp = any ? vi[0] : 0;
     // a thread with no valid point reports (value -1, index 0) like the reference (:93-94)
-    const int bk = best < 0.0f ? 0 : tid + bestp * T;
+    const int bk = best < 0.0f ? 0 : tid + fps_point_of_reg_rt<S, PG>(bestp) * T;
     const unsigned r = fps_block_argmax<T>(fps_val_bits(best), fps_rank(bk, lg_bs), slots, j);
     old = fps_unrank(r, lg_bs);
     if (tid == 0) out[j] = old;
@@ -210,15 +230,15 @@ static int ilog2_floor(int v) {
   return l;
 }
 
-template <int T, int P>
+template <int T, int P, int S = 0>
 static int launch_fps_reg(const float *data, int b, int n, int c, int m, int lg_bs, int *idx, float *centers,
                           cudaStream_t st) {
   const size_t smem = static_cast<size_t>(n) * sizeof(float4) + 2 * 32 * sizeof(uint2);
   if (smem > 48 * 1024) {
-    PDAE_CUDA_TRY(cudaFuncSetAttribute(fps_reg_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(fps_reg_kernel<T, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
   }
-  fps_reg_kernel<T, P><<<b, T, smem, st>>>(data, n, c, m, lg_bs, idx, centers);
+  fps_reg_kernel<T, P, S><<<b, T, smem, st>>>(data, n, c, m, lg_bs, idx, centers);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
@@ -240,24 +260,33 @@ static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx,
   // thread count must be a multiple of bs so that ascending k inside a thread is rank order
   // (bs <= 512 and bs <= n, so every configuration below satisfies T % bs == 0 or is rejected).
 #define PDAE_FPS_TRY(T, P)                                                                   \
-  if (want_t == (T) && want_p == (P) && n <= (T) * (P) && (T) % bs == 0)                      \
-    return launch_fps_reg<T, P>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (want_t == (T) && want_p == (P) && n <= (T) * (P)) {                                     \
+    if ((T) % bs == 0) return launch_fps_reg<T, P, 0>(data, b, n, c, m, lg_bs, idx, centers, st); \
+    if constexpr ((T) == 256 && (P) % 2 == 0) {                                               \
+      if (bs == 512) return launch_fps_reg<T, P, 1>(data, b, n, c, m, lg_bs, idx, centers, st); \
+    }                                                                                         \
+    if constexpr ((T) == 128 && (P) % 4 == 0) {                                               \
+      if (bs == 512) return launch_fps_reg<T, P, 2>(data, b, n, c, m, lg_bs, idx, centers, st); \
+    }                                                                                         \
+  }
   int want_t = 0, want_p = 0;
   if (const char *e = getenv("PDAE_FPS_CFG")) {  // tuning hook: "T,P"
     if (sscanf(e, "%d,%d", &want_t, &want_p) == 2) {
       PDAE_FPS_TRY(128, 8) PDAE_FPS_TRY(128, 16) PDAE_FPS_TRY(128, 32) PDAE_FPS_TRY(256, 4) PDAE_FPS_TRY(256, 8)
-      PDAE_FPS_TRY(256, 16) PDAE_FPS_TRY(512, 2) PDAE_FPS_TRY(512, 4) PDAE_FPS_TRY(512, 8) PDAE_FPS_TRY(512, 16)
-      PDAE_FPS_TRY(1024, 1) PDAE_FPS_TRY(1024, 2) PDAE_FPS_TRY(1024, 4) PDAE_FPS_TRY(1024, 8)
+      PDAE_FPS_TRY(256, 16) PDAE_FPS_TRY(256, 32) PDAE_FPS_TRY(512, 2) PDAE_FPS_TRY(512, 4) PDAE_FPS_TRY(512, 8)
+      PDAE_FPS_TRY(512, 16) PDAE_FPS_TRY(1024, 4) PDAE_FPS_TRY(1024, 8)
     }
   }
 #undef PDAE_FPS_TRY
+  // defaults from profiles/tune_kernels.py on B200: 8 warps per CTA keep the replicated reduction cheap
   if (n <= 128) return launch_fps_reg<128, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= 256) return launch_fps_reg<256, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 512) return launch_fps_reg<512, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 1024) return launch_fps_reg<512, 2>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 2048) return launch_fps_reg<512, 4>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 4096) return launch_fps_reg<1024, 4>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 8192) return launch_fps_reg<1024, 8>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n < 512) return launch_fps_reg<256, 2>(data, b, n, c, m, lg_bs, idx, centers, st);  // bs == 256
+  // from here on bs == 512 and the 256-thread CTA uses the rank-ordered register layout (S = 1)
+  if (n <= 1024) return launch_fps_reg<256, 4, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 2048) return launch_fps_reg<256, 8, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 4096) return launch_fps_reg<256, 16, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 8192) return launch_fps_reg<256, 32, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= FPS_REG_MAX_N) return launch_fps_reg<512, 24>(data, b, n, c, m, lg_bs, idx, centers, st);
   const size_t need = static_cast<size_t>(b) * n * sizeof(float);
   if (!ws || ws_bytes < need) return PDAE_E_WORKSPACE;

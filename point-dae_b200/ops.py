@@ -13,6 +13,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(dev):
+    """device guard for the launch: free when the tensor already lives on the current device (the
+    torch.cuda.device context manager costs several microseconds per op otherwise)."""
+    return _NO_GUARD if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+
 def _require_cuda(t, name):
     if not t.is_cuda:
         raise RuntimeError("%s: CPU not supported" % name)  # sampling.cpp:36,84 of the reference
@@ -59,7 +76,7 @@ def furthest_point_sample(xyz, npoint):
     b, n, _ = xyz.shape
     npoint = int(npoint)
     L = _native.lib()
-    with torch.cuda.device(xyz.device):
+    with _on(xyz.device):
         idx = torch.empty((b, npoint), dtype=torch.int32, device=xyz.device)
         nbytes = L.pdae_fps_workspace_bytes(b, n, npoint)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device) if nbytes else None
@@ -80,7 +97,7 @@ def fps_gather(data, number):
     b, n, c = src.shape
     number = int(number)
     L = _native.lib()
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         idx = torch.empty((b, number), dtype=torch.int32, device=src.device)
         centers = torch.empty((b, number, c), dtype=torch.float32, device=src.device)
         nbytes = L.pdae_fps_workspace_bytes(b, n, number)
@@ -99,7 +116,7 @@ def gather_points(features, idx):
     _require_cuda(idx, "gather_points")
     b, c, n = features.shape
     m = idx.size(1)
-    with torch.cuda.device(features.device):
+    with _on(features.device):
         out = torch.empty((b, c, m), dtype=torch.float32, device=features.device)
         rc = _native.lib().pdae_gather_f32(features.data_ptr(), idx.data_ptr(), b, c, n, m, out.data_ptr(), _stream())
     _native.check(rc, "pdae_gather_f32")
@@ -112,7 +129,7 @@ def gather_points_grad(grad_out, idx, n):
     _require_cuda(grad_out, "gather_points_grad")
     _require_cuda(idx, "gather_points_grad")
     b, c, m = grad_out.shape
-    with torch.cuda.device(grad_out.device):
+    with _on(grad_out.device):
         out = torch.empty((b, c, int(n)), dtype=torch.float32, device=grad_out.device)
         rc = _native.lib().pdae_gather_grad_f32(grad_out.data_ptr(), idx.data_ptr(), b, c, int(n), m, out.data_ptr(),
                                                 _stream())
@@ -133,7 +150,7 @@ def knn_points(ref, query, k, out_kq=False, want_dist=True):
     if not (1 <= k <= r):
         raise RuntimeError("k=%d must satisfy 1 <= k <= %d reference points" % (k, r))
     shape = (b, k, q) if out_kq else (b, q, k)
-    with torch.cuda.device(ref.device):
+    with _on(ref.device):
         idx = torch.empty(shape, dtype=torch.int64, device=ref.device)
         dist = torch.empty(shape, dtype=torch.float32, device=ref.device) if want_dist else None
         rc = _native.lib().pdae_knn_f32(ref.data_ptr(), query.data_ptr(), b, r, q, d, k, 1 if out_kq else 0,
@@ -152,7 +169,7 @@ def group_points_knn(xyz, center, group_size, want_idx=True):
     m = int(group_size)
     if not (1 <= m <= n):
         raise RuntimeError("group_size=%d must satisfy 1 <= group_size <= %d points" % (m, n))
-    with torch.cuda.device(xyz.device):
+    with _on(xyz.device):
         nb = torch.empty((b, g, m, 3), dtype=torch.float32, device=xyz.device)
         idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
         rc = _native.lib().pdae_group_f32(xyz.data_ptr(), center.data_ptr(), b, n, g, m,
@@ -184,7 +201,7 @@ def chamfer_forward(xyz1, xyz2, symmetric=True):
     if xyz2.size(0) != b:
         raise RuntimeError("batch sizes differ: %d vs %d" % (b, xyz2.size(0)))
     dev = xyz1.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
         dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
         idx1 = torch.empty((b, n), dtype=torch.int32, device=dev)
@@ -209,7 +226,7 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     dev = xyz1.device
     grad_dist1 = grad_dist1.contiguous().float()
     grad_dist2 = grad_dist2.contiguous().float()
-    with torch.cuda.device(dev):
+    with _on(dev):
         gx1 = torch.empty_like(xyz1)  # preserve_format: dense inputs keep their strides
         gx2 = torch.empty_like(xyz2)
         rc = _native.lib().pdae_chamfer_bwd_f32(xyz1.data_ptr(), xyz2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
@@ -226,7 +243,7 @@ def chamfer_min_keys(queries, refs, ref_offset):
     _require_cuda(queries, "chamfer_min_keys")
     b, nq, _ = queries.shape
     nr = refs.size(1)
-    with torch.cuda.device(queries.device):
+    with _on(queries.device):
         keys = torch.empty((b, nq), dtype=torch.int64, device=queries.device)
         rc = _native.lib().pdae_chamfer_min_keys_u64(queries.data_ptr(), refs.data_ptr(), b, nq, nr, int(ref_offset),
                                                      keys.data_ptr(), _stream())
@@ -236,7 +253,7 @@ def chamfer_min_keys(queries, refs, ref_offset):
 
 def chamfer_unpack_keys(keys):
     keys = keys.contiguous()
-    with torch.cuda.device(keys.device):
+    with _on(keys.device):
         dist = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
         idx = torch.empty(keys.shape, dtype=torch.int32, device=keys.device)
         rc = _native.lib().pdae_chamfer_unpack_keys(keys.data_ptr(), keys.numel(), dist.data_ptr(), idx.data_ptr(),
@@ -256,7 +273,7 @@ def feat_knn(x, k):
     k = int(k)
     if not (1 <= k <= n):
         raise RuntimeError("selected index k out of range")  # torch.topk's message
-    with torch.cuda.device(xc.device):
+    with _on(xc.device):
         idx = torch.empty((b, n, k), dtype=torch.int64, device=xc.device)
         rc = _native.lib().pdae_feat_knn_f32(xc.data_ptr(), b, c, n, k, idx.data_ptr(), _stream())
     _native.check(rc, "pdae_feat_knn_f32")
@@ -267,7 +284,7 @@ def _graph_feature_fwd(x, idx):
     b, c, n = x.shape
     k = idx.size(2)
     L = _native.lib()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         out = torch.empty((b, n, k, 2 * c), dtype=torch.float32, device=x.device)
         nbytes = L.pdae_graph_feature_workspace_bytes(b, c, n)
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
@@ -281,7 +298,7 @@ def _graph_feature_bwd(gout_phys, idx, c, n):
     b = gout_phys.size(0)
     k = idx.size(2)
     L = _native.lib()
-    with torch.cuda.device(gout_phys.device):
+    with _on(gout_phys.device):
         gx = torch.empty((b, c, n), dtype=torch.float32, device=gout_phys.device)
         nbytes = L.pdae_graph_feature_workspace_bytes(b, c, n)
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=gout_phys.device)
@@ -318,7 +335,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     _require_cuda(xyz, "ball_query")
     b, m, _ = new_xyz.shape
     n = xyz.size(1)
-    with torch.cuda.device(xyz.device):
+    with _on(xyz.device):
         idx = torch.empty((b, m, int(nsample)), dtype=torch.int32, device=xyz.device)
         rc = _native.lib().pdae_ball_query_f32(new_xyz.data_ptr(), xyz.data_ptr(), b, n, m, float(radius),
                                                int(nsample), idx.data_ptr(), _stream())
@@ -334,7 +351,7 @@ def group_points(points, idx):
     _require_cuda(idx, "group_points")
     b, c, n = points.shape
     _, p, s = idx.shape
-    with torch.cuda.device(points.device):
+    with _on(points.device):
         out = torch.empty((b, c, p, s), dtype=torch.float32, device=points.device)
         rc = _native.lib().pdae_group_points_f32(points.data_ptr(), idx.data_ptr(), b, c, n, p, s, out.data_ptr(),
                                                  _stream())
@@ -347,7 +364,7 @@ def group_points_grad(grad_out, idx, n):
     _require_i32_contig(idx, "idx")
     _require_cuda(grad_out, "group_points_grad")
     b, c, p, s = grad_out.shape
-    with torch.cuda.device(grad_out.device):
+    with _on(grad_out.device):
         out = torch.empty((b, c, int(n)), dtype=torch.float32, device=grad_out.device)
         rc = _native.lib().pdae_group_points_grad_f32(grad_out.data_ptr(), idx.data_ptr(), b, c, int(n), p, s,
                                                       out.data_ptr(), _stream())

@@ -31,16 +31,22 @@ def main():
     preds = [c + 0.02 * torch.randn_like(c) for c in clouds]
     res = {}
     if what in ("all", "fps"):
-        for cfg in (None, "128,16", "256,8", "512,4", "1024,2", "256,16", "128,32"):
+        for cfg in (None, "128,16", "256,8", "512,4", "256,16", "128,32"):
             if cfg: os.environ["PDAE_FPS_CFG"] = cfg
             else: os.environ.pop("PDAE_FPS_CFG", None)
             res["fps_2048_64[%s]" % cfg] = timeit(lambda i: ops.fps_gather(clouds[i], G), pool)
         os.environ.pop("PDAE_FPS_CFG", None)
         c1024 = [c[:, :1024].contiguous() for c in clouds]
-        for cfg in (None, "128,8", "256,4", "512,2", "1024,1"):
+        for cfg in (None, "128,8", "256,4", "512,2", "128,16"):
             if cfg: os.environ["PDAE_FPS_CFG"] = cfg
             else: os.environ.pop("PDAE_FPS_CFG", None)
             res["fps_1024_64[%s]" % cfg] = timeit(lambda i: ops.fps_gather(c1024[i], G), pool)
+        os.environ.pop("PDAE_FPS_CFG", None)
+        big = torch.from_numpy(synth.clouds(148, 8192, seed=5)).to(dev)
+        for cfg in (None, "512,16", "1024,8", "256,32"):
+            if cfg: os.environ["PDAE_FPS_CFG"] = cfg
+            else: os.environ.pop("PDAE_FPS_CFG", None)
+            res["fps_8192_512[%s]" % cfg] = timeit(lambda i: ops.fps_gather(big, 512), 1, reps=3)
         os.environ.pop("PDAE_FPS_CFG", None)
     if what in ("all", "knn"):
         centers = [ops.fps_gather(c, G)[1] for c in clouds]
