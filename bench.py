@@ -150,6 +150,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs: POOL distinct batches resident in HBM (rotated so no step re-reads L2-hot data)
