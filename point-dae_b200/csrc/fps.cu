@@ -22,7 +22,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pdae {
 
@@ -151,6 +155,142 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ da
   }
 }
 
+// ---- scene-scale clouds (12 288 < n <= CS*512*P): one thread-block CLUSTER per cloud --------------------------------
+// The cloud is split over the CS CTAs of a cluster (contiguous 512*P-point slices, all state still in registers +
+// the CTA's own shared memory).  Per iteration every CTA finds its local arg-max as above, its warp 0 posts
+// (value bits, rank, x, y, z) into the slot table of EVERY CTA of the cluster through distributed shared memory,
+// one cluster barrier makes the posts visible, and every warp picks the global winner from its CTA's local table.
+// Slot tables are double-buffered, so there is exactly one cluster barrier and one CTA barrier per iteration.
+struct FpsSlot {
+  unsigned vb, rank;
+  float x, y, z;
+  unsigned pad[3];
+};
+
+template <int P, int CS>
+__global__ void __launch_bounds__(512) fps_cluster_kernel(const float *__restrict__ data, int n, int c, int m, int lg_bs,
+                                                          int *__restrict__ idx, float *__restrict__ centers) {
+  constexpr int T = 512;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *sp = reinterpret_cast<float4 *>(smem_raw);                         // [T*P] this CTA's slice
+  FpsSlot *table = reinterpret_cast<FpsSlot *>(sp + T * P);                  // [2][CS]
+  uint2 *slots = reinterpret_cast<uint2 *>(table + 2 * CS);                  // [2][32] intra-CTA reduction
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = static_cast<int>(cluster.block_rank());
+  const int cloud_id = blockIdx.x / CS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int base = crank * T * P;  // multiple of 512: k mod bs == tid for every point of a thread
+  const float *__restrict__ cloud = data + static_cast<size_t>(cloud_id) * n * c;
+  int *__restrict__ out = idx + static_cast<size_t>(cloud_id) * m;
+
+  float px[P], py[P], pz[P], pt[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int k = base + tid + p * T;
+    float x = 0.f, y = 0.f, z = 0.f, t = -2.0f;
+    if (k < n) {
+      x = __ldg(cloud + static_cast<size_t>(k) * c);
+      y = __ldg(cloud + static_cast<size_t>(k) * c + 1);
+      z = __ldg(cloud + static_cast<size_t>(k) * c + 2);
+      t = (static_cast<double>(dist_yxz(x, y, z)) <= 1e-3) ? -2.0f : 1e10f;
+    }
+    sp[tid + p * T] = make_float4(x, y, z, 0.f);
+    px[p] = x; py[p] = y; pz[p] = z; pt[p] = t;
+  }
+  if (crank == 0 && tid == 0) out[0] = 0;
+  float ox = __ldg(cloud), oy = __ldg(cloud + 1), oz = __ldg(cloud + 2);  // point 0
+  __syncthreads();
+  cluster.sync();
+
+  for (int j = 1; j < m; ++j) {
+    float v[P];
+    int vi[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float d = dist_yxz(__fsub_rn(px[p], ox), __fsub_rn(py[p], oy), __fsub_rn(pz[p], oz));
+      pt[p] = fminf(d, pt[p]);
+      v[p] = pt[p];
+      vi[p] = p;
+    }
+#pragma unroll
+    for (int stride = 1; stride < P; stride *= 2) {
+#pragma unroll
+      for (int i = 0; i + stride < P; i += 2 * stride) {
+        const bool take = v[i + stride] > v[i];
+        v[i] = take ? v[i + stride] : v[i];
+        vi[i] = take ? vi[i + stride] : vi[i];
+      }
+    }
+    const bool any = v[0] > -1.0f;
+    const float best = any ? v[0] : -1.0f;
+    const int bk = any ? base + tid + vi[0] * T : 0;
+    const unsigned vb = fps_val_bits(best);
+    const unsigned r = fps_block_argmax<T>(vb, fps_rank(bk, lg_bs), slots, j);
+    // CTA-level value of the winner: recompute from the table of warp maxima (all warps hold the same r)
+    const unsigned full = 0xffffffffu;
+    const uint2 wv = lane < T / 32 ? slots[(j & 1) * 32 + lane] : make_uint2(0u, 0xffffffffu);
+    const unsigned cta_vb = __reduce_max_sync(full, wv.x);
+    FpsSlot *tab = table + (j & 1) * CS;
+    if (warp == 0) {
+      // local winner's coordinates (only meaningful when it is a real point of this CTA's slice)
+      const int kl = fps_unrank(r, lg_bs) - base;
+      const bool mine = cta_vb != 0u && kl >= 0 && kl < T * P;
+      const float4 w = sp[mine ? kl : 0];
+      if (lane < CS) {
+        FpsSlot *remote = cluster.map_shared_rank(tab, lane) + crank;
+        remote->vb = cta_vb;
+        remote->rank = cta_vb != 0u ? r : 0u;  // "no valid point" posts (value -1, index 0) like the reference
+        remote->x = w.x; remote->y = w.y; remote->z = w.z;
+      }
+    }
+    cluster.sync();
+    const FpsSlot sl = tab[lane < CS ? lane : 0];
+    const unsigned gvb = __reduce_max_sync(full, lane < CS ? sl.vb : 0u);
+    const unsigned gr = __reduce_min_sync(full, (lane < CS && sl.vb == gvb) ? sl.rank : 0xffffffffu);
+    const unsigned who = __ballot_sync(full, lane < CS && sl.vb == gvb && sl.rank == gr);
+    const int src = __ffs(who) - 1;
+    const int old = gvb != 0u ? fps_unrank(gr, lg_bs) : 0;
+    if (gvb != 0u) {
+      ox = __shfl_sync(full, sl.x, src); oy = __shfl_sync(full, sl.y, src); oz = __shfl_sync(full, sl.z, src);
+    } else {
+      ox = __ldg(cloud); oy = __ldg(cloud + 1); oz = __ldg(cloud + 2);  // every point skipped: the reference re-selects index 0
+    }
+    if (crank == 0 && tid == 0) out[j] = old;
+  }
+  cluster.sync();  // no CTA may exit while peers can still write into its shared memory
+  if (centers != nullptr && crank == 0) {
+    __syncthreads();
+    float *__restrict__ cen = centers + static_cast<size_t>(cloud_id) * m * c;
+    for (int e = tid; e < m * c; e += T) {
+      const int jj = e / c, ch = e - jj * c;
+      cen[e] = cloud[static_cast<size_t>(out[jj]) * c + ch];
+    }
+  }
+}
+
+template <int P, int CS>
+static int launch_fps_cluster(const float *data, int b, int n, int c, int m, int lg_bs, int *idx, float *centers,
+                              cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(512) * P * sizeof(float4) + 2 * CS * sizeof(FpsSlot) + 2 * 32 * sizeof(uint2);
+  auto kern = fps_cluster_kernel<P, CS>;
+  PDAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (CS > 8) PDAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(b) * CS, 1, 1);
+  cfg.blockDim = dim3(512, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PDAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, data, n, c, m, lg_bs, idx, centers));
+  return 0;
+}
+
 // ---- large-cloud fallback: running minima in a global workspace -------------------------------
 template <int T>
 __global__ void __launch_bounds__(T) fps_global_kernel(const float *__restrict__ data, int n, int c, int m, int lg_bs,
@@ -244,6 +384,7 @@ static int launch_fps_reg(const float *data, int b, int n, int c, int m, int lg_
 }
 
 constexpr int FPS_REG_MAX_N = 12288;
+constexpr int FPS_CLUSTER_MAX_N = 16 * 512 * 24;  // 196 608
 
 static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx, float *centers, void *ws,
                         size_t ws_bytes, cudaStream_t st) {
@@ -288,6 +429,10 @@ static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx,
   if (n <= 4096) return launch_fps_reg<256, 16, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= 8192) return launch_fps_reg<256, 32, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= FPS_REG_MAX_N) return launch_fps_reg<512, 24>(data, b, n, c, m, lg_bs, idx, centers, st);
+  // scene-scale clouds: a 16-CTA cluster per cloud (state in registers + DSMEM exchange), up to 196 608 points
+  if (n <= 16 * 512 * 8) return launch_fps_cluster<8, 16>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 16 * 512 * 13) return launch_fps_cluster<13, 16>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= FPS_CLUSTER_MAX_N) return launch_fps_cluster<24, 16>(data, b, n, c, m, lg_bs, idx, centers, st);
   const size_t need = static_cast<size_t>(b) * n * sizeof(float);
   if (!ws || ws_bytes < need) return PDAE_E_WORKSPACE;
   fps_global_kernel<1024><<<b, 1024, 0, st>>>(data, n, c, m, lg_bs, idx, centers, static_cast<float *>(ws));
@@ -312,7 +457,7 @@ extern "C" int pdae_fps_block_size(int n) {
 
 extern "C" size_t pdae_fps_workspace_bytes(int b, int n, int m) {
   (void)m;
-  if (b <= 0 || n <= FPS_REG_MAX_N) return 0;
+  if (b <= 0 || n <= FPS_CLUSTER_MAX_N) return 0;
   return static_cast<size_t>(b) * n * sizeof(float);
 }
 

@@ -33,6 +33,7 @@ FPS_CASES = [
     (4, 1024, 64, False), (2, 2048, 64, False), (3, 1024, 128, True), (2, 1000, 96, True), (2, 100, 40, False),
     (2, 256, 256, True), (2, 37, 37, True), (1, 8192, 512, False), (1, 5000, 64, True), (2, 4096, 128, True),
     (1, 12000, 32, True), (2, 513, 50, True), (3, 2, 2, False), (2, 1, 3, False), (1, 20000, 48, True),
+    (10, 30000, 40, True), (1, 100000, 64, True), (2, 150000, 16, False), (1, 200000, 8, True),  # cluster / global paths
 ]
 
 
