@@ -118,6 +118,12 @@ int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, 
 int pdae_chamfer_min_keys_u64(const float *queries, const float *refs, int b, int nq, int nr, int ref_offset,
                               uint64_t *keys, pdae_stream_t stream);
 int pdae_chamfer_unpack_keys(const uint64_t *keys, long long count, float *dist, int *idx, pdae_stream_t stream);
+/* one rank's whole share in a single pass (each pair evaluated once): xyz1 (b,n,3) replicated, xyz2_local
+ * (b,m_local,3) = points [ref_offset, ref_offset+m_local) of xyz2.  keys1 (b,n): packed row minima for the MIN
+ * all-reduce; dist2_local / idx2_local (b,m_local): final for the slice.  workspace: 8*b*m_local bytes.          */
+int pdae_chamfer_sharded_f32(const float *xyz1, const float *xyz2_local, int b, int n, int m_local, int ref_offset,
+                             uint64_t *keys1, float *dist2_local, int *idx2_local, void *workspace,
+                             size_t workspace_bytes, pdae_stream_t stream);
 
 /* ---- "next" rows: ball query + grouping (3DETR / PointNet++ configs) ------------------------
  * replaces: `ball_query` ball_query_gpu.cu:12-57, `group_points` / `_grad`

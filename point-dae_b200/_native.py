@@ -37,6 +37,7 @@ SIGNATURES = {
     "pdae_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_chamfer_min_keys_u64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_chamfer_unpack_keys": (_i, [_vp, _ll, _vp, _vp, _vp]),
+    "pdae_chamfer_sharded_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_ball_query_f32": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp]),
     "pdae_group_points_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pdae_group_points_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

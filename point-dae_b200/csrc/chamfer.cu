@@ -533,6 +533,50 @@ extern "C" int pdae_chamfer_min_keys_u64(const float *queries, const float *refs
   return launch_min<false>(d0, d1, b, st);
 }
 
+// one rank's share of a reference-set-sharded Chamfer forward: all of xyz1 against the local slice of xyz2,
+// every pair evaluated once (symmetric kernel): row minima leave as packed keys for the MIN all-reduce, column
+// minima are already final for the slice because every rank sees all of xyz1.
+extern "C" int pdae_chamfer_sharded_f32(const float *xyz1, const float *xyz2_local, int b, int n, int m_local,
+                                        int ref_offset, uint64_t *keys1, float *dist2_local, int *idx2_local,
+                                        void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
+  if (b < 0 || n < 0 || m_local < 0 || ref_offset < 0) return PDAE_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bn = static_cast<size_t>(b) * n, bm = static_cast<size_t>(b) * m_local;
+  if (b == 0) return 0;
+  if (bn && (!xyz1 || !keys1)) return PDAE_E_INVALID;
+  if (bm && (!xyz2_local || !dist2_local || !idx2_local)) return PDAE_E_INVALID;
+  if (b > 65535) return PDAE_E_UNSUPPORTED;
+  if (m_local == 0) {
+    if (bn) {
+      fill_keys_kernel<<<static_cast<unsigned>((bn + 255) / 256), 256, 0, st>>>(keys1, static_cast<long long>(bn));
+      PDAE_RETURN_IF_LAUNCH_FAILED();
+    }
+    return 0;
+  }
+  if (n == 0) {  // reference: outputs stay zero
+    PDAE_CUDA_TRY(cudaMemsetAsync(dist2_local, 0, bm * sizeof(float), st));
+    PDAE_CUDA_TRY(cudaMemsetAsync(idx2_local, 0, bm * sizeof(int), st));
+    return 0;
+  }
+  if (!workspace || workspace_bytes < bm * sizeof(uint64_t)) return PDAE_E_WORKSPACE;
+  uint64_t *ck = static_cast<uint64_t *>(workspace);
+  fill_keys_kernel<<<static_cast<unsigned>((bm + 255) / 256), 256, 0, st>>>(ck, static_cast<long long>(bm));
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  const int qpc = chamfer_qpc(n, true);
+  ChamferDir d0{xyz1, xyz2_local, nullptr, nullptr, keys1, ck, n, m_local, ceil_div(n, qpc), ref_offset};
+  ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+  const int rc = launch_min<true>(d0, d1, b, st);
+  if (rc) return rc;
+  const int v = chamfer_variant() % 10;
+  const dim3 rgrid(static_cast<unsigned>((static_cast<long long>(m_local) * 32 + 255) / 256), b);
+  if (v == 3 || v == 4)
+    chamfer_col_recover_kernel<64><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
+  else
+    chamfer_col_recover_kernel<128><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
 extern "C" int pdae_chamfer_unpack_keys(const uint64_t *keys, long long count, float *dist, int *idx,
                                         pdae_stream_t stream) {
   if (count < 0) return PDAE_E_INVALID;

@@ -251,6 +251,28 @@ def chamfer_min_keys(queries, refs, ref_offset):
     return keys
 
 
+def chamfer_sharded_local(xyz1, xyz2_local, ref_offset):
+    """One rank's share of a reference-set-sharded forward in a single pass (every pair evaluated once):
+    -> (keys1 (B,N) int64 for the MIN all-reduce, dist2_local (B,Ml) f32, idx2_local (B,Ml) int32)."""
+    _require_f32_contig(xyz1, "xyz1")
+    _require_f32_contig(xyz2_local, "xyz2_local")
+    _require_cuda(xyz1, "chamfer_sharded_local")
+    b, n, _ = xyz1.shape
+    ml = xyz2_local.size(1)
+    dev = xyz1.device
+    with _on(dev):
+        keys = torch.empty((b, n), dtype=torch.int64, device=dev)
+        d2 = torch.empty((b, ml), dtype=torch.float32, device=dev)
+        i2 = torch.empty((b, ml), dtype=torch.int32, device=dev)
+        nbytes = b * ml * 8
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        rc = _native.lib().pdae_chamfer_sharded_f32(xyz1.data_ptr(), xyz2_local.data_ptr(), b, n, ml, int(ref_offset),
+                                                    keys.data_ptr(), d2.data_ptr(), i2.data_ptr(), ws.data_ptr(), nbytes,
+                                                    _stream())
+    _native.check(rc, "pdae_chamfer_sharded_f32")
+    return keys, d2, i2
+
+
 def chamfer_unpack_keys(keys):
     keys = keys.contiguous()
     with _on(keys.device):

@@ -50,7 +50,16 @@ def chamfer_forward_sharded(xyz1, xyz2_local, xyz2_offset, group=None, keys_fn=N
 
     xyz1 (B,N,3) is replicated; rank r holds xyz2[:, off:off+m_local].  Returns dist1, idx1 for all of
     xyz1 (global indices into xyz2) and dist2_local, idx2_local for this rank's slice of xyz2 (its
-    nearest neighbours in the replicated xyz1 need no exchange)."""
+    nearest neighbours in the replicated xyz1 need no exchange).  On CUDA the rank's whole share is ONE pass
+    (pdae_chamfer_sharded_f32: every local pair evaluated once); `keys_fn` / `unpack_fn` let the CPU tests drive
+    the same host logic with the oracle."""
+    if keys_fn is None and unpack_fn is None:
+        from . import ops
+        keys, dist2_local, idx2_local = ops.chamfer_sharded_local(xyz1, xyz2_local, xyz2_offset)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+        dist1, idx1 = ops.chamfer_unpack_keys(keys)
+        return dist1, dist2_local, idx1, idx2_local
     dist1, idx1 = chamfer_direction_sharded(xyz1, xyz2_local, xyz2_offset, group, keys_fn, unpack_fn)
     keys_fn = keys_fn or _default_keys_fn
     unpack_fn = unpack_fn or _default_unpack_fn

@@ -44,7 +44,8 @@ def test_host_only_entry_points():
     assert L.pdae_strerror(0) == b"success"
     assert b"invalid" in L.pdae_strerror(-1)
     assert L.pdae_fps_workspace_bytes(4, 2048, 64) == 0
-    assert L.pdae_fps_workspace_bytes(2, 100000, 64) == 2 * 100000 * 4
+    assert L.pdae_fps_workspace_bytes(2, 100000, 64) == 0  # cluster kernel: state stays on chip
+    assert L.pdae_fps_workspace_bytes(2, 300000, 64) == 2 * 300000 * 4  # beyond a 16-CTA cluster: global running minima
     assert L.pdae_graph_feature_workspace_bytes(2, 64, 1024) == 2 * 64 * 1024 * 4
 
 

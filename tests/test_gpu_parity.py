@@ -281,6 +281,15 @@ def test_chamfer_sharded_keys_single_process():
         keys = k if keys is None else torch.minimum(keys, k)
     sd, si = ops.chamfer_unpack_keys(keys)
     assert torch.equal(sd, d1) and torch.equal(si, i1)
+    # single-pass per-rank share (symmetric kernel): keys for the all-reduce + final results for the slice
+    d1f, d2f, i1f, i2f = ops.chamfer_forward(t1, t2)
+    keys = None
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        k, d2l, i2l = ops.chamfer_sharded_local(t1, t2[:, lo:hi].contiguous(), lo)
+        keys = k if keys is None else torch.minimum(keys, k)
+        assert torch.equal(d2l, d2f[:, lo:hi]) and torch.equal(i2l, i2f[:, lo:hi])
+    sd, si = ops.chamfer_unpack_keys(keys)
+    assert torch.equal(sd, d1f) and torch.equal(si, i1f)
 
 
 # ----------------------------------------------------------------------------------------- DGCNN
