@@ -287,31 +287,60 @@ def run_ours(args):
     loss_h = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
 
+    capturing = [False]
+
     def prefetch(i):
         c_in, p_in = in_bufs[i % 2]
+        cur = torch.cuda.current_stream()
+        if capturing[0]:
+            # inside a graph: fork the copy stream from the capture stream; the join at the end of the graph orders
+            # it before the next replay (the other buffer was last read by the previous graph, already complete)
+            copy_stream.wait_stream(cur)
+            with torch.cuda.stream(copy_stream):
+                c_in.detach().copy_(clouds_h[i % POOL], non_blocking=True)
+                p_in.detach().copy_(preds_h[i % POOL], non_blocking=True)
+            return
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[i % 2])
-            c_in.copy_(clouds_h[i % POOL], non_blocking=True)
-            p_in.copy_(preds_h[i % POOL], non_blocking=True)
+            c_in.detach().copy_(clouds_h[i % POOL], non_blocking=True)
+            p_in.detach().copy_(preds_h[i % POOL], non_blocking=True)
             ready[i % 2].record(copy_stream)
 
-    def step_e2e(i, first):
-        """public module API, inputs from pinned host memory, loss read back (the call a user makes)."""
-        if first:
-            prefetch(i)
-        stream.wait_event(ready[i % 2])
+    def e2e_body(i):
+        """what one end-to-end step enqueues: prefetch of the NEXT batch (pinned host -> device, copy stream),
+        the public modules + autograd on THIS batch, the loss copied to pinned host memory."""
         prefetch(i + 1)
         c_in, p_in = in_bufs[i % 2]
-        p = p_in.detach().requires_grad_(True)
-        side.wait_stream(stream)
+        side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             nb, center = grouper(c_in)
-        loss = cd_l2(p, c_in)
+        loss = cd_l2(p_in, c_in)
         loss.backward()
-        stream.wait_stream(side)
-        consumed[i % 2].record(stream)
+        torch.cuda.current_stream().wait_stream(side)
         loss_h[i % 2].copy_(loss.detach(), non_blocking=True)
-        loss_ev[i % 2].record(stream)
+        return nb, center
+
+    for c_in, p_in in in_bufs:
+        p_in.requires_grad_(True)
+
+    e2e_graphs = []
+
+    def step_e2e(i, first):
+        """one end-to-end step; returns the loss of the previous step (read by the host one step late)."""
+        cur = torch.cuda.current_stream()
+        if first:
+            for ev in consumed:
+                ev.record(cur)
+            prefetch(i)
+            cur.wait_event(ready[i % 2])
+        if e2e_graphs:
+            e2e_graphs[i % POOL][0].replay()
+        else:
+            cur.wait_event(ready[i % 2])
+            in_bufs[i % 2][1].grad = None
+            e2e_body(i)
+            consumed[i % 2].record(cur)
+        loss_ev[i % 2].record(cur)
         if not first:
             loss_ev[(i - 1) % 2].synchronize()
             return float(loss_h[(i - 1) % 2])
@@ -330,7 +359,7 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing ----------------------------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 100)):  # at least 100 untimed steps (~30 ms) so clocks are at their loaded state
         run_step(i)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
@@ -355,18 +384,41 @@ def run_ours(args):
     cham_ms = statistics.median(a.elapsed_time(b) for a, b in kernel_ev)
 
     # ---- end-to-end timing (host buffers, public API) -----------------------------------------------
-    for ev in consumed:
-        ev.record(stream)
-    for i in range(args.warmup):
+    for i in range(3):  # eager warm-up (also what --no-graphs measures)
+        step_e2e(i, first=(i == 0))
+    torch.cuda.synchronize()
+    if not args.no_graphs:
+        # one CUDA graph per pool slot holding exactly what e2e_body enqueues (H2D of the next batch from pinned
+        # memory, Group, ChamferDistanceL2 forward, autograd backward, D2H of the loss)
+        capturing[0] = True
+        for i in range(POOL):
+            in_bufs[i % 2][1].grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                keep = e2e_body(i)
+                torch.cuda.current_stream().wait_stream(copy_stream)
+            e2e_graphs.append((g, keep, in_bufs[i % 2][1].grad))
+        capturing[0] = False
+    for i in range(max(args.warmup, 100)):
         step_e2e(i, first=(i == 0))
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
+    e2e_first = max(args.warmup, 100)
     for i in range(args.steps):
-        step_e2e(args.warmup + i, first=(i == 0))
+        step_e2e(e2e_first + i, first=(i == 0))
     e1.record(stream)
     barrier()
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    # sanity (outside the timed region): the loss the e2e arm read back for its last step equals the loss of the
+    # device-resident chain on the same pool slot
+    last = e2e_first + args.steps - 1
+    loss_ev[last % 2].synchronize()
+    e2e_loss = float(loss_h[last % 2])
+    dev_loss = float(step_device(last, overlap=False)[0])
+    e2e_checked = abs(e2e_loss - dev_loss) <= 1e-6 * abs(dev_loss)
+    if not e2e_checked:
+        raise RuntimeError("e2e loss %.9g != device-chain loss %.9g" % (e2e_loss, dev_loss))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -405,7 +457,10 @@ def run_ours(args):
                        "l2": "inputs rotate through %d distinct resident batches (%.0f MB > 126 MB L2)" % (
                            POOL, POOL * 2 * B * N * 12 / 1e6)},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * N * 12,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "loss_checked_against_device_chain": e2e_checked,
+                    "how": "public modules (Group, ChamferDistanceL2, autograd) on double-buffered inputs; every step "
+                           "copies the next batch from pinned host memory and the loss back to the host" + (
+                               "" if args.no_graphs else "; the step is replayed as a CUDA graph")},
             "gpu_launches": 6 * args.steps,
             "roofline": roofline,
             "clocks": clocks,
@@ -425,7 +480,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
