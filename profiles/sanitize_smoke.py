@@ -1,0 +1,33 @@
+"""Calls every kernel once on small shapes; run under compute-sanitizer (memcheck / racecheck / initcheck / synccheck)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from pointdae_b200 import ops, synth, group, dgcnn_util, pointnet2_utils, knn_cuda
+dev = "cuda:0"
+def cu(a): return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+x = cu(synth.adversarial(synth.clouds(3, 700, seed=1), seed=1))
+y = cu(synth.clouds(3, 1300, seed=2))
+for n in (700, 37, 1300, 2048 + 5):
+    pointnet2_utils.furthest_point_sample(cu(synth.clouds(2, n, seed=n)), min(n, 40))
+pointnet2_utils.furthest_point_sample(cu(synth.clouds(1, 20000, seed=3)), 16)     # cluster kernel
+pointnet2_utils.furthest_point_sample(cu(synth.clouds(1, 200000, seed=4)), 4)     # global fallback
+idx, cen = group.fps(x, 33)
+ops.group_points_knn(x, cen, 17)
+knn_cuda.KNN(5, True)(y, cen)                       # knn3, k<=32
+knn_cuda.KNN(40, True)(y, cen)                      # knn3, k<=64
+knn_cuda.KNN(100, True)(y, cen)                     # streaming warp-select
+knn_cuda.KNN(8, True)(torch.cat([y, y], 2), torch.cat([cen, cen], 2))  # dim 6
+big = cu(synth.clouds(1, 9000, seed=5)); knn_cuda.KNN(16, True)(big, big[:, :50].contiguous())  # multi-tile
+d = ops.chamfer_forward(x, y); ops.chamfer_forward(x, y, symmetric=False)
+ops.chamfer_backward(x, y, d[2], d[3], torch.rand_like(d[0]), torch.rand_like(d[1]))
+t = cu(synth.clouds(50, 36, seed=6)); ops.chamfer_forward(t, t[:, :32].contiguous())
+k, d2, i2 = ops.chamfer_sharded_local(x, y[:, 100:900].contiguous(), 100); ops.chamfer_unpack_keys(k)
+ops.chamfer_min_keys(x, y[:, :0].contiguous(), 0)
+for c in (3, 7, 64):
+    f = cu(synth.features(2, c, 300, seed=c)).requires_grad_(True)
+    g = dgcnn_util.get_graph_feature(f, k=9); g.sum().backward()
+bq = pointnet2_utils.ball_query(0.2, 16, y, cen)
+gp = pointnet2_utils.grouping_operation(y.transpose(1, 2).contiguous().requires_grad_(True), bq); gp.sum().backward()
+go = pointnet2_utils.gather_operation(y.transpose(1, 2).contiguous().requires_grad_(True), idx); go.sum().backward()
+torch.cuda.synchronize(); print("sanitize smoke done")
