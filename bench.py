@@ -71,7 +71,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline():
@@ -472,12 +472,31 @@ def run_ours(args):
                 line["ref_gpu"] = ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, ms_per_step)
             except Exception as e:  # evidence only; never part of the measured arm
                 line["ref_gpu"] = {"unavailable": str(e)[:200]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line, written to the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries (NCCL's version banner, torch warnings) may print to stdout; the contract is ONE JSON line there.
+    # Keep a private handle on the real stdout and point fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
