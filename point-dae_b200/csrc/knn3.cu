@@ -32,8 +32,9 @@ struct Knn3Args {
   int out_kq;
 };
 
-template <bool PLANAR, int E /*keys per lane in the final sort: 2 (k<=32) or 4 (k<=64)*/>
-__global__ void __launch_bounds__(KNN_THREADS) knn3_kernel(const Knn3Args a) {
+template <bool PLANAR, int E /*keys per lane in the final sort: 2 (k<=32) or 4 (k<=64)*/, int NW /*warps per CTA*/>
+__global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
+  constexpr int KNN_WARPS = NW, KNN_THREADS = NW * 32;  // shadow the file-scope defaults
   constexpr int CAP = 32 * E;
   constexpr int NS = E / 2;  // fallback warp-select slots (k <= 32 -> 1, k <= 64 -> 2)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -214,35 +215,35 @@ __global__ void __launch_bounds__(KNN_THREADS) knn3_kernel(const Knn3Args a) {
   }
 }
 
+template <bool PLANAR, int E, int NW>
+static int launch_knn3_cfg(const Knn3Args &a, int b, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(NW) * (32 * E + KNN3_LC * 32) * sizeof(uint64_t) +
+                      static_cast<size_t>(3) * a.tile * sizeof(float);
+  const dim3 grid(ceil_div(a.q, NW * a.qpw), b);
+  if (smem > 48 * 1024)
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(knn3_kernel<PLANAR, E, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  knn3_kernel<PLANAR, E, NW><<<grid, NW * 32, smem, st>>>(a);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
 template <bool PLANAR>
 static int launch_knn3(Knn3Args a, int b, cudaStream_t st) {
   if (b > 65535) return PDAE_E_UNSUPPORTED;
   // tile: whole cloud when it fits in 96 KB of planes (8192 points), else 4096-point tiles
   const int r64 = (a.r + 63) & ~63;
+  a.tile = r64 <= 8192 ? r64 : 4096;
+  // big tiles allow only one CTA per SM: give it 16 warps so every scheduler still has 4 to switch between
+  const int nw = a.tile > 4096 ? 16 : 8;
   if (r64 <= 8192) {
-    a.tile = r64;
     // enough CTAs for >= ~6 per SM while amortising the tile load over a few queries per warp
-    long long per = (static_cast<long long>(b) * a.q) / (148LL * KNN_WARPS * 6);
+    long long per = (static_cast<long long>(b) * a.q) / (148LL * nw * 6);
     a.qpw = per < 1 ? 1 : (per > 8 ? 8 : static_cast<int>(per));
   } else {
-    a.tile = 4096;
     a.qpw = 1;
   }
-  const int e = a.k <= 32 ? 2 : 4;
-  const size_t smem = static_cast<size_t>(KNN_WARPS) * (32 * e + KNN3_LC * 32) * sizeof(uint64_t) +
-                      static_cast<size_t>(3) * a.tile * sizeof(float);
-  const dim3 grid(ceil_div(a.q, KNN_WARPS * a.qpw), b);
-  if (e == 2) {
-    if (smem > 48 * 1024)
-      PDAE_CUDA_TRY(cudaFuncSetAttribute(knn3_kernel<PLANAR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    knn3_kernel<PLANAR, 2><<<grid, KNN_THREADS, smem, st>>>(a);
-  } else {
-    if (smem > 48 * 1024)
-      PDAE_CUDA_TRY(cudaFuncSetAttribute(knn3_kernel<PLANAR, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    knn3_kernel<PLANAR, 4><<<grid, KNN_THREADS, smem, st>>>(a);
-  }
-  PDAE_RETURN_IF_LAUNCH_FAILED();
-  return 0;
+  if (a.k <= 32) return nw == 16 ? launch_knn3_cfg<PLANAR, 2, 16>(a, b, st) : launch_knn3_cfg<PLANAR, 2, 8>(a, b, st);
+  return nw == 16 ? launch_knn3_cfg<PLANAR, 4, 16>(a, b, st) : launch_knn3_cfg<PLANAR, 4, 8>(a, b, st);
 }
 
 // entry points used by knn.cu / featknn.cu dispatch (k <= 64 only)
