@@ -117,118 +117,170 @@ __global__ void __launch_bounds__(256) graph_feature_grad_center_kernel(const fl
 // with the oracle); the reference materialises a B x N x N matrix through cuBLAS and runs topk on it
 // (models/dgcnn_util.py:7-12).  A CTA owns 64 queries and walks the cloud in 128-point tiles: each thread
 // accumulates a 4 x 8 block of pair distances over the channels (packed FADD2/FFMA2: 3 LDS.128 per 32 packed
-// ops), the 64 x 128 distance tile is parked in shared memory and each warp feeds its 8 queries' streaming
-// warp-select (state in registers, one candidate queue per query in shared memory).  FP32 FMA-pipe bound:
+// ops; operand stages of 16 channels are double-buffered, the next stage's global loads fly during the FMAs),
+// the 64 x 128 distance tile is parked in shared memory and each warp feeds its 8 queries' streaming
+// warp-select (state and candidate queue per query kept in shared memory between tiles).  FP32 FMA-pipe bound:
 // 2 lane-ops per pair and channel; tensor cores would change the rounding and therefore the neighbour order.
 constexpr int FT_Q = 64, FT_R = 128, FT_K = 16, FT_THREADS = 256, FT_DPAD = 4;
 
 __global__ void __launch_bounds__(FT_THREADS, 2) feat_knn_tiled_kernel(const float *__restrict__ x, int c, int n, int k,
                                                                        int64_t *__restrict__ idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t *queues = reinterpret_cast<uint64_t *>(smem_raw);                          // [8 warps][8 queries][64]
-  float *buf = reinterpret_cast<float *>(queues + 8 * 8 * 64);                        // operands / distance tile
-  float *qs = buf;                     // [FT_K][FT_Q]
-  float *rs = buf + FT_K * FT_Q;       // [FT_K][FT_R]
-  float *dt = buf;                     // [FT_Q][FT_R + FT_DPAD]   (aliases the operand stage)
+  uint64_t *queues = reinterpret_cast<uint64_t *>(smem_raw);                          // [64 queries][64] candidate queues
+  uint64_t *sel_l = queues + FT_Q * 64;                                               // [64 queries][32] sorted lists
+  uint64_t *sel_tau = sel_l + FT_Q * 32;                                              // [64 queries]
+  int *sel_qn = reinterpret_cast<int *>(sel_tau + FT_Q);                              // [64 queries]
+  float *ops0 = reinterpret_cast<float *>(sel_qn + FT_Q);                             // operand stage, 2 buffers
+  float *dt = ops0 + 2 * FT_K * (FT_Q + FT_R);                                        // [FT_Q][FT_R + FT_DPAD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads: 4 queries x (4 + 4) references each
   const int cloud = blockIdx.y;
   const int q0 = blockIdx.x * FT_Q;
   const float *__restrict__ X = x + static_cast<size_t>(cloud) * c * n;
   const float INF = __int_as_float(0x7f800000);
-  const int kslot = 0, klane = k - 1;
+  const int klane = k - 1;
+  constexpr int LD = FT_K * (FT_Q + FT_R) / FT_THREADS;  // floats staged per thread per stage (12)
 
-  WarpSelect<1> sel[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sel[i].init();
+  // per-query selection state lives in shared memory between tiles so that the selection code exists once
+  // (8 unrolled copies of a sort/merge network thrashed the instruction cache: 'no instruction' was the top stall)
+  for (int e = tid; e < FT_Q * 32; e += FT_THREADS) sel_l[e] = KEY_INF;
+  for (int e = tid; e < FT_Q; e += FT_THREADS) { sel_tau[e] = KEY_INF; sel_qn[e] = 0; }
 
-  for (int r0 = 0; r0 < n; r0 += FT_R) {
-    float2 acc[4][4];
+  const int nst = (c + FT_K - 1) / FT_K;              // channel stages per reference tile
+  const int ntiles = (n + FT_R - 1) / FT_R;
+  const int total = nst * ntiles;
+  float pre[LD];
+  // staging map (compile-time per element i, e = tid + i*256): i < 4 -> query operand, channel (tid>>6) + 4i, column
+  // tid & 63; i >= 4 -> reference operand, channel (tid>>7) + 2(i-4), column tid & 127.  Everything that does not
+  // depend on the stage is hoisted into two per-thread base pointers and two predicates.
+  static_assert(FT_K * FT_Q == 4 * FT_THREADS && FT_K * FT_R == 8 * FT_THREADS && FT_Q == 64 && FT_R == 128, "staging map");
+  const float *__restrict__ pq = X + static_cast<size_t>(tid >> 6) * n + q0 + (tid & 63);
+  const float *__restrict__ pr = X + static_cast<size_t>(tid >> 7) * n + (tid & 127);
+  const bool q_ok = q0 + (tid & 63) < n;
+  auto fetch = [&](int st) {
+    const int tile_i = st / nst;
+    const int r0 = tile_i * FT_R, c0 = (st - tile_i * nst) * FT_K;
+    const int kc = c - c0;  // channels left (>= 1); rows >= kc of the stage are zero-filled
+    const bool r_ok = r0 + (tid & 127) < n;
+    const float *bq = pq + static_cast<size_t>(c0) * n;
+    const float *br = pr + static_cast<size_t>(c0) * n + r0;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int i = 0; i < 4; ++i)
+      pre[i] = (q_ok && (tid >> 6) + 4 * i < kc) ? __ldg(bq + static_cast<size_t>(4 * i) * n) : 0.f;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
-    for (int c0 = 0; c0 < c; c0 += FT_K) {
-      __syncthreads();  // previous stage (or the distance tile) fully consumed
-      for (int e = tid; e < FT_K * FT_Q; e += FT_THREADS) {
-        const int cc = e / FT_Q, qq = e - cc * FT_Q;
-        qs[e] = (c0 + cc < c && q0 + qq < n) ? __ldg(X + static_cast<size_t>(c0 + cc) * n + q0 + qq) : 0.f;
-      }
-      for (int e = tid; e < FT_K * FT_R; e += FT_THREADS) {
-        const int cc = e / FT_R, rr = e - cc * FT_R;
-        rs[e] = (c0 + cc < c && r0 + rr < n) ? __ldg(X + static_cast<size_t>(c0 + cc) * n + r0 + rr) : 0.f;
-      }
-      __syncthreads();
-      const int kc = (c - c0) < FT_K ? (c - c0) : FT_K;
+    for (int i = 0; i < 8; ++i)
+      pre[4 + i] = (r_ok && (tid >> 7) + 2 * i < kc) ? __ldg(br + static_cast<size_t>(2 * i) * n) : 0.f;
+  };
+  auto stash = [&](int buf) {
+    float *dst = ops0 + buf * FT_K * (FT_Q + FT_R);
+#pragma unroll
+    for (int i = 0; i < LD; ++i) dst[tid + i * FT_THREADS] = pre[i];
+  };
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  float2 acc[4][4];
+  for (int st = 0; st < total; ++st) {
+    const int tile_i = st / nst, si = st - tile_i * nst;
+    const int r0 = tile_i * FT_R, c0 = si * FT_K;
+    if (si == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
+    }
+    if (st + 1 < total) fetch(st + 1);  // global loads of the next stage fly during this stage's FMAs
+    const float *qs = ops0 + (st & 1) * FT_K * (FT_Q + FT_R);
+    const float *rs = qs + FT_K * FT_Q;
+    const int kc = (c - c0) < FT_K ? (c - c0) : FT_K;
 #pragma unroll 4
-      for (int cc = 0; cc < kc; ++cc) {
-        const float4 qv = *reinterpret_cast<const float4 *>(qs + cc * FT_Q + ty * 4);
-        const float4 ra = *reinterpret_cast<const float4 *>(rs + cc * FT_R + tx * 4);
-        const float4 rb = *reinterpret_cast<const float4 *>(rs + cc * FT_R + 64 + tx * 4);
-        const float2 rp[4] = {make_float2(ra.x, ra.y), make_float2(ra.z, ra.w), make_float2(rb.x, rb.y), make_float2(rb.z, rb.w)};
-        const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+    for (int cc = 0; cc < kc; ++cc) {
+      const float4 qv = *reinterpret_cast<const float4 *>(qs + cc * FT_Q + ty * 4);
+      const float4 ra = *reinterpret_cast<const float4 *>(rs + cc * FT_R + tx * 4);
+      const float4 rb = *reinterpret_cast<const float4 *>(rs + cc * FT_R + 64 + tx * 4);
+      const float2 rp[4] = {make_float2(ra.x, ra.y), make_float2(ra.z, ra.w), make_float2(rb.x, rb.y), make_float2(rb.z, rb.w)};
+      const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const float2 q2 = make_float2(qq[a], qq[a]);
+      for (int a = 0; a < 4; ++a) {
+        const float2 q2 = make_float2(qq[a], qq[a]);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const float2 t = sub2(rp[b], q2);
-            acc[a][b] = fma2(t, t, acc[a][b]);
-          }
+        for (int b = 0; b < 4; ++b) {
+          const float2 t = sub2(rp[b], q2);
+          acc[a][b] = fma2(t, t, acc[a][b]);
         }
       }
     }
-    __syncthreads();  // operand stage no longer needed: reuse it for the distance tile
+    if (st + 1 < total) stash((st + 1) & 1);
+    if (si == nst - 1) {
+      // all channels of this reference tile done: park the 64 x 128 distances (references 4tx..4tx+3 and 64+4tx..)
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      float *row = dt + (ty * 4 + a) * (FT_R + FT_DPAD);
-      *reinterpret_cast<float4 *>(row + tx * 4) = make_float4(acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y);
-      *reinterpret_cast<float4 *>(row + 64 + tx * 4) = make_float4(acc[a][2].x, acc[a][2].y, acc[a][3].x, acc[a][3].y);
+      for (int a = 0; a < 4; ++a) {
+        float *row = dt + (ty * 4 + a) * (FT_R + FT_DPAD);
+        *reinterpret_cast<float4 *>(row + tx * 4) = make_float4(acc[a][0].x, acc[a][0].y, acc[a][1].x, acc[a][1].y);
+        *reinterpret_cast<float4 *>(row + 64 + tx * 4) = make_float4(acc[a][2].x, acc[a][2].y, acc[a][3].x, acc[a][3].y);
+      }
     }
     __syncthreads();
-    // ---- selection: warp w serves queries 8w .. 8w+7 of the tile -------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int ql = warp * 8 + i;
-      if (q0 + ql < n) {
+    if (si == nst - 1) {
+      // ---- selection: warp w serves queries 8w .. 8w+7 of the tile (dt is rewritten only after >= 1 more barrier)
+      // Streaming warp-select per query; its state (sorted list, threshold, queue fill) lives in shared memory
+      // between tiles so the selection code exists once.  (Measured alternatives, both slower on B200: rank
+      // insertion per candidate with an always-exact threshold, 0.70 ms; parallel threshold scan + per-lane
+      // insertion sort by two rotating warps, 0.88 ms; this version 0.65 ms at C=64, N=2048, B=16.)
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const int ql = warp * 8 + i;
+        if (q0 + ql >= n) continue;
         const float *row = dt + ql * (FT_R + FT_DPAD);
-        uint64_t *queue = queues + (warp * 8 + i) * 64;
+        const uint64_t tau_in = sel_tau[ql];
         uint64_t key[4];
-        bool pass[4], anyp = false;
+        bool anyp = false;
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const int r = h * 32 + lane;
           const bool in = r0 + r < n;
-          key[h] = pack_key(in ? row[r] : INF, static_cast<uint32_t>(r0 + r));
-          pass[h] = in && key[h] < sel[i].tau;
-          anyp |= pass[h];
+          key[h] = in ? pack_key(row[r], static_cast<uint32_t>(r0 + r)) : KEY_INF;
+          anyp |= key[h] < tau_in;
         }
-        if (__any_sync(0xffffffffu, anyp)) {
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            // tau may have dropped after a flush inside this loop; re-testing keeps the queue short (exactness
-            // does not depend on it)
-            sel[i].offer(pass[h] && key[h] < sel[i].tau, key[h], queue, lane, kslot, klane);
-          }
+        if (!__any_sync(0xffffffffu, anyp)) continue;
+        WarpSelect<1> s;
+        s.L[0] = sel_l[ql * 32 + lane];
+        s.tau = tau_in;
+        s.qn = sel_qn[ql];
+        uint64_t *queue = queues + ql * 64;
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          const uint64_t kk = h == 0 ? key[0] : (h == 1 ? key[1] : (h == 2 ? key[2] : key[3]));
+          s.offer(kk < s.tau, kk, queue, lane, 0, klane);  // tau may have dropped after a flush in this loop
         }
+        sel_l[ql * 32 + lane] = s.L[0];
+        if (lane == 0) { sel_tau[ql] = s.tau; sel_qn[ql] = s.qn; }
+        __syncwarp();
       }
+      if (nst == 1) __syncthreads();  // single-stage tiles: the next stage's park would otherwise race the selection
     }
   }
   // ---- epilogue ----------------------------------------------------------------------------------------------------
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) {
-    const int qg = q0 + warp * 8 + i;
+    const int ql = warp * 8 + i, qg = q0 + ql;
     if (qg < n) {
-      sel[i].finish(queues + (warp * 8 + i) * 64, lane);
-      if (lane < k) idx[(static_cast<size_t>(cloud) * n + qg) * k + lane] = static_cast<int64_t>(static_cast<uint32_t>(sel[i].L[0]));
+      WarpSelect<1> s;
+      s.L[0] = sel_l[ql * 32 + lane];
+      s.tau = sel_tau[ql];
+      s.qn = sel_qn[ql];
+      s.finish(queues + ql * 64, lane);
+      if (lane < k) idx[(static_cast<size_t>(cloud) * n + qg) * k + lane] = static_cast<int64_t>(static_cast<uint32_t>(s.L[0]));
     }
   }
 }
 
 static int launch_feat_knn_tiled(const float *x, int b, int c, int n, int k, int64_t *idx, cudaStream_t st) {
   if (b > 65535) return PDAE_E_UNSUPPORTED;
-  const size_t smem = 8 * 8 * 64 * sizeof(uint64_t) + static_cast<size_t>(FT_Q) * (FT_R + FT_DPAD) * sizeof(float);
-  static_assert(FT_K * (FT_Q + FT_R) <= FT_Q * (FT_R + FT_DPAD), "operand stage must fit inside the distance tile");
+  const size_t smem = (static_cast<size_t>(FT_Q) * 64 + FT_Q * 32 + FT_Q) * sizeof(uint64_t) + FT_Q * sizeof(int) +
+                      (2 * static_cast<size_t>(FT_K) * (FT_Q + FT_R) + static_cast<size_t>(FT_Q) * (FT_R + FT_DPAD)) * sizeof(float);
+  static_assert(FT_K * (FT_Q + FT_R) % FT_THREADS == 0, "operand stage must split evenly over the CTA");
   PDAE_CUDA_TRY(cudaFuncSetAttribute(feat_knn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const dim3 grid(ceil_div(n, FT_Q), b);
   feat_knn_tiled_kernel<<<grid, FT_THREADS, smem, st>>>(x, c, n, k, idx);

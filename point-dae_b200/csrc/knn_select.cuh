@@ -21,6 +21,11 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
   const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(v >> 32), src);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
+__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d) {
+  const unsigned lo = __shfl_up_sync(0xffffffffu, static_cast<unsigned>(v), d);
+  const unsigned hi = __shfl_up_sync(0xffffffffu, static_cast<unsigned>(v >> 32), d);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a < b ? b : a; }
 
