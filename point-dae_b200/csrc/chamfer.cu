@@ -396,55 +396,67 @@ __global__ void __launch_bounds__(256) fill_keys_kernel(uint64_t *__restrict__ k
 // symmetric mode, second half: one warp per column point b_j.  colkeys[j] = (min_i d(a_i, b_j), id of the
 // QPG-query group holding a minimiser; lowest such group).  Scanning that group in index order and taking
 // the first query whose distance equals the minimum bit for bit yields the lowest index overall.
-// QPG = queries per group (32 * QT of the main kernel).  A group's queries are contiguous: LPR lanes share one
-// column point and each takes QPG/LPR consecutive queries (float4 loads when the cloud base is 16-byte aligned), so
-// a warp resolves 32/LPR column points at once and the whole group is examined in one step; lanes are in index
-// order, hence ballot + ffs inside the LPR-lane segment gives the lowest index.
-template <int QPG, int LPR>
+// QPG = queries per group (32 * QT of the main kernel).  A group's queries are contiguous, so each lane takes
+// QPG/32 consecutive ones (float4 loads when the cloud base is 16-byte aligned) and the whole group is examined in
+// one step; lanes are in index order, hence ballot + ffs gives the lowest index.  A warp resolves RPW consecutive
+// column points with all their loads issued up front: the kernel is pure load latency (key -> group rows), so the
+// memory-level parallelism per warp is what sets its speed.
+template <int QPG, int RPW>
 __global__ void __launch_bounds__(256) chamfer_col_recover_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
                                                                   const uint64_t *__restrict__ colkeys, int n_rows,
                                                                   int n_cols,
                                                                   float *__restrict__ dist, int *__restrict__ idx) {
-  constexpr int PER = QPG / LPR;   // consecutive queries per lane
-  constexpr int RPW = 32 / LPR;    // column points per warp
-  static_assert(PER % 4 == 0 || PER < 4, "vector path needs whole float4 triples");
+  constexpr int PER = QPG / 32;  // consecutive queries per lane
   const int lane = threadIdx.x & 31;
-  const int seg = lane / LPR, sl = lane % LPR;
-  const int jw = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW;  // first column point of the warp
-  if (jw >= n_cols) return;
-  const int j = jw + seg;
-  const bool jvalid = j < n_cols;
+  const int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW;  // first column point of the warp
+  if (j0 >= n_cols) return;
   const size_t cloud = blockIdx.y;
-  const size_t gw = cloud * n_cols + (jvalid ? j : n_cols - 1);
-  const uint64_t key = colkeys[gw];
-  const float v = __uint_as_float(static_cast<uint32_t>(key >> 32));
-  const int base = static_cast<int>(static_cast<uint32_t>(key)) * QPG + sl * PER;
-  const float bx = __ldg(cols + 3 * gw), by = __ldg(cols + 3 * gw + 1), bz = __ldg(cols + 3 * gw + 2);
   const float *__restrict__ A = rows + cloud * n_rows * 3;
-  float c[3 * PER];
-  if ((n_rows & 3) == 0 && (PER & 3) == 0 && base + PER <= n_rows) {
-    const float4 *p4 = reinterpret_cast<const float4 *>(A + 3 * static_cast<size_t>(base));
+  const bool vec = (n_rows & 3) == 0 && PER == 4;
+  uint64_t key[RPW];
+  float bx[RPW], by[RPW], bz[RPW];
 #pragma unroll
-    for (int t = 0; t < 3 * PER / 4; ++t) {
-      const float4 w = __ldg(p4 + t);
-      c[4 * t] = w.x; c[4 * t + 1] = w.y; c[4 * t + 2] = w.z; c[4 * t + 3] = w.w;
+  for (int u = 0; u < RPW; ++u) {
+    const int j = j0 + u < n_cols ? j0 + u : n_cols - 1;
+    const size_t gw = cloud * n_cols + j;
+    key[u] = colkeys[gw];
+    bx[u] = __ldg(cols + 3 * gw); by[u] = __ldg(cols + 3 * gw + 1); bz[u] = __ldg(cols + 3 * gw + 2);
+  }
+  float c[RPW][3 * PER];
+  int base[RPW];
+#pragma unroll
+  for (int u = 0; u < RPW; ++u) {
+    base[u] = static_cast<int>(static_cast<uint32_t>(key[u])) * QPG + lane * PER;
+    if (vec && base[u] + PER <= n_rows) {
+      const float4 *p4 = reinterpret_cast<const float4 *>(A + 3 * static_cast<size_t>(base[u]));
+#pragma unroll
+      for (int t = 0; t < 3 * PER / 4; ++t) {
+        const float4 w = __ldg(p4 + t);
+        c[u][4 * t] = w.x; c[u][4 * t + 1] = w.y; c[u][4 * t + 2] = w.z; c[u][4 * t + 3] = w.w;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 3 * PER; ++t)
+        c[u][t] = (base[u] + t / 3 < n_rows) ? __ldg(A + 3 * static_cast<size_t>(base[u]) + t) : __int_as_float(0x7fc00000);
     }
-  } else {
-#pragma unroll
-    for (int t = 0; t < 3 * PER; ++t) c[t] = (base + t / 3 < n_rows) ? __ldg(A + 3 * static_cast<size_t>(base) + t) : __int_as_float(0x7fc00000);
   }
-  int first = PER;  // first matching query of this lane
 #pragma unroll
-  for (int t = PER - 1; t >= 0; --t) {
-    const float d = dist_yxz(__fsub_rn(bx, c[3 * t]), __fsub_rn(by, c[3 * t + 1]), __fsub_rn(bz, c[3 * t + 2]));
-    first = (d == v) ? t : first;  // NaN padding never matches
-  }
-  const unsigned mk = (__ballot_sync(0xffffffffu, first < PER) >> (seg * LPR)) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u));
-  const int src = seg * LPR + (mk ? __ffs(mk) - 1 : 0);
-  const int found = __shfl_sync(0xffffffffu, base + first, src);
-  if (sl == 0 && jvalid) {
-    dist[gw] = v;
-    idx[gw] = mk ? found : 0;
+  for (int u = 0; u < RPW; ++u) {
+    const float v = __uint_as_float(static_cast<uint32_t>(key[u] >> 32));
+    int first = PER;  // first matching query of this lane
+#pragma unroll
+    for (int t = PER - 1; t >= 0; --t) {
+      const float d = dist_yxz(__fsub_rn(bx[u], c[u][3 * t]), __fsub_rn(by[u], c[u][3 * t + 1]), __fsub_rn(bz[u], c[u][3 * t + 2]));
+      first = (d == v) ? t : first;  // NaN padding never matches
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, first < PER);
+    const int src = mk ? __ffs(mk) - 1 : 0;
+    const int found = __shfl_sync(0xffffffffu, base[u] + first, src);
+    if (lane == 0 && j0 + u < n_cols) {
+      const size_t gw = cloud * n_cols + j0 + u;
+      dist[gw] = v;
+      idx[gw] = mk ? found : 0;
+    }
   }
 }
 
@@ -507,12 +519,12 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
     const int rc = launch_min<true>(d0, d1, b, st);
     if (rc) return rc;
     const int v = chamfer_variant() % 10;
-    // one warp per column point (measured: 16 or 8 lanes per point are slower, 190 / 213 vs 185 us at H)
-    const dim3 rgrid(static_cast<unsigned>((nr_cols + 7) / 8), b);
+    // 4 column points per warp, 8 warps per CTA (splitting a warp across points was measured slower)
+    const dim3 rgrid(static_cast<unsigned>((nr_cols + 31) / 32), b);
     if (v == 3 || v == 4)  // queries per warp = 32 * QT of the variant launched
-      chamfer_col_recover_kernel<64, 32><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
+      chamfer_col_recover_kernel<64, 4><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
     else
-      chamfer_col_recover_kernel<128, 32><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
+      chamfer_col_recover_kernel<128, 4><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
     PDAE_RETURN_IF_LAUNCH_FAILED();
     return 0;
   }
@@ -575,11 +587,11 @@ extern "C" int pdae_chamfer_sharded_f32(const float *xyz1, const float *xyz2_loc
   const int rc = launch_min<true>(d0, d1, b, st);
   if (rc) return rc;
   const int v = chamfer_variant() % 10;
-  const dim3 rgrid(static_cast<unsigned>((m_local + 7) / 8), b);
+  const dim3 rgrid(static_cast<unsigned>((m_local + 31) / 32), b);
   if (v == 3 || v == 4)
-    chamfer_col_recover_kernel<64, 32><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
+    chamfer_col_recover_kernel<64, 4><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
   else
-    chamfer_col_recover_kernel<128, 32><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
+    chamfer_col_recover_kernel<128, 4><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }

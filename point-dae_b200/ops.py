@@ -116,6 +116,8 @@ def gather_points(features, idx):
     _require_cuda(idx, "gather_points")
     b, c, n = features.shape
     m = idx.size(1)
+    if idx.size(0) != b:
+        raise RuntimeError("features and idx disagree on the batch size")
     with _on(features.device):
         out = torch.empty((b, c, m), dtype=torch.float32, device=features.device)
         rc = _native.lib().pdae_gather_f32(features.data_ptr(), idx.data_ptr(), b, c, n, m, out.data_ptr(), _stream())
@@ -224,6 +226,15 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     b, n, _ = xyz1.shape
     m = xyz2.size(1)
     dev = xyz1.device
+    for t, name in ((xyz1, "xyz1"), (xyz2, "xyz2")):
+        _require_cuda(t, "chamfer.backward")
+        if t.dtype != torch.float32 or not _dense_storage(t):
+            raise RuntimeError("%s must be a float tensor that densely fills its storage" % name)
+    if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
+        raise RuntimeError("idx1 / idx2 must be the int tensors returned by chamfer.forward")
+    idx1, idx2 = idx1.contiguous(), idx2.contiguous()
+    if tuple(idx1.shape) != (b, n) or tuple(idx2.shape) != (b, m):
+        raise RuntimeError("idx1 / idx2 do not match the clouds' shapes")
     grad_dist1 = grad_dist1.contiguous().float()
     grad_dist2 = grad_dist2.contiguous().float()
     with _on(dev):
