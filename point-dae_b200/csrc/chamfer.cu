@@ -304,9 +304,11 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) chamfer_small_kernel(const f
 __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                                           const int *__restrict__ idx1, const int *__restrict__ idx2,
                                                           const float *__restrict__ gd1, const float *__restrict__ gd2,
-                                                          int n, int m, float *__restrict__ gx1, float *__restrict__ gx2) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // point of cloud 1 (i < n) or of cloud 2 (i - n < m)
-  const size_t cloud = blockIdx.y;
+                                                          int n, int m, int blocks_per_cloud, float *__restrict__ gx1,
+                                                          float *__restrict__ gx2) {
+  const unsigned cloud_u = blockIdx.x / blocks_per_cloud;  // 1-D grid: no 65535-cloud limit (the fine loss has thousands)
+  int i = (blockIdx.x - cloud_u * blocks_per_cloud) * blockDim.x + threadIdx.x;  // point of cloud 1 (i < n) or 2 (i - n < m)
+  const size_t cloud = cloud_u;
   const float *A, *Bp, *gd;
   const int *idx;
   float *ga, *gb;
@@ -619,9 +621,10 @@ extern "C" int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const 
   if (t2) PDAE_CUDA_TRY(cudaMemsetAsync(gx2, 0, static_cast<size_t>(t2) * 3 * sizeof(float), st));
   if (n == 0 || m == 0 || b == 0) return 0;  // reference: the loops never execute, grads stay zero
   if (!idx1 || !idx2 || !gd1 || !gd2) return PDAE_E_INVALID;
-  if (b > 65535) return PDAE_E_UNSUPPORTED;
-  const dim3 grid(static_cast<unsigned>((static_cast<long long>(n) + m + 255) / 256), b);
-  chamfer_bwd_kernel<<<grid, 256, 0, st>>>(xyz1, xyz2, idx1, idx2, gd1, gd2, n, m, gx1, gx2);
+  const long long bpc = (static_cast<long long>(n) + m + 255) / 256;
+  if (bpc * b > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  chamfer_bwd_kernel<<<static_cast<unsigned>(bpc * b), 256, 0, st>>>(xyz1, xyz2, idx1, idx2, gd1, gd2, n, m,
+                                                                    static_cast<int>(bpc), gx1, gx2);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }

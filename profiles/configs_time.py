@@ -28,6 +28,9 @@ for C in (3, 64, 128):
     res["C3 dgcnn knn C=%d N=2048 B=16" % C] = t_ms(lambda: dgcnn_util.knn(x, 20), reps=3)
     idx = dgcnn_util.knn(x, 20)
     res["C3 graph_feature C=%d" % C] = t_ms(lambda: ops._graph_feature_fwd(x, idx), reps=3)
+    g = torch.randn(16, 2048, 20, 2 * C, device=dev)
+    res["C3 graph_feature backward C=%d" % C] = t_ms(lambda: ops._graph_feature_bwd(g, idx, C, 2048), reps=3)
+    del g
 # C4
 c = cloud(256, 8192, 5)
 res["C4 fps 8192->512 (B=256)"] = t_ms(lambda: ops.fps_gather(c, 512), reps=3)

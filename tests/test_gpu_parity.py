@@ -248,6 +248,21 @@ def test_chamfer_transposed_input_reference_faithful():
         ops.chamfer_forward(cu(synth.clouds(2, 64, seed=1))[:, ::2], tgt[:2])  # gaps in storage
 
 
+def test_chamfer_tiny_clouds_huge_batch():
+    """more clouds than a CUDA grid's y dimension holds (the fine loss of a big batch): forward + backward"""
+    b = 70000
+    a = cu(synth.clouds(64, 12, seed=1)).repeat(b // 64 + 1, 1, 1)[:b].contiguous()
+    c = (a[:, :9] + 0.01).contiguous()
+    d1, d2, i1, i2 = ops.chamfer_forward(a, c)
+    w = oracle.chamfer_fwd(a[-50:].cpu().numpy(), c[-50:].cpu().numpy())
+    np.testing.assert_array_equal(i1[-50:].cpu().numpy(), w[2])
+    np.testing.assert_array_equal(d2[-50:].cpu().numpy(), w[1])
+    g1, g2 = ops.chamfer_backward(a, c, i1, i2, torch.ones_like(d1), torch.ones_like(d2))
+    wg1, wg2 = oracle.chamfer_bwd(a[-50:].cpu().numpy(), c[-50:].cpu().numpy(), w[2], w[3], np.ones((50, 12), np.float32), np.ones((50, 9), np.float32))
+    assert_grad_close(g1[-50:].cpu().numpy(), wg1)
+    assert_grad_close(g2[-50:].cpu().numpy(), wg2)
+
+
 def test_chamfer_losses_l1_l2():
     x1, x2 = _chamfer_inputs(4, 512, 512, "pred")
     wd1, wd2, _, _ = oracle.chamfer_fwd(x1, x2)
