@@ -1,9 +1,20 @@
-"""Mirror of `extensions.chamfer_dist` (extensions/chamfer_dist/__init__.py of the reference):
-ChamferFunction and the loss modules on the hot path, same names / arguments / return values.
+"""Mirror of `extensions.chamfer_dist` (extensions/chamfer_dist/__init__.py of the reference): the
+autograd function plus every loss module and helper that file exports, same names / arguments /
+return values, so `from extensions.chamfer_dist import ...` in models/*.py resolves unchanged
+(models/PointCAE_transformer.py:13, models/MaskSurf_v2.py:13-14, models/MaskFeat_transformer.py:13-14).
+
+Only `chamfer.forward` / `chamfer.backward` do geometry (sm_100a kernels); what sits on top of the
+returned distances and indices is the reference's own small torch arithmetic, restated here around
+three helpers (`_nearest_rows`, `_two_sided`, `_maybe_drop_zeros`) instead of per-class copies.
 """
+import math
+
 import torch
+import torch.nn.functional as F
 
 from . import chamfer
+
+_NOTHING = torch.rand(0)  # the reference's "argument not given" marker (default `torch.rand(0)`, __init__.py:130)
 
 
 class ChamferFunction(torch.autograd.Function):
@@ -21,52 +32,199 @@ class ChamferFunction(torch.autograd.Function):
         return grad_xyz1, grad_xyz2
 
 
-def _drop_zero_points(xyz1, xyz2):
+# ------------------------------------------------------------------------------------ point-wise metrics
+def dis_l2(normal1, normal2):
+    """squared Euclidean distance of matched rows (B,G,C)->(B,G); reference __init__.py:118-120"""
+    return (normal1 - normal2).pow(2).sum(2)
+
+
+def dis_normalized_l2_strict(normal1, normal2):
+    """dis_l2 of the unit vectors, sign kept; reference __init__.py:111-115"""
+    return dis_l2(F.normalize(normal1, dim=2), F.normalize(normal2, dim=2))
+
+
+def dis_normalized_l2(normal1, normal2):
+    """orientation-free: the smaller of |u-v|^2 and |u+v|^2; reference __init__.py:95-102"""
+    u, v = F.normalize(normal1, dim=2), F.normalize(normal2, dim=2)
+    return torch.min(dis_l2(u, v), dis_l2(u, -v))
+
+
+def dis_normalized_l1(normal1, normal2):
+    """orientation-free L1 of the unit vectors; reference __init__.py:105-109"""
+    u, v = F.normalize(normal1, dim=2), F.normalize(normal2, dim=2)
+    return torch.min((u - v).abs().sum(2), (u + v).abs().sum(2))
+
+
+def unoriented_included_angle(a, b):
+    """angle in degrees (0..90) between unoriented directions; reference __init__.py:200-204"""
+    cosine = (F.normalize(a, dim=2) * F.normalize(b, dim=2)).sum(-1).abs()
+    return torch.acos(cosine) / math.pi * 180
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def _nearest_rows(values, idx, like):
+    """values[b, idx[b, j], :] for every j, shaped like `like` (the reference's
+    torch.gather(values, 1, idx.long().unsqueeze(2).expand(like.size())))."""
+    return torch.gather(values, 1, idx.long().unsqueeze(2).expand(like.size()))
+
+
+def _two_sided(metric, a, b, idx1, idx2):
+    """mean over cloud 1 of metric(a_j, b_{idx1[j]}) + mean over cloud 2 of metric(b_j, a_{idx2[j]})"""
+    d1 = metric(a, _nearest_rows(b, idx1, a))
+    d2 = metric(b, _nearest_rows(a, idx2, b))
+    return torch.mean(d1) + torch.mean(d2)
+
+
+def _maybe_drop_zeros(module, xyz1, xyz2):
     # reference: __init__.py:38-42 (only taken when batch_size == 1 and ignore_zeros)
-    non_zeros1 = torch.sum(xyz1, dim=2).ne(0)
-    non_zeros2 = torch.sum(xyz2, dim=2).ne(0)
-    return xyz1[non_zeros1].unsqueeze(dim=0), xyz2[non_zeros2].unsqueeze(dim=0)
+    if xyz1.size(0) == 1 and module.ignore_zeros:
+        keep1 = torch.sum(xyz1, dim=2).ne(0)
+        keep2 = torch.sum(xyz2, dim=2).ne(0)
+        return xyz1[keep1].unsqueeze(dim=0), xyz2[keep2].unsqueeze(dim=0)
+    return xyz1, xyz2
 
 
-class ChamferDistanceL2(torch.nn.Module):
-    """reference: __init__.py:29-44.  mean(dist1) + mean(dist2)."""
-
+class _ChamferLoss(torch.nn.Module):
     def __init__(self, ignore_zeros=False):
         super().__init__()
         self.ignore_zeros = ignore_zeros
 
+
+# --------------------------------------------------------------------------------- plain L2 / L1 losses
+class ChamferDistanceL2(_ChamferLoss):
+    """reference: __init__.py:29-44.  mean(dist1) + mean(dist2)."""
+
     def forward(self, xyz1, xyz2):
-        if xyz1.size(0) == 1 and self.ignore_zeros:
-            xyz1, xyz2 = _drop_zero_points(xyz1, xyz2)
-        dist1, dist2, idx1, idx2 = ChamferFunction.apply(xyz1, xyz2)
+        xyz1, xyz2 = _maybe_drop_zeros(self, xyz1, xyz2)
+        dist1, dist2, _, _ = ChamferFunction.apply(xyz1, xyz2)
         return torch.mean(dist1) + torch.mean(dist2)
 
 
-class ChamferDistanceL2_split(torch.nn.Module):
+class ChamferDistanceL2_split(_ChamferLoss):
     """reference: __init__.py:379-395.  (mean(dist1), mean(dist2))."""
 
-    def __init__(self, ignore_zeros=False):
-        super().__init__()
-        self.ignore_zeros = ignore_zeros
-
     def forward(self, xyz1, xyz2):
-        if xyz1.size(0) == 1 and self.ignore_zeros:
-            xyz1, xyz2 = _drop_zero_points(xyz1, xyz2)
+        xyz1, xyz2 = _maybe_drop_zeros(self, xyz1, xyz2)
         dist1, dist2, _, _ = ChamferFunction.apply(xyz1, xyz2)
         return torch.mean(dist1), torch.mean(dist2)
 
 
-class ChamferDistanceL1(torch.nn.Module):
+class ChamferDistanceL1(_ChamferLoss):
     """reference: __init__.py:397-417.  (mean(sqrt(dist1)) + mean(sqrt(dist2))) / 2."""
 
+    def forward(self, xyz1, xyz2):
+        xyz1, xyz2 = _maybe_drop_zeros(self, xyz1, xyz2)
+        dist1, dist2, _, _ = ChamferFunction.apply(xyz1, xyz2)
+        return (torch.mean(torch.sqrt(dist1)) + torch.mean(torch.sqrt(dist2))) / 2
+
+
+class ChamferDistanceL2_corase2fine(_ChamferLoss):
+    """reference: __init__.py:53-85.  Coarse Chamfer between patch centres (B,P,3); the matched patches
+    (fine1/fine2: B,P,S,3) are then compared patch against patch with a second Chamfer over B*P clouds
+    of S points.  Returns (coarse loss, fine loss).  The reference builds its inner ChamferDistanceL2 with
+    .cuda() in the constructor; a parameter-free module needs no device move, so construction stays CUDA-free
+    (modules are built at import time in places)."""
+
     def __init__(self, ignore_zeros=False):
-        super().__init__()
-        self.ignore_zeros = ignore_zeros
+        super().__init__(ignore_zeros)
+        self.cd_loss = ChamferDistanceL2()
+
+    def forward(self, xyz1, xyz2, fine1, fine2):
+        _, _, patch_size, width = fine1.shape
+        dist1, dist2, idx1, idx2 = ChamferFunction.apply(xyz1, xyz2)
+
+        def matched(patches, idx, like):  # patches[b, idx[b,p]] for every patch p
+            return torch.gather(patches, 1, idx.long().unsqueeze(2).unsqueeze(3).expand(like.size()))
+
+        def as_clouds(t):
+            return t.reshape(-1, patch_size, width).contiguous()
+
+        fine_12 = self.cd_loss(as_clouds(fine1), as_clouds(matched(fine2, idx1, fine1)))
+        fine_21 = self.cd_loss(as_clouds(fine2), as_clouds(matched(fine1, idx2, fine2)))
+        return torch.mean(dist1) + torch.mean(dist2), torch.mean(fine_12) + torch.mean(fine_21)
+
+
+# ----------------------------------------------------------------- losses that reuse the match indices
+class ChamferDistanceL2_withnormal(_ChamferLoss):
+    """reference: __init__.py:123-167.  Chamfer on the points; the normals (and optionally curvature and
+    position maps) of the matched pairs are compared with their own metric.  Returns a 2-, 3- or 4-tuple
+    depending on which optional pairs are given."""
+
+    def forward(self, xyz1, xyz2, normal_rebuild, normal_gt, curve_rebuild=_NOTHING, curve_gt=_NOTHING,
+                position_rebuild=_NOTHING, position_gt=_NOTHING):
+        dist1, dist2, idx1, idx2 = ChamferFunction.apply(xyz1, xyz2)
+        out = [torch.mean(dist1) + torch.mean(dist2),
+               _two_sided(dis_normalized_l2, normal_rebuild, normal_gt, idx1, idx2)]
+        if curve_rebuild.size()[0] != 0:
+            out.append(_two_sided(dis_l2, curve_rebuild, curve_gt, idx1, idx2))
+            if position_rebuild.size()[0] != 0:
+                out.append(_two_sided(dis_l2, position_rebuild, position_gt, idx1, idx2))
+        return tuple(out)
+
+
+class ChamferDistanceL2_withnormal_visual(_ChamferLoss):
+    """reference: __init__.py:170-198.  For visualisation: nearest target point and normal of every rebuilt
+    point, their squared distance and the unoriented angle between the normals (degrees)."""
+
+    def forward(self, xyz1, xyz2, normal_rebuild, normal_gt, curve_rebuild=_NOTHING, curve_gt=_NOTHING):
+        _, _, idx1, _ = ChamferFunction.apply(xyz1, xyz2)
+        p1, p2 = xyz1[:, :, :3], xyz2[:, :, :3]
+        nearest_gt_points = _nearest_rows(p2, idx1, p1)
+        nearest_gt_normal = _nearest_rows(normal_gt, idx1, normal_rebuild)
+        return (nearest_gt_points, nearest_gt_normal, dis_l2(p1, nearest_gt_points),
+                unoriented_included_angle(normal_rebuild, nearest_gt_normal))
+
+
+class ChamferDistanceL2_withnormalL1(_ChamferLoss):
+    """reference: __init__.py:206-235.  As _withnormal with the L1 orientation-free normal metric."""
+
+    def forward(self, xyz1, xyz2, normal_rebuild, normal_gt):
+        dist1, dist2, idx1, idx2 = ChamferFunction.apply(xyz1, xyz2)
+        return (torch.mean(dist1) + torch.mean(dist2),
+                _two_sided(dis_normalized_l1, normal_rebuild, normal_gt, idx1, idx2))
+
+
+class ChamferDistanceL2_withnormal_strict(_ChamferLoss):
+    """reference: __init__.py:348-376.  As _withnormal with the sign-sensitive normal metric."""
+
+    def forward(self, xyz1, xyz2, normal_rebuild, normal_gt):
+        dist1, dist2, idx1, idx2 = ChamferFunction.apply(xyz1, xyz2)
+        return (torch.mean(dist1) + torch.mean(dist2),
+                _two_sided(dis_normalized_l2_strict, normal_rebuild, normal_gt, idx1, idx2))
+
+
+class ChamferDistanceL2_withnormal_strict_normalindex(_ChamferLoss):
+    """reference: __init__.py:237-272.  Inputs are (B,G,6) = xyz | normal; the match runs on the tensors as
+    given (the kernel walks their storage as [B][G][3], see ops.chamfer_forward), the two losses are
+    recomputed from the gathered halves."""
 
     def forward(self, xyz1, xyz2):
-        if xyz1.size(0) == 1 and self.ignore_zeros:
-            xyz1, xyz2 = _drop_zero_points(xyz1, xyz2)
-        dist1, dist2, _, _ = ChamferFunction.apply(xyz1, xyz2)
-        dist1 = torch.sqrt(dist1)
-        dist2 = torch.sqrt(dist2)
-        return (torch.mean(dist1) + torch.mean(dist2)) / 2
+        _, _, idx1, idx2 = ChamferFunction.apply(xyz1, xyz2)
+        return (_two_sided(dis_l2, xyz1[:, :, :3], xyz2[:, :, :3], idx1, idx2),
+                _two_sided(dis_normalized_l2_strict, xyz1[:, :, 3:], xyz2[:, :, 3:], idx1, idx2))
+
+
+class ChamferDistanceL2_withnormal_normalindex(_ChamferLoss):
+    """reference: __init__.py:274-310.  Match on the concatenation (xyz | unit normal), contiguous (B,G,6);
+    losses from the gathered xyz and unit normals."""
+
+    def forward(self, xyz1, xyz2, normal_rebuild, normal_gt):
+        unit_rebuild = F.normalize(normal_rebuild, dim=2)
+        unit_gt = F.normalize(normal_gt, dim=2)
+        joined1 = torch.cat((xyz1.clone(), unit_rebuild.clone()), 2).contiguous()
+        joined2 = torch.cat((xyz2.clone(), unit_gt.clone()), 2).contiguous()
+        _, _, idx1, idx2 = ChamferFunction.apply(joined1, joined2)
+        return (_two_sided(dis_l2, xyz1, xyz2, idx1, idx2),
+                _two_sided(dis_normalized_l2, unit_rebuild, unit_gt, idx1, idx2))
+
+
+class ChamferDistanceL2_withnormal_onlynormalindex(_ChamferLoss):
+    """reference: __init__.py:312-346.  Inputs (B,G,6); the match runs between the unit normals only and
+    the point loss is a constant zero."""
+
+    def forward(self, xyz1, xyz2):
+        n1, n2 = xyz1[:, :, 3:], xyz2[:, :, 3:]
+        _, _, idx1, idx2 = ChamferFunction.apply(F.normalize(n1, dim=2).contiguous(),
+                                                 F.normalize(n2, dim=2).contiguous())
+        normal_loss = _two_sided(dis_normalized_l2, n1, n2, idx1, idx2)
+        return torch.zeros(1).to(normal_loss.device), normal_loss

@@ -15,7 +15,9 @@ import sys
 import types
 
 
-def install():
+def install(loss_modules=False):
+    """loss_modules=True additionally serves `extensions.chamfer_dist` (the reference's Python loss classes,
+    which import `ipdb` at module level, extensions/chamfer_dist/__init__.py:12) from this package's mirror."""
     from . import chamfer, knn_cuda, pointnet2_ext, pointnet2_utils
 
     pkg = types.ModuleType("pointnet2_ops")
@@ -36,6 +38,19 @@ def install():
         sys.modules["pointnet2"] = p2
     p2._ext = pointnet2_ext
     sys.modules["pointnet2._ext"] = pointnet2_ext
+
+    if loss_modules:
+        from . import chamfer_dist
+        ext = sys.modules.get("extensions")
+        if ext is None:
+            try:
+                ext = importlib.import_module("extensions")
+            except Exception:
+                ext = types.ModuleType("extensions")
+                ext.__path__ = []
+                sys.modules["extensions"] = ext
+        ext.chamfer_dist = chamfer_dist
+        sys.modules["extensions.chamfer_dist"] = chamfer_dist
     return True
 
 

@@ -194,10 +194,12 @@ def chamfer_forward(xyz1, xyz2, symmetric=True):
         _require_cuda(t, "chamfer.forward")
         if t.dtype != torch.float32:
             raise RuntimeError("%s must be a float tensor" % name)
-        if t.dim() != 3 or t.size(2) != 3:
+        if t.dim() != 3 or t.size(2) < 3:
             raise RuntimeError("%s must have shape (B, N, 3)" % name)
         if not _dense_storage(t):
             raise RuntimeError("%s must densely fill its storage (the reference reads raw memory)" % name)
+        # size(2) > 3 (ChamferDistanceL2_withnormal_normalindex hands in (B,N,6), __init__.py:302-304): the
+        # reference still walks the storage as [B][size(1)][3]; that stays inside the allocation, so it is kept.
     b, n, _ = xyz1.shape
     m = xyz2.size(1)
     if xyz2.size(0) != b:
@@ -238,8 +240,9 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     grad_dist1 = grad_dist1.contiguous().float()
     grad_dist2 = grad_dist2.contiguous().float()
     with _on(dev):
-        gx1 = torch.empty_like(xyz1)  # preserve_format: dense inputs keep their strides
-        gx2 = torch.empty_like(xyz2)
+        # preserve_format: dense inputs keep their strides; wider-than-3 rows are only partly written -> zeros
+        gx1 = torch.empty_like(xyz1) if xyz1.size(2) == 3 else torch.zeros_like(xyz1)
+        gx2 = torch.empty_like(xyz2) if xyz2.size(2) == 3 else torch.zeros_like(xyz2)
         rc = _native.lib().pdae_chamfer_bwd_f32(xyz1.data_ptr(), xyz2.data_ptr(), idx1.data_ptr(), idx2.data_ptr(),
                                                 grad_dist1.data_ptr(), grad_dist2.data_ptr(), b, n, m, gx1.data_ptr(),
                                                 gx2.data_ptr(), _stream())
