@@ -110,6 +110,10 @@ int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int
 int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2, const float *gd1,
                          const float *gd2, int b, int n, int m, float *gx1, float *gx2, pdae_stream_t stream);
 
+/* tuning hook, no reference counterpart: select the CTA shape of the large-cloud forward kernel (ids as the
+ * PDAE_CHAMFER_CFG environment variable; v < 0 only queries).  Returns the previous id.  Not thread-safe.      */
+int pdae_tune_chamfer_variant(int v);
+
 /* reference-set sharding (scene-scale clouds; new, no reference counterpart):
  * one direction, queries (b,nq,3) against the local slice refs (b,nr,3) whose first point has
  * global index `ref_offset`; emits keys[b,nq] = (float_bits(min d) << 32) | global argmin, an
@@ -134,6 +138,19 @@ int pdae_group_points_f32(const float *points, const int *idx, int b, int c, int
                           float *out, pdae_stream_t stream);
 int pdae_group_points_grad_f32(const float *gout, const int *idx, int b, int c, int n, int npoints, int nsample,
                                float *gpoints, pdae_stream_t stream);
+
+/* ---- feature propagation: three_nn / three_interpolate (PointNet++ decoder) ------------------
+ * replaces: `three_nn` interpolate.cpp:17-46 -> interpolate_gpu.cu:12-72, `three_interpolate` /
+ *           `three_interpolate_grad` interpolate.cpp:48-106 -> interpolate_gpu.cu:76-158 (bindings.cpp:14-16).
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) SQUARED distances ascending (ties -> lower index; +inf and
+ * index 0 in slots that never fill when m < 3), idx (b,n,3) int32.
+ * points (b,c,m), idx / weight (b,n,3) -> out (b,c,n); grad: gout (b,c,n) -> gpoints (b,c,m) overwritten.   */
+int pdae_three_nn_f32(const float *unknown, const float *known, int b, int n, int m, float *dist2, int *idx,
+                      pdae_stream_t stream);
+int pdae_three_interpolate_f32(const float *points, const int *idx, const float *weight, int b, int c, int m, int n,
+                               float *out, pdae_stream_t stream);
+int pdae_three_interpolate_grad_f32(const float *gout, const int *idx, const float *weight, int b, int c, int n, int m,
+                                    float *gpoints, pdae_stream_t stream);
 
 #ifdef __cplusplus
 }

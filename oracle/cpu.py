@@ -199,3 +199,33 @@ def group_points_grad(gout, idx, n):
     out = np.zeros((b, c, n), dtype=np.float32)
     lib().pdae_oracle_group_points_grad(_p(gout), _p(idx), b, c, int(n), p, s, _p(out))
     return out
+
+
+def three_nn(unknown, known):
+    """interpolate_gpu.cu:12-62.  unknown (B,n,3), known (B,m,3) -> squared dist (B,n,3), idx (B,n,3) int32."""
+    unknown, known = _f32(unknown), _f32(known)
+    b, n, _ = unknown.shape
+    m = known.shape[1]
+    d = np.zeros((b, n, 3), dtype=np.float32)
+    i = np.zeros((b, n, 3), dtype=np.int32)
+    lib().pdae_oracle_three_nn(_p(unknown), _p(known), b, n, m, _p(d), _p(i))
+    return d, i
+
+
+def three_interpolate(points, idx, weight):
+    """interpolate_gpu.cu:76-104.  points (B,c,m), idx/weight (B,n,3) -> (B,c,n)."""
+    points, idx, weight = _f32(points), _i32(idx), _f32(weight)
+    b, c, m = points.shape
+    n = idx.shape[1]
+    out = np.zeros((b, c, n), dtype=np.float32)
+    lib().pdae_oracle_three_interpolate(_p(points), _p(idx), _p(weight), b, c, m, n, _p(out))
+    return out
+
+
+def three_interpolate_grad(gout, idx, weight, m):
+    """interpolate_gpu.cu:118-144.  gout (B,c,n) -> (B,c,m)."""
+    gout, idx, weight = _f32(gout), _i32(idx), _f32(weight)
+    b, c, n = gout.shape
+    out = np.zeros((b, c, int(m)), dtype=np.float32)
+    lib().pdae_oracle_three_interpolate_grad(_p(gout), _p(idx), _p(weight), b, c, n, int(m), _p(out))
+    return out

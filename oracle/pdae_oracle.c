@@ -437,3 +437,90 @@ void pdae_oracle_group_points_grad(const float *gout, const int *idx, int b, int
     }
   free(acc);
 }
+
+/* ============================================================================================
+ * feature propagation (PointNet++ decoder): three_nn, three_interpolate (+grad).
+ * reference: extensions/pointnet2/_ext_src/src/interpolate_gpu.cu:12-62 (three_nn), :76-104
+ *            (three_interpolate), :118-144 (grad).
+ * three_nn keeps the reference's literal double-precision insertion chain (best = 1e40, strict <);
+ * d is formed in fp32 as fma(dz,dz, fma(dx,dx, dy*dy)) with dx = u - k (SASS of the rebuilt reference).
+ * ========================================================================================== */
+#define THREE_NN_BODY                                                                           \
+  for (int bi = 0; bi < b; ++bi)                                                                \
+    for (int j = 0; j < n; ++j) {                                                               \
+      const float *U = unknown + ((size_t)bi * n + j) * 3;                                      \
+      double best[3] = {1e40, 1e40, 1e40};                                                      \
+      int besti[3] = {0, 0, 0};                                                                 \
+      for (int k = 0; k < m; ++k) {                                                             \
+        const float *K = known + ((size_t)bi * m + k) * 3;                                      \
+        const float dx = U[0] - K[0], dy = U[1] - K[1], dz = U[2] - K[2];                       \
+        const double d = (double)DIST3_XYZ(dx, dy, dz);                                         \
+        if (d < best[0]) {                                                                      \
+          best[2] = best[1], besti[2] = besti[1];                                               \
+          best[1] = best[0], besti[1] = besti[0];                                               \
+          best[0] = d, besti[0] = k;                                                            \
+        } else if (d < best[1]) {                                                               \
+          best[2] = best[1], besti[2] = besti[1];                                               \
+          best[1] = d, besti[1] = k;                                                            \
+        } else if (d < best[2]) {                                                               \
+          best[2] = d, besti[2] = k;                                                            \
+        }                                                                                       \
+      }                                                                                         \
+      for (int s = 0; s < 3; ++s) {                                                             \
+        dist2[((size_t)bi * n + j) * 3 + s] = (float)best[s];                                   \
+        idx[((size_t)bi * n + j) * 3 + s] = besti[s];                                           \
+      }                                                                                         \
+    }
+
+TGT_FMA static void three_nn_hw(const float *unknown, const float *known, int b, int n, int m, float *dist2,
+                                int *idx) { THREE_NN_BODY }
+static void three_nn_sw(const float *unknown, const float *known, int b, int n, int m, float *dist2, int *idx) {
+  THREE_NN_BODY
+}
+
+void pdae_oracle_three_nn(const float *unknown, const float *known, int b, int n, int m, float *dist2, int *idx) {
+  if (have_fma()) three_nn_hw(unknown, known, b, n, m, dist2, idx);
+  else three_nn_sw(unknown, known, b, n, m, dist2, idx);
+}
+
+/* points (b,c,m), idx / weight (b,n,3) -> out (b,c,n); nvcc contracts p1*w1 + p2*w2 + p3*w3 to
+ * fma(p3,w3, fma(p1,w1, rn(p2*w2))) (same shape as the distance expression). */
+#define THREE_INTERP_BODY                                                                       \
+  for (int bi = 0; bi < b; ++bi)                                                                \
+    for (int l = 0; l < c; ++l) {                                                               \
+      const float *P = points + ((size_t)bi * c + l) * m;                                       \
+      for (int j = 0; j < n; ++j) {                                                             \
+        const int *I = idx + ((size_t)bi * n + j) * 3;                                          \
+        const float *W = weight + ((size_t)bi * n + j) * 3;                                     \
+        out[((size_t)bi * c + l) * n + j] = fmaf(P[I[2]], W[2], fmaf(P[I[0]], W[0], P[I[1]] * W[1])); \
+      }                                                                                         \
+    }
+
+TGT_FMA static void three_interp_hw(const float *points, const int *idx, const float *weight, int b, int c, int m,
+                                    int n, float *out) { THREE_INTERP_BODY }
+static void three_interp_sw(const float *points, const int *idx, const float *weight, int b, int c, int m, int n,
+                            float *out) { THREE_INTERP_BODY }
+
+void pdae_oracle_three_interpolate(const float *points, const int *idx, const float *weight, int b, int c, int m,
+                                   int n, float *out) {
+  if (have_fma()) three_interp_hw(points, idx, weight, b, c, m, n, out);
+  else three_interp_sw(points, idx, weight, b, c, m, n, out);
+}
+
+/* gout (b,c,n) -> gpoints (b,c,m): sum of rn(g*w) terms, accumulated in double (the reference's atomics are
+ * order-free, so tests compare with a tolerance) */
+void pdae_oracle_three_interpolate_grad(const float *gout, const int *idx, const float *weight, int b, int c, int n,
+                                        int m, float *gpoints) {
+  double *acc = (double *)malloc(sizeof(double) * (size_t)(m > 0 ? m : 1));
+  for (int bi = 0; bi < b; ++bi)
+    for (int l = 0; l < c; ++l) {
+      memset(acc, 0, sizeof(double) * (size_t)m);
+      for (int j = 0; j < n; ++j) {
+        const float g = gout[((size_t)bi * c + l) * n + j];
+        for (int s = 0; s < 3; ++s)
+          acc[idx[((size_t)bi * n + j) * 3 + s]] += (double)(float)(g * weight[((size_t)bi * n + j) * 3 + s]);
+      }
+      for (int a = 0; a < m; ++a) gpoints[((size_t)bi * c + l) * m + a] = (float)acc[a];
+    }
+  free(acc);
+}

@@ -35,12 +35,16 @@ SIGNATURES = {
     "pdae_chamfer_fwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "pdae_chamfer_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_tune_chamfer_variant": (_i, [_i]),
     "pdae_chamfer_min_keys_u64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_chamfer_unpack_keys": (_i, [_vp, _ll, _vp, _vp, _vp]),
     "pdae_chamfer_sharded_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_ball_query_f32": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp]),
     "pdae_group_points_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pdae_group_points_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pdae_three_nn_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_three_interpolate_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "pdae_three_interpolate_grad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

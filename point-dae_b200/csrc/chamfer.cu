@@ -44,7 +44,8 @@ struct ChamferDir {
 // (FMNMX3 across the thread's queries, one REDUX.MIN across the lanes) and posts
 // (min bits << 32 | query-group id) with a 64-bit RED.MIN per CTA; chamfer_col_recover_kernel then
 // finds the lowest query index inside the winning group.  Halves the FMA-pipe work of the forward.
-template <int QT, int THREADS, int MINB, bool SYM, int CH_TILE = 512 /* reference points per shared-memory tile */>
+template <int QT, int THREADS, int MINB, bool SYM, int CH_TILE = 512 /* reference points per shared-memory tile */,
+          int STEP = 8 /* reference points per inner step (4 or 8): QT*STEP distances are live at once */>
 __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const ChamferDir d0, const ChamferDir d1) {
   constexpr int QPW = 32 * QT;                  // queries per warp
   constexpr int W = THREADS / 32;
@@ -131,8 +132,15 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
     if (more) fetch((tl + 1) * CH_TILE);
     if (tl > 0) flush_cols(tl - 1);
     const float *sx = tile[tl & 1][0], *sy = tile[tl & 1][1], *sz = tile[tl & 1][2];
-    unsigned pend[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    unsigned pend[STEP];
+#pragma unroll
+    for (int r = 0; r < STEP; ++r) pend[r] = 0u;
     int pend_off = -1;
+    auto store_pend = [&]() {  // lane 0 parks the warp's column minima of one step
+      uint4 *dst = reinterpret_cast<uint4 *>(&colmin[tl & 1][warp][pend_off]);
+#pragma unroll
+      for (int r = 0; r < STEP; r += 4) dst[r >> 2] = make_uint4(pend[r], pend[r + 1], pend[r + 2], pend[r + 3]);
+    };
     const int left = nr - tl * CH_TILE;
     const int ngroups = ((left < CH_TILE ? left : CH_TILE) + CH_GROUP - 1) / CH_GROUP;
     const int group_base = tl * (CH_TILE / CH_GROUP);
@@ -143,39 +151,40 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
 #pragma unroll
       for (int s = 0; s < QT; ++s) cur[s] = best[s];
 #pragma unroll
-      for (int h = 0; h < CH_GROUP; h += 8) {
-        const float4 X0 = *reinterpret_cast<const float4 *>(sx + g * CH_GROUP + h);
-        const float4 Y0 = *reinterpret_cast<const float4 *>(sy + g * CH_GROUP + h);
-        const float4 Z0 = *reinterpret_cast<const float4 *>(sz + g * CH_GROUP + h);
-        const float4 X1 = *reinterpret_cast<const float4 *>(sx + g * CH_GROUP + h + 4);
-        const float4 Y1 = *reinterpret_cast<const float4 *>(sy + g * CH_GROUP + h + 4);
-        const float4 Z1 = *reinterpret_cast<const float4 *>(sz + g * CH_GROUP + h + 4);
-        float2 dd[QT][4];
+      for (int h = 0; h < CH_GROUP; h += STEP) {
+        float4 X[STEP / 4], Y[STEP / 4], Z[STEP / 4];
+#pragma unroll
+        for (int v = 0; v < STEP / 4; ++v) {
+          X[v] = *reinterpret_cast<const float4 *>(sx + g * CH_GROUP + h + 4 * v);
+          Y[v] = *reinterpret_cast<const float4 *>(sy + g * CH_GROUP + h + 4 * v);
+          Z[v] = *reinterpret_cast<const float4 *>(sz + g * CH_GROUP + h + 4 * v);
+        }
+        float2 dd[QT][STEP / 2];
 #pragma unroll
         for (int s = 0; s < QT; ++s) {
-          dd[s][0] = dist_yxz2(sub2(make_float2(X0.x, X0.y), qx[s]), sub2(make_float2(Y0.x, Y0.y), qy[s]),
-                               sub2(make_float2(Z0.x, Z0.y), qz[s]));
-          dd[s][1] = dist_yxz2(sub2(make_float2(X0.z, X0.w), qx[s]), sub2(make_float2(Y0.z, Y0.w), qy[s]),
-                               sub2(make_float2(Z0.z, Z0.w), qz[s]));
-          dd[s][2] = dist_yxz2(sub2(make_float2(X1.x, X1.y), qx[s]), sub2(make_float2(Y1.x, Y1.y), qy[s]),
-                               sub2(make_float2(Z1.x, Z1.y), qz[s]));
-          dd[s][3] = dist_yxz2(sub2(make_float2(X1.z, X1.w), qx[s]), sub2(make_float2(Y1.z, Y1.w), qy[s]),
-                               sub2(make_float2(Z1.z, Z1.w), qz[s]));
-          const float t0 = min3(dd[s][0].x, dd[s][0].y, dd[s][1].x);
-          const float t1 = min3(dd[s][1].y, dd[s][2].x, dd[s][2].y);
-          const float t2 = min3(dd[s][3].x, dd[s][3].y, t0);
-          cur[s] = min3(cur[s], t1, t2);
+#pragma unroll
+          for (int v = 0; v < STEP / 4; ++v) {
+            dd[s][2 * v] = dist_yxz2(sub2(make_float2(X[v].x, X[v].y), qx[s]), sub2(make_float2(Y[v].x, Y[v].y), qy[s]),
+                                     sub2(make_float2(Z[v].x, Z[v].y), qz[s]));
+            dd[s][2 * v + 1] = dist_yxz2(sub2(make_float2(X[v].z, X[v].w), qx[s]), sub2(make_float2(Y[v].z, Y[v].w), qy[s]),
+                                         sub2(make_float2(Z[v].z, Z[v].w), qz[s]));
+          }
+          if (STEP == 8) {
+            const float t0 = min3(dd[s][0].x, dd[s][0].y, dd[s][1].x);
+            const float t1 = min3(dd[s][1].y, dd[s][2].x, dd[s][2].y);
+            const float t2 = min3(dd[s][STEP / 2 - 1].x, dd[s][STEP / 2 - 1].y, t0);
+            cur[s] = min3(cur[s], t1, t2);
+          } else {
+            const float t0 = min3(dd[s][0].x, dd[s][0].y, dd[s][1].x);
+            cur[s] = min3(cur[s], dd[s][1].y, t0);
+          }
         }
-        if (SYM) {  // column minima over this warp's 32*QT queries for the 8 reference points of the step
+        if (SYM) {  // column minima over this warp's 32*QT queries for the STEP reference points of the step
           // the REDUX results of the previous step are stored only now, a full step of FMA work later, so
           // their latency never stalls the warp
-          if (pend_off >= 0 && lane == 0) {
-            uint4 *dst = reinterpret_cast<uint4 *>(&colmin[tl & 1][warp][pend_off]);
-            dst[0] = make_uint4(pend[0], pend[1], pend[2], pend[3]);
-            dst[1] = make_uint4(pend[4], pend[5], pend[6], pend[7]);
-          }
+          if (pend_off >= 0 && lane == 0) store_pend();
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
+          for (int r = 0; r < STEP; ++r) {
             float c = (r & 1) ? dd[0][r >> 1].y : dd[0][r >> 1].x;
 #pragma unroll
             for (int s = 1; s + 1 < QT; s += 2)
@@ -192,11 +201,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
         best[s] = cur[s];
       }
     }
-    if (SYM && pend_off >= 0 && lane == 0) {
-      uint4 *dst = reinterpret_cast<uint4 *>(&colmin[tl & 1][warp][pend_off]);
-      dst[0] = make_uint4(pend[0], pend[1], pend[2], pend[3]);
-      dst[1] = make_uint4(pend[4], pend[5], pend[6], pend[7]);
-    }
+    if (SYM && pend_off >= 0 && lane == 0) store_pend();
     if (more) stash((tl + 1) & 1);
     __syncthreads();
   }
@@ -341,21 +346,29 @@ __global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t *__rest
 }
 
 // tuning hook: PDAE_CHAMFER_CFG selects the CTA shape of the large-cloud kernel
+static int g_chamfer_variant = -1;
 static int chamfer_variant() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_chamfer_variant < 0) {
     const char *e = getenv("PDAE_CHAMFER_CFG");
-    v = e ? atoi(e) : 0;
+    g_chamfer_variant = e ? atoi(e) : 0;
   }
-  return v;
+  return g_chamfer_variant;
+}
+// tuning hook (profiles/tune_kernels.py): switch the kernel shape inside one process; ids as PDAE_CHAMFER_CFG
+extern "C" int pdae_tune_chamfer_variant(int v) {
+  const int old = chamfer_variant();
+  if (v >= 0) g_chamfer_variant = v;
+  return old;
 }
 // queries per CTA of the kernel launch_min / launch_sym will pick (the callers size `qtiles` with it)
 static int chamfer_qpc(int nq_max, bool sym) {
   if (!sym && nq_max <= 256) return 128;
-  switch (chamfer_variant() % 10) {
+  switch (chamfer_variant() % 50) {
     case 3: return 512;   // <2,256>
     case 4: return 256;   // <2,128>
     case 5: case 6: case 7: return 256;   // <4,64>
+    case 8: case 10: return 512;   // <8,64>
+    case 9: case 11: return 256;   // <8,32>
     default: return 512;  // <4,128>
   }
 }
@@ -371,7 +384,7 @@ static int launch_min(const ChamferDir &d0, const ChamferDir &d1, int b, cudaStr
   if (!SYM && nq_max <= 256) {
     chamfer_min_kernel<1, 128, 1, false><<<g, 128, 0, st>>>(d0, d1);
   } else {
-    switch (chamfer_variant() % 10) {
+    switch (chamfer_variant() % 50) {
       case 1: chamfer_min_kernel<4, 128, 4, SYM><<<g, 128, 0, st>>>(d0, d1); break;
       case 2: chamfer_min_kernel<4, 128, 3, SYM><<<g, 128, 0, st>>>(d0, d1); break;
       case 3: chamfer_min_kernel<2, 256, 3, SYM><<<g, 256, 0, st>>>(d0, d1); break;
@@ -379,6 +392,10 @@ static int launch_min(const ChamferDir &d0, const ChamferDir &d1, int b, cudaStr
       case 5: chamfer_min_kernel<4, 64, 4, SYM, 256><<<g, 64, 0, st>>>(d0, d1); break;
       case 6: chamfer_min_kernel<4, 64, 8, SYM, 256><<<g, 64, 0, st>>>(d0, d1); break;
       case 7: chamfer_min_kernel<4, 64, 6, SYM, 256><<<g, 64, 0, st>>>(d0, d1); break;
+      case 8: chamfer_min_kernel<8, 64, 4, SYM, 256, 4><<<g, 64, 0, st>>>(d0, d1); break;
+      case 9: chamfer_min_kernel<8, 32, 8, SYM, 128, 4><<<g, 32, 0, st>>>(d0, d1); break;
+      case 10: chamfer_min_kernel<8, 64, 6, SYM, 256, 4><<<g, 64, 0, st>>>(d0, d1); break;
+      case 11: chamfer_min_kernel<8, 32, 12, SYM, 128, 4><<<g, 32, 0, st>>>(d0, d1); break;
       default: chamfer_min_kernel<4, 128, 1, SYM><<<g, 128, 0, st>>>(d0, d1); break;
     }
   }
@@ -414,7 +431,7 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_kernel(const float *_
   if (j0 >= n_cols) return;
   const size_t cloud = blockIdx.y;
   const float *__restrict__ A = rows + cloud * n_rows * 3;
-  const bool vec = (n_rows & 3) == 0 && PER == 4;
+  const bool vec = (n_rows & 3) == 0 && PER % 4 == 0;
   uint64_t key[RPW];
   float bx[RPW], by[RPW], bz[RPW];
 #pragma unroll
@@ -462,6 +479,103 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_kernel(const float *_
   }
 }
 
+// Group-major variant of the recovery for clouds up to a few thousand points: one CTA per (cloud, QPG-row group).
+// Every lane keeps QPG/32 consecutive rows of the group in registers for the whole CTA; the warps sweep the cloud's
+// column keys (coalesced), and only the columns whose key names this group are resolved, their coordinates and
+// minimum broadcast from the lane that read them.  The warp-per-column kernel above re-reads a whole group
+// (12*QPG bytes) per column -- 400 MB of L2 traffic at 128 x 2048^2; here the traffic is the keys once per group
+// (8*n_cols bytes per CTA), 10x less, and the rows never leave registers.  Traffic grows with n_rows*n_cols/QPG, so
+// the launcher keeps the warp-per-column kernel for large clouds.
+template <int QPG>
+__global__ void __launch_bounds__(256) chamfer_col_recover_grouped_kernel(const float *__restrict__ rows,
+                                                                          const float *__restrict__ cols,
+                                                                          const uint64_t *__restrict__ colkeys,
+                                                                          int n_rows, int n_cols,
+                                                                          float *__restrict__ dist, int *__restrict__ idx) {
+  constexpr int PER = QPG / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned g = blockIdx.x;
+  const size_t cloud = blockIdx.y;
+  const float *__restrict__ A = rows + cloud * n_rows * 3;
+  const int base = static_cast<int>(g) * QPG + lane * PER;
+  float rx[PER], ry[PER], rz[PER];
+  if ((n_rows & 3) == 0 && PER % 4 == 0 && base + PER <= n_rows) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(A + 3 * static_cast<size_t>(base));
+    float c[3 * PER];
+#pragma unroll
+    for (int t = 0; t < 3 * PER / 4; ++t) {
+      const float4 w = __ldg(p4 + t);
+      c[4 * t] = w.x; c[4 * t + 1] = w.y; c[4 * t + 2] = w.z; c[4 * t + 3] = w.w;
+    }
+#pragma unroll
+    for (int t = 0; t < PER; ++t) rx[t] = c[3 * t], ry[t] = c[3 * t + 1], rz[t] = c[3 * t + 2];
+  } else {
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+      const bool in = base + t < n_rows;  // NaN padding never matches
+      rx[t] = in ? __ldg(A + 3 * static_cast<size_t>(base + t)) : __int_as_float(0x7fc00000);
+      ry[t] = in ? __ldg(A + 3 * static_cast<size_t>(base + t) + 1) : 0.0f;
+      rz[t] = in ? __ldg(A + 3 * static_cast<size_t>(base + t) + 2) : 0.0f;
+    }
+  }
+  const uint64_t *__restrict__ K = colkeys + cloud * n_cols;
+  const float *__restrict__ C = cols + cloud * n_cols * 3;
+  for (int j0 = warp * 32; j0 < n_cols; j0 += 256) {
+    const int j = j0 + lane;
+    const uint64_t key = j < n_cols ? K[j] : ~0ull;
+    const bool match = static_cast<uint32_t>(key) == g && j < n_cols;
+    const float v = __uint_as_float(static_cast<uint32_t>(key >> 32));
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (match) cx = __ldg(C + 3 * j), cy = __ldg(C + 3 * j + 1), cz = __ldg(C + 3 * j + 2);
+    unsigned mk = __ballot_sync(0xffffffffu, match);
+    int mine = 0;
+    while (mk) {
+      const int src = __ffs(mk) - 1;
+      mk &= mk - 1;
+      const float bx = __shfl_sync(0xffffffffu, cx, src), by = __shfl_sync(0xffffffffu, cy, src);
+      const float bz = __shfl_sync(0xffffffffu, cz, src), want = __shfl_sync(0xffffffffu, v, src);
+      int first = PER;  // first matching row of this lane
+#pragma unroll
+      for (int t = PER - 1; t >= 0; --t) {
+        const float d = dist_yxz(__fsub_rn(bx, rx[t]), __fsub_rn(by, ry[t]), __fsub_rn(bz, rz[t]));
+        first = (d == want) ? t : first;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, first < PER);
+      const int found = __shfl_sync(0xffffffffu, base + first, hit ? __ffs(hit) - 1 : 0);
+      if (lane == src) mine = hit ? found : 0;
+    }
+    if (match) {
+      dist[cloud * n_cols + j] = v;
+      idx[cloud * n_cols + j] = mine;
+    }
+  }
+}
+
+// second half of the symmetric forward: picks the recovery kernel by cloud size (see the comment above)
+template <int QPG>
+static int launch_col_recover(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows, int n_cols,
+                              float *dcol, int *icol, cudaStream_t st) {
+  const long long groups = (static_cast<long long>(n_rows) + QPG - 1) / QPG;
+  if (groups <= QPG && chamfer_variant() < 50) {  // key sweeps (8*groups B per column) cheaper than row re-reads (12*QPG B)
+    const dim3 ggrid(static_cast<unsigned>(groups), b);
+    chamfer_col_recover_grouped_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
+  } else {
+    // 4 column points per warp, 8 warps per CTA (splitting a warp across points was measured slower)
+    const dim3 rgrid(static_cast<unsigned>((n_cols + 31) / 32), b);
+    chamfer_col_recover_kernel<QPG, 4><<<rgrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
+  }
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+static int launch_col_recover_for_variant(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows,
+                                          int n_cols, float *dcol, int *icol, cudaStream_t st) {
+  const int v = chamfer_variant() % 50;  // queries per warp = 32 * QT of the variant launched
+  if (v == 3 || v == 4) return launch_col_recover<64>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
+  if (v >= 8 && v <= 11) return launch_col_recover<256>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
+  return launch_col_recover<128>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
+}
+
 }  // namespace pdae
 
 using namespace pdae;
@@ -502,7 +616,7 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
   }
   const int nq_max = n > m ? n : m;
   const size_t need = pdae_chamfer_fwd_workspace_bytes(b, n, m);
-  const bool sym = workspace != nullptr && workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 10;
+  const bool sym = workspace != nullptr && workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 100;
   if (sym) {
     // rows (register-resident queries) = the larger cloud, columns = the smaller one
     const bool swap = m > n;
@@ -520,15 +634,7 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
     ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
     const int rc = launch_min<true>(d0, d1, b, st);
     if (rc) return rc;
-    const int v = chamfer_variant() % 10;
-    // 4 column points per warp, 8 warps per CTA (splitting a warp across points was measured slower)
-    const dim3 rgrid(static_cast<unsigned>((nr_cols + 31) / 32), b);
-    if (v == 3 || v == 4)  // queries per warp = 32 * QT of the variant launched
-      chamfer_col_recover_kernel<64, 4><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
-    else
-      chamfer_col_recover_kernel<128, 4><<<rgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
-    PDAE_RETURN_IF_LAUNCH_FAILED();
-    return 0;
+    return launch_col_recover_for_variant(rows, cols, ck, b, nr_rows, nr_cols, dcol, icol, st);
   }
   const int qpc = chamfer_qpc(nq_max, false);
   ChamferDir d0{xyz1, xyz2, dist1, idx1, nullptr, nullptr, n, m, ceil_div(n, qpc), 0};
@@ -588,14 +694,7 @@ extern "C" int pdae_chamfer_sharded_f32(const float *xyz1, const float *xyz2_loc
   ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
   const int rc = launch_min<true>(d0, d1, b, st);
   if (rc) return rc;
-  const int v = chamfer_variant() % 10;
-  const dim3 rgrid(static_cast<unsigned>((m_local + 31) / 32), b);
-  if (v == 3 || v == 4)
-    chamfer_col_recover_kernel<64, 4><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
-  else
-    chamfer_col_recover_kernel<128, 4><<<rgrid, 256, 0, st>>>(xyz1, xyz2_local, ck, n, m_local, dist2_local, idx2_local);
-  PDAE_RETURN_IF_LAUNCH_FAILED();
-  return 0;
+  return launch_col_recover_for_variant(xyz1, xyz2_local, ck, b, n, m_local, dist2_local, idx2_local, st);
 }
 
 extern "C" int pdae_chamfer_unpack_keys(const uint64_t *keys, long long count, float *dist, int *idx,

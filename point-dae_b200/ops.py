@@ -406,3 +406,56 @@ def group_points_grad(grad_out, idx, n):
                                                       out.data_ptr(), _stream())
     _native.check(rc, "pdae_group_points_grad_f32")
     return out
+
+
+# ------------------------------------------------------------------- three_nn / three_interpolate
+def three_nn(unknown, known):
+    """pointnet2._ext.three_nn(unknown (B,n,3), known (B,m,3)) -> [dist2 (B,n,3) squared, idx (B,n,3) int32]
+    (interpolate.cpp:17-46)."""
+    _require_f32_contig(unknown, "unknowns")
+    _require_f32_contig(known, "knows")
+    _require_cuda(unknown, "three_nn")
+    _require_cuda(known, "three_nn")
+    b, n, _ = unknown.shape
+    m = known.size(1)
+    with _on(unknown.device):
+        dist2 = torch.empty((b, n, 3), dtype=torch.float32, device=unknown.device)
+        idx = torch.empty((b, n, 3), dtype=torch.int32, device=unknown.device)
+        rc = _native.lib().pdae_three_nn_f32(unknown.data_ptr(), known.data_ptr(), b, n, m, dist2.data_ptr(),
+                                             idx.data_ptr(), _stream())
+    _native.check(rc, "pdae_three_nn_f32")
+    return [dist2, idx]
+
+
+def three_interpolate(points, idx, weight):
+    """pointnet2._ext.three_interpolate(points (B,c,m), idx (B,n,3) int32, weight (B,n,3)) -> (B,c,n)
+    (interpolate.cpp:48-77)."""
+    _require_f32_contig(points, "points")
+    _require_i32_contig(idx, "idx")
+    _require_f32_contig(weight, "weight")
+    for t in (points, idx, weight):
+        _require_cuda(t, "three_interpolate")
+    b, c, m = points.shape
+    n = idx.size(1)
+    with _on(points.device):
+        out = torch.empty((b, c, n), dtype=torch.float32, device=points.device)
+        rc = _native.lib().pdae_three_interpolate_f32(points.data_ptr(), idx.data_ptr(), weight.data_ptr(), b, c, m, n,
+                                                      out.data_ptr(), _stream())
+    _native.check(rc, "pdae_three_interpolate_f32")
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    """pointnet2._ext.three_interpolate_grad(grad_out (B,c,n), idx, weight, m) -> (B,c,m) (interpolate.cpp:78-106)."""
+    _require_f32_contig(grad_out, "grad_out")
+    _require_i32_contig(idx, "idx")
+    _require_f32_contig(weight, "weight")
+    for t in (grad_out, idx, weight):
+        _require_cuda(t, "three_interpolate_grad")
+    b, c, n = grad_out.shape
+    with _on(grad_out.device):
+        out = torch.empty((b, c, int(m)), dtype=torch.float32, device=grad_out.device)
+        rc = _native.lib().pdae_three_interpolate_grad_f32(grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), b, c,
+                                                           n, int(m), out.data_ptr(), _stream())
+    _native.check(rc, "pdae_three_interpolate_grad_f32")
+    return out

@@ -1,6 +1,5 @@
 """Drop-in for the compiled `pointnet2._ext` module (extensions/pointnet2/_ext_src/src/bindings.cpp:9-22),
-the functions on the hot path and its "next" rows.  three_nn / three_interpolate are only used by the
-part-segmentation FP modules (out of scope) and raise NotImplementedError."""
+all nine functions it exports, argument order as in the C++ bindings."""
 from . import ops
 
 
@@ -28,12 +27,13 @@ def group_points_grad(grad_out, idx, n):
     return ops.group_points_grad(grad_out, idx, n)
 
 
-def _out_of_scope(name):
-    def f(*a, **k):
-        raise NotImplementedError("pointnet2._ext.%s is outside the geometry hot path (FP modules only)" % name)
-    return f
+def three_nn(unknowns, knows):
+    return ops.three_nn(unknowns, knows)
 
 
-three_nn = _out_of_scope("three_nn")
-three_interpolate = _out_of_scope("three_interpolate")
-three_interpolate_grad = _out_of_scope("three_interpolate_grad")
+def three_interpolate(points, idx, weight):
+    return ops.three_interpolate(points, idx, weight)
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    return ops.three_interpolate_grad(grad_out, idx, weight, m)

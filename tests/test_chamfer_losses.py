@@ -30,6 +30,12 @@ def _check(name, device):
     for i, r in enumerate(results):
         want = GOLD["%s/out/%d" % (name, i)]
         assert r.shape == want.shape and r.dtype == want.dtype
+        if name == "withnormal_visual" and i == 3:
+            # angles in degrees from acos(): d(acos x)/dx is unbounded near x = 1, so one ulp of the cosine (CPU vs
+            # CUDA libm) moves small angles by far more than 1e-5 relative; compare the cosines instead
+            r, want = np.cos(np.deg2rad(r.astype(np.float64))), np.cos(np.deg2rad(want.astype(np.float64)))
+            np.testing.assert_allclose(r, want, rtol=0, atol=2e-6)
+            continue
         np.testing.assert_allclose(r, want, rtol=1e-5, atol=1e-6 * max(1.0, float(np.abs(want).max())))
     want_grads = {k.split("/")[-1]: GOLD[k] for k in GOLD.files if k.startswith(name + "/grad/")}
     assert set(grads) == set(want_grads)

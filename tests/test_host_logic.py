@@ -36,8 +36,8 @@ def test_install_makes_reference_imports_resolve():
     for name in ("furthest_point_sampling", "gather_points", "gather_points_grad", "ball_query", "group_points",
                  "group_points_grad", "three_nn", "three_interpolate", "three_interpolate_grad"):
         assert callable(getattr(ext, name))  # bindings.cpp:9-22
-    with pytest.raises(NotImplementedError):
-        ext.three_nn(None, None)
+    assert ext.three_nn is not None and p2u.three_nn is pointnet2_utils.three_nn
+    assert p2u.three_interpolate is pointnet2_utils.three_interpolate and hasattr(p2u, "GroupAll")
 
 
 def test_modules_construct_without_cuda():
