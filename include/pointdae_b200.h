@@ -110,6 +110,22 @@ int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int
 int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2, const float *gd1,
                          const float *gd2, int b, int n, int m, float *gx1, float *gx2, pdae_stream_t stream);
 
+/* Fused mean losses on top of the forward's outputs.
+ * replaces: the torch arithmetic of ChamferDistanceL2.forward `mean(dist1) + mean(dist2)`
+ *           (extensions/chamfer_dist/__init__.py:43), ChamferDistanceL2_split (:394-395) and ChamferDistanceL1
+ *           `(mean(sqrt(dist1)) + mean(sqrt(dist2))) / 2` (:413-417), and their autograd backward into
+ *           chamfer.backward.
+ * pdae_chamfer_loss_f32: loss3[0] = the loss (l1 = 0: L2, 1: L1), loss3[1], loss3[2] = the two mean terms;
+ *   deterministic two-launch reduction; workspace of pdae_chamfer_loss_workspace_bytes().
+ * pdae_chamfer_loss_bwd_f32: gradients of  w1 * mean(f(dist1)) + w2 * mean(f(dist2))  scaled by the device scalar
+ *   *gloss (f = identity or sqrt): gx1 (b,n,3), gx2 (b,m,3) overwritten.  dist1/dist2 are read only when l1 != 0. */
+size_t pdae_chamfer_loss_workspace_bytes(void);
+int pdae_chamfer_loss_f32(const float *dist1, const float *dist2, int b, int n, int m, int l1, float *loss3,
+                          void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+int pdae_chamfer_loss_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2, const float *dist1,
+                              const float *dist2, const float *gloss, float w1, float w2, int b, int n, int m, int l1,
+                              float *gx1, float *gx2, pdae_stream_t stream);
+
 /* tuning hook, no reference counterpart: select the CTA shape of the large-cloud forward kernel (ids as the
  * PDAE_CHAMFER_CFG environment variable; v < 0 only queries).  Returns the previous id.  Not thread-safe.      */
 int pdae_tune_chamfer_variant(int v);

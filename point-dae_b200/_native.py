@@ -36,6 +36,9 @@ SIGNATURES = {
     "pdae_chamfer_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_tune_chamfer_variant": (_i, [_i]),
+    "pdae_chamfer_loss_workspace_bytes": (_sz, []),
+    "pdae_chamfer_loss_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "pdae_chamfer_loss_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_chamfer_min_keys_u64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_chamfer_unpack_keys": (_i, [_vp, _ll, _vp, _vp, _vp]),
     "pdae_chamfer_sharded_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -32,6 +32,28 @@ class ChamferFunction(torch.autograd.Function):
         return grad_xyz1, grad_xyz2
 
 
+class _ChamferMeanLoss(torch.autograd.Function):
+    """ChamferFunction + the mean (L2) or mean-of-sqrt (L1) reduction as one autograd node: the forward adds two
+    small launches to chamfer.forward, the backward goes from the upstream scalar straight to the point gradients
+    (no materialised grad_dist arrays, no MeanBackward / SqrtBackward / AddBackward kernels).  Same values as the
+    reference's `torch.mean(dist1) + torch.mean(dist2)` up to the summation order (tests pin 1e-5 relative)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, l1):
+        dist1, dist2, idx1, idx2 = chamfer.forward(xyz1, xyz2)
+        loss3 = chamfer.mean_loss(dist1, dist2, l1)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2, dist1, dist2)
+        ctx.l1 = l1
+        return loss3[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        xyz1, xyz2, idx1, idx2, dist1, dist2 = ctx.saved_tensors
+        w = 0.5 if ctx.l1 else 1.0
+        gx1, gx2 = chamfer.loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, grad_loss, w, w, ctx.l1)
+        return gx1, gx2, None
+
+
 # ------------------------------------------------------------------------------------ point-wise metrics
 def dis_l2(normal1, normal2):
     """squared Euclidean distance of matched rows (B,G,C)->(B,G); reference __init__.py:118-120"""
@@ -96,8 +118,7 @@ class ChamferDistanceL2(_ChamferLoss):
 
     def forward(self, xyz1, xyz2):
         xyz1, xyz2 = _maybe_drop_zeros(self, xyz1, xyz2)
-        dist1, dist2, _, _ = ChamferFunction.apply(xyz1, xyz2)
-        return torch.mean(dist1) + torch.mean(dist2)
+        return _ChamferMeanLoss.apply(xyz1, xyz2, False)
 
 
 class ChamferDistanceL2_split(_ChamferLoss):
@@ -114,8 +135,7 @@ class ChamferDistanceL1(_ChamferLoss):
 
     def forward(self, xyz1, xyz2):
         xyz1, xyz2 = _maybe_drop_zeros(self, xyz1, xyz2)
-        dist1, dist2, _, _ = ChamferFunction.apply(xyz1, xyz2)
-        return (torch.mean(torch.sqrt(dist1)) + torch.mean(torch.sqrt(dist2))) / 2
+        return _ChamferMeanLoss.apply(xyz1, xyz2, True)
 
 
 class ChamferDistanceL2_corase2fine(_ChamferLoss):

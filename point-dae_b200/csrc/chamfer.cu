@@ -304,36 +304,119 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) chamfer_small_kernel(const f
 }
 
 // ---- backward: one thread per point of either cloud, scatter through the saved argmin ---------
-// reference: chamfer.cu:173-201 runs (1,16)x256 = 4096 threads over the whole batch; here the
-// grid covers all b*(n+m) points.  Float RED.ADD accumulation order is free, as in the reference.
+// reference: chamfer.cu:173-201 runs (1,16)x256 = 4096 threads over the whole batch and adds BOTH terms of every
+// pair with atomics into zero-filled buffers.  Every point receives exactly one "own" term (g * (a_j - b_idx[j]),
+// written by its own thread) plus the scattered terms of the points that chose it, so the work is split in two
+// launches over all b*(n+m) points: OWN stores the own term with a plain store (which also initialises the
+// buffer: no memset), SCATTER then adds -v to the matched point with RED.ADD.F32.  Half the atomics of the
+// reference scheme, accumulation order free as in the reference.
+//
+// GradSrc supplies d(loss)/d(dist) per point: the arrays handed to chamfer.backward, or -- for the fused mean
+// losses (ChamferDistanceL2 / L1) -- the upstream scalar times a constant, with the sqrt derivative for L1.
+struct GradArrays {
+  const float *gd1, *gd2;
+  __device__ __forceinline__ float at(bool second, size_t o) const { return __ldg((second ? gd2 : gd1) + o); }
+};
+struct GradMean {
+  const float *gloss;          // upstream gradient of the scalar loss (device)
+  const float *dist1, *dist2;  // squared distances of the forward (L1 only)
+  float w1, w2;                // d(loss)/d(mean term) / count
+  int l1;
+  __device__ __forceinline__ float at(bool second, size_t o) const {
+    const float g = __fmul_rn(__ldg(gloss), second ? w2 : w1);
+    if (!l1) return g;
+    // d sqrt(x) = g / (2 sqrt(x)); x == 0 gives inf like torch's SqrtBackward (and NaN after the multiply by 0)
+    return __fdiv_rn(g, __fmul_rn(2.0f, __fsqrt_rn(__ldg((second ? dist2 : dist1) + o))));
+  }
+};
+
+template <bool SCATTER, typename GradSrc>
 __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                                           const int *__restrict__ idx1, const int *__restrict__ idx2,
-                                                          const float *__restrict__ gd1, const float *__restrict__ gd2,
-                                                          int n, int m, int blocks_per_cloud, float *__restrict__ gx1,
-                                                          float *__restrict__ gx2) {
+                                                          const GradSrc gs, int n, int m, int blocks_per_cloud,
+                                                          float *__restrict__ gx1, float *__restrict__ gx2) {
   const unsigned cloud_u = blockIdx.x / blocks_per_cloud;  // 1-D grid: no 65535-cloud limit (the fine loss has thousands)
   int i = (blockIdx.x - cloud_u * blocks_per_cloud) * blockDim.x + threadIdx.x;  // point of cloud 1 (i < n) or 2 (i - n < m)
   const size_t cloud = cloud_u;
-  const float *A, *Bp, *gd;
+  const bool second = i >= n;
+  const float *A, *Bp;
   const int *idx;
   float *ga, *gb;
-  if (i < n) {
-    A = xyz1 + cloud * n * 3; Bp = xyz2 + cloud * m * 3; gd = gd1 + cloud * n; idx = idx1 + cloud * n;
+  size_t o;
+  if (!second) {
+    A = xyz1 + cloud * n * 3; Bp = xyz2 + cloud * m * 3; idx = idx1 + cloud * n; o = cloud * n + i;
     ga = gx1 + cloud * n * 3; gb = gx2 + cloud * m * 3;
   } else {
     i -= n;
     if (i >= m) return;
-    A = xyz2 + cloud * m * 3; Bp = xyz1 + cloud * n * 3; gd = gd2 + cloud * m; idx = idx2 + cloud * m;
+    A = xyz2 + cloud * m * 3; Bp = xyz1 + cloud * n * 3; idx = idx2 + cloud * m; o = cloud * m + i;
     ga = gx2 + cloud * m * 3; gb = gx1 + cloud * n * 3;
   }
   const int j2 = __ldg(idx + i);
-  const float g = __fmul_rn(__ldg(gd + i), 2.0f);
+  const float g = __fmul_rn(gs.at(second, o), 2.0f);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float v = __fmul_rn(g, __fsub_rn(__ldg(A + 3 * i + c), __ldg(Bp + 3 * j2 + c)));
-    atomicAdd(ga + 3 * i + c, v);
-    atomicAdd(gb + 3 * j2 + c, -v);
+    if (SCATTER) atomicAdd(gb + 3 * j2 + c, -v);
+    else ga[3 * i + c] = v;
   }
+}
+
+template <typename GradSrc>
+static int launch_chamfer_bwd(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2, const GradSrc &gs,
+                              int b, int n, int m, float *gx1, float *gx2, cudaStream_t st) {
+  const long long bpc = (static_cast<long long>(n) + m + 255) / 256;
+  if (bpc * b > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  const unsigned grid = static_cast<unsigned>(bpc * b);
+  chamfer_bwd_kernel<false, GradSrc><<<grid, 256, 0, st>>>(xyz1, xyz2, idx1, idx2, gs, n, m, static_cast<int>(bpc), gx1, gx2);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  chamfer_bwd_kernel<true, GradSrc><<<grid, 256, 0, st>>>(xyz1, xyz2, idx1, idx2, gs, n, m, static_cast<int>(bpc), gx1, gx2);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+// ---- fused mean losses: (mean f(dist1), mean f(dist2)) with f = identity (L2) or sqrt (L1) ------------------
+// reference: extensions/chamfer_dist/__init__.py:43 (L2: mean + mean) and :413-417 (L1: (mean sqrt + mean sqrt) / 2),
+// there two or four torch kernels plus the add.  Deterministic: fixed-size partial sums in fp32 per CTA (fp64 across
+// the CTA partials), summed in a fixed order by the second launch.
+constexpr int LOSS_BLOCKS = 128;
+
+__global__ void __launch_bounds__(256) chamfer_loss_partial_kernel(const float *__restrict__ dist1, const float *__restrict__ dist2,
+                                                                   long long c1, long long c2, int l1,
+                                                                   float *__restrict__ partial /*[2][LOSS_BLOCKS]*/) {
+  __shared__ float red[2][8];
+  float acc[2] = {0.f, 0.f};
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const float *__restrict__ d = side ? dist2 : dist1;
+    const long long cnt = side ? c2 : c1;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < cnt; i += 256LL * LOSS_BLOCKS) {
+      const float v = __ldg(d + i);
+      acc[side] += l1 ? __fsqrt_rn(v) : v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[side] += __shfl_xor_sync(0xffffffffu, acc[side], o);
+    if ((threadIdx.x & 31) == 0) red[side][threadIdx.x >> 5] = acc[side];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    partial[threadIdx.x * LOSS_BLOCKS + blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(32) chamfer_loss_final_kernel(const float *__restrict__ partial, long long c1, long long c2,
+                                                                int l1, float *__restrict__ out /*[3]*/) {
+  if (threadIdx.x >= 2) return;
+  double t = 0.0;
+  for (int i = 0; i < LOSS_BLOCKS; ++i) t += static_cast<double>(partial[threadIdx.x * LOSS_BLOCKS + i]);
+  const long long cnt = threadIdx.x ? c2 : c1;
+  const float mean = static_cast<float>(t / static_cast<double>(cnt));  // 0/0 = NaN like torch.mean of an empty tensor
+  out[1 + threadIdx.x] = mean;
+  const float other = __shfl_xor_sync(0x3u, mean, 1);
+  if (threadIdx.x == 0) out[0] = l1 ? __fmul_rn(__fadd_rn(mean, other), 0.5f) : __fadd_rn(mean, other);
 }
 
 __global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t *__restrict__ keys, long long count,
@@ -369,6 +452,8 @@ static int chamfer_qpc(int nq_max, bool sym) {
     case 5: case 6: case 7: return 256;   // <4,64>
     case 8: case 10: return 512;   // <8,64>
     case 9: case 11: return 256;   // <8,32>
+    case 12: case 13: return 128;  // <4,32>
+    case 14: case 15: return 1024; // <8,128>
     default: return 512;  // <4,128>
   }
 }
@@ -396,6 +481,10 @@ static int launch_min(const ChamferDir &d0, const ChamferDir &d1, int b, cudaStr
       case 9: chamfer_min_kernel<8, 32, 8, SYM, 128, 4><<<g, 32, 0, st>>>(d0, d1); break;
       case 10: chamfer_min_kernel<8, 64, 6, SYM, 256, 4><<<g, 64, 0, st>>>(d0, d1); break;
       case 11: chamfer_min_kernel<8, 32, 12, SYM, 128, 4><<<g, 32, 0, st>>>(d0, d1); break;
+      case 12: chamfer_min_kernel<4, 32, 16, SYM, 128, 8><<<g, 32, 0, st>>>(d0, d1); break;
+      case 13: chamfer_min_kernel<4, 32, 12, SYM, 128, 8><<<g, 32, 0, st>>>(d0, d1); break;
+      case 14: chamfer_min_kernel<8, 128, 1, SYM, 512, 4><<<g, 128, 0, st>>>(d0, d1); break;
+      case 15: chamfer_min_kernel<8, 128, 1, SYM, 512, 8><<<g, 128, 0, st>>>(d0, d1); break;
       default: chamfer_min_kernel<4, 128, 1, SYM><<<g, 128, 0, st>>>(d0, d1); break;
     }
   }
@@ -520,33 +609,43 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_grouped_kernel(const 
   }
   const uint64_t *__restrict__ K = colkeys + cloud * n_cols;
   const float *__restrict__ C = cols + cloud * n_cols * 3;
-  for (int j0 = warp * 32; j0 < n_cols; j0 += 256) {
-    const int j = j0 + lane;
-    const uint64_t key = j < n_cols ? K[j] : ~0ull;
-    const bool match = static_cast<uint32_t>(key) == g && j < n_cols;
-    const float v = __uint_as_float(static_cast<uint32_t>(key >> 32));
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    if (match) cx = __ldg(C + 3 * j), cy = __ldg(C + 3 * j + 1), cz = __ldg(C + 3 * j + 2);
-    unsigned mk = __ballot_sync(0xffffffffu, match);
-    int mine = 0;
-    while (mk) {
-      const int src = __ffs(mk) - 1;
-      mk &= mk - 1;
-      const float bx = __shfl_sync(0xffffffffu, cx, src), by = __shfl_sync(0xffffffffu, cy, src);
-      const float bz = __shfl_sync(0xffffffffu, cz, src), want = __shfl_sync(0xffffffffu, v, src);
-      int first = PER;  // first matching row of this lane
+  constexpr int UNR = 4;  // key sweeps in flight per warp: the loop is pure L2 latency otherwise
+  for (int j0 = warp * 32; j0 < n_cols; j0 += 256 * UNR) {
+    uint64_t key[UNR];
+    float cx[UNR], cy[UNR], cz[UNR];
 #pragma unroll
-      for (int t = PER - 1; t >= 0; --t) {
-        const float d = dist_yxz(__fsub_rn(bx, rx[t]), __fsub_rn(by, ry[t]), __fsub_rn(bz, rz[t]));
-        first = (d == want) ? t : first;
-      }
-      const unsigned hit = __ballot_sync(0xffffffffu, first < PER);
-      const int found = __shfl_sync(0xffffffffu, base + first, hit ? __ffs(hit) - 1 : 0);
-      if (lane == src) mine = hit ? found : 0;
+    for (int u = 0; u < UNR; ++u) {  // keys and coordinates fetched together (coalesced, no dependent second trip)
+      const int j = j0 + u * 256 + lane;
+      const bool in = j < n_cols;
+      key[u] = in ? K[j] : ~0ull;
+      cx[u] = in ? __ldg(C + 3 * j) : 0.f, cy[u] = in ? __ldg(C + 3 * j + 1) : 0.f, cz[u] = in ? __ldg(C + 3 * j + 2) : 0.f;
     }
-    if (match) {
-      dist[cloud * n_cols + j] = v;
-      idx[cloud * n_cols + j] = mine;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * 256 + lane;
+      const bool match = static_cast<uint32_t>(key[u]) == g && j < n_cols;
+      const float v = __uint_as_float(static_cast<uint32_t>(key[u] >> 32));
+      unsigned mk = __ballot_sync(0xffffffffu, match);
+      int mine = 0;
+      while (mk) {
+        const int src = __ffs(mk) - 1;
+        mk &= mk - 1;
+        const float bx = __shfl_sync(0xffffffffu, cx[u], src), by = __shfl_sync(0xffffffffu, cy[u], src);
+        const float bz = __shfl_sync(0xffffffffu, cz[u], src), want = __shfl_sync(0xffffffffu, v, src);
+        int first = PER;  // first matching row of this lane
+#pragma unroll
+        for (int t = PER - 1; t >= 0; --t) {
+          const float d = dist_yxz(__fsub_rn(bx, rx[t]), __fsub_rn(by, ry[t]), __fsub_rn(bz, rz[t]));
+          first = (d == want) ? t : first;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, first < PER);
+        const int found = __shfl_sync(0xffffffffu, base + first, hit ? __ffs(hit) - 1 : 0);
+        if (lane == src) mine = hit ? found : 0;
+      }
+      if (match) {
+        dist[cloud * n_cols + j] = v;
+        idx[cloud * n_cols + j] = mine;
+      }
     }
   }
 }
@@ -556,7 +655,8 @@ template <int QPG>
 static int launch_col_recover(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows, int n_cols,
                               float *dcol, int *icol, cudaStream_t st) {
   const long long groups = (static_cast<long long>(n_rows) + QPG - 1) / QPG;
-  if (groups <= QPG && chamfer_variant() < 50) {  // key sweeps (8*groups B per column) cheaper than row re-reads (12*QPG B)
+  const int glimit = chamfer_variant() >= 50 ? 0 : (getenv("PDAE_RECOVER_GROUPS") ? atoi(getenv("PDAE_RECOVER_GROUPS")) : 32);
+  if (groups <= glimit) {  // key + coordinate sweeps (20*groups B per column) cheaper than row re-reads (12*QPG B)
     const dim3 ggrid(static_cast<unsigned>(groups), b);
     chamfer_col_recover_grouped_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
   } else {
@@ -572,7 +672,7 @@ static int launch_col_recover_for_variant(const float *rows, const float *cols, 
                                           int n_cols, float *dcol, int *icol, cudaStream_t st) {
   const int v = chamfer_variant() % 50;  // queries per warp = 32 * QT of the variant launched
   if (v == 3 || v == 4) return launch_col_recover<64>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
-  if (v >= 8 && v <= 11) return launch_col_recover<256>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
+  if ((v >= 8 && v <= 11) || v == 14 || v == 15) return launch_col_recover<256>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
   return launch_col_recover<128>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
 }
 
@@ -716,14 +816,46 @@ extern "C" int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long t1 = static_cast<long long>(b) * n, t2 = static_cast<long long>(b) * m;
   if ((t1 && (!xyz1 || !gx1)) || (t2 && (!xyz2 || !gx2))) return PDAE_E_INVALID;
-  if (t1) PDAE_CUDA_TRY(cudaMemsetAsync(gx1, 0, static_cast<size_t>(t1) * 3 * sizeof(float), st));
-  if (t2) PDAE_CUDA_TRY(cudaMemsetAsync(gx2, 0, static_cast<size_t>(t2) * 3 * sizeof(float), st));
-  if (n == 0 || m == 0 || b == 0) return 0;  // reference: the loops never execute, grads stay zero
+  if (n == 0 || m == 0 || b == 0) {  // reference: the loops never execute, grads stay zero
+    if (t1) PDAE_CUDA_TRY(cudaMemsetAsync(gx1, 0, static_cast<size_t>(t1) * 3 * sizeof(float), st));
+    if (t2) PDAE_CUDA_TRY(cudaMemsetAsync(gx2, 0, static_cast<size_t>(t2) * 3 * sizeof(float), st));
+    return 0;
+  }
   if (!idx1 || !idx2 || !gd1 || !gd2) return PDAE_E_INVALID;
-  const long long bpc = (static_cast<long long>(n) + m + 255) / 256;
-  if (bpc * b > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
-  chamfer_bwd_kernel<<<static_cast<unsigned>(bpc * b), 256, 0, st>>>(xyz1, xyz2, idx1, idx2, gd1, gd2, n, m,
-                                                                    static_cast<int>(bpc), gx1, gx2);
+  return launch_chamfer_bwd(xyz1, xyz2, idx1, idx2, GradArrays{gd1, gd2}, b, n, m, gx1, gx2, st);
+}
+
+extern "C" size_t pdae_chamfer_loss_workspace_bytes(void) { return 2 * LOSS_BLOCKS * sizeof(float); }
+
+extern "C" int pdae_chamfer_loss_f32(const float *dist1, const float *dist2, int b, int n, int m, int l1, float *loss3,
+                                     void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || !loss3) return PDAE_E_INVALID;
+  if (!workspace || workspace_bytes < pdae_chamfer_loss_workspace_bytes()) return PDAE_E_WORKSPACE;
+  const long long c1 = static_cast<long long>(b) * n, c2 = static_cast<long long>(b) * m;
+  if ((c1 && !dist1) || (c2 && !dist2)) return PDAE_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *partial = static_cast<float *>(workspace);
+  chamfer_loss_partial_kernel<<<LOSS_BLOCKS, 256, 0, st>>>(dist1, dist2, c1, c2, l1 ? 1 : 0, partial);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  chamfer_loss_final_kernel<<<1, 32, 0, st>>>(partial, c1, c2, l1 ? 1 : 0, loss3);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
+}
+
+extern "C" int pdae_chamfer_loss_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2,
+                                         const float *dist1, const float *dist2, const float *gloss, float w1, float w2,
+                                         int b, int n, int m, int l1, float *gx1, float *gx2, pdae_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PDAE_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long t1 = static_cast<long long>(b) * n, t2 = static_cast<long long>(b) * m;
+  if ((t1 && (!xyz1 || !gx1)) || (t2 && (!xyz2 || !gx2))) return PDAE_E_INVALID;
+  if (n == 0 || m == 0 || b == 0) {
+    if (t1) PDAE_CUDA_TRY(cudaMemsetAsync(gx1, 0, static_cast<size_t>(t1) * 3 * sizeof(float), st));
+    if (t2) PDAE_CUDA_TRY(cudaMemsetAsync(gx2, 0, static_cast<size_t>(t2) * 3 * sizeof(float), st));
+    return 0;
+  }
+  if (!idx1 || !idx2 || !gloss || (l1 && (!dist1 || !dist2))) return PDAE_E_INVALID;
+  const float n1 = static_cast<float>(t1), n2 = static_cast<float>(t2);
+  return launch_chamfer_bwd(xyz1, xyz2, idx1, idx2, GradMean{gloss, dist1, dist2, w1 / n1, w2 / n2, l1 ? 1 : 0}, b, n, m, gx1,
+                            gx2, st);
 }

@@ -139,13 +139,15 @@ __global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
       for (int j0 = 0; j0 < tn64; j0 += 64) {
         const int j = j0 + 2 * lane;
         const float2 d = dist_pair(j);
-        if (d.x <= tau0 && j < tn) {
-          if (cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.x, static_cast<uint32_t>(tbase + j));
-          ++cnt;
-        }
-        if (d.y <= tau0 && j + 1 < tn) {
-          if (cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.y, static_cast<uint32_t>(tbase + j + 1));
-          ++cnt;
+        if (fminf(d.x, d.y) <= tau0) {  // rare (~k of r points): one test per pair keeps the common path short
+          if (d.x <= tau0 && j < tn) {
+            if (cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.x, static_cast<uint32_t>(tbase + j));
+            ++cnt;
+          }
+          if (d.y <= tau0 && j + 1 < tn) {
+            if (cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.y, static_cast<uint32_t>(tbase + j + 1));
+            ++cnt;
+          }
         }
       }
     }

@@ -250,6 +250,55 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     return [gx1, gx2]
 
 
+def chamfer_mean_loss(dist1, dist2, l1=False):
+    """Fused loss epilogue: -> float32 tensor (3,) = [loss, mean term 1, mean term 2] with
+    loss = mean(dist1) + mean(dist2) (L2, extensions/chamfer_dist/__init__.py:43) or
+    (mean(sqrt(dist1)) + mean(sqrt(dist2))) / 2 (L1, :413-417).  Two launches, deterministic."""
+    for t in (dist1, dist2):
+        _require_cuda(t, "chamfer_mean_loss")
+        _require_f32_contig(t, "dist")
+    b, n = dist1.shape
+    m = dist2.size(1)
+    dev = dist1.device
+    L = _native.lib()
+    with _on(dev):
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        nbytes = L.pdae_chamfer_loss_workspace_bytes()
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = L.pdae_chamfer_loss_f32(dist1.data_ptr(), dist2.data_ptr(), b, n, m, 1 if l1 else 0, out.data_ptr(),
+                                     ws.data_ptr(), nbytes, _stream())
+    _native.check(rc, "pdae_chamfer_loss_f32")
+    return out
+
+
+def chamfer_loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, grad_loss, w1, w2, l1=False):
+    """Gradients of w1*mean(f(dist1)) + w2*mean(f(dist2)) (f = identity, or sqrt when l1) times the device scalar
+    grad_loss, straight from the saved argmin -- what autograd reaches through MeanBackward (+SqrtBackward) and
+    chamfer.backward in the reference.  Same stride rules as chamfer_backward."""
+    b, n, _ = xyz1.shape
+    m = xyz2.size(1)
+    dev = xyz1.device
+    for t, name in ((xyz1, "xyz1"), (xyz2, "xyz2")):
+        _require_cuda(t, "chamfer_loss_backward")
+        if t.dtype != torch.float32 or not _dense_storage(t):
+            raise RuntimeError("%s must be a float tensor that densely fills its storage" % name)
+    if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
+        raise RuntimeError("idx1 / idx2 must be the int tensors returned by chamfer.forward")
+    grad_loss = grad_loss.reshape(-1)
+    if grad_loss.numel() != 1 or not grad_loss.is_cuda:
+        raise RuntimeError("grad_loss must be a one-element CUDA tensor")
+    grad_loss = grad_loss.float().contiguous()
+    with _on(dev):
+        gx1 = torch.empty_like(xyz1) if xyz1.size(2) == 3 else torch.zeros_like(xyz1)
+        gx2 = torch.empty_like(xyz2) if xyz2.size(2) == 3 else torch.zeros_like(xyz2)
+        rc = _native.lib().pdae_chamfer_loss_bwd_f32(
+            xyz1.data_ptr(), xyz2.data_ptr(), idx1.contiguous().data_ptr(), idx2.contiguous().data_ptr(),
+            dist1.contiguous().data_ptr(), dist2.contiguous().data_ptr(), grad_loss.data_ptr(), float(w1), float(w2), b, n,
+            m, 1 if l1 else 0, gx1.data_ptr(), gx2.data_ptr(), _stream())
+    _native.check(rc, "pdae_chamfer_loss_bwd_f32")
+    return [gx1, gx2]
+
+
 def chamfer_min_keys(queries, refs, ref_offset):
     """One Chamfer direction against a local slice of the reference set -> packed int64 keys (B,Nq)."""
     _require_f32_contig(queries, "queries")

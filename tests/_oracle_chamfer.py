@@ -41,3 +41,21 @@ def backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     g1, g2 = oracle.chamfer_bwd(_as_points(xyz1), _as_points(xyz2), idx1.numpy(), idx2.numpy(),
                                 grad_dist1.contiguous().numpy(), grad_dist2.contiguous().numpy())
     return [_write_back(xyz1, g1), _write_back(xyz2, g2)]
+
+
+def mean_loss(dist1, dist2, l1=False):
+    """CPU stand-in of the fused loss epilogue: the reference's own torch arithmetic (__init__.py:43, :413-417)"""
+    if l1:
+        a, b = torch.mean(torch.sqrt(dist1)), torch.mean(torch.sqrt(dist2))
+        return torch.stack([(a + b) / 2, a, b])
+    a, b = torch.mean(dist1), torch.mean(dist2)
+    return torch.stack([a + b, a, b])
+
+
+def loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, grad_loss, w1, w2, l1=False):
+    g = grad_loss.reshape(()).float()
+    gd1 = torch.full_like(dist1, 1.0) * (g * w1 / dist1.numel())
+    gd2 = torch.full_like(dist2, 1.0) * (g * w2 / dist2.numel())
+    if l1:
+        gd1, gd2 = gd1 / (2 * torch.sqrt(dist1)), gd2 / (2 * torch.sqrt(dist2))
+    return backward(xyz1, xyz2, idx1, idx2, gd1, gd2)

@@ -356,3 +356,47 @@ def test_ball_query_group_points(radius, ns):
     ext = _refmods.ref_pointnet2()
     if ext is not None:
         assert torch.equal(idx, ext.ball_query(centers, t, radius, ns))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("l1", [False, True])
+def test_fused_mean_loss_and_backward_match_the_unfused_ops(l1):
+    """pdae_chamfer_loss_f32 / _loss_bwd_f32 against the reference's torch arithmetic over chamfer.forward/backward
+    (extensions/chamfer_dist/__init__.py:43, :413-417), 1e-5 relative (BASELINE north_star tolerance)."""
+    a = cu(synth.prediction(synth.clouds(5, 700, seed=91), seed=91))
+    c = cu(synth.clouds(5, 900, seed=92))
+    d1, d2, i1, i2 = ops.chamfer_forward(a, c)
+    loss3 = ops.chamfer_mean_loss(d1, d2, l1)
+    f = (lambda t: t.sqrt()) if l1 else (lambda t: t)
+    m1, m2 = f(d1.double()).mean(), f(d2.double()).mean()
+    want = (m1 + m2) / 2 if l1 else m1 + m2
+    assert abs(float(loss3[0]) - float(want)) <= 1e-6 * abs(float(want))
+    assert abs(float(loss3[1]) - float(m1)) <= 1e-6 * float(m1) and abs(float(loss3[2]) - float(m2)) <= 1e-6 * float(m2)
+    g = torch.full((1,), 0.37, device=DEV)
+    w = 0.5 if l1 else 1.0
+    gx1, gx2 = ops.chamfer_loss_backward(a, c, i1, i2, d1, d2, g, w, w, l1)
+    gd1 = torch.full_like(d1, 0.37 * w / d1.numel())
+    gd2 = torch.full_like(d2, 0.37 * w / d2.numel())
+    if l1:
+        gd1, gd2 = gd1 / (2 * d1.sqrt()), gd2 / (2 * d2.sqrt())
+    r1, r2 = ops.chamfer_backward(a, c, i1, i2, gd1, gd2)
+    for got, ref in ((gx1, r1), (gx2, r2)):
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
+
+
+@pytest.mark.gpu
+def test_fused_loss_modules_follow_autograd_like_the_reference_expression():
+    from pointdae_b200 import chamfer_dist
+    a0 = synth.prediction(synth.clouds(3, 300, seed=93), seed=93)
+    c = cu(synth.clouds(3, 300, seed=94))
+    for mod, expr in ((chamfer_dist.ChamferDistanceL2(), lambda d1, d2: d1.mean() + d2.mean()),
+                      (chamfer_dist.ChamferDistanceL1(), lambda d1, d2: (d1.sqrt().mean() + d2.sqrt().mean()) / 2)):
+        a = cu(a0).requires_grad_(True)
+        loss = mod(a, c)
+        (3.0 * loss).backward()
+        b = cu(a0).requires_grad_(True)
+        d1, d2, _, _ = chamfer_dist.ChamferFunction.apply(b, c)
+        ref = expr(d1, d2)
+        (3.0 * ref).backward()
+        assert abs(float(loss) - float(ref)) <= 1e-6 * abs(float(ref))
+        assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-5 * float(b.grad.abs().max()))
