@@ -61,6 +61,29 @@ __global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
       for (int c = 0; c < 3; ++c)
         for (int p = tid; p < tn64; p += KNN_THREADS)
           planes[c * tile + p] = p < tn ? __ldg(R + static_cast<size_t>(c) * r + tbase + p) : (c == 0 ? INF : 0.f);
+    } else if ((r & 3) == 0 && (tbase & 3) == 0) {
+      // four points = three aligned float4 loads (the cloud base is 16-byte aligned when r % 4 == 0); all loads of a
+      // thread are in flight together, then one 128-bit store per plane
+      const float4 *src4 = reinterpret_cast<const float4 *>(R + static_cast<size_t>(tbase) * 3);
+      const int nquad = tn >> 2;  // whole quads of real points
+      for (int g = tid; g < (tn64 >> 2); g += KNN_THREADS) {
+        float4 X = make_float4(INF, INF, INF, INF), Y = make_float4(0.f, 0.f, 0.f, 0.f), Z = Y;
+        if (g < nquad) {
+          const float4 a0 = __ldg(src4 + 3 * g), a1 = __ldg(src4 + 3 * g + 1), a2 = __ldg(src4 + 3 * g + 2);
+          X = make_float4(a0.x, a0.w, a1.z, a2.y);
+          Y = make_float4(a0.y, a1.x, a1.w, a2.z);
+          Z = make_float4(a0.z, a1.y, a2.x, a2.w);
+        } else if (4 * g < tn) {  // the last, partial quad
+          float *xs = &X.x, *ys = &Y.x, *zs = &Z.x;
+          for (int e = 0; e < 4 && 4 * g + e < tn; ++e) {
+            const float *pt = R + (static_cast<size_t>(tbase) + 4 * g + e) * 3;
+            xs[e] = __ldg(pt); ys[e] = __ldg(pt + 1); zs[e] = __ldg(pt + 2);
+          }
+        }
+        *reinterpret_cast<float4 *>(planes + 4 * g) = X;
+        *reinterpret_cast<float4 *>(planes + tile + 4 * g) = Y;
+        *reinterpret_cast<float4 *>(planes + 2 * tile + 4 * g) = Z;
+      }
     } else {
       const float *src = R + static_cast<size_t>(tbase) * 3;
       for (int f = tid; f < tn64 * 3; f += KNN_THREADS) {
@@ -128,29 +151,29 @@ __global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
     const float tau0 = __shfl_sync(0xffffffffu, kth, klane);
 
     // ---- pass 2: collect every point with d <= tau0 into lane-private lists ---------------------
+    // Branch-free: a predicated 64-bit store through a bumped pointer per value (most 64-point steps of a warp hold
+    // at least one candidate, so a warp-level skip would not pay).  Padding has d = +inf and can only pass the test
+    // when tau0 itself is +inf (fewer than k finite distances): that case goes to the exact fallback below.
     int cnt = 0;
+    const bool degenerate = !(tau0 < INF);
     for (int tl = 0; tl < ntiles; ++tl) {
       const int tbase = tl * tile;
       const int tn = (r - tbase) < tile ? (r - tbase) : tile;
       if (ntiles > 1) load_tile(tbase, tn);
       if (!qvalid) continue;
       const int tn64 = (tn + 63) & ~63;
+      uint32_t jg = static_cast<uint32_t>(tbase + 2 * lane);
 #pragma unroll 2
-      for (int j0 = 0; j0 < tn64; j0 += 64) {
-        const int j = j0 + 2 * lane;
-        const float2 d = dist_pair(j);
-        if (fminf(d.x, d.y) <= tau0) {  // rare (~k of r points): one test per pair keeps the common path short
-          if (d.x <= tau0 && j < tn) {
-            if (cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.x, static_cast<uint32_t>(tbase + j));
-            ++cnt;
-          }
-          if (d.y <= tau0 && j + 1 < tn) {
-            if (cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.y, static_cast<uint32_t>(tbase + j + 1));
-            ++cnt;
-          }
-        }
+      for (int j0 = 0; j0 < tn64; j0 += 64, jg += 64) {
+        const float2 d = dist_pair(j0 + 2 * lane);
+        const bool c0 = d.x <= tau0, c1 = d.y <= tau0;
+        if (c0 && cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.x, jg);
+        cnt += c0;
+        if (c1 && cnt < KNN3_LC) lq[cnt * 32 + lane] = pack_key(d.y, jg + 1);
+        cnt += c1;
       }
     }
+    if (degenerate && qvalid) cnt = KNN3_LC + 1;  // idle warps (qvalid false) keep cnt = 0 and touch no list
     // compaction: exclusive scan of the lane counts
     int incl = cnt;
 #pragma unroll

@@ -30,4 +30,17 @@ for c in (3, 7, 64):
 bq = pointnet2_utils.ball_query(0.2, 16, y, cen)
 gp = pointnet2_utils.grouping_operation(y.transpose(1, 2).contiguous().requires_grad_(True), bq); gp.sum().backward()
 go = pointnet2_utils.gather_operation(y.transpose(1, 2).contiguous().requires_grad_(True), idx); go.sum().backward()
+# fused loss epilogue + scalar-gradient backward, both recovery kernels, odd query counts (idle warps in knn3)
+from pointdae_b200 import _native, chamfer_dist
+loss3 = ops.chamfer_mean_loss(d[0], d[1], True)
+ops.chamfer_loss_backward(x, y, d[2], d[3], d[0], d[1], torch.ones(1, device=dev), 0.5, 0.5, True)
+xp = x.clone().requires_grad_(True); chamfer_dist.ChamferDistanceL2()(xp, y).backward()
+_native.lib().pdae_tune_chamfer_variant(50); ops.chamfer_forward(x, y); _native.lib().pdae_tune_chamfer_variant(0)
+q300 = cu(synth.clouds(2, 300, seed=8)); knn_cuda.KNN(20, True)(q300, q300)
+# three_nn / three_interpolate
+dist3, idx3 = pointnet2_utils.three_nn(y, cen)
+w3 = torch.softmax(-dist3, dim=2).contiguous()
+feat = torch.rand(3, 7, cen.size(1), device=dev, requires_grad=True)
+pointnet2_utils.three_interpolate(feat, idx3, w3).sum().backward()
+pointnet2_utils.three_nn(y, cen[:, :2].contiguous())
 torch.cuda.synchronize(); print("sanitize smoke done")
