@@ -145,6 +145,17 @@ int pdae_chamfer_sharded_f32(const float *xyz1, const float *xyz2_local, int b, 
                              uint64_t *keys1, float *dist2_local, int *idx2_local, void *workspace,
                              size_t workspace_bytes, pdae_stream_t stream);
 
+/* kNN with the reference set sharded across ranks (scene-scale clouds; new, no reference counterpart).
+ * pdae_knn_keys_u64: this rank's k best candidates per query from its slice ref_local (b,r_local,dim), whose first
+ *   point has global index ref_offset: keys (b,q,k) ascending, (squared-distance bits << 32 | global index);
+ *   slots beyond r_local hold 0xffff...f.  The ranks all-gather their lists into (w,b,q,k).
+ * pdae_knn_merge_keys_u64: W-way merge of the gathered lists -> the same dist / idx pdae_knn_f32 returns on the whole
+ *   reference cloud (Euclidean distances, int64 indices, (b,q,k) or (b,k,q) layout).  w <= 16.                     */
+int pdae_knn_keys_u64(const float *ref_local, const float *query, int b, int r_local, int q, int dim, int k,
+                      long long ref_offset, uint64_t *keys, pdae_stream_t stream);
+int pdae_knn_merge_keys_u64(const uint64_t *keys_all, int w, int b, int q, int k, int out_kq, float *dist, int64_t *idx,
+                            pdae_stream_t stream);
+
 /* ---- "next" rows: ball query + grouping (3DETR / PointNet++ configs) ------------------------
  * replaces: `ball_query` ball_query_gpu.cu:12-57, `group_points` / `_grad`
  *           group_points_gpu.cu:11-78 (bindings.cpp:18-21).                                    */

@@ -25,6 +25,8 @@ struct KnnArgs {
   float *dist;         // optional, Euclidean
   int64_t *idx;        // optional
   float *group;        // optional (b, q, k, 3): ref[idx] - query   (dim == 3, !PLANAR)
+  uint64_t *keys;      // optional (b, q, k): raw (squared-distance bits << 32 | ref_offset + index) for sharded merges
+  uint32_t ref_offset; // global index of ref[0] (keys output only)
   int r, q, dim, k;
   int tile;            // reference points per shared-memory tile (multiple of 32)
   int qpw;             // queries per warp (1 when the cloud spans several tiles)
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnArgs a) {
         const size_t o = a.out_kq ? (static_cast<size_t>(cloud) * k + p) * q + qidx : bq * k + p;
         if (a.idx) a.idx[o] = static_cast<int64_t>(ji);
         if (a.dist) a.dist[o] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(key >> 32)));
+        if (a.keys) a.keys[bq * k + p] = key == KEY_INF ? KEY_INF : key + a.ref_offset;
         if (D == 3 && !PLANAR && a.group) {
           float *g = a.group + (bq * k + p) * 3;
           g[0] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji)), q0);
@@ -172,10 +175,75 @@ extern "C" int pdae_knn_f32(const float *ref, const float *query, int b, int r, 
   if (!ref || !query || (!dist && !idx)) return PDAE_E_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dim == 3 && k <= 64) return knn3_points(ref, query, b, r, q, k, out_kq ? 1 : 0, dist, idx, nullptr, st);
-  KnnArgs a{ref, query, dist, idx, nullptr, r, q, dim, k, 0, 1, out_kq ? 1 : 0};
+  KnnArgs a{ref, query, dist, idx, nullptr, nullptr, 0u, r, q, dim, k, 0, 1, out_kq ? 1 : 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
   return dim == 3 ? launch_knn<3, false>(a, b, st) : launch_knn<0, false>(a, b, st);
+}
+
+// ---- reference-set sharding (scene-scale clouds): per-rank top-k as packed keys + W-way merge ----
+// A rank scans all queries against its slice of the reference cloud and emits, per query, its k best candidates
+// as ascending (squared-distance bits << 32 | global index) keys; the ranks all-gather the lists (W*Q*k*8 bytes)
+// and every rank merges them: the k smallest keys overall are exactly the unsharded result, because the key order
+// is the (distance, lower index first) order of the single-GPU kernel.
+__global__ void __launch_bounds__(256) knn_merge_keys_kernel(const uint64_t *__restrict__ keys /*(w, nq, k)*/, int w,
+                                                             long long nq, int q, int k, int out_kq,
+                                                             float *__restrict__ dist, int64_t *__restrict__ idx) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (cloud, query)
+  if (t >= nq) return;
+  int head[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) head[s] = 0;
+  const long long cloud = t / q, qi = t - cloud * q;
+  for (int p = 0; p < k; ++p) {
+    uint64_t best = KEY_INF;
+    int who = 0;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      if (s < w && head[s] < k) {
+        const uint64_t c = keys[(static_cast<long long>(s) * nq + t) * k + head[s]];
+        if (c < best) best = c, who = s;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 16; ++s) head[s] += (s == who && best != KEY_INF) ? 1 : 0;
+    const long long o = out_kq ? (cloud * k + p) * q + qi : t * k + p;
+    if (idx) idx[o] = static_cast<int64_t>(static_cast<uint32_t>(best));
+    if (dist) dist[o] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(best >> 32)));
+  }
+}
+
+extern "C" int pdae_knn_keys_u64(const float *ref_local, const float *query, int b, int r_local, int q, int dim, int k,
+                                 long long ref_offset, uint64_t *keys, pdae_stream_t stream) {
+  if (b < 0 || r_local < 0 || q < 0 || dim <= 0 || k <= 0 || ref_offset < 0 || ref_offset + r_local > 0xffffffffLL)
+    return PDAE_E_INVALID;
+  if (b == 0 || q == 0) return 0;
+  if (k > KNN_MAX_K || !query || !keys || (r_local && !ref_local)) return PDAE_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t off = static_cast<uint32_t>(ref_offset);
+  if (r_local == 0) {  // empty slice: every candidate is +inf
+    PDAE_CUDA_TRY(cudaMemsetAsync(keys, 0xff, static_cast<size_t>(b) * q * k * sizeof(uint64_t), st));
+    return 0;
+  }
+  if (dim == 3 && k <= 64) return knn3_points(ref_local, query, b, r_local, q, k, 0, nullptr, nullptr, nullptr, st, keys, off);
+  KnnArgs a{ref_local, query, nullptr, nullptr, nullptr, keys, off, r_local, q, dim, k, 0, 1, 0};
+  const int rc = knn_plan(a, b);
+  if (rc) return rc;
+  return dim == 3 ? launch_knn<3, false>(a, b, st) : launch_knn<0, false>(a, b, st);
+}
+
+extern "C" int pdae_knn_merge_keys_u64(const uint64_t *keys_all, int w, int b, int q, int k, int out_kq, float *dist,
+                                       int64_t *idx, pdae_stream_t stream) {
+  if (w <= 0 || w > 16 || b < 0 || q < 0 || k <= 0) return PDAE_E_INVALID;
+  const long long nq = static_cast<long long>(b) * q;
+  if (nq == 0) return 0;
+  if (!keys_all || (!dist && !idx)) return PDAE_E_INVALID;
+  const long long grid = (nq + 255) / 256;
+  if (grid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  knn_merge_keys_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      keys_all, w, nq, q, k, out_kq ? 1 : 0, dist, idx);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
 }
 
 extern "C" int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
@@ -185,7 +253,7 @@ extern "C" int pdae_group_f32(const float *xyz, const float *center, int b, int 
   if (m > n || m > KNN_MAX_K) return PDAE_E_INVALID;
   if (!xyz || !center || !neighborhood) return PDAE_E_INVALID;
   if (m <= 64) return knn3_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, static_cast<cudaStream_t>(stream));
-  KnnArgs a{xyz, center, nullptr, idx, neighborhood, n, g, 3, m, 0, 1, 0};
+  KnnArgs a{xyz, center, nullptr, idx, neighborhood, nullptr, 0u, n, g, 3, m, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
   return launch_knn<3, false>(a, b, static_cast<cudaStream_t>(stream));
@@ -200,7 +268,7 @@ int pdae::feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *
   if (k > n || k > KNN_MAX_K) return PDAE_E_INVALID;
   if (!x || !idx) return PDAE_E_INVALID;
   if (c == 3 && k <= 64) return knn3_planar(x, b, n, k, idx, st);
-  KnnArgs a{x, nullptr, nullptr, idx, nullptr, n, n, c, k, 0, 1, 0};
+  KnnArgs a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, n, n, c, k, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
   return c == 3 ? launch_knn<3, true>(a, b, st) : launch_knn<0, true>(a, b, st);

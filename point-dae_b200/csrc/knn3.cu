@@ -26,6 +26,8 @@ struct Knn3Args {
   float *dist;         // optional, Euclidean
   int64_t *idx;        // optional
   float *group;        // optional (b, q, k, 3): ref[idx] - query
+  uint64_t *keys;      // optional (b, q, k): raw (squared-distance bits << 32 | ref_offset + index) for sharded merges
+  uint32_t ref_offset; // global index of ref[0] (keys output only)
   int r, q, k;
   int tile;            // reference points per shared-memory tile (multiple of 64)
   int qpw;             // queries per warp (1 when the cloud spans several tiles)
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
         const size_t o = a.out_kq ? (static_cast<size_t>(cloud) * k + p) * q + qidx : bq * k + p;
         if (a.idx) a.idx[o] = static_cast<int64_t>(ji);
         if (a.dist) a.dist[o] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(key >> 32)));
+        if (a.keys) a.keys[bq * k + p] = key == KEY_INF ? KEY_INF : key + a.ref_offset;  // fewer than k points: +inf keys
         if (!PLANAR && a.group) {
           float *g = a.group + (bq * k + p) * 3;
           g[0] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji)), q0);
@@ -273,12 +276,12 @@ static int launch_knn3(Knn3Args a, int b, cudaStream_t st) {
 
 // entry points used by knn.cu / featknn.cu dispatch (k <= 64 only)
 int knn3_points(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
-                float *group, cudaStream_t st) {
-  Knn3Args a{ref, query, dist, idx, group, r, q, k, 0, 1, out_kq};
+                float *group, cudaStream_t st, uint64_t *keys, uint32_t ref_offset) {
+  Knn3Args a{ref, query, dist, idx, group, keys, ref_offset, r, q, k, 0, 1, out_kq};
   return launch_knn3<false>(a, b, st);
 }
 int knn3_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st) {
-  Knn3Args a{x, nullptr, nullptr, idx, nullptr, n, n, k, 0, 1, 0};
+  Knn3Args a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, n, n, k, 0, 1, 0};
   return launch_knn3<true>(a, b, st);
 }
 

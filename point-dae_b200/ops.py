@@ -161,6 +161,42 @@ def knn_points(ref, query, k, out_kq=False, want_dist=True):
     return dist, idx
 
 
+def knn_keys(ref_local, query, k, ref_offset):
+    """This rank's k best candidates per query from its slice of the reference cloud (global index of the slice's first
+    point = ref_offset): int64 (B,Q,k), ascending packed (squared-distance bits << 32 | global index) keys."""
+    _require_cuda(ref_local, "knn_keys")
+    _require_cuda(query, "knn_keys")
+    _require_f32_contig(ref_local, "ref_local")
+    _require_f32_contig(query, "query")
+    b, r, d = ref_local.shape
+    q = query.size(1)
+    if query.size(0) != b or query.size(2) != d:
+        raise RuntimeError("ref.shape=%s != query.shape=%s" % (tuple(ref_local.shape), tuple(query.shape)))
+    with _on(query.device):
+        keys = torch.empty((b, q, int(k)), dtype=torch.int64, device=query.device)
+        rc = _native.lib().pdae_knn_keys_u64(ref_local.data_ptr(), query.data_ptr(), b, r, q, d, int(k), int(ref_offset),
+                                             keys.data_ptr(), _stream())
+    _native.check(rc, "pdae_knn_keys_u64")
+    return keys
+
+
+def knn_merge_keys(keys_all, out_kq=False, want_dist=True):
+    """keys_all int64 (W,B,Q,k): the all-gathered per-rank candidate lists -> (dist, idx) exactly as knn_points on the
+    whole reference cloud."""
+    _require_cuda(keys_all, "knn_merge_keys")
+    if keys_all.dtype != torch.int64 or keys_all.dim() != 4 or not keys_all.is_contiguous():
+        raise RuntimeError("keys_all must be a contiguous int64 tensor of shape (W, B, Q, k)")
+    w, b, q, k = keys_all.shape
+    shape = (b, k, q) if out_kq else (b, q, k)
+    with _on(keys_all.device):
+        idx = torch.empty(shape, dtype=torch.int64, device=keys_all.device)
+        dist = torch.empty(shape, dtype=torch.float32, device=keys_all.device) if want_dist else None
+        rc = _native.lib().pdae_knn_merge_keys_u64(keys_all.data_ptr(), w, b, q, k, 1 if out_kq else 0,
+                                                   dist.data_ptr() if want_dist else None, idx.data_ptr(), _stream())
+    _native.check(rc, "pdae_knn_merge_keys_u64")
+    return dist, idx
+
+
 def group_points_knn(xyz, center, group_size, want_idx=True):
     """Fused Group tail: xyz (B,N,3), center (B,G,3) -> (neighborhood (B,G,M,3), idx (B,G,M) int64|None)."""
     _require_cuda(xyz, "group")

@@ -6,7 +6,11 @@
   reference cloud, scans all queries against it and emits packed keys
   (float_bits(min d) << 32 | global argmin); ONE all-reduce(MIN) over int64 per direction yields
   the global (distance, lowest argmin); the key is order-preserving because d >= 0.
-  The backward then needs one all-reduce(SUM) of the scattered gradient of the sharded cloud.
+  The backward needs one all-reduce(SUM) of the gradient of the replicated cloud (the sharded cloud's gradient is
+  final on the rank that owns the slice).
+* reference-set sharding for kNN: each rank emits its k best candidates per query as ascending packed keys, the
+  lists are all-gathered (W*Q*k*8 bytes) and merged W-way on every rank -- same (distance, lower index) order as
+  the single-GPU kernel, so the result is bit-identical.
 
 The collectives are torch.distributed calls (NCCL over NVLink on the GPU box, gloo in the CPU
 tests); the per-rank compute is pdae_chamfer_min_keys_u64 / pdae_chamfer_unpack_keys.  `keys_fn` /
@@ -65,3 +69,47 @@ def chamfer_forward_sharded(xyz1, xyz2_local, xyz2_offset, group=None, keys_fn=N
     unpack_fn = unpack_fn or _default_unpack_fn
     dist2_local, idx2_local = unpack_fn(keys_fn(xyz2_local, xyz1, 0))
     return dist1, dist2_local, idx1, idx2_local
+
+
+def chamfer_backward_sharded(xyz1, xyz2_local, xyz2_offset, idx1, idx2_local, grad_dist1, grad_dist2_local, group=None,
+                             backward_fn=None):
+    """Backward of chamfer_forward_sharded.  idx1 holds GLOBAL indices into xyz2; a pair (a_j, b_idx1[j]) can only be
+    differentiated by the rank that owns b, so every rank runs the ordinary backward kernels on its slice with the
+    foreign pairs masked out (zero upstream gradient), which yields the final gradient of its slice of xyz2 and a
+    partial gradient of the replicated xyz1; ONE all-reduce(SUM) completes the latter.
+    Returns (grad_xyz1 (B,N,3) complete on every rank, grad_xyz2_local (B,m_local,3))."""
+    if backward_fn is None:
+        from . import ops
+        backward_fn = ops.chamfer_backward
+    m_local = xyz2_local.size(1)
+    local = (idx1 >= xyz2_offset) & (idx1 < xyz2_offset + m_local)
+    idx1_local = torch.where(local, idx1 - xyz2_offset, torch.zeros_like(idx1)).to(torch.int32)
+    gd1 = torch.where(local, grad_dist1, torch.zeros_like(grad_dist1))
+    if m_local == 0:
+        gx1, gx2_local = torch.zeros_like(xyz1), torch.zeros_like(xyz2_local)
+    else:
+        gx1, gx2_local = backward_fn(xyz1, xyz2_local, idx1_local, idx2_local, gd1, grad_dist2_local)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(gx1, op=dist.ReduceOp.SUM, group=group)
+    return gx1, gx2_local
+
+
+def knn_sharded(ref_local, query, k, ref_offset, group=None, transpose_out=False, keys_fn=None, merge_fn=None):
+    """knn_cuda.KNN over a reference cloud sharded along its points: ref_local (B,r_local,D) = points
+    [ref_offset, ref_offset + r_local) of the cloud, query (B,Q,D) replicated.  Returns (dist, idx) identical to the
+    unsharded KNN(k, transpose_mode=True) (or the (B,k,Q) layout of transpose_mode=False with transpose_out)."""
+    if keys_fn is None:
+        from . import ops
+        keys_fn = ops.knn_keys
+    if merge_fn is None:
+        from . import ops
+        merge_fn = ops.knn_merge_keys
+    keys = keys_fn(ref_local, query, k, ref_offset)  # (B,Q,k) int64
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world > 1:
+        flat = torch.empty((world * keys.size(0),) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+        dist.all_gather_into_tensor(flat, keys, group=group)  # rank-major concatenation along dim 0
+        gathered = flat.view((world,) + tuple(keys.shape))
+    else:
+        gathered = keys.unsqueeze(0)
+    return merge_fn(gathered.contiguous(), transpose_out)

@@ -1,4 +1,4 @@
-"""Multi-GPU check of reference-set-sharded Chamfer (BASELINE config 5) over NCCL.  Launch with
+"""Multi-GPU check of reference-set-sharded Chamfer (forward + backward) and kNN (BASELINE config 5) over NCCL.  Launch with
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tests/multi_gpu/run_sharded_nccl.py [n_points]
@@ -57,12 +57,55 @@ def main():
         ops.chamfer_forward(xyz1, xyz2)
     e1.record()
     torch.cuda.synchronize()
+    cham_unsharded_ms = e0.elapsed_time(e1) / reps
+
+    # ---- backward: masked local backward + one all_reduce(SUM) of the replicated cloud's gradient -------------------
+    g1 = torch.full_like(fd1, 1.0 / fd1.numel())
+    g2 = torch.full_like(fd2, 1.0 / fd2.numel())
+    gx1, gx2l = sharded.chamfer_backward_sharded(xyz1, local_refs, lo, i1, i2l, g1, g2[:, lo:hi].contiguous())
+    w1, w2 = ops.chamfer_backward(xyz1, xyz2, fi1, fi2, g1, g2)
+    ok_b = (torch.allclose(gx1, w1, rtol=1e-5, atol=1e-6 * float(w1.abs().max()))
+            and torch.allclose(gx2l, w2[:, lo:hi], rtol=1e-5, atol=1e-6 * float(w2.abs().max())))
+    flag_b = torch.tensor([1 if ok_b else 0], device=dev)
+    dist.all_reduce(flag_b, op=dist.ReduceOp.MIN)
+
+    # ---- kNN with the reference set sharded (BASELINE config 5: FPS 2048 centres, k = 64) ------------------------------
+    q, k = 2048, 64
+    centers = ops.fps_gather(xyz2, q)[1]
+
+    def run_knn():
+        return sharded.knn_sharded(local_refs, centers, k, lo)
+
+    for _ in range(3):
+        run_knn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        kd, ki = run_knn()
+    e1.record()
+    torch.cuda.synchronize()
+    tk = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+    wd, wi = ops.knn_points(xyz2, centers, k)
+    flag_k = torch.tensor([1 if (torch.equal(kd, wd) and torch.equal(ki, wi)) else 0], device=dev)
+    dist.all_reduce(flag_k, op=dist.ReduceOp.MIN)
+    e0.record()
+    for _ in range(reps):
+        ops.knn_points(xyz2, centers, k)
+    e1.record()
+    torch.cuda.synchronize()
+    good = bool(flag.item()) and bool(flag_b.item()) and bool(flag_k.item())
     if rank == 0:
-        print(json.dumps({"test": "ref-set-sharded chamfer over NCCL", "n_points": n, "world": world,
-                          "bit_exact_vs_unsharded": bool(flag.item()), "sharded_ms": float(t.item()),
-                          "unsharded_1gpu_ms": e0.elapsed_time(e1) / reps}), flush=True)
+        print(json.dumps({"test": "ref-set-sharded chamfer + kNN over NCCL", "n_points": n, "world": world,
+                          "chamfer_bit_exact_vs_unsharded": bool(flag.item()), "chamfer_sharded_ms": float(t.item()),
+                          "chamfer_unsharded_1gpu_ms": cham_unsharded_ms,
+                          "chamfer_backward_matches_unsharded": bool(flag_b.item()),
+                          "knn": {"queries": q, "k": k, "bit_exact_vs_unsharded": bool(flag_k.item()),
+                                  "sharded_ms": float(tk.item()), "unsharded_1gpu_ms": e0.elapsed_time(e1) / reps}}),
+              flush=True)
     dist.destroy_process_group()
-    sys.exit(0 if flag.item() else 1)
+    sys.exit(0 if good else 1)
 
 
 if __name__ == "__main__":

@@ -400,3 +400,48 @@ def test_fused_loss_modules_follow_autograd_like_the_reference_expression():
         (3.0 * ref).backward()
         assert abs(float(loss) - float(ref)) <= 1e-6 * abs(float(ref))
         assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-5 * float(b.grad.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("r,q,dim,k,world", [(5000, 97, 3, 32, 4), (1300, 40, 3, 64, 8), (900, 33, 6, 16, 3), (70, 9, 3, 48, 4),
+                                             (20000, 64, 3, 100, 2)])
+def test_knn_keys_merge_equals_unsharded(r, q, dim, k, world):
+    """Reference-set-sharded kNN in one process: per-slice candidate keys (incl. slices smaller than k and an empty
+    slice) merged W-way must reproduce the unsharded kernel bit for bit."""
+    from pointdae_b200 import sharded
+    rng = np.random.default_rng(r)
+    ref = synth.adversarial(synth.clouds(2, r, seed=500 + r), seed=r, n_small=0, n_dup=min(32, r // 4))
+    if dim > 3:
+        ref = np.concatenate([ref, rng.standard_normal((2, r, dim - 3)).astype(np.float32)], axis=2)
+    query = ref[:, rng.integers(0, r, size=q)].copy()
+    query[:, ::2] += np.float32(0.01)
+    R, Q = cu(ref), cu(query)
+    wantD, wantI = ops.knn_points(R, Q, k)
+    bounds = [sharded.shard_bounds(r, world - 1, i) for i in range(world - 1)] + [(r, r)]  # last rank: empty slice
+    keys = torch.stack([ops.knn_keys(R[:, lo:hi].contiguous(), Q, k, lo) for lo, hi in bounds], 0).contiguous()
+    D, I = ops.knn_merge_keys(keys)
+    assert torch.equal(I, wantI) and torch.equal(D, wantD)
+    D2, I2 = ops.knn_merge_keys(keys, out_kq=True)
+    assert torch.equal(I2, wantI.transpose(1, 2)) and torch.equal(D2, wantD.transpose(1, 2))
+    # world of one through the public helper
+    D3, I3 = sharded.knn_sharded(R, Q, k, 0)
+    assert torch.equal(I3, wantI) and torch.equal(D3, wantD)
+
+
+@pytest.mark.gpu
+def test_chamfer_backward_sharded_single_process_sum_of_ranks():
+    """The per-rank masked backward summed over ranks equals the unsharded backward (what the SUM all-reduce does)."""
+    from pointdae_b200 import sharded
+    x1 = cu(synth.prediction(synth.clouds(2, 1500, seed=71), seed=71))
+    x2 = cu(synth.clouds(2, 1500, seed=71))
+    d1, d2, i1, i2 = ops.chamfer_forward(x1, x2)
+    g1, g2 = torch.rand_like(d1), torch.rand_like(d2)
+    w1, w2 = ops.chamfer_backward(x1, x2, i1, i2, g1, g2)
+    acc = torch.zeros_like(x1)
+    for rank in range(3):
+        lo, hi = sharded.shard_bounds(1500, 3, rank)
+        gx1, gx2l = sharded.chamfer_backward_sharded(x1, x2[:, lo:hi].contiguous(), lo, i1, i2[:, lo:hi].contiguous(), g1,
+                                                     g2[:, lo:hi].contiguous())
+        acc += gx1
+        assert torch.allclose(gx2l, w2[:, lo:hi], rtol=1e-5, atol=1e-6 * float(w2.abs().max()))
+    assert torch.allclose(acc, w1, rtol=1e-5, atol=1e-6 * float(w1.abs().max()))
