@@ -80,6 +80,11 @@ int pdae_knn_f32(const float *ref, const float *query, int b, int r, int q, int 
 int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
                    float *neighborhood, pdae_stream_t stream);
 
+/* same search, neighbours NOT re-centred: patches (b,g,m,3) = xyz[idx].  The patch gather of
+ * datasets/corrupt_util_tensor.py:592-616 `dropout_patch_random` (FPS 64 + KNN 32 + advanced indexing).            */
+int pdae_group_gather_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
+                          float *patches, pdae_stream_t stream);
+
 /* ---- DGCNN kNN + graph feature --------------------------------------------------------------
  * replaces: models/dgcnn_util.py:7-12 `knn(x, k)` and :15-36 `get_graph_feature`.
  * x (b,c,n) channel-major.  idx (b,n,k) int64 nearest-first, self included, direct-form

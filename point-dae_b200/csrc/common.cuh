@@ -66,7 +66,7 @@ static inline int ceil_div(long long a, long long b) { return static_cast<int>((
 int feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *idx, cudaStream_t st);
 // knn3.cu: 3-D fast path (k <= 64): row-major points with optional fused Group output, and planar (b,3,n) self-kNN.
 int knn3_points(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
-                float *group, cudaStream_t st, uint64_t *keys = nullptr, uint32_t ref_offset = 0u);
+                float *group, cudaStream_t st, uint64_t *keys = nullptr, uint32_t ref_offset = 0u, int raw_group = 0);
 int knn3_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st);
 
 }  // namespace pdae

@@ -27,6 +27,7 @@ struct KnnArgs {
   float *group;        // optional (b, q, k, 3): ref[idx] - query   (dim == 3, !PLANAR)
   uint64_t *keys;      // optional (b, q, k): raw (squared-distance bits << 32 | ref_offset + index) for sharded merges
   uint32_t ref_offset; // global index of ref[0] (keys output only)
+  int raw_group;       // 1: `group` receives ref[idx] itself instead of ref[idx] - query
   int r, q, dim, k;
   int tile;            // reference points per shared-memory tile (multiple of 32)
   int qpw;             // queries per warp (1 when the cloud spans several tiles)
@@ -114,10 +115,13 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnArgs a) {
         if (a.dist) a.dist[o] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(key >> 32)));
         if (a.keys) a.keys[bq * k + p] = key == KEY_INF ? KEY_INF : key + a.ref_offset;
         if (D == 3 && !PLANAR && a.group) {
+          const bool raw = a.raw_group != 0;
           float *g = a.group + (bq * k + p) * 3;
-          g[0] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji)), q0);
-          g[1] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji) + 1), q1);
-          g[2] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji) + 2), q2);
+          const float x = __ldg(R + 3 * static_cast<size_t>(ji)), y = __ldg(R + 3 * static_cast<size_t>(ji) + 1);
+          const float z = __ldg(R + 3 * static_cast<size_t>(ji) + 2);
+          g[0] = raw ? x : __fsub_rn(x, q0);
+          g[1] = raw ? y : __fsub_rn(y, q1);
+          g[2] = raw ? z : __fsub_rn(z, q2);
         }
       }
     }
@@ -175,7 +179,7 @@ extern "C" int pdae_knn_f32(const float *ref, const float *query, int b, int r, 
   if (!ref || !query || (!dist && !idx)) return PDAE_E_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dim == 3 && k <= 64) return knn3_points(ref, query, b, r, q, k, out_kq ? 1 : 0, dist, idx, nullptr, st);
-  KnnArgs a{ref, query, dist, idx, nullptr, nullptr, 0u, r, q, dim, k, 0, 1, out_kq ? 1 : 0};
+  KnnArgs a{ref, query, dist, idx, nullptr, nullptr, 0u, 0, r, q, dim, k, 0, 1, out_kq ? 1 : 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
   return dim == 3 ? launch_knn<3, false>(a, b, st) : launch_knn<0, false>(a, b, st);
@@ -226,7 +230,7 @@ extern "C" int pdae_knn_keys_u64(const float *ref_local, const float *query, int
     return 0;
   }
   if (dim == 3 && k <= 64) return knn3_points(ref_local, query, b, r_local, q, k, 0, nullptr, nullptr, nullptr, st, keys, off);
-  KnnArgs a{ref_local, query, nullptr, nullptr, nullptr, keys, off, r_local, q, dim, k, 0, 1, 0};
+  KnnArgs a{ref_local, query, nullptr, nullptr, nullptr, keys, off, 0, r_local, q, dim, k, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
   return dim == 3 ? launch_knn<3, false>(a, b, st) : launch_knn<0, false>(a, b, st);
@@ -246,17 +250,27 @@ extern "C" int pdae_knn_merge_keys_u64(const uint64_t *keys_all, int w, int b, i
   return 0;
 }
 
-extern "C" int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
-                              float *neighborhood, pdae_stream_t stream) {
+static int group_impl(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx, float *neighborhood,
+                      bool raw, cudaStream_t st) {
   if (b < 0 || n < 0 || g < 0 || m <= 0) return PDAE_E_INVALID;
   if (b == 0 || g == 0) return 0;
   if (m > n || m > KNN_MAX_K) return PDAE_E_INVALID;
   if (!xyz || !center || !neighborhood) return PDAE_E_INVALID;
-  if (m <= 64) return knn3_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, static_cast<cudaStream_t>(stream));
-  KnnArgs a{xyz, center, nullptr, idx, neighborhood, nullptr, 0u, n, g, 3, m, 0, 1, 0};
+  if (m <= 64) return knn3_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, st, nullptr, 0u, raw ? 1 : 0);
+  KnnArgs a{xyz, center, nullptr, idx, neighborhood, nullptr, 0u, raw ? 1 : 0, n, g, 3, m, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
-  return launch_knn<3, false>(a, b, static_cast<cudaStream_t>(stream));
+  return launch_knn<3, false>(a, b, st);
+}
+
+extern "C" int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
+                              float *neighborhood, pdae_stream_t stream) {
+  return group_impl(xyz, center, b, n, g, m, idx, neighborhood, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pdae_group_gather_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
+                                     float *patches, pdae_stream_t stream) {
+  return group_impl(xyz, center, b, n, g, m, idx, patches, true, static_cast<cudaStream_t>(stream));
 }
 
 // DGCNN kNN: x (b, c, n) channel-major, every point is a query.  Low channel counts (the first
@@ -268,7 +282,7 @@ int pdae::feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *
   if (k > n || k > KNN_MAX_K) return PDAE_E_INVALID;
   if (!x || !idx) return PDAE_E_INVALID;
   if (c == 3 && k <= 64) return knn3_planar(x, b, n, k, idx, st);
-  KnnArgs a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, n, n, c, k, 0, 1, 0};
+  KnnArgs a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, 0, n, n, c, k, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
   return c == 3 ? launch_knn<3, true>(a, b, st) : launch_knn<0, true>(a, b, st);

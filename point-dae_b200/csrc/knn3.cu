@@ -28,6 +28,7 @@ struct Knn3Args {
   float *group;        // optional (b, q, k, 3): ref[idx] - query
   uint64_t *keys;      // optional (b, q, k): raw (squared-distance bits << 32 | ref_offset + index) for sharded merges
   uint32_t ref_offset; // global index of ref[0] (keys output only)
+  int raw_group;       // 1: `group` receives ref[idx] itself instead of ref[idx] - query
   int r, q, k;
   int tile;            // reference points per shared-memory tile (multiple of 64)
   int qpw;             // queries per warp (1 when the cloud spans several tiles)
@@ -233,10 +234,14 @@ __global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
         if (a.dist) a.dist[o] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(key >> 32)));
         if (a.keys) a.keys[bq * k + p] = key == KEY_INF ? KEY_INF : key + a.ref_offset;  // fewer than k points: +inf keys
         if (!PLANAR && a.group) {
+          // Group: neighbours relative to the centre; dropout_patch_random: the neighbours themselves
+          const bool raw = a.raw_group != 0;
           float *g = a.group + (bq * k + p) * 3;
-          g[0] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji)), q0);
-          g[1] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji) + 1), q1);
-          g[2] = __fsub_rn(__ldg(R + 3 * static_cast<size_t>(ji) + 2), q2);
+          const float x = __ldg(R + 3 * static_cast<size_t>(ji)), y = __ldg(R + 3 * static_cast<size_t>(ji) + 1);
+          const float z = __ldg(R + 3 * static_cast<size_t>(ji) + 2);
+          g[0] = raw ? x : __fsub_rn(x, q0);
+          g[1] = raw ? y : __fsub_rn(y, q1);
+          g[2] = raw ? z : __fsub_rn(z, q2);
         }
       }
     }
@@ -276,12 +281,12 @@ static int launch_knn3(Knn3Args a, int b, cudaStream_t st) {
 
 // entry points used by knn.cu / featknn.cu dispatch (k <= 64 only)
 int knn3_points(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
-                float *group, cudaStream_t st, uint64_t *keys, uint32_t ref_offset) {
-  Knn3Args a{ref, query, dist, idx, group, keys, ref_offset, r, q, k, 0, 1, out_kq};
+                float *group, cudaStream_t st, uint64_t *keys, uint32_t ref_offset, int raw_group) {
+  Knn3Args a{ref, query, dist, idx, group, keys, ref_offset, raw_group, r, q, k, 0, 1, out_kq};
   return launch_knn3<false>(a, b, st);
 }
 int knn3_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st) {
-  Knn3Args a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, n, n, k, 0, 1, 0};
+  Knn3Args a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, 0, n, n, k, 0, 1, 0};
   return launch_knn3<true>(a, b, st);
 }
 

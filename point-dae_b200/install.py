@@ -74,6 +74,13 @@ def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentat
         patched.append("utils.misc.fps")
     except Exception:
         pass
+    try:  # the Drop-Patch corruption run inside forward (datasets/corrupt_util_tensor.py:592-616)
+        from . import corrupt_util_tensor
+        cut = importlib.import_module("datasets.corrupt_util_tensor")
+        cut.dropout_patch_random = corrupt_util_tensor.dropout_patch_random
+        patched.append("datasets.corrupt_util_tensor.dropout_patch_random")
+    except Exception:
+        pass
     for name in ("models.PointCAE_transformer", "models.Point_MAE", "models.Point_MlMAE"):
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "Group"):

@@ -197,8 +197,9 @@ def knn_merge_keys(keys_all, out_kq=False, want_dist=True):
     return dist, idx
 
 
-def group_points_knn(xyz, center, group_size, want_idx=True):
-    """Fused Group tail: xyz (B,N,3), center (B,G,3) -> (neighborhood (B,G,M,3), idx (B,G,M) int64|None)."""
+def group_points_knn(xyz, center, group_size, want_idx=True, subtract_center=True):
+    """Fused Group tail: xyz (B,N,3), center (B,G,3) -> (neighborhood (B,G,M,3), idx (B,G,M) int64|None).
+    subtract_center=False returns the neighbours themselves (xyz[idx]), the gather of dropout_patch_random."""
     _require_cuda(xyz, "group")
     _require_f32_contig(xyz, "xyz")
     _require_f32_contig(center, "center")
@@ -210,8 +211,9 @@ def group_points_knn(xyz, center, group_size, want_idx=True):
     with _on(xyz.device):
         nb = torch.empty((b, g, m, 3), dtype=torch.float32, device=xyz.device)
         idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
-        rc = _native.lib().pdae_group_f32(xyz.data_ptr(), center.data_ptr(), b, n, g, m,
-                                          idx.data_ptr() if want_idx else None, nb.data_ptr(), _stream())
+        fn = _native.lib().pdae_group_f32 if subtract_center else _native.lib().pdae_group_gather_f32
+        rc = fn(xyz.data_ptr(), center.data_ptr(), b, n, g, m, idx.data_ptr() if want_idx else None, nb.data_ptr(),
+                _stream())
     _native.check(rc, "pdae_group_f32")
     return nb, idx
 

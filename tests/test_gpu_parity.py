@@ -445,3 +445,34 @@ def test_chamfer_backward_sharded_single_process_sum_of_ranks():
         acc += gx1
         assert torch.allclose(gx2l, w2[:, lo:hi], rtol=1e-5, atol=1e-6 * float(w2.abs().max()))
     assert torch.allclose(acc, w1, rtol=1e-5, atol=1e-6 * float(w1.abs().max()))
+
+
+@pytest.mark.gpu
+def test_dropout_patch_random_matches_the_reference_recipe():
+    """datasets/corrupt_util_tensor.py:592-616 restated literally over the (already pinned) FPS / gather / KNN drop-ins,
+    same seeds -> same patches, bit for bit."""
+    import random
+    from pointdae_b200 import corrupt_util_tensor
+    pc = cu(synth.adversarial(synth.clouds(3, 1024, seed=97), seed=97))
+
+    def reference_recipe(pc_tensor, level=None):
+        if level is None:
+            level = random.random() * 4
+        prob = level / 10.0 + 0.5
+        batch_size, num_points, _ = pc_tensor.shape
+        fps_idx = pointnet2_utils.furthest_point_sample(pc_tensor[:, :, :3].contiguous(), 64)
+        center = pointnet2_utils.gather_operation(pc_tensor.transpose(1, 2).contiguous(), fps_idx).transpose(1, 2).contiguous()
+        _, idx = knn_cuda.KNN(k=32, transpose_mode=True)(pc_tensor, center)
+        idx = (idx + torch.arange(0, batch_size, device=pc_tensor.device).view(-1, 1, 1) * num_points).view(-1)
+        neighborhood = pc_tensor.view(batch_size * num_points, -1)[idx, :].view(batch_size, 64, 32, 3).contiguous()
+        group_mask = torch.rand(64) > prob
+        if group_mask.sum().item() == 0:
+            group_mask[0] = True
+        return neighborhood[:, group_mask.to(pc_tensor.device)].view(batch_size, -1, 3)
+
+    for level in (None, 0, 3.9):
+        random.seed(5); torch.manual_seed(5)
+        want = reference_recipe(pc, level)
+        random.seed(5); torch.manual_seed(5)
+        got = corrupt_util_tensor.dropout_patch_random(pc, level)
+        assert got.shape == want.shape and torch.equal(got, want)
