@@ -446,7 +446,7 @@ extern "C" int pdae_tune_chamfer_variant(int v) {
 // queries per CTA of the kernel launch_min / launch_sym will pick (the callers size `qtiles` with it)
 static int chamfer_qpc(int nq_max, bool sym) {
   if (!sym && nq_max <= 256) return 128;
-  switch (chamfer_variant() % 50) {
+  switch (chamfer_variant() % 25) {
     case 3: return 512;   // <2,256>
     case 4: return 256;   // <2,128>
     case 5: case 6: case 7: return 256;   // <4,64>
@@ -469,7 +469,7 @@ static int launch_min(const ChamferDir &d0, const ChamferDir &d1, int b, cudaStr
   if (!SYM && nq_max <= 256) {
     chamfer_min_kernel<1, 128, 1, false><<<g, 128, 0, st>>>(d0, d1);
   } else {
-    switch (chamfer_variant() % 50) {
+    switch (chamfer_variant() % 25) {
       case 1: chamfer_min_kernel<4, 128, 4, SYM><<<g, 128, 0, st>>>(d0, d1); break;
       case 2: chamfer_min_kernel<4, 128, 3, SYM><<<g, 128, 0, st>>>(d0, d1); break;
       case 3: chamfer_min_kernel<2, 256, 3, SYM><<<g, 256, 0, st>>>(d0, d1); break;
@@ -650,15 +650,90 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_grouped_kernel(const 
   }
 }
 
+// List variant of the group-major recovery (default for clouds up to 32 groups): the CTA of (cloud, group) stages the
+// group's QPG rows in shared memory as planes, every thread tests a strided share of the cloud's column keys and
+// appends the columns won by this group to a shared list, and then ONE THREAD PER LISTED COLUMN walks the group's rows
+// (broadcast LDS.64 of two rows per plane, packed distance, compare with the recorded minimum bit for bit), back to
+// front so that the lowest matching row is the one kept.  No shuffles or ballots in the walk: ~6.5 instructions per
+// (column, row) against ~14 in the warp-cooperative kernel above.
+constexpr int RECOVER_LIST_MAX = 4096;  // columns examined per pass (list of int in shared memory)
+
+template <int QPG>
+__global__ void __launch_bounds__(256) chamfer_col_recover_list_kernel(const float *__restrict__ rows,
+                                                                       const float *__restrict__ cols,
+                                                                       const uint64_t *__restrict__ colkeys, int n_rows,
+                                                                       int n_cols, float *__restrict__ dist,
+                                                                       int *__restrict__ idx) {
+  __shared__ __align__(16) float sx[QPG], sy[QPG], sz[QPG];
+  __shared__ int list[RECOVER_LIST_MAX];
+  __shared__ int count;
+  const unsigned g = blockIdx.x;
+  const size_t cloud = blockIdx.y;
+  const float *__restrict__ A = rows + cloud * n_rows * 3;
+  const uint64_t *__restrict__ K = colkeys + cloud * n_cols;
+  const float *__restrict__ C = cols + cloud * n_cols * 3;
+  const int tid = threadIdx.x;
+  if (tid == 0) count = 0;
+  for (int e = tid; e < 3 * QPG; e += 256) {  // coalesced AoS read of the group's rows; NaN padding never matches
+    const int r = e / 3, c = e - 3 * r;
+    const long long row = static_cast<long long>(g) * QPG + r;
+    const float v = row < n_rows ? __ldg(A + row * 3 + c) : __int_as_float(0x7fc00000);
+    (c == 0 ? sx : c == 1 ? sy : sz)[r] = v;
+  }
+  __syncthreads();
+  constexpr int UNR = 8;
+  for (int c0 = 0; c0 < n_cols; c0 += RECOVER_LIST_MAX) {  // the list holds one chunk of columns at a time
+    const int c1 = c0 + RECOVER_LIST_MAX < n_cols ? c0 + RECOVER_LIST_MAX : n_cols;
+    for (int j0 = c0 + tid; j0 < c1; j0 += 256 * UNR) {
+      uint32_t gid[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int j = j0 + u * 256;
+        gid[u] = j < c1 ? static_cast<uint32_t>(K[j]) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if (gid[u] == g) list[atomicAdd(&count, 1)] = j0 + u * 256;
+    }
+    __syncthreads();
+    const int total = count;
+    for (int m = tid; m < total; m += 256) {
+      const int j = list[m];
+      const float want = __uint_as_float(static_cast<uint32_t>(K[j] >> 32));
+      const float bx = __ldg(C + 3 * j), by = __ldg(C + 3 * j + 1), bz = __ldg(C + 3 * j + 2);
+      const float2 cx = make_float2(bx, bx), cy = make_float2(by, by), cz = make_float2(bz, bz);
+      int found = 0;
+#pragma unroll 8
+      for (int r = QPG - 2; r >= 0; r -= 2) {
+        const float2 d = dist_yxz2(sub2(cx, *reinterpret_cast<const float2 *>(sx + r)),
+                                   sub2(cy, *reinterpret_cast<const float2 *>(sy + r)),
+                                   sub2(cz, *reinterpret_cast<const float2 *>(sz + r)));
+        found = (d.y == want) ? r + 1 : found;
+        found = (d.x == want) ? r : found;
+      }
+      dist[cloud * n_cols + j] = want;
+      idx[cloud * n_cols + j] = static_cast<int>(g) * QPG + found;
+    }
+    __syncthreads();
+    if (tid == 0) count = 0;
+    __syncthreads();
+  }
+}
+
 // second half of the symmetric forward: picks the recovery kernel by cloud size (see the comment above)
 template <int QPG>
 static int launch_col_recover(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows, int n_cols,
                               float *dcol, int *icol, cudaStream_t st) {
   const long long groups = (static_cast<long long>(n_rows) + QPG - 1) / QPG;
-  const int glimit = chamfer_variant() >= 50 ? 0 : (getenv("PDAE_RECOVER_GROUPS") ? atoi(getenv("PDAE_RECOVER_GROUPS")) : 32);
+  // group-major recovery while its key sweeps (8*groups B per column) stay cheaper than re-reading a group per column
+  const int gdefault = chamfer_variant() < 25 ? 128 : 32;
+  const int glimit = chamfer_variant() >= 50 ? 0 : (getenv("PDAE_RECOVER_GROUPS") ? atoi(getenv("PDAE_RECOVER_GROUPS")) : gdefault);
   if (groups <= glimit) {  // key + coordinate sweeps (20*groups B per column) cheaper than row re-reads (12*QPG B)
     const dim3 ggrid(static_cast<unsigned>(groups), b);
-    chamfer_col_recover_grouped_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
+    if (chamfer_variant() < 25)
+      chamfer_col_recover_list_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
+    else
+      chamfer_col_recover_grouped_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
   } else {
     // 4 column points per warp, 8 warps per CTA (splitting a warp across points was measured slower)
     const dim3 rgrid(static_cast<unsigned>((n_cols + 31) / 32), b);
@@ -670,7 +745,7 @@ static int launch_col_recover(const float *rows, const float *cols, const uint64
 
 static int launch_col_recover_for_variant(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows,
                                           int n_cols, float *dcol, int *icol, cudaStream_t st) {
-  const int v = chamfer_variant() % 50;  // queries per warp = 32 * QT of the variant launched
+  const int v = chamfer_variant() % 25;  // queries per warp = 32 * QT of the variant launched
   if (v == 3 || v == 4) return launch_col_recover<64>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
   if ((v >= 8 && v <= 11) || v == 14 || v == 15) return launch_col_recover<256>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
   return launch_col_recover<128>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
