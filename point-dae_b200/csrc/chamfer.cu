@@ -44,30 +44,23 @@ struct ChamferDir {
 // (FMNMX3 across the thread's queries, one REDUX.MIN across the lanes) and posts
 // (min bits << 32 | query-group id) with a 64-bit RED.MIN per CTA; chamfer_col_recover_kernel then
 // finds the lowest query index inside the winning group.  Halves the FMA-pipe work of the forward.
-template <int QT, int THREADS, int MINB, bool SYM, int CH_TILE = 512 /* reference points per shared-memory tile */,
-          int STEP = 8 /* reference points per inner step (4 or 8): QT*STEP distances are live at once */>
-__global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const ChamferDir d0, const ChamferDir d1) {
+// One pass of a CTA: rows [row_base, row_base + QT*THREADS) of cloud `Q` (clamped to nq) against all nr points of
+// `R`.  VARGROUP selects how a warp names itself in the column keys: false = id of its 32*QT-row group
+// (row_base / (32*QT) + warp, uniform groups); true = (first row / 32) << 3 | QT, for the balanced kernel whose
+// passes have different QT.  The shared-memory buffers belong to the caller, so several instantiations can share them.
+template <int QT, int THREADS, bool SYM, int CH_TILE, int STEP, bool VARGROUP>
+__device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, const float *__restrict__ R, int nq, int nr,
+                                                 int row_base, size_t cloud, float *dist, int *idx, uint64_t *keys,
+                                                 int ref_offset, uint64_t *colkeys, float (*tile)[3][CH_TILE],
+                                                 unsigned (*colmin)[THREADS / 32][SYM ? CH_TILE : 4]) {
   constexpr int QPW = 32 * QT;                  // queries per warp
   constexpr int W = THREADS / 32;
   constexpr int LD = 3 * CH_TILE / THREADS;     // floats staged per thread per tile
   static_assert(3 * CH_TILE % THREADS == 0, "tile must split evenly over the CTA");
   static_assert(CH_TILE % CH_GROUP == 0, "tile must hold whole bookkeeping groups");
 
-  __shared__ __align__(16) float tile[2][3][CH_TILE];
-  __shared__ __align__(16) unsigned colmin[SYM ? 2 : 1][SYM ? W : 1][SYM ? CH_TILE : 4];
-
-  const int per_cloud = d0.qtiles + d1.qtiles;
-  const int cloud = blockIdx.x / per_cloud;
-  int t = blockIdx.x - cloud * per_cloud;
-  const bool second = t >= d0.qtiles;
-  if (second) t -= d0.qtiles;
-  const int nq = second ? d1.nq : d0.nq;
-  const int nr = second ? d1.nr : d0.nr;
-  const float *__restrict__ Q = (second ? d1.q : d0.q) + static_cast<size_t>(cloud) * nq * 3;
-  const float *__restrict__ R = (second ? d1.r : d0.r) + static_cast<size_t>(cloud) * nr * 3;
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qbase = t * (QT * THREADS) + warp * QPW;
+  const int qbase = row_base + warp * QPW;
 
   float2 qx[QT], qy[QT], qz[QT];
   float best[QT];
@@ -107,7 +100,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
   // SYM: post the per-warp column minima of tile `tp` (complete since the last barrier)
   auto flush_cols = [&](int tp) {
     if (!SYM) return;
-    uint64_t *ck = d0.colkeys + static_cast<size_t>(cloud) * nr;
+    uint64_t *ck = colkeys + cloud * nr;
     const int tb = tp * CH_TILE;
     for (int j = tid; j < CH_TILE && tb + j < nr; j += THREADS) {
       unsigned v = colmin[tp & 1][0][j];
@@ -118,8 +111,9 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
         wm = u < v ? w : wm;
         v = u < v ? u : v;
       }
-      atomicMin(reinterpret_cast<unsigned long long *>(ck + tb + j),
-                (static_cast<unsigned long long>(v) << 32) | static_cast<unsigned>(t * W + wm));
+      const unsigned who = VARGROUP ? (static_cast<unsigned>((row_base + wm * QPW) >> 5) << 3) | static_cast<unsigned>(QT)
+                                    : static_cast<unsigned>(row_base / QPW + wm);
+      atomicMin(reinterpret_cast<unsigned long long *>(ck + tb + j), (static_cast<unsigned long long>(v) << 32) | who);
     }
   };
 
@@ -242,15 +236,11 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
     myidx[s] = found;
   }
 
-  float *dist = second ? d1.dist : d0.dist;
-  int *idx = second ? d1.idx : d0.idx;
-  uint64_t *keys = second ? d1.keys : d0.keys;
-  const int ref_offset = second ? d1.ref_offset : d0.ref_offset;
 #pragma unroll
   for (int s = 0; s < QT; ++s) {
     const int q = qbase + s * 32 + lane;
     if (q < nq) {
-      const size_t o = static_cast<size_t>(cloud) * nq + q;
+      const size_t o = cloud * nq + q;
       if (keys) {
         keys[o] = pack_key(best[s], static_cast<uint32_t>(myidx[s] + ref_offset));
       } else {
@@ -258,6 +248,61 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
         idx[o] = myidx[s];
       }
     }
+  }
+}
+
+template <int QT, int THREADS, int MINB, bool SYM, int CH_TILE = 512 /* reference points per shared-memory tile */,
+          int STEP = 8 /* reference points per inner step (4 or 8): QT*STEP distances are live at once */>
+__global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const ChamferDir d0, const ChamferDir d1) {
+  constexpr int W = THREADS / 32;
+  __shared__ __align__(16) float tile[2][3][CH_TILE];
+  __shared__ __align__(16) unsigned colmin[SYM ? 2 : 1][W][SYM ? CH_TILE : 4];
+
+  const int per_cloud = d0.qtiles + d1.qtiles;
+  const int cloud = blockIdx.x / per_cloud;
+  int t = blockIdx.x - cloud * per_cloud;
+  const bool second = t >= d0.qtiles;
+  if (second) t -= d0.qtiles;
+  const ChamferDir &d = second ? d1 : d0;
+  chamfer_min_body<QT, THREADS, SYM, CH_TILE, STEP, false>(
+      d.q + static_cast<size_t>(cloud) * d.nq * 3, d.r + static_cast<size_t>(cloud) * d.nr * 3, d.nq, d.nr,
+      t * (QT * THREADS), static_cast<size_t>(cloud), d.dist, d.idx, d.keys, d.ref_offset, d.colkeys, tile, colmin);
+}
+
+// Balanced variant of the symmetric forward (default for the module path).  The uniform kernel above hands every CTA
+// 128*QT rows; at 128 x 2048^2 that is 512 equal CTAs for 296 resident slots, and since ONE 4-warp CTA already
+// saturates an SM's FMA issue the SMs that receive three CTAs instead of four idle for the last eighth of the kernel
+// (FMA pipe 67 % of active but 57 % of elapsed cycles).  Here the rows of the whole batch are cut into 128-row
+// slices, the slices are dealt out evenly to a persistent grid (two CTAs per SM), and every CTA walks its share in
+// passes of up to four slices of one cloud (QT = 4, 3, 2 or 1 queries per thread): the per-scheduler work differs by
+// at most one slice (7 against 6.92 at the headline shape).  Warps name themselves in the column keys by
+// (first row / 32) << 3 | QT because passes of different QT give 32*QT-row groups.
+template <int THREADS, int CH_TILE, int STEP>
+__global__ void __launch_bounds__(THREADS, 1) chamfer_min_balanced_kernel(const ChamferDir d, int slices_per_cloud,
+                                                                          long long total_slices) {
+  constexpr int W = THREADS / 32;
+  __shared__ __align__(16) float tile[2][3][CH_TILE];
+  __shared__ __align__(16) unsigned colmin[2][W][CH_TILE];
+  long long cur = static_cast<long long>(blockIdx.x) * total_slices / gridDim.x;
+  const long long end = static_cast<long long>(blockIdx.x + 1) * total_slices / gridDim.x;
+  while (cur < end) {
+    const long long cloud = cur / slices_per_cloud;
+    const int s0 = static_cast<int>(cur - cloud * slices_per_cloud);
+    long long cnt = end - cur;
+    if (cnt > slices_per_cloud - s0) cnt = slices_per_cloud - s0;
+    if (cnt > 4) cnt = 4;
+    const float *Q = d.q + static_cast<size_t>(cloud) * d.nq * 3, *R = d.r + static_cast<size_t>(cloud) * d.nr * 3;
+    const int row_base = s0 * THREADS;
+    __syncthreads();  // the previous pass is done with the shared buffers
+#define PDAE_PASS(QT)                                                                                                   \
+  chamfer_min_body<QT, THREADS, true, CH_TILE, STEP, true>(Q, R, d.nq, d.nr, row_base, static_cast<size_t>(cloud), d.dist, \
+                                                          d.idx, d.keys, d.ref_offset, d.colkeys, tile, colmin)
+    if (cnt == 4) PDAE_PASS(4);
+    else if (cnt == 3) PDAE_PASS(3);
+    else if (cnt == 2) PDAE_PASS(2);
+    else PDAE_PASS(1);
+#undef PDAE_PASS
+    cur += cnt;
   }
 }
 
@@ -429,6 +474,18 @@ __global__ void __launch_bounds__(256) unpack_keys_kernel(const uint64_t *__rest
 }
 
 // tuning hook: PDAE_CHAMFER_CFG selects the CTA shape of the large-cloud kernel
+// SMs of the current device (cached per device index; the grid of the balanced kernel is two CTAs per SM)
+static int sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
+
 static int g_chamfer_variant = -1;
 static int chamfer_variant() {
   if (g_chamfer_variant < 0) {
@@ -720,6 +777,75 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_list_kernel(const flo
   }
 }
 
+// Recovery for the balanced kernel: its column keys name the winning warp's rows as (first row / 32) << 3 | QT, a
+// 32-aligned range of 32*QT <= 128 rows.  One CTA per (cloud, aligned 128-row block g) stages rows
+// [128 g, 128 g + 224) -- a range that starts in the block ends before that -- collects the columns whose range starts
+// in the block and walks exactly the range, back to front (lowest matching row kept), as the list kernel above.
+__global__ void __launch_bounds__(256) chamfer_col_recover_var_kernel(const float *__restrict__ rows,
+                                                                      const float *__restrict__ cols,
+                                                                      const uint64_t *__restrict__ colkeys, int n_rows,
+                                                                      int n_cols, float *__restrict__ dist,
+                                                                      int *__restrict__ idx) {
+  constexpr int SPAN = 224;
+  __shared__ __align__(16) float sx[SPAN], sy[SPAN], sz[SPAN];
+  __shared__ int list[RECOVER_LIST_MAX];
+  __shared__ int count;
+  const unsigned g = blockIdx.x;
+  const size_t cloud = blockIdx.y;
+  const float *__restrict__ A = rows + cloud * n_rows * 3;
+  const uint64_t *__restrict__ K = colkeys + cloud * n_cols;
+  const float *__restrict__ C = cols + cloud * n_cols * 3;
+  const int tid = threadIdx.x;
+  if (tid == 0) count = 0;
+  for (int e = tid; e < 3 * SPAN; e += 256) {  // NaN padding (rows past the cloud) never matches
+    const int r = e / 3, c = e - 3 * r;
+    const long long row = static_cast<long long>(g) * 128 + r;
+    const float v = row < n_rows ? __ldg(A + row * 3 + c) : __int_as_float(0x7fc00000);
+    (c == 0 ? sx : c == 1 ? sy : sz)[r] = v;
+  }
+  __syncthreads();
+  constexpr int UNR = 8;
+  for (int c0 = 0; c0 < n_cols; c0 += RECOVER_LIST_MAX) {
+    const int c1 = c0 + RECOVER_LIST_MAX < n_cols ? c0 + RECOVER_LIST_MAX : n_cols;
+    for (int j0 = c0 + tid; j0 < c1; j0 += 256 * UNR) {
+      uint32_t who[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int j = j0 + u * 256;
+        who[u] = j < c1 ? static_cast<uint32_t>(K[j]) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if ((who[u] >> 5) == g) list[atomicAdd(&count, 1)] = j0 + u * 256;  // (first row / 32) / 4 == block
+    }
+    __syncthreads();
+    const int total = count;
+    for (int m = tid; m < total; m += 256) {
+      const int j = list[m];
+      const uint64_t key = K[j];
+      const float want = __uint_as_float(static_cast<uint32_t>(key >> 32));
+      const int lo = static_cast<int>((static_cast<uint32_t>(key) >> 3) & 3u) * 32;  // range start inside the block
+      const int len = static_cast<int>(static_cast<uint32_t>(key) & 7u) * 32;
+      const float bx = __ldg(C + 3 * j), by = __ldg(C + 3 * j + 1), bz = __ldg(C + 3 * j + 2);
+      const float2 cx = make_float2(bx, bx), cy = make_float2(by, by), cz = make_float2(bz, bz);
+      int found = lo;
+#pragma unroll 8
+      for (int r = lo + len - 2; r >= lo; r -= 2) {
+        const float2 d = dist_yxz2(sub2(cx, *reinterpret_cast<const float2 *>(sx + r)),
+                                   sub2(cy, *reinterpret_cast<const float2 *>(sy + r)),
+                                   sub2(cz, *reinterpret_cast<const float2 *>(sz + r)));
+        found = (d.y == want) ? r + 1 : found;
+        found = (d.x == want) ? r : found;
+      }
+      dist[cloud * n_cols + j] = want;
+      idx[cloud * n_cols + j] = static_cast<int>(g) * 128 + found;
+    }
+    __syncthreads();
+    if (tid == 0) count = 0;
+    __syncthreads();
+  }
+}
+
 // second half of the symmetric forward: picks the recovery kernel by cloud size (see the comment above)
 template <int QPG>
 static int launch_col_recover(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows, int n_cols,
@@ -804,6 +930,19 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
     if (b > 65535) return PDAE_E_UNSUPPORTED;
     fill_keys_kernel<<<static_cast<unsigned>((ncol + 255) / 256), 256, 0, st>>>(ck, ncol);
     PDAE_RETURN_IF_LAUNCH_FAILED();
+    const long long slices_per_cloud = (static_cast<long long>(nr_rows) + 127) / 128;
+    if (chamfer_variant() == 0 && slices_per_cloud <= 128) {  // balanced persistent grid (see chamfer_min_balanced_kernel)
+      const long long total = slices_per_cloud * b;
+      const long long slots = 2LL * sm_count();
+      ChamferDir d{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, 0, 0};
+      chamfer_min_balanced_kernel<128, 512, 8><<<static_cast<unsigned>(total < slots ? total : slots), 128, 0, st>>>(
+          d, static_cast<int>(slices_per_cloud), total);
+      PDAE_RETURN_IF_LAUNCH_FAILED();
+      const dim3 vgrid(static_cast<unsigned>(slices_per_cloud), b);
+      chamfer_col_recover_var_kernel<<<vgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
+      PDAE_RETURN_IF_LAUNCH_FAILED();
+      return 0;
+    }
     const int qpc = chamfer_qpc(nr_rows, true);
     ChamferDir d0{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, ceil_div(nr_rows, qpc), 0};
     ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
