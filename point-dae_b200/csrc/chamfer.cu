@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
       t * (QT * THREADS), static_cast<size_t>(cloud), d.dist, d.idx, d.keys, d.ref_offset, d.colkeys, tile, colmin);
 }
 
-// Balanced variant of the symmetric forward (default for the module path).  The uniform kernel above hands every CTA
+// Balanced variant of the symmetric forward (opt-in, PDAE_CHAMFER_CFG=17; measured NOT faster, kept as the record of
+// the experiment).  The uniform kernel above hands every CTA
 // 128*QT rows; at 128 x 2048^2 that is 512 equal CTAs for 296 resident slots, and since ONE 4-warp CTA already
 // saturates an SM's FMA issue the SMs that receive three CTAs instead of four idle for the last eighth of the kernel
 // (FMA pipe 67 % of active but 57 % of elapsed cycles).  Here the rows of the whole batch are cut into 128-row
@@ -277,6 +278,11 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
 // passes of up to four slices of one cloud (QT = 4, 3, 2 or 1 queries per thread): the per-scheduler work differs by
 // at most one slice (7 against 6.92 at the headline shape).  Warps name themselves in the column keys by
 // (first row / 32) << 3 | QT because passes of different QT give 32*QT-row groups.
+// Result on B200 (profiles/r01/probe_chamfer_balanced.csv): 161.9 us against 161.1 us for the uniform kernel under ncu.
+// Cloud boundaries force passes narrower than four slices (at 16 slices per cloud and ~7 per CTA: 352 passes of QT 3,
+// 208 of QT 4, 64 of QT 2, 32 of QT 1), and a narrow pass pays the per-column work (tile reads, column reductions,
+// REDUX, key posts) for fewer rows: the in-loop FMA rate drops from 67 % to 61.5 % and the SMs are no better balanced
+// (active cycles min/avg/max 242k/279k/297k).
 template <int THREADS, int CH_TILE, int STEP>
 __global__ void __launch_bounds__(THREADS, 1) chamfer_min_balanced_kernel(const ChamferDir d, int slices_per_cloud,
                                                                           long long total_slices) {
@@ -288,9 +294,10 @@ __global__ void __launch_bounds__(THREADS, 1) chamfer_min_balanced_kernel(const 
   while (cur < end) {
     const long long cloud = cur / slices_per_cloud;
     const int s0 = static_cast<int>(cur - cloud * slices_per_cloud);
-    long long cnt = end - cur;
-    if (cnt > slices_per_cloud - s0) cnt = slices_per_cloud - s0;
-    if (cnt > 4) cnt = 4;
+    long long seg = end - cur;  // what is left of this CTA's share inside the current cloud ...
+    if (seg > slices_per_cloud - s0) seg = slices_per_cloud - s0;
+    const long long passes = (seg + 3) / 4;  // ... walked in as few passes as possible, of (nearly) equal width:
+    const long long cnt = (seg + passes - 1) / passes;  // 5 -> 3+2, 6 -> 3+3, 7 -> 4+3 (narrow passes run at a lower FMA rate)
     const float *Q = d.q + static_cast<size_t>(cloud) * d.nq * 3, *R = d.r + static_cast<size_t>(cloud) * d.nr * 3;
     const int row_base = s0 * THREADS;
     __syncthreads();  // the previous pass is done with the shared buffers
@@ -931,7 +938,7 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
     fill_keys_kernel<<<static_cast<unsigned>((ncol + 255) / 256), 256, 0, st>>>(ck, ncol);
     PDAE_RETURN_IF_LAUNCH_FAILED();
     const long long slices_per_cloud = (static_cast<long long>(nr_rows) + 127) / 128;
-    if (chamfer_variant() == 0 && slices_per_cloud <= 128) {  // balanced persistent grid (see chamfer_min_balanced_kernel)
+    if (chamfer_variant() == 17 && slices_per_cloud <= 128) {  // opt-in: balanced persistent grid (measured no faster)
       const long long total = slices_per_cloud * b;
       const long long slots = 2LL * sm_count();
       ChamferDir d{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, 0, 0};
