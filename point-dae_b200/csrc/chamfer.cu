@@ -48,7 +48,7 @@ struct ChamferDir {
 // `R`.  VARGROUP selects how a warp names itself in the column keys: false = id of its 32*QT-row group
 // (row_base / (32*QT) + warp, uniform groups); true = (first row / 32) << 3 | QT, for the balanced kernel whose
 // passes have different QT.  The shared-memory buffers belong to the caller, so several instantiations can share them.
-template <int QT, int THREADS, bool SYM, int CH_TILE, int STEP, bool VARGROUP>
+template <int QT, int THREADS, bool SYM, int CH_TILE, int STEP, bool VARGROUP, bool PACKED = true>
 __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, const float *__restrict__ R, int nq, int nr,
                                                  int row_base, size_t cloud, float *dist, int *idx, uint64_t *keys,
                                                  int ref_offset, uint64_t *colkeys, float (*tile)[3][CH_TILE],
@@ -158,10 +158,18 @@ __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, co
         for (int s = 0; s < QT; ++s) {
 #pragma unroll
           for (int v = 0; v < STEP / 4; ++v) {
-            dd[s][2 * v] = dist_yxz2(sub2(make_float2(X[v].x, X[v].y), qx[s]), sub2(make_float2(Y[v].x, Y[v].y), qy[s]),
-                                     sub2(make_float2(Z[v].x, Z[v].y), qz[s]));
-            dd[s][2 * v + 1] = dist_yxz2(sub2(make_float2(X[v].z, X[v].w), qx[s]), sub2(make_float2(Y[v].z, Y[v].w), qy[s]),
-                                         sub2(make_float2(Z[v].z, Z[v].w), qz[s]));
+            if (PACKED) {
+              dd[s][2 * v] = dist_yxz2(sub2(make_float2(X[v].x, X[v].y), qx[s]), sub2(make_float2(Y[v].x, Y[v].y), qy[s]),
+                                       sub2(make_float2(Z[v].x, Z[v].y), qz[s]));
+              dd[s][2 * v + 1] = dist_yxz2(sub2(make_float2(X[v].z, X[v].w), qx[s]), sub2(make_float2(Y[v].z, Y[v].w), qy[s]),
+                                           sub2(make_float2(Z[v].z, Z[v].w), qz[s]));
+            } else {  // scalar FADD/FMUL/FFMA (same values): experiment for the issue-slot model, see DESIGN.md
+              const float ax = qx[s].x, ay = qy[s].x, az = qz[s].x;
+              dd[s][2 * v] = make_float2(dist_yxz(__fsub_rn(X[v].x, ax), __fsub_rn(Y[v].x, ay), __fsub_rn(Z[v].x, az)),
+                                         dist_yxz(__fsub_rn(X[v].y, ax), __fsub_rn(Y[v].y, ay), __fsub_rn(Z[v].y, az)));
+              dd[s][2 * v + 1] = make_float2(dist_yxz(__fsub_rn(X[v].z, ax), __fsub_rn(Y[v].z, ay), __fsub_rn(Z[v].z, az)),
+                                             dist_yxz(__fsub_rn(X[v].w, ax), __fsub_rn(Y[v].w, ay), __fsub_rn(Z[v].w, az)));
+            }
           }
           if (STEP == 8) {
             const float t0 = min3(dd[s][0].x, dd[s][0].y, dd[s][1].x);
@@ -252,7 +260,8 @@ __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, co
 }
 
 template <int QT, int THREADS, int MINB, bool SYM, int CH_TILE = 512 /* reference points per shared-memory tile */,
-          int STEP = 8 /* reference points per inner step (4 or 8): QT*STEP distances are live at once */>
+          int STEP = 8 /* reference points per inner step (4 or 8): QT*STEP distances are live at once */,
+          bool PACKED = true /* fp32x2 arithmetic */>
 __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const ChamferDir d0, const ChamferDir d1) {
   constexpr int W = THREADS / 32;
   __shared__ __align__(16) float tile[2][3][CH_TILE];
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
   const bool second = t >= d0.qtiles;
   if (second) t -= d0.qtiles;
   const ChamferDir &d = second ? d1 : d0;
-  chamfer_min_body<QT, THREADS, SYM, CH_TILE, STEP, false>(
+  chamfer_min_body<QT, THREADS, SYM, CH_TILE, STEP, false, PACKED>(
       d.q + static_cast<size_t>(cloud) * d.nq * 3, d.r + static_cast<size_t>(cloud) * d.nr * 3, d.nq, d.nr,
       t * (QT * THREADS), static_cast<size_t>(cloud), d.dist, d.idx, d.keys, d.ref_offset, d.colkeys, tile, colmin);
 }
@@ -549,6 +558,7 @@ static int launch_min(const ChamferDir &d0, const ChamferDir &d1, int b, cudaStr
       case 13: chamfer_min_kernel<4, 32, 12, SYM, 128, 8><<<g, 32, 0, st>>>(d0, d1); break;
       case 14: chamfer_min_kernel<8, 128, 1, SYM, 512, 4><<<g, 128, 0, st>>>(d0, d1); break;
       case 15: chamfer_min_kernel<8, 128, 1, SYM, 512, 8><<<g, 128, 0, st>>>(d0, d1); break;
+      case 18: chamfer_min_kernel<4, 128, 1, SYM, 512, 8, false><<<g, 128, 0, st>>>(d0, d1); break;
       default: chamfer_min_kernel<4, 128, 1, SYM><<<g, 128, 0, st>>>(d0, d1); break;
     }
   }
