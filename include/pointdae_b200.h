@@ -112,6 +112,14 @@ int pdae_graph_feature_grad_f32(const float *gout, const int64_t *idx, int b, in
 size_t pdae_chamfer_fwd_workspace_bytes(int b, int n, int m);
 int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
                          int *idx1, int *idx2, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+/* The same forward in two calls, so that the caller can put a stream event between them: phase 1 = the scan (the
+ * FMA-bound part: every output of the larger cloud final, the other cloud's minima parked in the workspace), phase 2 =
+ * the recovery of the other cloud's dist / idx from the workspace.  Work that should overlap the latency-bound tail of
+ * the step rather than the scan (the patchifier's kNN in bench.py) waits on that event.  Same arguments in both
+ * calls; phase 1 then phase 2 is identical to pdae_chamfer_fwd_f32.                                                  */
+int pdae_chamfer_fwd_phase_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
+                               int *idx1, int *idx2, void *workspace, size_t workspace_bytes, int phase,
+                               pdae_stream_t stream);
 int pdae_chamfer_bwd_f32(const float *xyz1, const float *xyz2, const int *idx1, const int *idx2, const float *gd1,
                          const float *gd2, int b, int n, int m, float *gx1, float *gx2, pdae_stream_t stream);
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "pdae_graph_feature_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pdae_chamfer_fwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "pdae_chamfer_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pdae_chamfer_fwd_phase_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "pdae_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_tune_chamfer_variant": (_i, [_i]),
     "pdae_chamfer_loss_workspace_bytes": (_sz, []),

@@ -904,14 +904,22 @@ extern "C" size_t pdae_chamfer_fwd_workspace_bytes(int b, int n, int m) {
   return static_cast<size_t>(b) * (n < m ? n : m) * sizeof(uint64_t);
 }
 
-extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1,
-                                    float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
-                                    pdae_stream_t stream) {
+// phase 0: the whole forward; 1: everything except the column recovery of the symmetric path (the "scan": row
+// results final, column minima parked in the workspace); 2: only that recovery.  Paths without a separate recovery
+// (tiny clouds, two-scan, empty inputs) do all their work in phase 1 and nothing in phase 2.
+static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
+                            int *idx1, int *idx2, void *workspace, size_t workspace_bytes, pdae_stream_t stream,
+                            int phase) {
   if (b < 0 || n < 0 || m < 0) return PDAE_E_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t bn = static_cast<size_t>(b) * n, bm = static_cast<size_t>(b) * m;
   if ((bn && (!xyz1 || !dist1 || !idx1)) || (bm && (!xyz2 || !dist2 || !idx2))) return PDAE_E_INVALID;
   if (b == 0) return 0;
+  const int nq_max = n > m ? n : m;
+  const size_t need = pdae_chamfer_fwd_workspace_bytes(b, n, m);
+  const bool sym = n > 0 && m > 0 && !(n <= SMALL_MAX && m <= SMALL_MAX) && workspace != nullptr &&
+                   workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 100;
+  if (phase == 2 && !sym) return 0;
   if (n == 0 || m == 0) {  // reference: outputs stay at their zero initialisation (chamfer.cu:152-157)
     if (bn) {
       PDAE_CUDA_TRY(cudaMemsetAsync(dist1, 0, bn * sizeof(float), st));
@@ -932,9 +940,6 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
     PDAE_RETURN_IF_LAUNCH_FAILED();
     return 0;
   }
-  const int nq_max = n > m ? n : m;
-  const size_t need = pdae_chamfer_fwd_workspace_bytes(b, n, m);
-  const bool sym = workspace != nullptr && workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 100;
   if (sym) {
     // rows (register-resident queries) = the larger cloud, columns = the smaller one
     const bool swap = m > n;
@@ -945,32 +950,52 @@ extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b,
     uint64_t *ck = static_cast<uint64_t *>(workspace);
     const long long ncol = static_cast<long long>(b) * nr_cols;
     if (b > 65535) return PDAE_E_UNSUPPORTED;
-    fill_keys_kernel<<<static_cast<unsigned>((ncol + 255) / 256), 256, 0, st>>>(ck, ncol);
-    PDAE_RETURN_IF_LAUNCH_FAILED();
     const long long slices_per_cloud = (static_cast<long long>(nr_rows) + 127) / 128;
-    if (chamfer_variant() == 17 && slices_per_cloud <= 128) {  // opt-in: balanced persistent grid (measured no faster)
-      const long long total = slices_per_cloud * b;
-      const long long slots = 2LL * sm_count();
-      ChamferDir d{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, 0, 0};
-      chamfer_min_balanced_kernel<128, 512, 8><<<static_cast<unsigned>(total < slots ? total : slots), 128, 0, st>>>(
-          d, static_cast<int>(slices_per_cloud), total);
+    const bool balanced = chamfer_variant() == 17 && slices_per_cloud <= 128;  // opt-in (measured no faster)
+    if (phase != 2) {
+      fill_keys_kernel<<<static_cast<unsigned>((ncol + 255) / 256), 256, 0, st>>>(ck, ncol);
       PDAE_RETURN_IF_LAUNCH_FAILED();
+      if (balanced) {
+        const long long total = slices_per_cloud * b;
+        const long long slots = 2LL * sm_count();
+        ChamferDir d{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, 0, 0};
+        chamfer_min_balanced_kernel<128, 512, 8><<<static_cast<unsigned>(total < slots ? total : slots), 128, 0, st>>>(
+            d, static_cast<int>(slices_per_cloud), total);
+        PDAE_RETURN_IF_LAUNCH_FAILED();
+      } else {
+        const int qpc = chamfer_qpc(nr_rows, true);
+        ChamferDir d0{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, ceil_div(nr_rows, qpc), 0};
+        ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+        const int rc = launch_min<true>(d0, d1, b, st);
+        if (rc) return rc;
+      }
+    }
+    if (phase == 1) return 0;
+    if (balanced) {
       const dim3 vgrid(static_cast<unsigned>(slices_per_cloud), b);
       chamfer_col_recover_var_kernel<<<vgrid, 256, 0, st>>>(rows, cols, ck, nr_rows, nr_cols, dcol, icol);
       PDAE_RETURN_IF_LAUNCH_FAILED();
       return 0;
     }
-    const int qpc = chamfer_qpc(nr_rows, true);
-    ChamferDir d0{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, ceil_div(nr_rows, qpc), 0};
-    ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
-    const int rc = launch_min<true>(d0, d1, b, st);
-    if (rc) return rc;
     return launch_col_recover_for_variant(rows, cols, ck, b, nr_rows, nr_cols, dcol, icol, st);
   }
   const int qpc = chamfer_qpc(nq_max, false);
   ChamferDir d0{xyz1, xyz2, dist1, idx1, nullptr, nullptr, n, m, ceil_div(n, qpc), 0};
   ChamferDir d1{xyz2, xyz1, dist2, idx2, nullptr, nullptr, m, n, ceil_div(m, qpc), 0};
   return launch_min<false>(d0, d1, b, st);
+}
+
+extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1,
+                                    float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
+                                    pdae_stream_t stream) {
+  return chamfer_fwd_impl(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, workspace, workspace_bytes, stream, 0);
+}
+
+extern "C" int pdae_chamfer_fwd_phase_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1,
+                                          float *dist2, int *idx1, int *idx2, void *workspace, size_t workspace_bytes,
+                                          int phase, pdae_stream_t stream) {
+  if (phase != 1 && phase != 2) return PDAE_E_INVALID;
+  return chamfer_fwd_impl(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, workspace, workspace_bytes, stream, phase);
 }
 
 extern "C" int pdae_chamfer_min_keys_u64(const float *queries, const float *refs, int b, int nq, int nr,

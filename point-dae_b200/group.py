@@ -2,6 +2,7 @@
 (models/PointCAE_transformer.py:54-86, byte-identical copies in models/Point_MAE.py:51-83 etc.)
 and for `utils/misc.py:13-20 fps`.  Two launches (FPS+centre gather, kNN+gather+centre-subtract)
 replace the reference's ~1500."""
+import torch
 import torch.nn as nn
 
 from . import ops
@@ -20,10 +21,15 @@ class Group(nn.Module):  # FPS + KNN
         self.group_size = group_size
         self.knn = KNN(k=self.group_size, transpose_mode=True)  # kept for attribute parity
 
-    def forward(self, xyz):
-        """input: B N 3  ->  neighborhood: B G M 3 (centre-subtracted), center: B G 3"""
+    def forward(self, xyz, knn_after=None):
+        """input: B N 3  ->  neighborhood: B G M 3 (centre-subtracted), center: B G 3
+        knn_after (optional, not in the reference): a torch.cuda.Event the kNN launch waits for on the current
+        stream -- lets a caller that runs the patchifier on a side stream keep the issue-bound kNN out of the way of
+        an FMA-bound kernel (ops.chamfer_scan_event); FPS is latency-bound and starts at once."""
         batch_size, num_points, _ = xyz.shape
         xyz = xyz.float().contiguous()
         _, center = fps(xyz, self.num_group)  # B G 3
+        if knn_after is not None:
+            torch.cuda.current_stream().wait_event(knn_after)
         neighborhood, _ = ops.group_points_knn(xyz.detach(), center, self.group_size, want_idx=False)
         return neighborhood, center

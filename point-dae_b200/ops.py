@@ -4,6 +4,8 @@ PyTorch is plumbing here (device memory, streams, autograd glue); every computat
 hand-written sm_100a kernel in csrc/.  No function in this module has a CPU or torch fallback:
 a CPU tensor raises, a missing library raises.
 """
+import threading
+
 import torch
 
 from . import _native
@@ -219,8 +221,31 @@ def group_points_knn(xyz, center, group_size, want_idx=True, subtract_center=Tru
 
 
 # -------------------------------------------------------------------------------------- Chamfer
-def chamfer_forward(xyz1, xyz2, symmetric=True):
+_scan_events = threading.local()
+
+
+class chamfer_scan_event:
+    """`with ops.chamfer_scan_event(ev): loss = ChamferDistanceL2()(a, b)` -- the next chamfer_forward on this thread
+    records the torch.cuda.Event `ev` on its stream right after the FMA-bound scan kernel (before the latency-bound
+    column recovery).  Work on another stream that should overlap the tail of the step instead of the scan -- the
+    patchifier's kNN in bench.py -- waits on it (`Group.forward(xyz, knn_after=ev)`).  Scheduling only: results are
+    unchanged."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def __enter__(self):
+        _scan_events.pending = self.event
+        return self.event
+
+    def __exit__(self, *a):
+        _scan_events.pending = None
+        return False
+
+
+def chamfer_forward(xyz1, xyz2, symmetric=True, scan_done=None):
     """chamfer.forward: returns [dist1 (B,N), dist2 (B,M), idx1 int32, idx2 int32].
+    scan_done: optional torch.cuda.Event recorded between the scan and the column recovery (see chamfer_scan_event).
 
     Reference-faithful storage semantics (chamfer.cu:159-164 reads raw data_ptr): a tensor whose
     elements densely fill their storage is read in *storage order* as [B][size(1)][3], even when it
@@ -253,9 +278,18 @@ def chamfer_forward(xyz1, xyz2, symmetric=True):
         # each direction is scanned separately -- same results, twice the arithmetic
         nbytes = L.pdae_chamfer_fwd_workspace_bytes(b, n, m) if symmetric else 0
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
-        rc = L.pdae_chamfer_fwd_f32(xyz1.data_ptr(), xyz2.data_ptr(), b, n, m, dist1.data_ptr(), dist2.data_ptr(),
-                                    idx1.data_ptr(), idx2.data_ptr(), ws.data_ptr() if nbytes else None, nbytes,
-                                    _stream())
+        args = (xyz1.data_ptr(), xyz2.data_ptr(), b, n, m, dist1.data_ptr(), dist2.data_ptr(), idx1.data_ptr(),
+                idx2.data_ptr(), ws.data_ptr() if nbytes else None, nbytes)
+        if scan_done is None:
+            scan_done = getattr(_scan_events, "pending", None)
+            _scan_events.pending = None  # one-shot: only the first forward inside the context records
+        if scan_done is None:
+            rc = L.pdae_chamfer_fwd_f32(*args, _stream())
+        else:
+            rc = L.pdae_chamfer_fwd_phase_f32(*args, 1, _stream())
+            _native.check(rc, "pdae_chamfer_fwd_phase_f32")
+            scan_done.record(torch.cuda.current_stream())
+            rc = L.pdae_chamfer_fwd_phase_f32(*args, 2, _stream())
     _native.check(rc, "pdae_chamfer_fwd_f32")
     return [dist1, dist2, idx1, idx2]
 

@@ -5,7 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from torch.profiler import profile, ProfilerActivity
-from pointdae_b200 import ops, synth
+from pointdae_b200 import graphs, ops, synth
+
+PRIO = len(sys.argv) > 1 and sys.argv[1] == "prio"
+DEFER = len(sys.argv) > 1 and sys.argv[1] == "defer"  # patchifier branch forked after the forward instead of before
 
 dev = torch.device("cuda:0")
 B, N, G, M, POOL = 128, 2048, 64, 32, 8
@@ -18,11 +21,17 @@ side = torch.cuda.Stream()
 
 def step(i):
     main = torch.cuda.current_stream()
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        _, cen = ops.fps_gather(clouds[i], G)
-        nb = ops.group_points_knn(clouds[i], cen, M, want_idx=False)
+    if not DEFER:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _, cen = ops.fps_gather(clouds[i], G)
+            nb = ops.group_points_knn(clouds[i], cen, M, want_idx=False)
     d1, d2, i1, i2 = ops.chamfer_forward(preds[i], clouds[i])
+    if DEFER:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _, cen = ops.fps_gather(clouds[i], G)
+            nb = ops.group_points_knn(clouds[i], cen, M, want_idx=False)
     l = ops.chamfer_mean_loss(d1, d2)
     g = ops.chamfer_loss_backward(preds[i], clouds[i], i1, i2, d1, d2, gone, 1.0, 1.0)
     main.wait_stream(side)
@@ -32,8 +41,8 @@ for i in range(3): step(i)
 torch.cuda.synchronize()
 gs = []
 for i in range(POOL):
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    g = graphs.PriorityGraph() if PRIO else torch.cuda.CUDAGraph()
+    with (g.capture() if PRIO else torch.cuda.graph(g)):
         keep = step(i)
     gs.append((g, keep))
 for _ in range(3):
