@@ -918,7 +918,8 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
   const int nq_max = n > m ? n : m;
   const size_t need = pdae_chamfer_fwd_workspace_bytes(b, n, m);
   const bool sym = n > 0 && m > 0 && !(n <= SMALL_MAX && m <= SMALL_MAX) && workspace != nullptr &&
-                   workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 100;
+                   workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 100 &&
+                   b <= 65535;  // the recovery kernels index clouds with gridDim.y; larger batches take the two-scan path
   if (phase == 2 && !sym) return 0;
   if (n == 0 || m == 0) {  // reference: outputs stay at their zero initialisation (chamfer.cu:152-157)
     if (bn) {
@@ -949,7 +950,6 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
     int *irow = swap ? idx2 : idx1, *icol = swap ? idx1 : idx2;
     uint64_t *ck = static_cast<uint64_t *>(workspace);
     const long long ncol = static_cast<long long>(b) * nr_cols;
-    if (b > 65535) return PDAE_E_UNSUPPORTED;
     const long long slices_per_cloud = (static_cast<long long>(nr_rows) + 127) / 128;
     const bool balanced = chamfer_variant() == 17 && slices_per_cloud <= 128;  // opt-in (measured no faster)
     if (phase != 2) {
