@@ -92,6 +92,12 @@ int pdae_group_gather_f32(const float *xyz, const float *center, int b, int n, i
  * graph_feature: out physical (b,n,k,2c): [0:c] = x[:,idx]-x_i, [c:2c] = x_i (the reference's
  * permuted view).  grad: gout same layout -> gx (b,c,n) overwritten.                          */
 int pdae_feat_knn_f32(const float *x, int b, int c, int n, int k, int64_t *idx, pdae_stream_t stream);
+/* Same search with a caller-owned workspace (pdae_feat_knn_workspace_bytes, up to 1 GiB): for c >= 8 and k <= 32 the
+ * distances go through a materialised (n x n) matrix per cloud and a threshold pre-pass, which is faster than the
+ * streaming selection of pdae_feat_knn_f32 (same result bit for bit); other shapes ignore the workspace.          */
+size_t pdae_feat_knn_workspace_bytes(int b, int c, int n, int k);
+int pdae_feat_knn_ws_f32(const float *x, int b, int c, int n, int k, int64_t *idx, void *workspace,
+                         size_t workspace_bytes, pdae_stream_t stream);
 /* workspace for graph_feature / _grad: one (b,n,c) fp32 transposed copy. */
 size_t pdae_graph_feature_workspace_bytes(int b, int c, int n);
 int pdae_graph_feature_f32(const float *x, const int64_t *idx, int b, int c, int n, int k, float *out,

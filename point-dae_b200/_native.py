@@ -32,6 +32,8 @@ SIGNATURES = {
     "pdae_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_group_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_feat_knn_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "pdae_feat_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pdae_feat_knn_ws_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pdae_graph_feature_workspace_bytes": (_sz, [_i, _i, _i]),
     "pdae_graph_feature_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pdae_graph_feature_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),

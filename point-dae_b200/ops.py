@@ -432,7 +432,13 @@ def feat_knn(x, k):
         raise RuntimeError("selected index k out of range")  # torch.topk's message
     with _on(xc.device):
         idx = torch.empty((b, n, k), dtype=torch.int64, device=xc.device)
-        rc = _native.lib().pdae_feat_knn_f32(xc.data_ptr(), b, c, n, k, idx.data_ptr(), _stream())
+        L = _native.lib()
+        nbytes = L.pdae_feat_knn_workspace_bytes(b, c, n, k)  # > 0: distance-matrix path (wide layers, k <= 32)
+        if nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=xc.device)
+            rc = L.pdae_feat_knn_ws_f32(xc.data_ptr(), b, c, n, k, idx.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        else:
+            rc = L.pdae_feat_knn_f32(xc.data_ptr(), b, c, n, k, idx.data_ptr(), _stream())
     _native.check(rc, "pdae_feat_knn_f32")
     return idx
 
