@@ -499,3 +499,29 @@ def test_chamfer_forward_kernel_variants_agree_bit_for_bit(b, n, m):
     for v in (17, 41, 66, 100):
         for got, want in zip(outs[v], outs[0]):
             assert torch.equal(got, want), v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,c,n,k", [(2, 8, 100, 1), (1, 20, 1000, 32), (2, 64, 2049, 20), (3, 16, 33, 32), (1, 12, 130, 7),
+                                     (2, 64, 700, 20), (1, 9, 20, 20)])
+def test_dgcnn_knn_matrix_and_fused_paths_agree_with_oracle(b, c, n, k):
+    """Wide-layer DGCNN kNN on awkward shapes (n not a multiple of 4 / 64 / 128, k = 1, k = 32, k = n, channel counts
+    that are not a multiple of the 16-channel stage, duplicated features -> exact ties): the distance-matrix path
+    (ops.feat_knn with a workspace) and the fused streaming kernel (pdae_feat_knn_f32) against the oracle, bit-exact."""
+    from pointdae_b200 import _native
+    x = synth.features(b, c, n, seed=3 * c + n)
+    x[:, :, n // 2:n // 2 + min(8, n // 2)] = x[:, :, : min(8, n // 2)]  # exact duplicates
+    want, _ = oracle.feat_knn(x, k)
+    t = cu(x)
+    np.testing.assert_array_equal(ops.feat_knn(t, k).cpu().numpy(), want)  # matrix path (workspace given)
+    idx = torch.empty((b, n, k), dtype=torch.int64, device=DEV)
+    rc = _native.lib().pdae_feat_knn_f32(t.data_ptr(), b, c, n, k, idx.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    np.testing.assert_array_equal(idx.cpu().numpy(), want)
+    # chunked walk of the batch: a workspace that holds a single cloud
+    per = (n * n + n) * 4
+    ws = torch.empty(per, dtype=torch.uint8, device=DEV)
+    idx2 = torch.empty_like(idx)
+    rc = _native.lib().pdae_feat_knn_ws_f32(t.data_ptr(), b, c, n, k, idx2.data_ptr(), ws.data_ptr(), per,
+                                            torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and torch.equal(idx2, idx)
