@@ -79,22 +79,80 @@ __device__ __forceinline__ unsigned fps_block_argmax(unsigned vb, unsigned rank,
   return r;
 }
 
+// block-wide arg-max for the register-resident kernel: per-warp winners are posted as ONE 64-bit key
+// (value bits << 32 | ~rank: larger value first, then smaller rank) and every thread folds the W keys with a
+// register tree after the barrier -- two broadcast LDS.128 and log2(W) dependent 64-bit max instead of a second pair
+// of REDUX + uniform-to-vector moves on the critical path of every iteration.
+template <int T>
+__device__ __forceinline__ unsigned fps_block_argmax_keys(unsigned vb, unsigned rank, unsigned long long *slots /*[2][32]*/,
+                                                          int it) {
+  constexpr int W = T / 32;
+  const unsigned full = 0xffffffffu;
+  const unsigned m = __reduce_max_sync(full, vb);
+  const unsigned r = __reduce_min_sync(full, vb == m ? rank : 0xffffffffu);
+  if (W == 1) return r;
+  if constexpr (W > 16) {
+    return fps_block_argmax<T>(vb, rank, reinterpret_cast<uint2 *>(slots), it);
+  } else {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *buf = slots + (it & 1) * 32;
+    if (lane == 0) buf[warp] = (static_cast<unsigned long long>(m) << 32) | static_cast<unsigned>(~r);
+    __syncthreads();
+    unsigned long long kk[W];
+#pragma unroll
+    for (int w = 0; w < W; w += 2) {
+      const ulonglong2 two = *reinterpret_cast<const ulonglong2 *>(buf + w);
+      kk[w] = two.x;
+      kk[w + 1] = two.y;
+    }
+#pragma unroll
+    for (int stride = 1; stride < W; stride *= 2)
+#pragma unroll
+      for (int i = 0; i + stride < W; i += 2 * stride) kk[i] = kk[i] > kk[i + stride] ? kk[i] : kk[i + stride];
+    return ~static_cast<unsigned>(kk[0]);
+  }
+}
+
 // ---- register-resident variant: n <= T*P -----------------------------------------------------
 // S = log2(bs / T) when the CTA is narrower than the reference's block (T < bs = 512): a thread then owns
 // 2^S different reference slots, and its registers are laid out in tie-rank order (slot sub-index
 // bit-reversed first, then k / bs) so that the in-thread first-maximum scan still reproduces the rule.
+// The tie rank of the point in register i needs no bit reversal in the loop: the reversed slot of a thread is a
+// constant (its high part) plus the register's slot sub-index, and k / bs is linear in i.  The staged cloud is stored
+// in RANK order -- position (reversed slot) * ceil(n / bs) + k / bs -- with the point's index in .w, so the winner's
+// coordinates and index are one multiply-add and one LDS.128 away from the reduced rank.
 template <int T, int P, int S>
 __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ data, int n, int c, int m, int lg_bs,
                                                     int *__restrict__ idx, float *__restrict__ centers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *sp = reinterpret_cast<float4 *>(smem_raw);            // [n] staged cloud
-  uint2 *slots = reinterpret_cast<uint2 *>(sp + n);             // [2][32]
+  const int npb = (n + (1 << lg_bs) - 1) >> lg_bs;               // points per reference slot (k / bs < npb)
+  float4 *sp = reinterpret_cast<float4 *>(smem_raw);            // [bs * npb] staged cloud in rank order
+  unsigned long long *slots = reinterpret_cast<unsigned long long *>(sp + (static_cast<size_t>(npb) << lg_bs));  // [2][32]
   const int tid = threadIdx.x;
   const float *__restrict__ cloud = data + static_cast<size_t>(blockIdx.x) * n * c;
   int *__restrict__ out = idx + static_cast<size_t>(blockIdx.x) * m;
 
   static_assert(P % (1 << S) == 0, "points per thread must cover whole slot groups");
   constexpr int PG = P >> S;  // points per slot sub-index
+  constexpr int LOG2T = T == 128 ? 7 : T == 256 ? 8 : T == 512 ? 9 : 10;
+  // rank of register i = rank_base + rank_of_reg(i):
+  //   S == 0 (T >= bs): reversed slot = brev(tid mod bs), k / bs = (tid >> lg_bs) + i * (T >> lg_bs)
+  //   S  > 0 (T <  bs): reversed slot = brev_T(tid) << S | sub(i), k / bs = i mod PG           (sub = i / PG)
+  unsigned rank_base;
+  if (S == 0) {
+    const unsigned slot = static_cast<unsigned>(tid) & ((1u << lg_bs) - 1u);
+    const unsigned rev = lg_bs ? (__brev(slot) >> (32 - lg_bs)) : 0u;
+    rank_base = (rev << 22) | (static_cast<unsigned>(tid) >> lg_bs);
+  } else {
+    rank_base = (__brev(static_cast<unsigned>(tid)) >> (32 - LOG2T)) << (22 + S);
+  }
+  const unsigned hi_step = S == 0 ? static_cast<unsigned>(T >> lg_bs) : 1u;
+  auto rank_of_reg = [&](int i) -> unsigned {
+    if (S == 0) return rank_base + static_cast<unsigned>(i) * hi_step;
+    return rank_base + (static_cast<unsigned>(i / PG) << 22) + static_cast<unsigned>(i % PG);
+  };
+  auto pos_of_rank = [&](unsigned r) -> unsigned { return (r >> 22) * static_cast<unsigned>(npb) + (r & 0x3fffffu); };
+
   float px[P], py[P], pz[P], pt[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) {
@@ -106,16 +164,15 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ da
       z = __ldg(cloud + static_cast<size_t>(k) * c + 2);
       const float mag = dist_yxz(x, y, z);
       t = (static_cast<double>(mag) <= 1e-3) ? -2.0f : 1e10f;  // sampling_gpu.cu:103-104
-      sp[k] = make_float4(x, y, z, 0.f);
+      sp[pos_of_rank(rank_of_reg(p))] = make_float4(x, y, z, __int_as_float(k));
     }
     px[p] = x; py[p] = y; pz[p] = z; pt[p] = t;
   }
   if (tid == 0) out[0] = 0;
   __syncthreads();
 
-  int old = 0;
+  float4 o = sp[0];  // point 0 has rank 0
   for (int j = 1; j < m; ++j) {
-    const float4 o = sp[old];
     float v[P];
     int vi[P];
 #pragma unroll
@@ -137,12 +194,11 @@ __global__ void __launch_bounds__(T) fps_reg_kernel(const float *__restrict__ da
     }
     const bool any = v[0] > -1.0f;
     const float best = any ? v[0] : -1.0f;
-    const int bestp = any ? vi[0] : 0;
-    // a thread with no valid point reports (value -1, index 0) like the reference (:93-94)
-    const int bk = best < 0.0f ? 0 : tid + fps_point_of_reg_rt<S, PG>(bestp) * T;
-    const unsigned r = fps_block_argmax<T>(fps_val_bits(best), fps_rank(bk, lg_bs), slots, j);
-    old = fps_unrank(r, lg_bs);
-    if (tid == 0) out[j] = old;
+    // a thread with no valid point reports (value -1, index 0) like the reference (:93-94); point 0 has rank 0
+    const unsigned myrank = any ? rank_of_reg(vi[0]) : 0u;
+    const unsigned r = fps_block_argmax_keys<T>(fps_val_bits(best), myrank, slots, j);
+    o = sp[pos_of_rank(r)];
+    if (tid == 0) out[j] = __float_as_int(o.w);
   }
 
   if (centers != nullptr) {  // fused utils/misc.py:18-19 gather of the sampled rows
@@ -373,7 +429,8 @@ static int ilog2_floor(int v) {
 template <int T, int P, int S = 0>
 static int launch_fps_reg(const float *data, int b, int n, int c, int m, int lg_bs, int *idx, float *centers,
                           cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(n) * sizeof(float4) + 2 * 32 * sizeof(uint2);
+  const size_t table = static_cast<size_t>((n + (1 << lg_bs) - 1) >> lg_bs) << lg_bs;  // rank-ordered positions, >= n
+  const size_t smem = table * sizeof(float4) + 2 * 32 * sizeof(unsigned long long);
   if (smem > 48 * 1024) {
     PDAE_CUDA_TRY(cudaFuncSetAttribute(fps_reg_kernel<T, P, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
@@ -384,6 +441,7 @@ static int launch_fps_reg(const float *data, int b, int n, int c, int m, int lg_
 }
 
 constexpr int FPS_REG_MAX_N = 12288;
+constexpr int FPS_T4096 = 128, FPS_P4096 = 32, FPS_S4096 = 2;  // 2049..4096 points (64.5 us vs 67.0 us for 256 x 16)
 constexpr int FPS_CLUSTER_MAX_N = 16 * 512 * 24;  // 196 608
 
 static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx, float *centers, void *ws,
@@ -409,6 +467,9 @@ static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx,
     if constexpr ((T) == 128 && (P) % 4 == 0) {                                               \
       if (bs == 512) return launch_fps_reg<T, P, 2>(data, b, n, c, m, lg_bs, idx, centers, st); \
     }                                                                                         \
+    if constexpr ((T) == 128 && (P) % 2 == 0) {                                               \
+      if (bs == 256) return launch_fps_reg<T, P, 1>(data, b, n, c, m, lg_bs, idx, centers, st); \
+    }                                                                                         \
   }
   int want_t = 0, want_p = 0;
   if (const char *e = getenv("PDAE_FPS_CFG")) {  // tuning hook: "T,P"
@@ -419,14 +480,15 @@ static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx,
     }
   }
 #undef PDAE_FPS_TRY
-  // defaults from profiles/tune_kernels.py on B200: 8 warps per CTA keep the replicated reduction cheap
+  // defaults from profiles/tune_kernels.py on B200: one warp per scheduler (128 threads) gives the shortest iteration
+  // once the block reduction is a 4-key register tree (2048 -> 64: 16.7 us against 23.0 us with 256 threads)
   if (n <= 128) return launch_fps_reg<128, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 256) return launch_fps_reg<256, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n < 512) return launch_fps_reg<256, 2>(data, b, n, c, m, lg_bs, idx, centers, st);  // bs == 256
-  // from here on bs == 512 and the 256-thread CTA uses the rank-ordered register layout (S = 1)
-  if (n <= 1024) return launch_fps_reg<256, 4, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 2048) return launch_fps_reg<256, 8, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 4096) return launch_fps_reg<256, 16, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n < 256) return launch_fps_reg<128, 2>(data, b, n, c, m, lg_bs, idx, centers, st);       // bs == 128
+  if (n < 512) return launch_fps_reg<128, 4, 1>(data, b, n, c, m, lg_bs, idx, centers, st);    // bs == 256
+  // from here on bs == 512: the narrower CTAs use the rank-ordered register layout (S = log2(512 / T))
+  if (n <= 1024) return launch_fps_reg<128, 8, 2>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 2048) return launch_fps_reg<128, 16, 2>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 4096) return launch_fps_reg<FPS_T4096, FPS_P4096, FPS_S4096>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= 8192) return launch_fps_reg<256, 32, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= FPS_REG_MAX_N) return launch_fps_reg<512, 24>(data, b, n, c, m, lg_bs, idx, centers, st);
   // scene-scale clouds: a 16-CTA cluster per cloud (state in registers + DSMEM exchange), up to 196 608 points

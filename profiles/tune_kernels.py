@@ -42,6 +42,14 @@ def main():
             else: os.environ.pop("PDAE_FPS_CFG", None)
             res["fps_1024_64[%s]" % cfg] = timeit(lambda i: ops.fps_gather(c1024[i], G), pool)
         os.environ.pop("PDAE_FPS_CFG", None)
+        c4096 = [torch.from_numpy(synth.clouds(B, 4096, seed=40 + i)).to(dev) for i in range(4)]
+        for cfg in (None, "128,32", "256,16", "512,8"):
+            if cfg: os.environ["PDAE_FPS_CFG"] = cfg
+            else: os.environ.pop("PDAE_FPS_CFG", None)
+            res["fps_4096_128[%s]" % cfg] = timeit(lambda i: ops.fps_gather(c4096[i], 128), 4, reps=8)
+        os.environ.pop("PDAE_FPS_CFG", None)
+        c300 = torch.from_numpy(synth.clouds(B, 300, seed=50)).to(dev)
+        res["fps_300_64[None]"] = timeit(lambda i: ops.fps_gather(c300, 64), 1)
         big = torch.from_numpy(synth.clouds(148, 8192, seed=5)).to(dev)
         for cfg in (None, "512,16", "1024,8", "256,32"):
             if cfg: os.environ["PDAE_FPS_CFG"] = cfg
