@@ -91,7 +91,7 @@ __device__ __forceinline__ unsigned fps_block_argmax_keys(unsigned vb, unsigned 
   const unsigned m = __reduce_max_sync(full, vb);
   const unsigned r = __reduce_min_sync(full, vb == m ? rank : 0xffffffffu);
   if (W == 1) return r;
-  if constexpr (W > 16) {
+  if constexpr (W > 4) {  // 8+ keys per thread cost more than the second pair of REDUX (measured: 23.0 vs 20.5 us at W = 8)
     return fps_block_argmax<T>(vb, rank, reinterpret_cast<uint2 *>(slots), it);
   } else {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -441,7 +441,7 @@ static int launch_fps_reg(const float *data, int b, int n, int c, int m, int lg_
 }
 
 constexpr int FPS_REG_MAX_N = 12288;
-constexpr int FPS_T4096 = 128, FPS_P4096 = 32, FPS_S4096 = 2;  // 2049..4096 points (64.5 us vs 67.0 us for 256 x 16)
+constexpr int FPS_T4096 = 512, FPS_P4096 = 8, FPS_S4096 = 0;  // 2049..4096 points: 51.5 us (4096 -> 128) vs 60.8 / 64.5 us for 256 x 16 / 128 x 32
 constexpr int FPS_CLUSTER_MAX_N = 16 * 512 * 24;  // 196 608
 
 static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx, float *centers, void *ws,
@@ -489,7 +489,7 @@ static int fps_dispatch(const float *data, int b, int n, int c, int m, int *idx,
   if (n <= 1024) return launch_fps_reg<128, 8, 2>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= 2048) return launch_fps_reg<128, 16, 2>(data, b, n, c, m, lg_bs, idx, centers, st);
   if (n <= 4096) return launch_fps_reg<FPS_T4096, FPS_P4096, FPS_S4096>(data, b, n, c, m, lg_bs, idx, centers, st);
-  if (n <= 8192) return launch_fps_reg<256, 32, 1>(data, b, n, c, m, lg_bs, idx, centers, st);
+  if (n <= 8192) return launch_fps_reg<512, 16>(data, b, n, c, m, lg_bs, idx, centers, st);  // 366 us vs 392 us for 256 x 32 (8192 -> 512)
   if (n <= FPS_REG_MAX_N) return launch_fps_reg<512, 24>(data, b, n, c, m, lg_bs, idx, centers, st);
   // scene-scale clouds: a 16-CTA cluster per cloud (state in registers + DSMEM exchange), up to 196 608 points
   if (n <= 16 * 512 * 8) return launch_fps_cluster<8, 16>(data, b, n, c, m, lg_bs, idx, centers, st);
