@@ -198,6 +198,25 @@ int pdae_three_interpolate_f32(const float *points, const int *idx, const float 
 int pdae_three_interpolate_grad_f32(const float *gout, const int *idx, const float *weight, int b, int c, int n, int m,
                                     float *gpoints, pdae_stream_t stream);
 
+/* ---- affine corruptions between the patchifier and the encoder ----------------------
+ * replaces: the torch chains of `corrupt_scale_nonorm`, `corrupt_tranlate`, `corrupt_rotate_360`,
+ *           `corrupt_rotate_z_360`, `corrupt_reflection`, `corrupt_shear` (datasets/corrupt_util_tensor.py:59-343)
+ *           as composed by `corrupt_data` (:706-728) and used in models/PointCAE_transformer.py:1011-1017.
+ * mats (b,t,3,3): the per-cloud matrices in the order the reference would apply them; a point is a ROW vector,
+ * p <- p @ mats[cloud][s] for s = 0..t-1 (fp32, one fma chain per output coordinate, no composition of the
+ * matrices, so diagonal steps equal the reference's elementwise products bit for bit).  0 <= t <= 8.
+ *
+ * pdae_affine_points_f32: points (b,p,3) and center (b,g,3) -> out_points, out_center (may alias the inputs).
+ * pdae_group_affine_f32:  the Group tail (see pdae_group_f32) that ALSO emits what the reference's forward
+ *   derives from it: neighborhood = ((x - c) + c) - c, t_center = affine(c),
+ *   t_neighborhood = affine((x - c) + c) - affine(c), each rounded as the reference's separate kernels round. */
+#define PDAE_AFFINE_MAX_CHAIN 8
+int pdae_affine_points_f32(const float *points, const float *center, const float *mats, int b, int p, int g, int t,
+                           float *out_points, float *out_center, pdae_stream_t stream);
+int pdae_group_affine_f32(const float *xyz, const float *center, const float *mats, int b, int n, int g, int m, int t,
+                          int64_t *idx, float *neighborhood, float *t_neighborhood, float *t_center,
+                          pdae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,3 +229,32 @@ def three_interpolate_grad(gout, idx, weight, m):
     out = np.zeros((b, c, int(m)), dtype=np.float32)
     lib().pdae_oracle_three_interpolate_grad(_p(gout), _p(idx), _p(weight), b, c, n, int(m), _p(out))
     return out
+
+
+def affine_points(points, center, mats):
+    """datasets/corrupt_util_tensor.py:59-343 chained as in `corrupt_data` :706-728.  points (B,...,3), center (B,G,3),
+    mats (B,T,3,3) applied in order to row vectors -> (points', center')."""
+    points, center, mats = _f32(points), _f32(center), _f32(mats)
+    b, t = mats.shape[0], mats.shape[1]
+    p = points.size // (3 * b) if b else 0
+    g = center.size // (3 * b) if b else 0
+    out_p, out_c = np.zeros_like(points), np.zeros_like(center)
+    lib().pdae_oracle_affine_points(_p(points), _p(center), _p(mats), b, p, g, t, _p(out_p), _p(out_c))
+    return out_p, out_c
+
+
+def group_affine(xyz, num_group, group_size, mats):
+    """models/PointCAE_transformer.py:1010-1017: Group.forward + corrupt_data + re-centring.
+    -> neighborhood, center, t_neighborhood, t_center, idx."""
+    xyz, mats = _f32(xyz), _f32(mats)
+    b, n, _ = xyz.shape
+    t = mats.shape[1]
+    fps_idx = np.zeros((b, num_group), dtype=np.int32)
+    center = np.zeros((b, num_group, 3), dtype=np.float32)
+    idx = np.zeros((b, num_group, group_size), dtype=np.int64)
+    nb = np.zeros((b, num_group, group_size, 3), dtype=np.float32)
+    tnb = np.zeros_like(nb)
+    tc = np.zeros_like(center)
+    lib().pdae_oracle_group_affine(_p(xyz), _p(mats), b, n, int(num_group), int(group_size), t, _p(fps_idx), _p(center),
+                                   _p(idx), _p(nb), _p(tnb), _p(tc))
+    return nb, center, tnb, tc, idx

@@ -524,3 +524,67 @@ void pdae_oracle_three_interpolate_grad(const float *gout, const int *idx, const
     }
   free(acc);
 }
+
+/* ============================================================================================
+ * "next" rows: the affine corruptions applied between the patchifier and the
+ * encoder.  reference: datasets/corrupt_util_tensor.py:59-343 -- every corruption is either a broadcast
+ * product with a per-cloud 3-vector (`corrupt_scale_nonorm` :59-85, `corrupt_tranlate` :88-113, which
+ * multiplies as well) or `torch.matmul(points, R)` with a per-cloud 3x3 matrix (:139-343) -- chained by
+ * `corrupt_data` :706-728, and the arithmetic the model wraps around it, models/PointCAE_transformer.py
+ * :1011-1017.  A point is a row vector; a chain of t matrices is applied one matrix at a time.  The order
+ * of the three products inside a row-times-matrix is not specified by the reference (a BLAS call): this
+ * restatement fixes it to fma(z,R2j, fma(y,R1j, rn(x*R0j))), which for diagonal matrices equals the
+ * reference's elementwise product exactly; for rotations / shears parity is to rounding (1e-6 relative).
+ * ========================================================================================== */
+static void affine_chain(const float *mats, int t, float *v) {
+  for (int s = 0; s < t; ++s) {
+    const float *R = mats + (size_t)s * 9;
+    const float x = v[0], y = v[1], z = v[2];
+    for (int j = 0; j < 3; ++j) v[j] = fmaf(z, R[6 + j], fmaf(y, R[3 + j], x * R[j]));
+  }
+}
+
+void pdae_oracle_affine_points(const float *points, const float *center, const float *mats, int b, int p,
+                               int g, int t, float *out_points, float *out_center) {
+  for (int bi = 0; bi < b; ++bi) {
+    const float *M = mats + (size_t)bi * t * 9;
+    for (int j = 0; j < p; ++j) {
+      float v[3];
+      memcpy(v, points + ((size_t)bi * p + j) * 3, sizeof v);
+      affine_chain(M, t, v);
+      memcpy(out_points + ((size_t)bi * p + j) * 3, v, sizeof v);
+    }
+    for (int j = 0; j < g; ++j) {
+      float v[3];
+      memcpy(v, center + ((size_t)bi * g + j) * 3, sizeof v);
+      affine_chain(M, t, v);
+      memcpy(out_center + ((size_t)bi * g + j) * 3, v, sizeof v);
+    }
+  }
+}
+
+/* models/PointCAE_transformer.py:1010-1017 over Group.forward: neighborhood = ((x - c) + c) - c,
+ * t_center = chain(c), t_neighborhood = chain((x - c) + c) - chain(c). */
+void pdae_oracle_group_affine(const float *xyz, const float *mats, int b, int n, int g, int m, int t,
+                              int *fps_idx, float *center, int64_t *idx, float *neighborhood,
+                              float *t_neighborhood, float *t_center) {
+  pdae_oracle_group(xyz, b, n, g, m, fps_idx, center, idx, neighborhood);
+  for (int bi = 0; bi < b; ++bi) {
+    const float *M = mats + (size_t)bi * t * 9;
+    for (int j = 0; j < g; ++j) {
+      const float *c = center + ((size_t)bi * g + j) * 3;
+      float tc[3] = {c[0], c[1], c[2]};
+      affine_chain(M, t, tc);
+      memcpy(t_center + ((size_t)bi * g + j) * 3, tc, sizeof tc);
+      for (int q = 0; q < m; ++q) {
+        float *nb = neighborhood + (((size_t)bi * g + j) * m + q) * 3;
+        float *tn = t_neighborhood + (((size_t)bi * g + j) * m + q) * 3;
+        float a[3];
+        for (int k = 0; k < 3; ++k) a[k] = nb[k] + c[k];
+        for (int k = 0; k < 3; ++k) nb[k] = a[k] - c[k];
+        affine_chain(M, t, a);
+        for (int k = 0; k < 3; ++k) tn[k] = a[k] - tc[k];
+      }
+    }
+  }
+}

@@ -54,6 +54,8 @@ SIGNATURES = {
     "pdae_three_nn_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_three_interpolate_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_three_interpolate_grad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "pdae_affine_points_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_group_affine_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -53,6 +53,27 @@ __device__ __forceinline__ float dist_seq3(float dx, float dy, float dz) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Row vector times a stack of t row-major 3x3 matrices, one after the other (the reference applies its affine
+// corruptions sequentially with torch.matmul(points, R), datasets/corrupt_util_tensor.py:59-343): every step is
+// out_j = fma(z, R[2][j], fma(y, R[1][j], rn(x * R[0][j]))), which for the diagonal matrices of scale / translate /
+// reflection is exactly the reference's elementwise product.
+__device__ __forceinline__ void affine_seq(const float *__restrict__ mats, int t, float &x, float &y, float &z) {
+  for (int s = 0; s < t; ++s, mats += 9) {
+    const float nx = __fmaf_rn(z, __ldg(mats + 6), __fmaf_rn(y, __ldg(mats + 3), __fmul_rn(x, __ldg(mats + 0))));
+    const float ny = __fmaf_rn(z, __ldg(mats + 7), __fmaf_rn(y, __ldg(mats + 4), __fmul_rn(x, __ldg(mats + 1))));
+    const float nz = __fmaf_rn(z, __ldg(mats + 8), __fmaf_rn(y, __ldg(mats + 5), __fmul_rn(x, __ldg(mats + 2))));
+    x = nx, y = ny, z = nz;
+  }
+}
+
+// optional second output of the fused Group epilogue (knn3.cu): the corrupted copy of every patch.
+struct GroupAffine {
+  const float *mats;  // (b, t, 3, 3)
+  int t;
+  float *tgroup;      // (b, q, k, 3): affine(((x - c) + c)) - affine(c)
+  float *tcenter;     // (b, q, 3):    affine(c)
+};
+
 // ascending-order key of a (non-negative distance, index) pair: a plain unsigned compare orders
 // by distance first and by index on ties.
 __device__ __forceinline__ uint64_t pack_key(float d, uint32_t i) {
@@ -66,7 +87,8 @@ static inline int ceil_div(long long a, long long b) { return static_cast<int>((
 int feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *idx, cudaStream_t st);
 // knn3.cu: 3-D fast path (k <= 64): row-major points with optional fused Group output, and planar (b,3,n) self-kNN.
 int knn3_points(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
-                float *group, cudaStream_t st, uint64_t *keys = nullptr, uint32_t ref_offset = 0u, int raw_group = 0);
+                float *group, cudaStream_t st, uint64_t *keys = nullptr, uint32_t ref_offset = 0u, int raw_group = 0,
+                const GroupAffine *affine = nullptr);
 int knn3_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st);
 
 }  // namespace pdae

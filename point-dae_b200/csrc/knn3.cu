@@ -29,13 +29,17 @@ struct Knn3Args {
   uint64_t *keys;      // optional (b, q, k): raw (squared-distance bits << 32 | ref_offset + index) for sharded merges
   uint32_t ref_offset; // global index of ref[0] (keys output only)
   int raw_group;       // 1: `group` receives ref[idx] itself instead of ref[idx] - query
+  GroupAffine aff;     // aff.mats != NULL: also write the corrupted patches / centres, and `group` becomes
+                       // ((x - c) + c) - c, the value the reference's forward ends up with
+                       // (models/PointCAE_transformer.py:1011-1017)
   int r, q, k;
   int tile;            // reference points per shared-memory tile (multiple of 64)
   int qpw;             // queries per warp (1 when the cloud spans several tiles)
   int out_kq;
 };
 
-template <bool PLANAR, int E /*keys per lane in the final sort: 2 (k<=32) or 4 (k<=64)*/, int NW /*warps per CTA*/>
+template <bool PLANAR, int E /*keys per lane in the final sort: 2 (k<=32) or 4 (k<=64)*/, int NW /*warps per CTA*/,
+          bool AFF /*fused corruption epilogue (a.aff)*/>
 __global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
   constexpr int KNN_WARPS = NW, KNN_THREADS = NW * 32;  // shadow the file-scope defaults
   constexpr int CAP = 32 * E;
@@ -239,23 +243,41 @@ __global__ void __launch_bounds__(NW * 32) knn3_kernel(const Knn3Args a) {
           float *g = a.group + (bq * k + p) * 3;
           const float x = __ldg(R + 3 * static_cast<size_t>(ji)), y = __ldg(R + 3 * static_cast<size_t>(ji) + 1);
           const float z = __ldg(R + 3 * static_cast<size_t>(ji) + 2);
-          g[0] = raw ? x : __fsub_rn(x, q0);
-          g[1] = raw ? y : __fsub_rn(y, q1);
-          g[2] = raw ? z : __fsub_rn(z, q2);
+          if constexpr (!AFF) {
+            g[0] = raw ? x : __fsub_rn(x, q0);
+            g[1] = raw ? y : __fsub_rn(y, q1);
+            g[2] = raw ? z : __fsub_rn(z, q2);
+          } else {
+            // fused corrupt_data: the reference re-adds the centre to the centred patch, transforms patch and
+            // centre with the same matrices, and subtracts the centres again
+            const float *mats = a.aff.mats + static_cast<size_t>(cloud) * a.aff.t * 9;
+            float ax = __fadd_rn(__fsub_rn(x, q0), q0), ay = __fadd_rn(__fsub_rn(y, q1), q1);
+            float az = __fadd_rn(__fsub_rn(z, q2), q2);
+            g[0] = __fsub_rn(ax, q0), g[1] = __fsub_rn(ay, q1), g[2] = __fsub_rn(az, q2);
+            float cx = q0, cy = q1, cz = q2;
+            affine_seq(mats, a.aff.t, ax, ay, az);
+            affine_seq(mats, a.aff.t, cx, cy, cz);
+            float *tg = a.aff.tgroup + (bq * k + p) * 3;
+            tg[0] = __fsub_rn(ax, cx), tg[1] = __fsub_rn(ay, cy), tg[2] = __fsub_rn(az, cz);
+            if (p == 0) {
+              float *tc = a.aff.tcenter + bq * 3;
+              tc[0] = cx, tc[1] = cy, tc[2] = cz;
+            }
+          }
         }
       }
     }
   }
 }
 
-template <bool PLANAR, int E, int NW>
+template <bool PLANAR, int E, int NW, bool AFF>
 static int launch_knn3_cfg(const Knn3Args &a, int b, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(NW) * (32 * E + KNN3_LC * 32) * sizeof(uint64_t) +
                       static_cast<size_t>(3) * a.tile * sizeof(float);
   const dim3 grid(ceil_div(a.q, NW * a.qpw), b);
   if (smem > 48 * 1024)
-    PDAE_CUDA_TRY(cudaFuncSetAttribute(knn3_kernel<PLANAR, E, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  knn3_kernel<PLANAR, E, NW><<<grid, NW * 32, smem, st>>>(a);
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(knn3_kernel<PLANAR, E, NW, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  knn3_kernel<PLANAR, E, NW, AFF><<<grid, NW * 32, smem, st>>>(a);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
@@ -275,18 +297,26 @@ static int launch_knn3(Knn3Args a, int b, cudaStream_t st) {
   } else {
     a.qpw = 1;
   }
-  if (a.k <= 32) return nw == 16 ? launch_knn3_cfg<PLANAR, 2, 16>(a, b, st) : launch_knn3_cfg<PLANAR, 2, 8>(a, b, st);
-  return nw == 16 ? launch_knn3_cfg<PLANAR, 4, 16>(a, b, st) : launch_knn3_cfg<PLANAR, 4, 8>(a, b, st);
+  if constexpr (!PLANAR) {
+    if (a.aff.mats != nullptr) {
+      if (a.k <= 32) return nw == 16 ? launch_knn3_cfg<false, 2, 16, true>(a, b, st) : launch_knn3_cfg<false, 2, 8, true>(a, b, st);
+      return nw == 16 ? launch_knn3_cfg<false, 4, 16, true>(a, b, st) : launch_knn3_cfg<false, 4, 8, true>(a, b, st);
+    }
+  }
+  if (a.k <= 32) return nw == 16 ? launch_knn3_cfg<PLANAR, 2, 16, false>(a, b, st) : launch_knn3_cfg<PLANAR, 2, 8, false>(a, b, st);
+  return nw == 16 ? launch_knn3_cfg<PLANAR, 4, 16, false>(a, b, st) : launch_knn3_cfg<PLANAR, 4, 8, false>(a, b, st);
 }
 
 // entry points used by knn.cu / featknn.cu dispatch (k <= 64 only)
 int knn3_points(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
-                float *group, cudaStream_t st, uint64_t *keys, uint32_t ref_offset, int raw_group) {
-  Knn3Args a{ref, query, dist, idx, group, keys, ref_offset, raw_group, r, q, k, 0, 1, out_kq};
+                float *group, cudaStream_t st, uint64_t *keys, uint32_t ref_offset, int raw_group,
+                const GroupAffine *affine) {
+  Knn3Args a{ref, query, dist, idx, group, keys, ref_offset, raw_group, affine ? *affine : GroupAffine{nullptr, 0, nullptr, nullptr},
+             r, q, k, 0, 1, out_kq};
   return launch_knn3<false>(a, b, st);
 }
 int knn3_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st) {
-  Knn3Args a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, 0, n, n, k, 0, 1, 0};
+  Knn3Args a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, 0, GroupAffine{nullptr, 0, nullptr, nullptr}, n, n, k, 0, 1, 0};
   return launch_knn3<true>(a, b, st);
 }
 

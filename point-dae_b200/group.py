@@ -33,3 +33,19 @@ class Group(nn.Module):  # FPS + KNN
             torch.cuda.current_stream().wait_event(knn_after)
         neighborhood, _ = ops.group_points_knn(xyz.detach(), center, self.group_size, want_idx=False)
         return neighborhood, center
+
+    def forward_corrupted(self, xyz, corrupt_type=('affine_r3',), mats=None):
+        """The first seven lines of the reference model's forward in two launches
+        (models/PointCAE_transformer.py:1010-1017: Group, `+ center`, `corrupt_data`, `- center` twice):
+        -> neighborhood, center, transformed_neighborhood, transformed_center.
+        `mats` (B,T,3,3) overrides the random draw of `corrupt_util_tensor.corrupt_stack(B, corrupt_type)`, which
+        consumes the host RNGs exactly as the reference's `corrupt_data` does."""
+        from . import corrupt_util_tensor
+        xyz = xyz.float().contiguous()
+        _, center = fps(xyz, self.num_group)
+        if mats is None:
+            mats = corrupt_util_tensor.corrupt_stack(xyz.size(0), list(corrupt_type))
+        if mats is None:  # clean / Drop-Patch only: the transformed copies are the clean ones, round trip included
+            mats = torch.zeros((xyz.size(0), 0, 3, 3))
+        nb, tnb, tc, _ = ops.group_affine(xyz.detach(), center, self.group_size, mats)
+        return nb, center, tnb, tc

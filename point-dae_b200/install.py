@@ -79,6 +79,17 @@ def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentat
         cut = importlib.import_module("datasets.corrupt_util_tensor")
         cut.dropout_patch_random = corrupt_util_tensor.dropout_patch_random
         patched.append("datasets.corrupt_util_tensor.dropout_patch_random")
+        # the affine corruptions between the patchifier and the encoder (:59-343, :706-728): one launch per chain
+        for fn in ("corrupt_data", "corrupt_scale_nonorm", "corrupt_tranlate", "corrupt_rotate_360",
+                   "corrupt_rotate_z_360", "corrupt_reflection", "corrupt_shear"):
+            setattr(cut, fn, getattr(corrupt_util_tensor, fn))
+        cut.corruptions.update(corrupt_util_tensor.corruptions)
+        patched.append("datasets.corrupt_util_tensor.corrupt_data")
+        for name in ("models.PointCAE_transformer", "models.Point_M2AE"):  # `from ... import corrupt_data`
+            mod = sys.modules.get(name)
+            if mod is not None and hasattr(mod, "corrupt_data"):
+                mod.corrupt_data = corrupt_util_tensor.corrupt_data
+                patched.append(name + ".corrupt_data")
     except Exception:
         pass
     for name in ("models.PointCAE_transformer", "models.Point_MAE", "models.Point_MlMAE"):

@@ -220,6 +220,87 @@ def group_points_knn(xyz, center, group_size, want_idx=True, subtract_center=Tru
     return nb, idx
 
 
+# -------------------------------------------------------------------- affine corruptions
+def _affine_mats(mats, b, dev):
+    """(B,T,3,3) matrices, any device -> contiguous fp32 on `dev` (one small H2D copy when they come from the host,
+    where the reference builds them too)."""
+    if mats.dim() != 4 or mats.size(0) != b or tuple(mats.shape[2:]) != (3, 3):
+        raise RuntimeError("mats must have shape (B, T, 3, 3) with B = %d" % b)
+    return mats.to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _affine_launch(points, center, mats):
+    b, t = mats.size(0), mats.size(1)
+    p = points.numel() // (3 * b) if b else 0
+    g = center.numel() // (3 * b) if b else 0
+    with _on(points.device):
+        out_p, out_c = torch.empty_like(points), torch.empty_like(center)
+        rc = _native.lib().pdae_affine_points_f32(points.data_ptr(), center.data_ptr(), mats.data_ptr(), b, p, g, t,
+                                                  out_p.data_ptr(), out_c.data_ptr(), _stream())
+    _native.check(rc, "pdae_affine_points_f32")
+    return out_p, out_c
+
+
+class _AffinePoints(torch.autograd.Function):
+    """y = x @ R_0 @ ... @ R_{T-1} per cloud; grad_x = grad_y @ R_{T-1}^T @ ... @ R_0^T (same kernel)."""
+
+    @staticmethod
+    def forward(ctx, points, center, mats):
+        ctx.save_for_backward(mats)
+        return _affine_launch(points, center, mats)
+
+    @staticmethod
+    def backward(ctx, gp, gc):
+        (mats,) = ctx.saved_tensors
+        back = mats.flip(1).transpose(2, 3).contiguous()
+        gp, gc = _affine_launch(gp.contiguous(), gc.contiguous(), back)
+        return gp, gc, None
+
+
+def affine_points(points, center, mats):
+    """One-launch `corrupt_data` (datasets/corrupt_util_tensor.py:706-728): points (B,...,3) and center (B,G,3) fp32
+    CUDA, mats (B,T,3,3) applied in order to row vectors -> (points', center') with the input shapes."""
+    _require_cuda(points, "corrupt_data")
+    _require_cuda(center, "corrupt_data")
+    if points.size(-1) != 3 or center.size(-1) != 3 or points.size(0) != center.size(0):
+        raise RuntimeError("points (B,...,3) and center (B,G,3) expected")
+    if mats.size(1) > 8:
+        raise RuntimeError("at most 8 chained matrices")
+    pts = points if points.dtype == torch.float32 and points.is_contiguous() else points.float().contiguous()
+    ctr = center if center.dtype == torch.float32 and center.is_contiguous() else center.float().contiguous()
+    mats = _affine_mats(mats, points.size(0), points.device)
+    if pts.requires_grad or ctr.requires_grad:
+        return _AffinePoints.apply(pts, ctr, mats)
+    return _affine_launch(pts, ctr, mats)
+
+
+def group_affine(xyz, center, group_size, mats, want_idx=False):
+    """Fused Group tail + corrupt_data + re-centring (models/PointCAE_transformer.py:1010-1017):
+    xyz (B,N,3), center (B,G,3), mats (B,T,3,3) -> neighborhood (B,G,M,3) [= ((x-c)+c)-c], t_neighborhood (B,G,M,3),
+    t_center (B,G,3), idx (B,G,M) int64 | None.  No gradient (the patchifier has none in the reference either)."""
+    _require_cuda(xyz, "group")
+    _require_f32_contig(xyz, "xyz")
+    _require_f32_contig(center, "center")
+    b, n, _ = xyz.shape
+    g = center.size(1)
+    m = int(group_size)
+    if not (1 <= m <= n):
+        raise RuntimeError("group_size=%d must satisfy 1 <= group_size <= %d points" % (m, n))
+    if mats.size(1) > 8:
+        raise RuntimeError("at most 8 chained matrices")
+    mats = _affine_mats(mats, b, xyz.device)
+    with _on(xyz.device):
+        nb = torch.empty((b, g, m, 3), dtype=torch.float32, device=xyz.device)
+        tnb = torch.empty_like(nb)
+        tc = torch.empty((b, g, 3), dtype=torch.float32, device=xyz.device)
+        idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
+        rc = _native.lib().pdae_group_affine_f32(xyz.data_ptr(), center.data_ptr(), mats.data_ptr(), b, n, g, m, mats.size(1),
+                                                 idx.data_ptr() if want_idx else None, nb.data_ptr(), tnb.data_ptr(),
+                                                 tc.data_ptr(), _stream())
+    _native.check(rc, "pdae_group_affine_f32")
+    return nb, tnb, tc, idx
+
+
 # -------------------------------------------------------------------------------------- Chamfer
 _scan_events = threading.local()
 
