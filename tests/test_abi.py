@@ -57,6 +57,12 @@ def test_argument_validation_needs_no_gpu():
     assert L.pdae_chamfer_fwd_workspace_bytes(2, 2048, 1024) == 2 * 1024 * 8
     assert L.pdae_knn_f32(None, None, 1, 8, 4, 3, 0, 0, None, None, None) == -1
     assert L.pdae_fps_f32(None, 0, 16, 4, None, None, 0, None) == 0  # empty batch is a no-op
+    # affine corruptions: chain length 0..8, null pointers, empty batch
+    assert L.pdae_affine_points_f32(None, None, None, 2, 4, 4, 9, None, None, None) == -1
+    assert L.pdae_affine_points_f32(None, None, None, 2, 4, 4, 1, None, None, None) == -1
+    assert L.pdae_affine_points_f32(None, None, None, 0, 4, 4, 1, None, None, None) == 0
+    assert L.pdae_group_affine_f32(None, None, None, 2, 64, 4, 8, 1, None, None, None, None, None) == -1
+    assert L.pdae_group_affine_f32(None, None, None, 0, 64, 4, 8, 1, None, None, None, None, None) == 0
 
 
 def test_source_is_sm100a_only():

@@ -93,3 +93,38 @@ def test_key_packing_orders_by_distance_then_index():
     order = np.argsort(keys.view(np.int64), kind="stable")
     assert list(order) == [0, 1, 3, 2, 4, 5]
     assert (keys < np.uint64(0x7fffffffffffffff)).all()  # identity of the MIN all-reduce stays on top
+
+
+def test_patch_models_rebinds_the_corruptions_where_the_models_imported_them():
+    """`from datasets.corrupt_util_tensor import corrupt_data` (models/PointCAE_transformer.py:15, models/Point_M2AE.py:13)
+    binds the name inside the model module: patch_models must rebind it there too."""
+    import sys
+    import types
+    import pointdae_b200
+    from pointdae_b200 import corrupt_util_tensor as cut
+    saved = {k: sys.modules.get(k) for k in ("datasets", "datasets.corrupt_util_tensor", "models", "models.PointCAE_transformer")}
+    try:
+        pkg = types.ModuleType("datasets")
+        pkg.__path__ = []
+        ref = types.ModuleType("datasets.corrupt_util_tensor")
+        ref.corrupt_data = ref.dropout_patch_random = lambda *a, **k: "reference"
+        ref.corruptions = {"rotate": None, "jitter": "kept"}
+        pkg.corrupt_util_tensor = ref
+        mpkg = types.ModuleType("models")
+        mpkg.__path__ = []
+        model = types.ModuleType("models.PointCAE_transformer")
+        model.corrupt_data = ref.corrupt_data
+        model.Group = object
+        sys.modules.update({"datasets": pkg, "datasets.corrupt_util_tensor": ref, "models": mpkg,
+                            "models.PointCAE_transformer": model})
+        patched = pointdae_b200.patch_models(names=())
+        assert ref.corrupt_data is cut.corrupt_data and model.corrupt_data is cut.corrupt_data
+        assert ref.dropout_patch_random is cut.dropout_patch_random and ref.corrupt_shear is cut.corrupt_shear
+        assert ref.corruptions["rotate"] is cut.corrupt_rotate_360 and ref.corruptions["jitter"] == "kept"
+        assert "models.PointCAE_transformer.corrupt_data" in patched and "models.PointCAE_transformer.Group" in patched
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
