@@ -111,10 +111,12 @@ int pdae_graph_feature_grad_f32(const float *gout, const int64_t *idx, int b, in
  * xyz1 (b,n,3), xyz2 (b,m,3) read as dense storage exactly like the reference's raw data_ptr
  * access.  dist1 (b,n), dist2 (b,m) squared distances; idx1, idx2 int32, lowest index on ties.
  * backward: gx1 (b,n,3), gx2 (b,m,3) overwritten.                                             */
-/* Optional workspace (pdae_chamfer_fwd_workspace_bytes, 8 bytes per point of the smaller cloud): when given,
+/* Optional workspace (pdae_chamfer_fwd_workspace_bytes, 8 bytes per point of both clouds): when given,
  * every point pair is evaluated ONCE and feeds both directions (the squared distance is symmetric bit for
- * bit), halving the arithmetic; with workspace == NULL each direction is scanned separately.  Results are
- * identical either way.                                                                          */
+ * bit), halving the arithmetic; with workspace == NULL each direction is scanned separately.  With at least
+ * 8 bytes per point of the smaller cloud the symmetric kernel runs; with the full size it may also cut every
+ * row block's sweep into column chunks merged through packed keys, which evens out the load of the SMs when
+ * the batch gives fewer than ~8 CTAs per SM.  Results are identical in all cases.                          */
 size_t pdae_chamfer_fwd_workspace_bytes(int b, int n, int m);
 int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
                          int *idx1, int *idx2, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
@@ -148,6 +150,10 @@ int pdae_chamfer_loss_bwd_f32(const float *xyz1, const float *xyz2, const int *i
 /* tuning hook, no reference counterpart: select the CTA shape of the large-cloud forward kernel (ids as the
  * PDAE_CHAMFER_CFG environment variable; v < 0 only queries).  Returns the previous id.  Not thread-safe.      */
 int pdae_tune_chamfer_variant(int v);
+/* tuning hook, no reference counterpart: number of column chunks every 512-row block of the symmetric forward is cut
+ * into (ids as the PDAE_CHAMFER_SPLIT environment variable: 0 = automatic, 1 = never split; nc < 0 only queries).
+ * Returns the previous setting.  Results do not depend on it.  Not thread-safe.                                 */
+int pdae_tune_chamfer_split(int nc);
 
 /* reference-set sharding (scene-scale clouds; new, no reference counterpart):
  * one direction, queries (b,nq,3) against the local slice refs (b,nr,3) whose first point has

@@ -36,6 +36,8 @@ struct ChamferDir {
   int nq, nr;
   int qtiles;       // CTAs per cloud for this direction (0 = direction absent)
   int ref_offset;   // global index of r[0] (sharded mode)
+  int csplit;       // column chunks per row block (0 or 1 = a CTA streams the whole reference cloud)
+  uint64_t *rowkeys;  // (b, nq) csplit > 1: (row minimum, lowest index) merged across the chunks with RED.MIN
 };
 
 // SYM: the squared distance is symmetric bit for bit (the operands of every product only change
@@ -52,7 +54,8 @@ template <int QT, int THREADS, bool SYM, int CH_TILE, int STEP, bool VARGROUP, b
 __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, const float *__restrict__ R, int nq, int nr,
                                                  int row_base, size_t cloud, float *dist, int *idx, uint64_t *keys,
                                                  int ref_offset, uint64_t *colkeys, float (*tile)[3][CH_TILE],
-                                                 unsigned (*colmin)[THREADS / 32][SYM ? CH_TILE : 4]) {
+                                                 unsigned (*colmin)[THREADS / 32][SYM ? CH_TILE : 4], int tile_begin = 0,
+                                                 int tile_end = 0x7fffffff, uint64_t *rowkeys = nullptr) {
   constexpr int QPW = 32 * QT;                  // queries per warp
   constexpr int W = THREADS / 32;
   constexpr int LD = 3 * CH_TILE / THREADS;     // floats staged per thread per tile
@@ -117,14 +120,16 @@ __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, co
     }
   };
 
-  const int ntiles = (nr + CH_TILE - 1) / CH_TILE;
-  fetch(0);
-  stash(0);
+  // a CTA streams tiles [tile_begin, ntiles) of the reference cloud: all of them, or one column chunk of a split unit
+  const int ntiles_all = (nr + CH_TILE - 1) / CH_TILE;
+  const int ntiles = tile_end < ntiles_all ? tile_end : ntiles_all;
+  fetch(tile_begin * CH_TILE);
+  stash(tile_begin & 1);
   __syncthreads();
-  for (int tl = 0; tl < ntiles; ++tl) {
+  for (int tl = tile_begin; tl < ntiles; ++tl) {
     const bool more = tl + 1 < ntiles;
     if (more) fetch((tl + 1) * CH_TILE);
-    if (tl > 0) flush_cols(tl - 1);
+    if (tl > tile_begin) flush_cols(tl - 1);
     const float *sx = tile[tl & 1][0], *sy = tile[tl & 1][1], *sz = tile[tl & 1][2];
     unsigned pend[STEP];
 #pragma unroll
@@ -249,7 +254,9 @@ __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, co
     const int q = qbase + s * 32 + lane;
     if (q < nq) {
       const size_t o = cloud * nq + q;
-      if (keys) {
+      if (rowkeys) {  // column-split unit: the (distance, index) order of the key is the reference's tie rule
+        atomicMin(reinterpret_cast<unsigned long long *>(rowkeys + o), pack_key(best[s], static_cast<uint32_t>(myidx[s])));
+      } else if (keys) {
         keys[o] = pack_key(best[s], static_cast<uint32_t>(myidx[s] + ref_offset));
       } else {
         dist[o] = best[s];
@@ -267,15 +274,27 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
   __shared__ __align__(16) float tile[2][3][CH_TILE];
   __shared__ __align__(16) unsigned colmin[SYM ? 2 : 1][W][SYM ? CH_TILE : 4];
 
-  const int per_cloud = d0.qtiles + d1.qtiles;
+  // column split (symmetric forward only, d1 absent): consecutive blocks are the chunks of one row block
+  const int nc = d0.csplit > 1 ? d0.csplit : 1;
+  const int per_cloud = (d0.qtiles + d1.qtiles) * nc;
   const int cloud = blockIdx.x / per_cloud;
   int t = blockIdx.x - cloud * per_cloud;
+  const int chunk = t % nc;
+  t /= nc;
   const bool second = t >= d0.qtiles;
   if (second) t -= d0.qtiles;
   const ChamferDir &d = second ? d1 : d0;
+  int tile_begin = 0, tile_end = 0x7fffffff;
+  if (nc > 1) {
+    const int ntiles = (d.nr + CH_TILE - 1) / CH_TILE, tpc = (ntiles + nc - 1) / nc;
+    tile_begin = chunk * tpc;
+    tile_end = tile_begin + tpc;
+    if (tile_begin >= ntiles) return;  // uniform for the CTA
+  }
   chamfer_min_body<QT, THREADS, SYM, CH_TILE, STEP, false, PACKED>(
       d.q + static_cast<size_t>(cloud) * d.nq * 3, d.r + static_cast<size_t>(cloud) * d.nr * 3, d.nq, d.nr,
-      t * (QT * THREADS), static_cast<size_t>(cloud), d.dist, d.idx, d.keys, d.ref_offset, d.colkeys, tile, colmin);
+      t * (QT * THREADS), static_cast<size_t>(cloud), d.dist, d.idx, d.keys, d.ref_offset, d.colkeys, tile, colmin,
+      tile_begin, tile_end, nc > 1 ? d.rowkeys : nullptr);
 }
 
 // Balanced variant of the symmetric forward (opt-in, PDAE_CHAMFER_CFG=17; measured NOT faster, kept as the record of
@@ -533,7 +552,7 @@ static int chamfer_qpc(int nq_max, bool sym) {
 
 template <bool SYM>
 static int launch_min(const ChamferDir &d0, const ChamferDir &d1, int b, cudaStream_t st) {
-  const long long per_cloud = static_cast<long long>(d0.qtiles) + d1.qtiles;
+  const long long per_cloud = (static_cast<long long>(d0.qtiles) + d1.qtiles) * (d0.csplit > 1 ? d0.csplit : 1);
   const long long grid = per_cloud * b;
   if (grid <= 0) return 0;
   if (grid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
@@ -737,7 +756,9 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_list_kernel(const flo
                                                                        const float *__restrict__ cols,
                                                                        const uint64_t *__restrict__ colkeys, int n_rows,
                                                                        int n_cols, float *__restrict__ dist,
-                                                                       int *__restrict__ idx) {
+                                                                       int *__restrict__ idx,
+                                                                       const uint64_t *__restrict__ rowkeys,
+                                                                       float *__restrict__ drow, int *__restrict__ irow) {
   __shared__ __align__(16) float sx[QPG], sy[QPG], sz[QPG];
   __shared__ int list[RECOVER_LIST_MAX];
   __shared__ int count;
@@ -748,6 +769,16 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_list_kernel(const flo
   const float *__restrict__ C = cols + cloud * n_cols * 3;
   const int tid = threadIdx.x;
   if (tid == 0) count = 0;
+  if (rowkeys != nullptr) {  // column-split forward: this CTA's rows leave their merged keys here (no extra launch)
+    for (int r = tid; r < QPG; r += 256) {
+      const long long row = static_cast<long long>(g) * QPG + r;
+      if (row < n_rows) {
+        const uint64_t key = rowkeys[cloud * n_rows + row];
+        drow[cloud * n_rows + row] = __uint_as_float(static_cast<uint32_t>(key >> 32));
+        irow[cloud * n_rows + row] = static_cast<int>(static_cast<uint32_t>(key));
+      }
+    }
+  }
   for (int e = tid; e < 3 * QPG; e += 256) {  // coalesced AoS read of the group's rows; NaN padding never matches
     const int r = e / 3, c = e - 3 * r;
     const long long row = static_cast<long long>(g) * QPG + r;
@@ -866,18 +897,22 @@ __global__ void __launch_bounds__(256) chamfer_col_recover_var_kernel(const floa
 // second half of the symmetric forward: picks the recovery kernel by cloud size (see the comment above)
 template <int QPG>
 static int launch_col_recover(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows, int n_cols,
-                              float *dcol, int *icol, cudaStream_t st) {
+                              float *dcol, int *icol, cudaStream_t st, const uint64_t *rowkeys = nullptr,
+                              float *drow = nullptr, int *irow = nullptr) {
   const long long groups = (static_cast<long long>(n_rows) + QPG - 1) / QPG;
   // group-major recovery while its key sweeps (8*groups B per column) stay cheaper than re-reading a group per column
   const int gdefault = chamfer_variant() < 25 ? 128 : 32;
   const int glimit = chamfer_variant() >= 50 ? 0 : (getenv("PDAE_RECOVER_GROUPS") ? atoi(getenv("PDAE_RECOVER_GROUPS")) : gdefault);
   if (groups <= glimit) {  // key + coordinate sweeps (20*groups B per column) cheaper than row re-reads (12*QPG B)
     const dim3 ggrid(static_cast<unsigned>(groups), b);
-    if (chamfer_variant() < 25)
-      chamfer_col_recover_list_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
-    else
+    if (chamfer_variant() < 25) {
+      chamfer_col_recover_list_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol, rowkeys, drow, irow);
+    } else {
+      if (rowkeys) return PDAE_E_INVALID;  // only the list kernel unpacks row keys (recover_unpacks_rows)
       chamfer_col_recover_grouped_kernel<QPG><<<ggrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
+    }
   } else {
+    if (rowkeys) return PDAE_E_INVALID;
     // 4 column points per warp, 8 warps per CTA (splitting a warp across points was measured slower)
     const dim3 rgrid(static_cast<unsigned>((n_cols + 31) / 32), b);
     chamfer_col_recover_kernel<QPG, 4><<<rgrid, 256, 0, st>>>(rows, cols, ck, n_rows, n_cols, dcol, icol);
@@ -886,22 +921,67 @@ static int launch_col_recover(const float *rows, const float *cols, const uint64
   return 0;
 }
 
+// true when the recovery of an (unphased) column-split forward can unpack the row keys itself: default kernel shape
+// (the only one that splits) and few enough 128-row groups for the list kernel, which visits every row exactly once
+static bool recover_unpacks_rows(int n_rows) {
+  const int glimit = getenv("PDAE_RECOVER_GROUPS") ? atoi(getenv("PDAE_RECOVER_GROUPS")) : 128;
+  return chamfer_variant() == 0 && (static_cast<long long>(n_rows) + 127) / 128 <= glimit;
+}
+
 static int launch_col_recover_for_variant(const float *rows, const float *cols, const uint64_t *ck, int b, int n_rows,
-                                          int n_cols, float *dcol, int *icol, cudaStream_t st) {
+                                          int n_cols, float *dcol, int *icol, cudaStream_t st,
+                                          const uint64_t *rowkeys = nullptr, float *drow = nullptr, int *irow = nullptr) {
   const int v = chamfer_variant() % 25;  // queries per warp = 32 * QT of the variant launched
   if (v == 3 || v == 4) return launch_col_recover<64>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
   if ((v >= 8 && v <= 11) || v == 14 || v == 15) return launch_col_recover<256>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
-  return launch_col_recover<128>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st);
+  return launch_col_recover<128>(rows, cols, ck, b, n_rows, n_cols, dcol, icol, st, rowkeys, drow, irow);
 }
 
 }  // namespace pdae
 
 using namespace pdae;
 
+// column keys of the smaller cloud + (for column-split units) row keys of the larger one.  A workspace of only the
+// first part (b * min(n, m) keys, the size this function returned before the split existed) is still accepted: the
+// forward then runs unsplit.
 extern "C" size_t pdae_chamfer_fwd_workspace_bytes(int b, int n, int m) {
   if (b <= 0 || n <= 0 || m <= 0) return 0;
   if (n <= SMALL_MAX && m <= SMALL_MAX) return 0;
-  return static_cast<size_t>(b) * (n < m ? n : m) * sizeof(uint64_t);
+  return static_cast<size_t>(b) * (static_cast<size_t>(n) + m) * sizeof(uint64_t);
+}
+
+// Column chunks per 512-row block for the symmetric forward.  One 4-warp CTA saturates an SM's FMA issue, so an SM
+// works through its CTAs at a fixed rate and the kernel ends when the SM with the most CTAs ends: with U equal units
+// on S SMs that is ceil(U / S) unit times.  512 row blocks on 148 SMs (128 x 2048^2) make 4 against an average of
+// 3.46; cutting every block's column sweep in two makes 7 half-units against 6.92.  A unit costs its tiles plus a
+// fixed prologue / epilogue (first tile not overlapped, query loads, 16-point rescan, key posts), put at a quarter
+// of a 512-point tile.  PDAE_CHAMFER_SPLIT forces a value (1 = never split).
+static int g_chamfer_split = -1;
+static int chamfer_split_forced() {
+  if (g_chamfer_split < 0) {
+    const char *e = getenv("PDAE_CHAMFER_SPLIT");
+    g_chamfer_split = e ? atoi(e) : 0;
+  }
+  return g_chamfer_split;
+}
+static int chamfer_csplit(long long row_units, int ntiles) {
+  const int forced = chamfer_split_forced();
+  if (ntiles <= 1) return 1;
+  if (forced > 0) return forced < ntiles ? forced : ntiles;
+  const long long sms = sm_count();
+  int best_nc = 1;
+  double best_cost = 0.0;
+  for (int nc = 1; nc <= ntiles && nc <= 16; ++nc) {
+    const int tpc = (ntiles + nc - 1) / nc;
+    const long long chunks = (ntiles + tpc - 1) / tpc;  // chunks that actually hold tiles
+    const long long waves = (row_units * chunks + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (tpc + 0.25);
+    if (nc == 1 || cost < best_cost * 0.97) {  // split only for a clear (> 3 %) gain
+      best_cost = cost;
+      best_nc = nc;
+    }
+  }
+  return best_nc;
 }
 
 // phase 0: the whole forward; 1: everything except the column recovery of the symmetric path (the "scan": row
@@ -916,7 +996,7 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
   if ((bn && (!xyz1 || !dist1 || !idx1)) || (bm && (!xyz2 || !dist2 || !idx2))) return PDAE_E_INVALID;
   if (b == 0) return 0;
   const int nq_max = n > m ? n : m;
-  const size_t need = pdae_chamfer_fwd_workspace_bytes(b, n, m);
+  const size_t need = static_cast<size_t>(b) * (n < m ? n : m) * sizeof(uint64_t);  // column keys (the row keys are optional)
   const bool sym = n > 0 && m > 0 && !(n <= SMALL_MAX && m <= SMALL_MAX) && workspace != nullptr &&
                    workspace_bytes >= need && nq_max > 256 && chamfer_variant() < 100 &&
                    b <= 65535;  // the recovery kernels index clouds with gridDim.y; larger batches take the two-scan path
@@ -952,8 +1032,17 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
     const long long ncol = static_cast<long long>(b) * nr_cols;
     const long long slices_per_cloud = (static_cast<long long>(nr_rows) + 127) / 128;
     const bool balanced = chamfer_variant() == 17 && slices_per_cloud <= 128;  // opt-in (measured no faster)
+    const long long nrow = static_cast<long long>(b) * nr_rows;
+    // column split: default kernel shape only (512-row blocks, 512-point tiles), and only with room for the row keys
+    const int nsplit = (!balanced && chamfer_variant() == 0 &&
+                        workspace_bytes >= static_cast<size_t>(ncol + nrow) * sizeof(uint64_t))
+                           ? chamfer_csplit(static_cast<long long>(b) * ceil_div(nr_rows, 512), ceil_div(nr_cols, 512))
+                           : 1;
+    // the whole forward in one call: the list recovery writes the rows' results while it is there
+    const bool fused_unpack = nsplit > 1 && phase == 0 && recover_unpacks_rows(nr_rows);
     if (phase != 2) {
-      fill_keys_kernel<<<static_cast<unsigned>((ncol + 255) / 256), 256, 0, st>>>(ck, ncol);
+      const long long nfill = nsplit > 1 ? ncol + nrow : ncol;
+      fill_keys_kernel<<<static_cast<unsigned>((nfill + 255) / 256), 256, 0, st>>>(ck, nfill);
       PDAE_RETURN_IF_LAUNCH_FAILED();
       if (balanced) {
         const long long total = slices_per_cloud * b;
@@ -966,8 +1055,16 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
         const int qpc = chamfer_qpc(nr_rows, true);
         ChamferDir d0{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, ceil_div(nr_rows, qpc), 0};
         ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+        if (nsplit > 1) {
+          d0.csplit = nsplit;
+          d0.rowkeys = ck + ncol;
+        }
         const int rc = launch_min<true>(d0, d1, b, st);
         if (rc) return rc;
+        if (nsplit > 1 && !fused_unpack) {  // merged row keys -> dist / idx of the larger cloud
+          unpack_keys_kernel<<<static_cast<unsigned>((nrow + 255) / 256), 256, 0, st>>>(ck + ncol, nrow, drow, irow);
+          PDAE_RETURN_IF_LAUNCH_FAILED();
+        }
       }
     }
     if (phase == 1) return 0;
@@ -977,12 +1074,21 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
       PDAE_RETURN_IF_LAUNCH_FAILED();
       return 0;
     }
+    if (fused_unpack) return launch_col_recover_for_variant(rows, cols, ck, b, nr_rows, nr_cols, dcol, icol, st, ck + ncol, drow, irow);
     return launch_col_recover_for_variant(rows, cols, ck, b, nr_rows, nr_cols, dcol, icol, st);
   }
   const int qpc = chamfer_qpc(nq_max, false);
   ChamferDir d0{xyz1, xyz2, dist1, idx1, nullptr, nullptr, n, m, ceil_div(n, qpc), 0};
   ChamferDir d1{xyz2, xyz1, dist2, idx2, nullptr, nullptr, m, n, ceil_div(m, qpc), 0};
   return launch_min<false>(d0, d1, b, st);
+}
+
+// tuning / test hook: force the number of column chunks inside one process (0 = automatic, 1 = never split);
+// returns the previous setting, a negative argument only queries.
+extern "C" int pdae_tune_chamfer_split(int nc) {
+  const int old = chamfer_split_forced();
+  if (nc >= 0) g_chamfer_split = nc;
+  return old;
 }
 
 extern "C" int pdae_chamfer_fwd_f32(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1,

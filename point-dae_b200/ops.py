@@ -324,6 +324,28 @@ class chamfer_scan_event:
         return False
 
 
+class chamfer_column_split:
+    """`with ops.chamfer_column_split(False): ...` -- forwards issued by this thread inside the block get a workspace
+    for the column keys only, so the library runs every row block against the whole reference cloud in one CTA.
+    The split (default: automatic, see pdae_chamfer_fwd_workspace_bytes) shortens a forward that has the GPU to
+    itself by evening out the SMs' load (128 x 2048^2: 178 -> 168 us; 1 x 100k^2: 3.6 -> 2.4 ms); a caller that
+    overlaps other kernels with the forward on a second stream (bench.py's patchifier branch) already fills the idle
+    tail with them and is better off without the split's extra prologues (step 232 vs 239 us).  Scheduling only:
+    results are identical."""
+
+    def __init__(self, enabled):
+        self.enabled = bool(enabled)
+
+    def __enter__(self):
+        self.prev = getattr(_scan_events, "split", True)
+        _scan_events.split = self.enabled
+        return self
+
+    def __exit__(self, *a):
+        _scan_events.split = self.prev
+        return False
+
+
 def chamfer_forward(xyz1, xyz2, symmetric=True, scan_done=None):
     """chamfer.forward: returns [dist1 (B,N), dist2 (B,M), idx1 int32, idx2 int32].
     scan_done: optional torch.cuda.Event recorded between the scan and the column recovery (see chamfer_scan_event).
@@ -358,6 +380,8 @@ def chamfer_forward(xyz1, xyz2, symmetric=True, scan_done=None):
         # with the workspace every pair is evaluated once for both directions; without it (symmetric=False)
         # each direction is scanned separately -- same results, twice the arithmetic
         nbytes = L.pdae_chamfer_fwd_workspace_bytes(b, n, m) if symmetric else 0
+        if nbytes and not getattr(_scan_events, "split", True):
+            nbytes = b * min(n, m) * 8  # column keys only: no column split (see chamfer_column_split)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
         args = (xyz1.data_ptr(), xyz2.data_ptr(), b, n, m, dist1.data_ptr(), dist2.data_ptr(), idx1.data_ptr(),
                 idx2.data_ptr(), ws.data_ptr() if nbytes else None, nbytes)

@@ -54,7 +54,7 @@ def test_argument_validation_needs_no_gpu():
     # negative sizes / null pointers are rejected before any CUDA call
     assert L.pdae_chamfer_fwd_f32(None, None, -1, 4, 4, None, None, None, None, None, 0, None) == -1
     assert L.pdae_chamfer_fwd_f32(None, None, 2, 4, 4, None, None, None, None, None, 0, None) == -1
-    assert L.pdae_chamfer_fwd_workspace_bytes(2, 2048, 1024) == 2 * 1024 * 8
+    assert L.pdae_chamfer_fwd_workspace_bytes(2, 2048, 1024) == 2 * (2048 + 1024) * 8  # column keys + row keys
     assert L.pdae_knn_f32(None, None, 1, 8, 4, 3, 0, 0, None, None, None) == -1
     assert L.pdae_fps_f32(None, 0, 16, 4, None, None, 0, None) == 0  # empty batch is a no-op
     # affine corruptions: chain length 0..8, null pointers, empty batch
