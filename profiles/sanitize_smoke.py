@@ -43,4 +43,11 @@ w3 = torch.softmax(-dist3, dim=2).contiguous()
 feat = torch.rand(3, 7, cen.size(1), device=dev, requires_grad=True)
 pointnet2_utils.three_interpolate(feat, idx3, w3).sum().backward()
 pointnet2_utils.three_nn(y, cen[:, :2].contiguous())
+# column-split Chamfer units (every chunk count, fused and separate row-key unpack), affine corruptions
+for nc in (1, 2, 3, 16, 0):
+    _native.lib().pdae_tune_chamfer_split(nc); ops.chamfer_forward(y, x); ops.chamfer_forward(x, y, scan_done=torch.cuda.Event())
+_native.lib().pdae_tune_chamfer_split(0)
+mats = torch.randn(3, 3, 3, 3)
+ops.affine_points(x, cen, mats)
+ops.group_affine(x, cen, 17, mats, want_idx=True); ops.group_affine(x, cen, 40, mats); ops.group_affine(x, cen, 80, mats[:, :0])
 torch.cuda.synchronize(); print("sanitize smoke done")
