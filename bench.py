@@ -497,6 +497,10 @@ def run_ours(args):
                           "SMs' load); the timed step runs the unsplit form (ms_per_launch_unsplit, used for "
                           "share_of_step) because the patchifier on the second stream fills the wave tail there",
         }
+        try:
+            others = other_kernels(dev, clouds_d, preds_d, peaks, props) if world == 1 else None
+        except Exception as e:  # evidence only
+            others = {"error": repr(e)[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -513,6 +517,7 @@ def run_ours(args):
                                "" if args.no_graphs else "; the step is replayed as a CUDA graph")},
             "gpu_launches": 9 * args.steps,
             "roofline": roofline,
+            "other_kernels": others,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -525,6 +530,69 @@ def run_ours(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_kernels(dev, clouds_d, preds_d, peaks, props):
+    """the path's other kernels, each timed alone with CUDA events over replayed graphs (outside the
+    timed region): FPS as us per sequential iteration, the 3-D kNN against the FP32 FMA pipe, graph feature and the
+    Chamfer backward against the measured HBM copy peak.  Evidence only; a failure here never breaks the bench line."""
+    import torch
+    from pointdae_b200 import dgcnn_util, ops, synth
+
+    def eager_us(fn, reps=10):  # long kernels: launch overhead is noise, no capture needed
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / reps
+
+    def timed_us(fn, reps=40):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = [fn() for _ in range(4)]
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        del keep
+        return a.elapsed_time(b) * 1e3 / (4 * reps)
+
+    out = {}
+    hbm = float(peaks.get("hbm_gbs", 6556.5))
+    fma = props.multi_processor_count * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6  # lane-ops / s
+    c, p = clouds_d[0], preds_d[0]
+    t = timed_us(lambda: ops.fps_gather(c, G))
+    out["fps+centre gather %dx%d->%d" % (B, N, G)] = {"us": t, "us_per_iteration": t / (G - 1), "bound": "latency (one CTA per cloud, %d of %d SMs)" % (min(B, props.multi_processor_count), props.multi_processor_count)}
+    center = ops.fps_gather(c, G)[1]
+    t = timed_us(lambda: ops.group_points_knn(c, center, M, want_idx=False))
+    out["group kNN %d + gather" % M] = {"us": t, "fma_pipe_frac_algorithmic": B * G * N * 6.0 / (t * 1e-6) / fma,
+                                    "bound": "instruction issue (selection), see DESIGN.md 4.4"}
+    d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+    gone = torch.ones(1, device=dev)
+    t = timed_us(lambda: ops.chamfer_loss_backward(p, c, i1, i2, d1, d2, gone, 1.0, 1.0))
+    out["chamfer backward (2 launches)"] = {"us": t, "GBps": 2 * B * N * 56 / (t * 1e-6) / 1e9, "hbm_frac": 2 * B * N * 56 / (t * 1e-6) / 1e9 / hbm,
+                                           "bound": "L2 atomics / launch latency (56 B per point, L2 resident)"}
+    Cf, Bf, kf = 128, 16, 20
+    x = torch.from_numpy(synth.features(Bf, Cf, N, seed=Cf)).to(dev)
+    t = eager_us(lambda: dgcnn_util.knn(x, kf))
+    out["dgcnn knn C=%d k=%d %dx%d" % (Cf, kf, Bf, N)] = {"us": t, "fma_pipe_frac": Bf * N * N * Cf * 1.0 / (t * 1e-6) / fma,
+                                                       "bound": "FP32 FMA pipe (direct form, 2C flop per pair)"}
+    idx = dgcnn_util.knn(x, kf)
+    t = eager_us(lambda: ops._graph_feature_fwd(x, idx))
+    nbytes = Bf * N * kf * 2 * Cf * 4 + Bf * Cf * N * 4 + Bf * N * kf * 8
+    out["graph feature C=%d" % Cf] = {"us": t, "GBps": nbytes / (t * 1e-6) / 1e9, "hbm_frac": nbytes / (t * 1e-6) / 1e9 / hbm,
+                                      "bound": "HBM write stream", "peak_GBps": hbm}
+    return out
 
 
 _REAL_STDOUT = None
