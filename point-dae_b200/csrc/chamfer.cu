@@ -36,8 +36,8 @@ struct ChamferDir {
   int nq, nr;
   int qtiles;       // CTAs per cloud for this direction (0 = direction absent)
   int ref_offset;   // global index of r[0] (sharded mode)
-  int csplit;       // column chunks per row block (0 or 1 = a CTA streams the whole reference cloud)
-  uint64_t *rowkeys;  // (b, nq) csplit > 1: (row minimum, lowest index) merged across the chunks with RED.MIN
+  int csplit;       // column chunks per row block (0 or 1 = a CTA streams the whole reference cloud); > 1 needs `keys`,
+                    // pre-filled with the MIN identity: the chunks merge their (row minimum, lowest index) with RED.MIN
 };
 
 // SYM: the squared distance is symmetric bit for bit (the operands of every product only change
@@ -55,7 +55,7 @@ __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, co
                                                  int row_base, size_t cloud, float *dist, int *idx, uint64_t *keys,
                                                  int ref_offset, uint64_t *colkeys, float (*tile)[3][CH_TILE],
                                                  unsigned (*colmin)[THREADS / 32][SYM ? CH_TILE : 4], int tile_begin = 0,
-                                                 int tile_end = 0x7fffffff, uint64_t *rowkeys = nullptr) {
+                                                 int tile_end = 0x7fffffff, bool merge = false) {
   constexpr int QPW = 32 * QT;                  // queries per warp
   constexpr int W = THREADS / 32;
   constexpr int LD = 3 * CH_TILE / THREADS;     // floats staged per thread per tile
@@ -254,10 +254,11 @@ __device__ __forceinline__ void chamfer_min_body(const float *__restrict__ Q, co
     const int q = qbase + s * 32 + lane;
     if (q < nq) {
       const size_t o = cloud * nq + q;
-      if (rowkeys) {  // column-split unit: the (distance, index) order of the key is the reference's tie rule
-        atomicMin(reinterpret_cast<unsigned long long *>(rowkeys + o), pack_key(best[s], static_cast<uint32_t>(myidx[s])));
-      } else if (keys) {
-        keys[o] = pack_key(best[s], static_cast<uint32_t>(myidx[s] + ref_offset));
+      if (keys) {
+        const uint64_t key = pack_key(best[s], static_cast<uint32_t>(myidx[s] + ref_offset));
+        // column-split unit: the (distance, index) order of the key is the reference's tie rule
+        if (merge) atomicMin(reinterpret_cast<unsigned long long *>(keys + o), key);
+        else keys[o] = key;
       } else {
         dist[o] = best[s];
         idx[o] = myidx[s];
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, MINB) chamfer_min_kernel(const Chamfe
   chamfer_min_body<QT, THREADS, SYM, CH_TILE, STEP, false, PACKED>(
       d.q + static_cast<size_t>(cloud) * d.nq * 3, d.r + static_cast<size_t>(cloud) * d.nr * 3, d.nq, d.nr,
       t * (QT * THREADS), static_cast<size_t>(cloud), d.dist, d.idx, d.keys, d.ref_offset, d.colkeys, tile, colmin,
-      tile_begin, tile_end, nc > 1 ? d.rowkeys : nullptr);
+      tile_begin, tile_end, nc > 1);
 }
 
 // Balanced variant of the symmetric forward (opt-in, PDAE_CHAMFER_CFG=17; measured NOT faster, kept as the record of
@@ -1055,9 +1056,11 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
         const int qpc = chamfer_qpc(nr_rows, true);
         ChamferDir d0{rows, cols, drow, irow, nullptr, ck, nr_rows, nr_cols, ceil_div(nr_rows, qpc), 0};
         ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
-        if (nsplit > 1) {
+        if (nsplit > 1) {  // rows leave as merged keys instead of dist / idx
           d0.csplit = nsplit;
-          d0.rowkeys = ck + ncol;
+          d0.keys = ck + ncol;
+          d0.dist = nullptr;
+          d0.idx = nullptr;
         }
         const int rc = launch_min<true>(d0, d1, b, st);
         if (rc) return rc;
@@ -1119,6 +1122,12 @@ extern "C" int pdae_chamfer_min_keys_u64(const float *queries, const float *refs
   const int qpc = chamfer_qpc(nq, false);
   ChamferDir d0{queries, refs, nullptr, nullptr, keys, nullptr, nq, nr, ceil_div(nq, qpc), ref_offset};
   ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+  const int nsplit = (chamfer_variant() == 0 && nq > 256) ? chamfer_csplit(static_cast<long long>(b) * ceil_div(nq, 512), ceil_div(nr, 512)) : 1;
+  if (nsplit > 1) {  // column-split units merge into the output keys
+    fill_keys_kernel<<<static_cast<unsigned>((bq + 255) / 256), 256, 0, st>>>(keys, static_cast<long long>(bq));
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+    d0.csplit = nsplit;
+  }
   return launch_min<false>(d0, d1, b, st);
 }
 
@@ -1154,6 +1163,14 @@ extern "C" int pdae_chamfer_sharded_f32(const float *xyz1, const float *xyz2_loc
   const int qpc = chamfer_qpc(n, true);
   ChamferDir d0{xyz1, xyz2_local, nullptr, nullptr, keys1, ck, n, m_local, ceil_div(n, qpc), ref_offset};
   ChamferDir d1{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+  // a single scene-scale cloud gives few row blocks (100 000 points: 196 for 148 SMs): column-split units, merged
+  // through the very keys this call returns
+  const int nsplit = chamfer_variant() == 0 ? chamfer_csplit(static_cast<long long>(b) * ceil_div(n, 512), ceil_div(m_local, 512)) : 1;
+  if (nsplit > 1) {
+    fill_keys_kernel<<<static_cast<unsigned>((bn + 255) / 256), 256, 0, st>>>(keys1, static_cast<long long>(bn));
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+    d0.csplit = nsplit;
+  }
   const int rc = launch_min<true>(d0, d1, b, st);
   if (rc) return rc;
   return launch_col_recover_for_variant(xyz1, xyz2_local, ck, b, n, m_local, dist2_local, idx2_local, st);

@@ -73,3 +73,24 @@ def test_split_forward_feeds_the_fused_loss_and_backward(split_hook):
         outs.append((loss.detach().clone(), p.grad.clone()))
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-9)  # atomics: order-free sums
+
+
+@pytest.mark.parametrize("n,m,lo,hi", [(3000, 5000, 1000, 3600), (100000, 30000, 0, 12500), (700, 2000, 1999, 2000)])
+def test_sharded_entry_points_merge_their_chunks_into_the_returned_keys(split_hook, n, m, lo, hi):
+    """pdae_chamfer_sharded_f32 / pdae_chamfer_min_keys_u64: the packed row keys a rank hands to the MIN all-reduce are
+    themselves the merge target of its column-split units (global indices, identity-filled first)."""
+    a = cu(synth.prediction(synth.clouds(1, max(n, m), seed=n), seed=n)[:, :n])
+    c = cu(synth.clouds(1, max(n, m), seed=n)[:, :m])
+    c[:, lo + 1 if lo + 1 < hi else lo] = c[:, lo]  # duplicate inside the slice
+    sl = c[:, lo:hi].contiguous()
+    split_hook(1)
+    want = ops.chamfer_sharded_local(a, sl, lo)
+    want_keys = ops.chamfer_min_keys(a, sl, lo)
+    assert torch.equal(want[0], want_keys)
+    d, i = ops.chamfer_unpack_keys(want[0])
+    assert int(i.min()) >= lo and int(i.max()) < hi
+    for nc in (2, 3, 7, 0):
+        split_hook(nc)
+        got = ops.chamfer_sharded_local(a, sl, lo)
+        assert all(torch.equal(g, w) for g, w in zip(got, want)), nc
+        assert torch.equal(ops.chamfer_min_keys(a, sl, lo), want_keys), nc
