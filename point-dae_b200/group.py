@@ -49,3 +49,55 @@ class Group(nn.Module):  # FPS + KNN
             mats = torch.zeros((xyz.size(0), 0, 3, 3))
         nb, tnb, tc, _ = ops.group_affine(xyz.detach(), center, self.group_size, mats)
         return nb, center, tnb, tc
+
+
+def _patches_with_idx(xyz_only, num_group, group_size):
+    """FPS + centre gather, kNN + gather + centre-subtract with the int64 neighbour indices kept: two launches."""
+    fps_idx, center = fps(xyz_only, num_group)
+    neighborhood, idx = ops.group_points_knn(xyz_only.detach(), center, group_size, want_idx=True)
+    return fps_idx, center, neighborhood, idx
+
+
+def _gather_rows(attribute, idx):
+    """attribute (B,N,A), idx (B,G,M) int64 -> (B,G,M,A): the reference's `view(B*N,-1)[idx + b*N]` (plain torch
+    indexing, differentiable like the reference's)."""
+    b, n, a = attribute.shape
+    flat = (idx + torch.arange(b, device=idx.device).view(-1, 1, 1) * n).view(-1)
+    return attribute.reshape(b * n, a)[flat, :].view(b, idx.size(1), idx.size(2), a).contiguous()
+
+
+class GroupWithIndex(Group):
+    """`Group` of models/Point_M2AE_modules.py:  -> neighborhood, center, idx, with idx the flattened batch-global
+    neighbour indices `(idx + arange(B)*N).view(-1)` the multi-scale encoder reuses."""
+
+    def forward(self, xyz):
+        batch_size, num_points, _ = xyz.shape
+        xyz = xyz.float().contiguous()
+        _, center, neighborhood, idx = _patches_with_idx(xyz, self.num_group, self.group_size)
+        idx = idx + torch.arange(0, batch_size, device=xyz.device).view(-1, 1, 1) * num_points
+        return neighborhood, center, idx.view(-1)
+
+
+class GroupNormal(Group):
+    """`Group` of models/MaskSurf.py: input B N 6 (xyz + normal) -> neighborhood_no_normal (centre-subtracted),
+    neighborhood_only_normal (the neighbours' normals, untouched), center."""
+
+    def forward(self, xyz):
+        xyz_no_normal = xyz[:, :, :3].float().contiguous()
+        xyz_only_normal = xyz[:, :, 3:6].contiguous()
+        _, center, neighborhood, idx = _patches_with_idx(xyz_no_normal, self.num_group, self.group_size)
+        return neighborhood, _gather_rows(xyz_only_normal, idx), center
+
+
+class GroupAttribute(Group):
+    """`Group` of models/MaskSurf_v2.py, models/MaskFeat_transformer.py, models/MaskFeat_DGCNN.py: input B N 3+A ->
+    neighborhood_xyz_only, neighborhood_attribute_only (B G M A), center, center_attribute (B G A)."""
+
+    def forward(self, xyz):
+        xyz_only = xyz[:, :, :3].float().contiguous()
+        attribute_only = xyz[:, :, 3:].contiguous()
+        fps_idx, center, neighborhood, idx = _patches_with_idx(xyz_only, self.num_group, self.group_size)
+        b, n, a = attribute_only.shape
+        flat = (fps_idx.long() + torch.arange(b, device=xyz.device).view(-1, 1) * n).view(-1)
+        center_attribute = attribute_only.reshape(b * n, a)[flat, :].view(b, self.num_group, a).contiguous()
+        return neighborhood, _gather_rows(attribute_only, idx), center, center_attribute

@@ -92,9 +92,15 @@ def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentat
                 patched.append(name + ".corrupt_data")
     except Exception:
         pass
-    for name in ("models.PointCAE_transformer", "models.Point_MAE", "models.Point_MlMAE"):
+    # every flavour of the patchifier class the reference defines, by the module that defines it
+    flavours = {"models.PointCAE_transformer": group.Group, "models.Point_MAE": group.Group,
+                "models.Point_MlMAE": group.Group, "models.PointCAE_pointnetv2": group.Group,
+                "models.Point_M2AE_modules": group.GroupWithIndex, "models.MaskSurf": group.GroupNormal,
+                "models.MaskSurf_v2": group.GroupAttribute, "models.MaskFeat_transformer": group.GroupAttribute,
+                "models.MaskFeat_DGCNN": group.GroupAttribute}
+    for name, cls in flavours.items():
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "Group"):
-            mod.Group = group.Group
+            mod.Group = cls
             patched.append(name + ".Group")
     return patched

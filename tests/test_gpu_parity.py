@@ -525,3 +525,34 @@ def test_dgcnn_knn_matrix_and_fused_paths_agree_with_oracle(b, c, n, k):
     rc = _native.lib().pdae_feat_knn_ws_f32(t.data_ptr(), b, c, n, k, idx2.data_ptr(), ws.data_ptr(), per,
                                             torch.cuda.current_stream().cuda_stream)
     assert rc == 0 and torch.equal(idx2, idx)
+
+
+# ---- the reference's other patchifier flavours (models/Point_M2AE_modules.py, MaskSurf.py, MaskSurf_v2.py) ----------
+@pytest.mark.gpu
+def test_group_flavours_match_the_reference_sequences():
+    from pointdae_b200 import group
+    b, n, g, m = 3, 1500, 24, 16
+    xyz = synth.adversarial(synth.clouds(b, n, seed=21), seed=21)
+    rng = np.random.default_rng(21)
+    attr = rng.standard_normal((b, n, 4)).astype(np.float32)
+    want_nb, want_c, want_idx, want_fps = oracle.group(xyz, g, m)
+    flat = (want_idx + np.arange(b).reshape(-1, 1, 1) * n).reshape(-1)
+    x6 = torch.from_numpy(np.concatenate([xyz, attr], axis=2)).to(DEV)
+
+    nb, c, idx = group.GroupWithIndex(g, m)(torch.from_numpy(xyz).to(DEV))
+    assert idx.dtype == torch.int64 and idx.dim() == 1
+    np.testing.assert_array_equal(nb.cpu().numpy(), want_nb)
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(idx.cpu().numpy(), flat)
+
+    nb, nrm, c = group.GroupNormal(g, m)(x6[:, :, :6].contiguous())
+    np.testing.assert_array_equal(nb.cpu().numpy(), want_nb)
+    np.testing.assert_array_equal(nrm.cpu().numpy(), attr[:, :, :3].reshape(b * n, 3)[flat].reshape(b, g, m, 3))
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+
+    nb, na, c, ca = group.GroupAttribute(g, m)(x6)
+    np.testing.assert_array_equal(nb.cpu().numpy(), want_nb)
+    np.testing.assert_array_equal(na.cpu().numpy(), attr.reshape(b * n, 4)[flat].reshape(b, g, m, 4))
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+    fflat = (want_fps.astype(np.int64) + np.arange(b).reshape(-1, 1) * n).reshape(-1)
+    np.testing.assert_array_equal(ca.cpu().numpy(), attr.reshape(b * n, 4)[fflat].reshape(b, g, 4))

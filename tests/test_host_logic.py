@@ -115,13 +115,18 @@ def test_patch_models_rebinds_the_corruptions_where_the_models_imported_them():
         model = types.ModuleType("models.PointCAE_transformer")
         model.corrupt_data = ref.corrupt_data
         model.Group = object
+        surf = types.ModuleType("models.MaskSurf_v2")
+        surf.Group = object
+        saved["models.MaskSurf_v2"] = sys.modules.get("models.MaskSurf_v2")
         sys.modules.update({"datasets": pkg, "datasets.corrupt_util_tensor": ref, "models": mpkg,
-                            "models.PointCAE_transformer": model})
+                            "models.PointCAE_transformer": model, "models.MaskSurf_v2": surf})
         patched = pointdae_b200.patch_models(names=())
         assert ref.corrupt_data is cut.corrupt_data and model.corrupt_data is cut.corrupt_data
         assert ref.dropout_patch_random is cut.dropout_patch_random and ref.corrupt_shear is cut.corrupt_shear
         assert ref.corruptions["rotate"] is cut.corrupt_rotate_360 and ref.corruptions["jitter"] == "kept"
         assert "models.PointCAE_transformer.corrupt_data" in patched and "models.PointCAE_transformer.Group" in patched
+        from pointdae_b200 import group
+        assert model.Group is group.Group and surf.Group is group.GroupAttribute  # each module gets its own flavour
     finally:
         for k, v in saved.items():
             if v is None:
