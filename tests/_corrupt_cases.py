@@ -47,3 +47,13 @@ def inputs(name, b, g, m):
 def next_draws():
     """One draw from each host generator the corruptions use: equal values <=> equal stream positions."""
     return np.array([random.random(), np.random.rand(), float(torch.rand(1, dtype=torch.float64))], dtype=np.float64)
+
+
+# dropout_patch_random(pc, level): name -> (batch, points, level)
+DROP_PATCH = {"drop_level_none": (3, 1024, None), "drop_level_0": (2, 700, 0), "drop_level_4": (2, 2048, 4),
+              "drop_all_masked": (1, 256, 60)}  # level 60 -> prob 6.5: no patch survives the draw, patch 0 is forced
+
+
+def drop_patch_input(name, b, n):
+    from pointdae_b200 import synth
+    return synth.adversarial(synth.clouds(b, n, seed=sum(map(ord, name))), seed=1)

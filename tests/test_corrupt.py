@@ -198,3 +198,32 @@ def test_gpu_affine_points_gradient():
         rp, rc = torch.matmul(rp, R.unsqueeze(1)), torch.matmul(rc, R)
     ((rp * wp).sum() + (rc * wc).sum()).backward()
     assert torch.allclose(got[0], nb.grad, rtol=1e-4, atol=1e-5) and torch.allclose(got[1], c.grad, rtol=1e-4, atol=1e-5)
+
+
+# ---- Drop-Patch (datasets/corrupt_util_tensor.py:592-616): golden = the reference's own function over oracle stand-ins
+@pytest.mark.parametrize("name", sorted(cases.DROP_PATCH))
+def test_drop_patch_recipe_from_the_oracle_matches_reference(name):
+    b, n, level = cases.DROP_PATCH[name]
+    pc = cases.drop_patch_input(name, b, n)
+    cases.seed_all(name)
+    if level is None:
+        level = random.random() * 4
+    prob = level / 10.0 + 0.5
+    idx = oracle.group(pc, cut.NUM_GROUP, cut.GROUP_SIZE)[2]
+    patches = pc.reshape(b * n, 3)[(idx + np.arange(b).reshape(-1, 1, 1) * n).reshape(-1)].reshape(b, 64, 32, 3)
+    mask = (torch.rand(cut.NUM_GROUP) > prob).numpy()
+    if mask.sum() == 0:
+        mask[0] = True
+    assert np.array_equal(cases.next_draws(), GOLD["drop_patch/%s/rng_after" % name])
+    assert np.array_equal(patches[:, mask].reshape(b, -1, 3), GOLD["drop_patch/%s/points" % name])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(cases.DROP_PATCH))
+def test_gpu_drop_patch_matches_reference_golden(name):
+    b, n, level = cases.DROP_PATCH[name]
+    pc = torch.from_numpy(cases.drop_patch_input(name, b, n)).to(_dev())
+    cases.seed_all(name)
+    kept = cut.dropout_patch_random(pc, level)
+    assert np.array_equal(cases.next_draws(), GOLD["drop_patch/%s/rng_after" % name])
+    assert np.array_equal(kept.cpu().numpy(), GOLD["drop_patch/%s/points" % name])
