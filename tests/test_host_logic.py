@@ -133,3 +133,32 @@ def test_patch_models_rebinds_the_corruptions_where_the_models_imported_them():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_get_graph_feature_offsets_a_supplied_idx_in_place_and_keeps_backward_alive(monkeypatch):
+    """models/dgcnn_util.py:27 offsets the caller's idx in place; autograd here must still hold the per-cloud indices
+    (regression: the saved tensor used to BE the caller's tensor, so backward raised on the GPU)."""
+    import torch
+    from pointdae_b200 import dgcnn_util, ops
+
+    class Stub(torch.autograd.Function):  # same save-for-backward contract as ops.GraphFeatureFunction, no CUDA
+        @staticmethod
+        def forward(ctx, x, idx):
+            ctx.save_for_backward(idx)
+            b, c, n = x.shape
+            return x.new_zeros(b, n, idx.size(2), 2 * c).permute(0, 3, 1, 2) + x.sum()
+
+        @staticmethod
+        def backward(ctx, g):
+            (idx,) = ctx.saved_tensors
+            assert int(idx.max()) < 7  # per-cloud, not offset
+            return torch.ones(2, 3, 7) * g.sum(), None
+
+    monkeypatch.setattr(ops, "GraphFeatureFunction", Stub)
+    x = torch.randn(2, 3, 7, requires_grad=True)
+    idx = torch.randint(0, 7, (2, 7, 4))
+    before = idx.clone()
+    feat = dgcnn_util.get_graph_feature(x, k=4, idx=idx)
+    assert torch.equal(idx, before + torch.arange(2).view(-1, 1, 1) * 7)
+    feat.sum().backward()
+    assert x.grad.shape == x.shape
