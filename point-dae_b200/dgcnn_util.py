@@ -25,7 +25,7 @@ def get_graph_feature(x, k=20, idx=None, extra_dim=False):
     k = idx.size(2)
     if idx is caller_idx:
         # the caller's tensor is offset in place below (as the reference does); autograd must keep the per-cloud
-        # indices, so the function saves its own copy (found by tests/test_dgcnn_ref.py: backward raised otherwise)
+        # indices, so the function saves its own copy (found by tests/test_ref_dgcnn.py: backward raised otherwise)
         idx = idx.clone()
     feature = ops.GraphFeatureFunction.apply(x.float(), idx)
     if caller_idx is not None and caller_idx.dtype == torch.int64:
