@@ -2,7 +2,7 @@
 main.py run unchanged:
 
     import pointdae_b200; pointdae_b200.install()
-    # now: from pointnet2_ops import pointnet2_utils ; from knn_cuda import KNN ; import chamfer ;
+    # now: from pointnet2_ops import pointnet2_utils (and pointnet2_ops.pointnet2_modules) ; from knn_cuda import KNN ; import chamfer ;
     #      import pointnet2._ext  -> all served by the sm_100a kernels
 
 Only the *compiled / third-party* modules are replaced (the reference's own Python, e.g.
@@ -18,14 +18,16 @@ import types
 def install(loss_modules=False):
     """loss_modules=True additionally serves `extensions.chamfer_dist` (the reference's Python loss classes,
     which import `ipdb` at module level, extensions/chamfer_dist/__init__.py:12) from this package's mirror."""
-    from . import chamfer, knn_cuda, pointnet2_ext, pointnet2_utils
+    from . import chamfer, knn_cuda, pointnet2_ext, pointnet2_modules, pointnet2_utils
 
     pkg = types.ModuleType("pointnet2_ops")
     pkg.__path__ = []  # mark as package
     pkg.pointnet2_utils = pointnet2_utils
+    pkg.pointnet2_modules = pointnet2_modules  # models/pointnetv2_util.py:317, pulled in by `import models`
     pkg.__version__ = "3.0.0"
     sys.modules["pointnet2_ops"] = pkg
     sys.modules["pointnet2_ops.pointnet2_utils"] = pointnet2_utils
+    sys.modules["pointnet2_ops.pointnet2_modules"] = pointnet2_modules
 
     sys.modules["knn_cuda"] = knn_cuda
     sys.modules["chamfer"] = chamfer
