@@ -1,0 +1,72 @@
+"""Run as a script (own process).  Builds the reference's flagship model `PointCAE_transformer` (the config of
+cfgs/pretrain_PointCAE_transformer_dropout_patch_affine_r3_maskpatch.yaml with a narrower / shallower transformer so it
+runs in seconds on CPU), UNMODIFIED from /root/reference, and runs one seeded training forward + backward on CPU in one
+of four set-ups, printing one JSON object (loss, a gradient checksum, the host RNG positions afterwards):
+
+  reference    the reference's own glue over oracle-backed stand-ins for its compiled / third-party modules
+  install      pointdae_b200.install(): this repo's knn_cuda / pointnet2_utils / chamfer host layer (ops -> oracle)
+  patched      + patch_models(): fused Group, one-launch corrupt_data, misc.fps
+  patched_loss + install(loss_modules=True): the fused mean-loss autograd node instead of the reference's loss file
+"""
+import json
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODE = sys.argv[1]
+REF = sys.argv[2] if len(sys.argv) > 2 else "/root/reference"
+for p in (REF, os.path.join(ROOT, "tests", "golden"), os.path.join(ROOT, "tests"), ROOT):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import _ref_stubs  # noqa: E402
+
+torch.nn.Module.cuda = lambda self, *a, **k: self  # build_loss_func calls `.cuda()` on the loss module (:1000-1002)
+if MODE == "reference":
+    import types
+    import _oracle_chamfer
+    import _standins
+    _standins.install_modules()
+    sys.modules["chamfer"] = _oracle_chamfer
+    sys.modules["pointnet2_ops"].__path__ = []
+    _ref_stubs.stub("pointnet2_ops.pointnet2_modules")  # only the PointNet++ encoder file needs it
+    p2 = types.ModuleType("pointnet2")
+    p2.__path__ = []
+    sys.modules["pointnet2"] = p2
+    _ref_stubs.stub("pointnet2._ext")
+else:
+    import pointdae_b200
+    import _oracle_ops
+    pointdae_b200.install(loss_modules=(MODE == "patched_loss"))
+    _oracle_ops.apply()
+_ref_stubs.install_third_party()
+models, _ = _ref_stubs.import_with_stubs("models")
+patched = pointdae_b200.patch_models() if MODE in ("patched", "patched_loss") else []
+
+from easydict import EasyDict  # noqa: E402
+from pointdae_b200 import synth  # noqa: E402
+
+cfg = EasyDict(NAME="PointCAE_transformer", corrupt_type=["affine_r3", "Drop-Patch"], all_patch="False", group_size=32,
+               num_group=64, loss="cdl2",
+               transformer_config=EasyDict(rand_ratio="True", mask_ratio=0.6, mask_type="rand", trans_dim=48,
+                                           encoder_dims=48, depth=2, drop_path_rate=0.1, num_heads=2, decoder_depth=1,
+                                           decoder_num_heads=2))
+random.seed(0), np.random.seed(0), torch.manual_seed(0)
+model = models.build_model_from_cfg(cfg)
+pts = torch.from_numpy(synth.clouds(3, 1024, seed=9))
+random.seed(1), np.random.seed(1), torch.manual_seed(1)
+model.train()
+loss = model(pts, pts)[0]
+loss.backward()
+grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+first = sorted(grads)[0]
+print(json.dumps({
+    "mode": MODE, "loss": float(loss), "n_params_with_grad": len(grads),
+    "grad_abs_sum": float(sum(g.double().abs().sum() for g in grads.values())),
+    "grad_probe": [float(v) for v in grads[first].reshape(-1)[:4]], "grad_probe_name": first,
+    "group_class": type(model.group_divider).__module__, "loss_class": type(model.loss_func).__module__,
+    "rng_after": [random.random(), float(np.random.rand()), float(torch.rand(1, dtype=torch.float64))],
+    "patched": len(patched)}))
