@@ -82,7 +82,34 @@ def chamfer_loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, grad_loss, w1, w
     return _oracle_chamfer.backward(xyz1, xyz2, idx1, idx2, gd1, gd2)
 
 
-NAMES = ("furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "affine_points", "group_affine",
+def feat_knn(x, k):
+    idx, _ = oracle.feat_knn(x.detach().float().contiguous().numpy(), int(k))
+    return _t(idx)
+
+
+def _graph_feature_fwd(x, idx):
+    return _t(np.ascontiguousarray(oracle.graph_feature(x.detach().numpy(), idx.numpy()).transpose(0, 2, 3, 1)))  # physical (B,N,k,2C)
+
+
+def _graph_feature_bwd(gout_phys, idx, c, n):
+    return _t(oracle.graph_feature_grad(gout_phys.numpy().transpose(0, 3, 1, 2), idx.numpy()))
+
+
+class GraphFeatureFunction(torch.autograd.Function):  # same contract as ops.GraphFeatureFunction
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.cn = (x.size(1), x.size(2))
+        return _graph_feature_fwd(x.contiguous(), idx).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        c, n = ctx.cn
+        return _graph_feature_bwd(grad.permute(0, 2, 3, 1).contiguous().float(), idx, c, n), None
+
+
+NAMES = ("feat_knn", "_graph_feature_fwd", "_graph_feature_bwd", "GraphFeatureFunction", "furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "affine_points", "group_affine",
          "chamfer_forward", "chamfer_backward", "chamfer_mean_loss", "chamfer_loss_backward")
 EXT_NAMES = ("gather_points", "gather_points_grad", "ball_query", "group_points", "group_points_grad", "three_nn",
              "three_interpolate", "three_interpolate_grad")

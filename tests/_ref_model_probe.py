@@ -16,6 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MODE = sys.argv[1]
 REF = sys.argv[2] if len(sys.argv) > 2 else "/root/reference"
+MODEL = sys.argv[3] if len(sys.argv) > 3 else "transformer"
 for p in (REF, os.path.join(ROOT, "tests", "golden"), os.path.join(ROOT, "tests"), ROOT):
     sys.path.insert(0, p)
 
@@ -54,9 +55,13 @@ cfg = EasyDict(NAME="PointCAE_transformer", corrupt_type=["affine_r3", "Drop-Pat
                transformer_config=EasyDict(rand_ratio="True", mask_ratio=0.6, mask_type="rand", trans_dim=48,
                                            encoder_dims=48, depth=2, drop_path_rate=0.1, num_heads=2, decoder_depth=1,
                                            decoder_num_heads=2))
+if MODEL == "dgcnn":
+    # models/PointCAE_DGCNN.py:26-143: DGCNN encoder (get_graph_feature k=20 on 3 / 64 / 64 / 128 channels), folding decoder,
+    # ChamferL1 on the coarse and the fine cloud, Drop-Patch corruption inside forward
+    cfg = EasyDict(NAME="Point_CAE_DGCNN", corrupt_type=["dropout_patch_pointmae"], loss="cdl1")
 random.seed(0), np.random.seed(0), torch.manual_seed(0)
 model = models.build_model_from_cfg(cfg)
-pts = torch.from_numpy(synth.clouds(3, 1024, seed=9))
+pts = torch.from_numpy(synth.clouds(3 if MODEL == "transformer" else 2, 1024, seed=9))
 random.seed(1), np.random.seed(1), torch.manual_seed(1)
 model.train()
 loss = model(pts, pts)[0]
@@ -67,6 +72,7 @@ print(json.dumps({
     "mode": MODE, "loss": float(loss), "n_params_with_grad": len(grads),
     "grad_abs_sum": float(sum(g.double().abs().sum() for g in grads.values())),
     "grad_probe": [float(v) for v in grads[first].reshape(-1)[:4]], "grad_probe_name": first,
-    "group_class": type(model.group_divider).__module__, "loss_class": type(model.loss_func).__module__,
+    "group_class": type(model.group_divider).__module__ if hasattr(model, "group_divider") else None,
+    "loss_class": type(model.loss_func).__module__,
     "rng_after": [random.random(), float(np.random.rand()), float(torch.rand(1, dtype=torch.float64))],
     "patched": len(patched)}))

@@ -19,9 +19,8 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), 
 MODES = ("reference", "install", "patched", "patched_loss")
 
 
-@pytest.fixture(scope="module")
-def runs():
-    procs = {m: subprocess.Popen([sys.executable, os.path.join(HERE, "_ref_model_probe.py"), m, REF], cwd="/tmp",
+def _run_all(model):
+    procs = {m: subprocess.Popen([sys.executable, os.path.join(HERE, "_ref_model_probe.py"), m, REF, model], cwd="/tmp",
                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for m in MODES}
     out = {}
     for m, p in procs.items():
@@ -29,6 +28,16 @@ def runs():
         assert p.returncode == 0, (m, stderr[-3000:])
         out[m] = json.loads(stdout.strip().splitlines()[-1])
     return out
+
+
+@pytest.fixture(scope="module")
+def runs():
+    return _run_all("transformer")
+
+
+@pytest.fixture(scope="module")
+def dgcnn_runs():
+    return _run_all("dgcnn")
 
 
 def test_install_alone_is_bit_identical_inside_the_model(runs):
@@ -49,3 +58,18 @@ def test_fused_host_classes_are_interchangeable_inside_the_model(runs, mode):
     assert got["grad_probe_name"] == ref["grad_probe_name"]
     for a, b in zip(got["grad_probe"], ref["grad_probe"]):
         assert abs(a - b) <= 1e-5 * max(abs(b), 1e-3)
+
+
+@pytest.mark.parametrize("mode", ["install", "patched", "patched_loss"])
+def test_dgcnn_model_runs_unchanged_on_the_drop_in(dgcnn_runs, mode):
+    """`Point_CAE_DGCNN` (models/PointCAE_DGCNN.py:26-143): DGCNN encoder over get_graph_feature (k = 20; 3, 64, 64, 128
+    channels), folding decoder, ChamferL1 on a 1 024- and a 16 384-point prediction, Drop-Patch inside forward.  With
+    patch_models() the encoder's knn / get_graph_feature are this repo's (direct-form kNN, fused feature + gradient)."""
+    ref, got = dgcnn_runs["reference"], dgcnn_runs[mode]
+    assert (got["patched"] == 0) == (mode == "install")
+    assert got["loss_class"] == ("pointdae_b200.chamfer_dist" if mode == "patched_loss" else "extensions.chamfer_dist")
+    assert got["rng_after"] == ref["rng_after"] and got["n_params_with_grad"] == ref["n_params_with_grad"] == 21
+    assert abs(got["loss"] - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    assert abs(got["grad_abs_sum"] - ref["grad_abs_sum"]) <= 1e-6 * ref["grad_abs_sum"]
+    for a, b in zip(got["grad_probe"], ref["grad_probe"]):
+        assert abs(a - b) <= 1e-4 * max(abs(b), 1e-4)
