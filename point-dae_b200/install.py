@@ -57,41 +57,40 @@ def install(loss_modules=False):
 
 
 def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentation.models.dgcnn_util")):
-    """Rebind knn / get_graph_feature in the reference's already-importable modules, misc.fps, and Group."""
-    from . import dgcnn_util, group
+    """Rebind the pure-torch hot functions that live inside the reference's own packages: knn / get_graph_feature,
+    misc.fps, the corruptions executed inside forward, and every flavour of the `Group` patchifier.  Names that other
+    reference modules imported from the defining module (`from .Point_M2AE_modules import *`,
+    `from datasets.corrupt_util_tensor import corrupt_data`) are rebound there too.  Returns what was rebound."""
+    from . import corrupt_util_tensor, dgcnn_util, group
 
-    patched = []
+    patched, replaced = [], {}
+
+    def rebind(mod, attr, new, where):
+        old = getattr(mod, attr, None)
+        if old is None or old is new:
+            return
+        if callable(old):
+            replaced[id(old)] = (old, new)
+        setattr(mod, attr, new)
+        patched.append(where + "." + attr)
+
     for name in names:
         try:
             mod = importlib.import_module(name)
         except Exception:
             continue
         for fn in ("knn", "get_graph_feature"):
-            if hasattr(mod, fn):
-                setattr(mod, fn, getattr(dgcnn_util, fn))
-                patched.append(name + "." + fn)
+            rebind(mod, fn, getattr(dgcnn_util, fn), name)
     try:
-        misc = importlib.import_module("utils.misc")
-        misc.fps = group.fps
-        patched.append("utils.misc.fps")
+        rebind(importlib.import_module("utils.misc"), "fps", group.fps, "utils.misc")
     except Exception:
         pass
-    try:  # the Drop-Patch corruption run inside forward (datasets/corrupt_util_tensor.py:592-616)
-        from . import corrupt_util_tensor
-        cut = importlib.import_module("datasets.corrupt_util_tensor")
-        cut.dropout_patch_random = corrupt_util_tensor.dropout_patch_random
-        patched.append("datasets.corrupt_util_tensor.dropout_patch_random")
-        # the affine corruptions between the patchifier and the encoder (:59-343, :706-728): one launch per chain
-        for fn in ("corrupt_data", "corrupt_scale_nonorm", "corrupt_tranlate", "corrupt_rotate_360",
+    try:  # corruptions run inside forward: Drop-Patch (datasets/corrupt_util_tensor.py:592-616) and the affine chain
+        cut = importlib.import_module("datasets.corrupt_util_tensor")  # (:59-343, :706-728), one launch per chain
+        for fn in ("dropout_patch_random", "corrupt_data", "corrupt_scale_nonorm", "corrupt_tranlate", "corrupt_rotate_360",
                    "corrupt_rotate_z_360", "corrupt_reflection", "corrupt_shear"):
-            setattr(cut, fn, getattr(corrupt_util_tensor, fn))
+            rebind(cut, fn, getattr(corrupt_util_tensor, fn), "datasets.corrupt_util_tensor")
         cut.corruptions.update(corrupt_util_tensor.corruptions)
-        patched.append("datasets.corrupt_util_tensor.corrupt_data")
-        for name in ("models.PointCAE_transformer", "models.Point_M2AE"):  # `from ... import corrupt_data`
-            mod = sys.modules.get(name)
-            if mod is not None and hasattr(mod, "corrupt_data"):
-                mod.corrupt_data = corrupt_util_tensor.corrupt_data
-                patched.append(name + ".corrupt_data")
     except Exception:
         pass
     # every flavour of the patchifier class the reference defines, by the module that defines it
@@ -102,7 +101,15 @@ def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentat
                 "models.MaskFeat_DGCNN": group.GroupAttribute}
     for name, cls in flavours.items():
         mod = sys.modules.get(name)
-        if mod is not None and hasattr(mod, "Group"):
-            mod.Group = cls
-            patched.append(name + ".Group")
+        if mod is not None:
+            rebind(mod, "Group", cls, name)
+    # the same objects under other names: modules that imported them from the defining module
+    for mname, mod in list(sys.modules.items()):
+        if mod is None or mname.split(".")[0] not in ("models", "datasets", "utils", "tools", "segmentation"):
+            continue
+        for attr, val in list(vars(mod).items()):
+            hit = replaced.get(id(val))
+            if hit is not None and hit[0] is val:
+                setattr(mod, attr, hit[1])
+                patched.append(mname + "." + attr)
     return patched

@@ -26,6 +26,7 @@ import torch  # noqa: E402
 import _ref_stubs  # noqa: E402
 
 torch.nn.Module.cuda = lambda self, *a, **k: self  # build_loss_func calls `.cuda()` on the loss module (:1000-1002)
+torch.Tensor.cuda = lambda self, *a, **k: self     # ... and some forwards on fresh tensors (models/Point_M2AE.py:116)
 if MODE == "reference":
     import types
     import _oracle_chamfer
@@ -59,6 +60,13 @@ if MODEL == "dgcnn":
     # models/PointCAE_DGCNN.py:26-143: DGCNN encoder (get_graph_feature k=20 on 3 / 64 / 64 / 128 channels), folding decoder,
     # ChamferL1 on the coarse and the fine cloud, Drop-Patch corruption inside forward
     cfg = EasyDict(NAME="Point_CAE_DGCNN", corrupt_type=["dropout_patch_pointmae"], loss="cdl1")
+if MODEL == "m2ae":
+    # models/Point_M2AE.py: three-scale tokenizer (Group of models/Point_M2AE_modules.py, which returns the flattened
+    # neighbour indices), corrupt_data on LISTS of patches / centres, ChamferL2 on the finest masked patches
+    cfg = EasyDict(NAME="Point_M2AE", corrupt_type=["affine_r3", "Drop-Patch"], mask_ratio=0.8, group_sizes=[16, 8, 8],
+                   num_groups=[128, 64, 16], encoder_depths=[1, 1, 1], encoder_dims=[24, 48, 96],
+                   local_radius=[0.32, 0.64, 1.28], decoder_depths=[1, 1], decoder_dims=[96, 48], decoder_up_blocks=[1, 1],
+                   drop_path_rate=0.1, num_heads=2)
 random.seed(0), np.random.seed(0), torch.manual_seed(0)
 model = models.build_model_from_cfg(cfg)
 pts = torch.from_numpy(synth.clouds(3 if MODEL == "transformer" else 2, 1024, seed=9))
@@ -72,7 +80,8 @@ print(json.dumps({
     "mode": MODE, "loss": float(loss), "n_params_with_grad": len(grads),
     "grad_abs_sum": float(sum(g.double().abs().sum() for g in grads.values())),
     "grad_probe": [float(v) for v in grads[first].reshape(-1)[:4]], "grad_probe_name": first,
-    "group_class": type(model.group_divider).__module__ if hasattr(model, "group_divider") else None,
-    "loss_class": type(model.loss_func).__module__,
+    "group_class": (type(model.group_divider).__module__ if hasattr(model, "group_divider") else
+                    type(model.group_dividers[0]).__module__ if hasattr(model, "group_dividers") else None),
+    "loss_class": type(getattr(model, "loss_func", None) or getattr(model, "rec_loss")).__module__,
     "rng_after": [random.random(), float(np.random.rand()), float(torch.rand(1, dtype=torch.float64))],
     "patched": len(patched)}))

@@ -108,6 +108,7 @@ def test_patch_models_rebinds_the_corruptions_where_the_models_imported_them():
         pkg.__path__ = []
         ref = types.ModuleType("datasets.corrupt_util_tensor")
         ref.corrupt_data = ref.dropout_patch_random = lambda *a, **k: "reference"
+        ref.corrupt_shear = lambda *a, **k: "reference shear"
         ref.corruptions = {"rotate": None, "jitter": "kept"}
         pkg.corrupt_util_tensor = ref
         mpkg = types.ModuleType("models")

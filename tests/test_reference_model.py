@@ -40,6 +40,11 @@ def dgcnn_runs():
     return _run_all("dgcnn")
 
 
+@pytest.fixture(scope="module")
+def m2ae_runs():
+    return _run_all("m2ae")
+
+
 def test_install_alone_is_bit_identical_inside_the_model(runs):
     ref, got = runs["reference"], runs["install"]
     assert got["group_class"] == "models.PointCAE_transformer" and got["loss_class"] == "extensions.chamfer_dist"
@@ -73,3 +78,19 @@ def test_dgcnn_model_runs_unchanged_on_the_drop_in(dgcnn_runs, mode):
     assert abs(got["grad_abs_sum"] - ref["grad_abs_sum"]) <= 1e-6 * ref["grad_abs_sum"]
     for a, b in zip(got["grad_probe"], ref["grad_probe"]):
         assert abs(a - b) <= 1e-4 * max(abs(b), 1e-4)
+
+
+@pytest.mark.parametrize("mode", ["install", "patched", "patched_loss"])
+def test_m2ae_model_runs_unchanged_on_the_drop_in(m2ae_runs, mode):
+    """`Point_M2AE` (models/Point_M2AE.py): three-scale tokenizer built on the index-returning `Group` of
+    models/Point_M2AE_modules.py (star-imported into the model file: patch_models must rebind it THERE),
+    `corrupt_data` on lists of patches / centres, ChamferL2 as `rec_loss`."""
+    ref, got = m2ae_runs["reference"], m2ae_runs[mode]
+    assert ref["group_class"] == "models.Point_M2AE_modules"
+    assert got["group_class"] == ("models.Point_M2AE_modules" if mode == "install" else "pointdae_b200.group")
+    assert got["loss_class"] == ("pointdae_b200.chamfer_dist" if mode == "patched_loss" else "extensions.chamfer_dist")
+    assert got["rng_after"] == ref["rng_after"] and got["n_params_with_grad"] == ref["n_params_with_grad"]
+    assert abs(got["loss"] - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    assert abs(got["grad_abs_sum"] - ref["grad_abs_sum"]) <= 1e-6 * ref["grad_abs_sum"]
+    for a, b in zip(got["grad_probe"], ref["grad_probe"]):
+        assert abs(a - b) <= 1e-5 * max(abs(b), 1e-3)
