@@ -67,12 +67,23 @@ if MODEL == "m2ae":
                    num_groups=[128, 64, 16], encoder_depths=[1, 1, 1], encoder_dims=[24, 48, 96],
                    local_radius=[0.32, 0.64, 1.28], decoder_depths=[1, 1], decoder_dims=[96, 48], decoder_up_blocks=[1, 1],
                    drop_path_rate=0.1, num_heads=2)
+if MODEL == "masksurf":
+    # models/MaskSurf.py:342-488 (cfgs/pretrain_MaskSurf.yaml): xyz + normal input, the normal-aware `Group`, and
+    # ChamferDistanceL2_withnormal, which reuses the Chamfer match indices to compare normals
+    cfg.NAME, cfg.corrupt_type, cfg.loss = "MaskSurf", ["clean"], "cdl2normal"
 random.seed(0), np.random.seed(0), torch.manual_seed(0)
 model = models.build_model_from_cfg(cfg)
-pts = torch.from_numpy(synth.clouds(3 if MODEL == "transformer" else 2, 1024, seed=9))
+pts = torch.from_numpy(synth.clouds(2 if MODEL == "dgcnn" else 3, 1024, seed=9))
+if MODEL == "masksurf":
+    nrm = torch.nn.functional.normalize(torch.randn(pts.shape, generator=torch.Generator().manual_seed(3)), dim=2)
+    pts = torch.cat([pts, nrm], dim=2)
 random.seed(1), np.random.seed(1), torch.manual_seed(1)
 model.train()
-loss = model(pts, pts)[0]
+if MODEL == "masksurf":
+    loss_xyz, loss_normal = model(pts)  # forward(pts, vis=False) -> (Chamfer term, normal term)
+    loss = loss_xyz + loss_normal
+else:
+    loss = model(pts, pts)[0]
 loss.backward()
 grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
 first = sorted(grads)[0]

@@ -45,6 +45,11 @@ def m2ae_runs():
     return _run_all("m2ae")
 
 
+@pytest.fixture(scope="module")
+def masksurf_runs():
+    return _run_all("masksurf")
+
+
 def test_install_alone_is_bit_identical_inside_the_model(runs):
     ref, got = runs["reference"], runs["install"]
     assert got["group_class"] == "models.PointCAE_transformer" and got["loss_class"] == "extensions.chamfer_dist"
@@ -88,6 +93,21 @@ def test_m2ae_model_runs_unchanged_on_the_drop_in(m2ae_runs, mode):
     ref, got = m2ae_runs["reference"], m2ae_runs[mode]
     assert ref["group_class"] == "models.Point_M2AE_modules"
     assert got["group_class"] == ("models.Point_M2AE_modules" if mode == "install" else "pointdae_b200.group")
+    assert got["loss_class"] == ("pointdae_b200.chamfer_dist" if mode == "patched_loss" else "extensions.chamfer_dist")
+    assert got["rng_after"] == ref["rng_after"] and got["n_params_with_grad"] == ref["n_params_with_grad"]
+    assert abs(got["loss"] - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    assert abs(got["grad_abs_sum"] - ref["grad_abs_sum"]) <= 1e-6 * ref["grad_abs_sum"]
+    for a, b in zip(got["grad_probe"], ref["grad_probe"]):
+        assert abs(a - b) <= 1e-5 * max(abs(b), 1e-3)
+
+
+@pytest.mark.parametrize("mode", ["install", "patched", "patched_loss"])
+def test_masksurf_model_runs_unchanged_on_the_drop_in(masksurf_runs, mode):
+    """`MaskSurf` (models/MaskSurf.py:342-488, cfgs/pretrain_MaskSurf.yaml): xyz + normal input through the normal-aware
+    `Group`, loss `ChamferDistanceL2_withnormal` (normals compared through the Chamfer match indices)."""
+    ref, got = masksurf_runs["reference"], masksurf_runs[mode]
+    assert ref["group_class"] == "models.MaskSurf"
+    assert got["group_class"] == ("models.MaskSurf" if mode == "install" else "pointdae_b200.group")
     assert got["loss_class"] == ("pointdae_b200.chamfer_dist" if mode == "patched_loss" else "extensions.chamfer_dist")
     assert got["rng_after"] == ref["rng_after"] and got["n_params_with_grad"] == ref["n_params_with_grad"]
     assert abs(got["loss"] - ref["loss"]) <= 1e-6 * abs(ref["loss"])
