@@ -71,9 +71,13 @@ if MODEL == "masksurf":
     # models/MaskSurf.py:342-488 (cfgs/pretrain_MaskSurf.yaml): xyz + normal input, the normal-aware `Group`, and
     # ChamferDistanceL2_withnormal, which reuses the Chamfer match indices to compare normals
     cfg.NAME, cfg.corrupt_type, cfg.loss = "MaskSurf", ["clean"], "cdl2normal"
+if MODEL == "pointnetv2":
+    # models/PointCAE_pointnetv2.py:62-174 (cfgs/pretrain_PointCAE_affine_r3_dropout_local_4xlonger.yaml): the PointNet++
+    # encoder of models/pointnetv2_util.py:320-325 over pointnet2_ops.pointnet2_modules (un-vendored: drop-in modes only)
+    cfg = EasyDict(NAME="Point_CAE_PointNetv2", corrupt_type=["dropout_patch_pointmae"], num_group=64, loss="cdl2")
 random.seed(0), np.random.seed(0), torch.manual_seed(0)
 model = models.build_model_from_cfg(cfg)
-pts = torch.from_numpy(synth.clouds(2 if MODEL == "dgcnn" else 3, 1024, seed=9))
+pts = torch.from_numpy(synth.clouds(2 if MODEL in ("dgcnn", "pointnetv2") else 3, 1024, seed=9))
 if MODEL == "masksurf":
     nrm = torch.nn.functional.normalize(torch.randn(pts.shape, generator=torch.Generator().manual_seed(3)), dim=2)
     pts = torch.cat([pts, nrm], dim=2)

@@ -19,9 +19,9 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), 
 MODES = ("reference", "install", "patched", "patched_loss")
 
 
-def _run_all(model):
+def _run_all(model, modes=MODES):
     procs = {m: subprocess.Popen([sys.executable, os.path.join(HERE, "_ref_model_probe.py"), m, REF, model], cwd="/tmp",
-                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for m in MODES}
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for m in modes}
     out = {}
     for m, p in procs.items():
         stdout, stderr = p.communicate(timeout=900)
@@ -114,3 +114,17 @@ def test_masksurf_model_runs_unchanged_on_the_drop_in(masksurf_runs, mode):
     assert abs(got["grad_abs_sum"] - ref["grad_abs_sum"]) <= 1e-6 * ref["grad_abs_sum"]
     for a, b in zip(got["grad_probe"], ref["grad_probe"]):
         assert abs(a - b) <= 1e-5 * max(abs(b), 1e-3)
+
+
+def test_pointnet2_model_builds_and_trains_on_the_drop_in_modules():
+    """`Point_CAE_PointNetv2` (models/PointCAE_pointnetv2.py:62-174): its PointNet++ encoder is written against
+    `pointnet2_ops.pointnet2_modules` (un-vendored, so there is no reference run to compare with): on the drop-in's
+    PointnetSAModule the reference's model constructs, produces a finite loss and sends gradients to all three
+    set-abstraction levels; the fused loss node changes nothing."""
+    import math
+    runs = _run_all("pointnetv2", modes=("install", "patched_loss"))
+    a, b = runs["install"], runs["patched_loss"]
+    assert math.isfinite(a["loss"]) and a["loss"] > 0 and a["n_params_with_grad"] == 33 and a["grad_abs_sum"] > 0
+    assert b["loss_class"] == "pointdae_b200.chamfer_dist" and a["loss_class"] == "extensions.chamfer_dist"
+    assert abs(a["loss"] - b["loss"]) <= 1e-6 * a["loss"] and abs(a["grad_abs_sum"] - b["grad_abs_sum"]) <= 1e-6 * a["grad_abs_sum"]
+    assert a["rng_after"] == b["rng_after"]
