@@ -75,6 +75,8 @@ if MODEL == "pointnetv2":
     # models/PointCAE_pointnetv2.py:62-174 (cfgs/pretrain_PointCAE_affine_r3_dropout_local_4xlonger.yaml): the PointNet++
     # encoder of models/pointnetv2_util.py:320-325 over pointnet2_ops.pointnet2_modules (un-vendored: drop-in modes only)
     cfg = EasyDict(NAME="Point_CAE_PointNetv2", corrupt_type=["dropout_patch_pointmae"], num_group=64, loss="cdl2")
+if os.environ.get("PDAE_PROBE_NAME"):  # sweep helper: same configuration, another registered class of the same family
+    cfg.NAME = os.environ["PDAE_PROBE_NAME"]
 random.seed(0), np.random.seed(0), torch.manual_seed(0)
 model = models.build_model_from_cfg(cfg)
 pts = torch.from_numpy(synth.clouds(2 if MODEL in ("dgcnn", "pointnetv2") else 3, 1024, seed=9))
