@@ -86,8 +86,11 @@ if MODEL == "masksurf":
 random.seed(1), np.random.seed(1), torch.manual_seed(1)
 model.train()
 if MODEL == "masksurf":
-    loss_xyz, loss_normal = model(pts)  # forward(pts, vis=False) -> (Chamfer term, normal term)
-    loss = loss_xyz + loss_normal
+    try:
+        out = model(pts)  # MaskSurf.forward(pts, vis=False) -> (Chamfer term, normal term)
+    except TypeError:
+        out = model(pts, pts)  # the v2 classes take (corrupted_pts, pts)
+    loss = sum(o for o in out if torch.is_tensor(o) and o.dim() == 0 and o.requires_grad)
 else:
     loss = model(pts, pts)[0]
 loss.backward()

@@ -19,8 +19,9 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), 
 MODES = ("reference", "install", "patched", "patched_loss")
 
 
-def _run_all(model, modes=MODES):
-    procs = {m: subprocess.Popen([sys.executable, os.path.join(HERE, "_ref_model_probe.py"), m, REF, model], cwd="/tmp",
+def _run_all(model, modes=MODES, name=None):
+    env = dict(os.environ, **({"PDAE_PROBE_NAME": name} if name else {}))
+    procs = {m: subprocess.Popen([sys.executable, os.path.join(HERE, "_ref_model_probe.py"), m, REF, model], cwd="/tmp", env=env,
                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for m in modes}
     out = {}
     for m, p in procs.items():
@@ -128,3 +129,14 @@ def test_pointnet2_model_builds_and_trains_on_the_drop_in_modules():
     assert b["loss_class"] == "pointdae_b200.chamfer_dist" and a["loss_class"] == "extensions.chamfer_dist"
     assert abs(a["loss"] - b["loss"]) <= 1e-6 * a["loss"] and abs(a["grad_abs_sum"] - b["grad_abs_sum"]) <= 1e-6 * a["grad_abs_sum"]
     assert a["rng_after"] == b["rng_after"]
+
+
+def test_masksurf_v2_attribute_group_inside_the_model():
+    """`MaskSurf_v2_local_point_normal` (models/MaskSurf_v2.py:1380-1594): the attribute-carrying `Group` (xyz + extra
+    channels -> patches, patch attributes, centres, centre attributes) inside a real model."""
+    runs = _run_all("masksurf", modes=("reference", "patched_loss"), name="MaskSurf_v2_local_point_normal")
+    ref, got = runs["reference"], runs["patched_loss"]
+    assert ref["group_class"] == "models.MaskSurf_v2" and got["group_class"] == "pointdae_b200.group"
+    assert got["loss_class"] == "pointdae_b200.chamfer_dist" and got["rng_after"] == ref["rng_after"]
+    assert abs(got["loss"] - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    assert abs(got["grad_abs_sum"] - ref["grad_abs_sum"]) <= 1e-6 * ref["grad_abs_sum"]
