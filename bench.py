@@ -480,7 +480,7 @@ def run_ours(args):
         achieved = pairs * 6 * 2 / (cham_ms * 1e-3) / 1e12
         roofline = {
             "kernel": "Chamfer forward = fill_keys + chamfer_min_kernel<4,128,1,SYM> (512-row x 1024-column units) + "
-                      "unpack_keys + chamfer_col_recover_list_kernel",
+                      "chamfer_col_recover_list_kernel (row-key unpack fused)",
             "bound": "fp32-fma-pipe", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops, "traffic": 8.44e6,
             "note": "achieved = ALGORITHMIC 2*B*N*N pairs x 6 FMA-pipe lane-ops x 2 / CUDA-event time per forward "
