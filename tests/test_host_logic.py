@@ -163,3 +163,30 @@ def test_get_graph_feature_offsets_a_supplied_idx_in_place_and_keeps_backward_al
     assert torch.equal(idx, before + torch.arange(2).view(-1, 1, 1) * 7)
     feat.sum().backward()
     assert x.grad.shape == x.shape
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 7])
+def test_column_chunks_merge_through_packed_keys_to_the_unsplit_result(chunks):
+    """The rule behind the column-split Chamfer units and the reference-set sharding: per-chunk (min distance, lowest
+    index) pairs packed as (float bits << 32 | global index) and reduced with an unsigned MIN give the unsplit
+    (distance, lowest argmin) -- including exact ties that straddle chunk boundaries."""
+    import numpy as np
+    from oracle import cpu as oracle
+    from pointdae_b200 import synth
+    a = synth.prediction(synth.clouds(2, 900, seed=4), seed=4)
+    c = synth.clouds(2, 1300, seed=5)
+    c[:, 1200] = c[:, 7]      # duplicates in different chunks: the lower index must survive the merge
+    c[:, 650] = c[:, 7]
+    a[:, 3] = c[:, 7]         # a query that hits the tie exactly
+    want_d, _, want_i, _ = oracle.chamfer_fwd(a, c)
+    bounds = np.linspace(0, c.shape[1], chunks + 1).astype(int)
+    merged = np.full(want_d.shape, np.iinfo(np.uint64).max, dtype=np.uint64)
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        d, _, i, _ = oracle.chamfer_fwd(a, np.ascontiguousarray(c[:, lo:hi]))
+        keys = (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (i.astype(np.uint64) + np.uint64(lo))
+        merged = np.minimum(merged, keys)
+    got_d = (merged >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    got_i = (merged & np.uint64(0xffffffff)).astype(np.int32)
+    np.testing.assert_array_equal(got_d, want_d)
+    np.testing.assert_array_equal(got_i, want_i)
+    assert want_i[0, 3] == 7 and want_d[0, 3] == 0.0
