@@ -258,3 +258,15 @@ def group_affine(xyz, num_group, group_size, mats):
     lib().pdae_oracle_group_affine(_p(xyz), _p(mats), b, n, int(num_group), int(group_size), t, _p(fps_idx), _p(center),
                                    _p(idx), _p(nb), _p(tnb), _p(tc))
     return nb, center, tnb, tc, idx
+
+
+def edge_conv_max(x, idx, weight, scale, shift, slope=0.2):
+    """models/dgcnn_util.py:114-126, one eval-mode EdgeConv layer: x (B,C,N), idx (B,N,k), weight (Co,2C),
+    BatchNorm folded to scale / shift (Co) -> (B,Co,N) = max_k LeakyReLU(BN(conv([x_j - x_i; x_i])))."""
+    x, idx, weight, scale, shift = _f32(x), _i64(idx), _f32(weight), _f32(scale), _f32(shift)
+    b, c, n = x.shape
+    k, co = idx.shape[2], weight.shape[0]
+    out = np.zeros((b, co, n), dtype=np.float32)
+    lib().pdae_oracle_edge_conv_max.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_float] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    lib().pdae_oracle_edge_conv_max(_p(x), _p(idx), _p(weight), _p(scale), _p(shift), float(slope), b, c, n, k, co, _p(out))
+    return out

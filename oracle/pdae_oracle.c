@@ -588,3 +588,37 @@ void pdae_oracle_group_affine(const float *xyz, const float *mats, int b, int n,
     }
   }
 }
+
+/* ============================================================================================
+ * "next" rows, oracle only so far: one EdgeConv layer of the DGCNN encoder in eval mode.
+ * reference: models/dgcnn_util.py:114-126 (`get_graph_feature` -> Conv2d(2C, Co, 1, bias=False) -> BatchNorm2d
+ * (running statistics) -> LeakyReLU(0.2) -> max over the k neighbours).  x (b,c,n), idx (b,n,k) per-cloud,
+ * w (co, 2c) = the convolution weight, scale / shift (co) = BatchNorm folded to y*scale + shift.
+ * The convolution is a library call in the reference (summation order unspecified): this restatement accumulates in
+ * double and rounds once, the centre both the reference and a kernel must stay within fp32 rounding of.
+ * ========================================================================================== */
+void pdae_oracle_edge_conv_max(const float *x, const int64_t *idx, const float *w, const float *scale,
+                               const float *shift, float slope, int b, int c, int n, int k, int co, float *out) {
+#pragma omp parallel for schedule(static)
+  for (long long bi_i = 0; bi_i < (long long)b * n; ++bi_i) {
+    const int bi = (int)(bi_i / n), i = (int)(bi_i % n);
+    const float *X = x + (size_t)bi * c * n;
+    for (int o = 0; o < co; ++o) {
+      const float *W1 = w + (size_t)o * 2 * c, *W2 = W1 + c;
+      float best = -INFINITY;
+      for (int j = 0; j < k; ++j) {
+        const int64_t nb = idx[((size_t)bi * n + i) * k + j];
+        double acc = 0.0;
+        for (int ch = 0; ch < c; ++ch) {
+          const float xi = X[(size_t)ch * n + i];
+          const float d = X[(size_t)ch * n + nb] - xi; /* the feature tensor holds this fp32 difference */
+          acc += (double)W1[ch] * (double)d + (double)W2[ch] * (double)xi;
+        }
+        float y = (float)acc * scale[o] + shift[o];
+        y = y >= 0.0f ? y : y * slope;
+        if (y > best) best = y;
+      }
+      out[((size_t)bi * co + o) * n + i] = best;
+    }
+  }
+}
