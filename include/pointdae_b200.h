@@ -223,6 +223,18 @@ int pdae_group_affine_f32(const float *xyz, const float *center, const float *ma
                           int64_t *idx, float *neighborhood, float *t_neighborhood, float *t_center,
                           pdae_stream_t stream);
 
+/* ---- EdgeConv, eval mode (first stage, NOT YET VERIFIED ON A GPU) ----------------------
+ * replaces: the tail of one EdgeConv layer of `dgcnn_encoder`, models/dgcnn_util.py:114-126: Conv2d(2C,Co,1) over the
+ *           graph feature -> BatchNorm2d (running statistics) -> LeakyReLU -> max over the k neighbours, once the
+ *           convolution has been split into p = x^T W1^T and q = x^T (W2 - W1)^T (two GEMMs, caller's).
+ * p, q (b,n,co) row-major, idx (b,n,k) int64 per-cloud neighbour indices, scale / shift (co) = BatchNorm folded to
+ * y*scale + shift, slope = LeakyReLU negative slope.
+ * out (b,co,n): out[b][o][i] = act(scale[o] * (ext_j p[b][idx[b][i][j]][o] + q[b][i][o]) + shift[o]),
+ * ext = max where scale[o] >= 0, min where scale[o] < 0.                                                        */
+int pdae_edge_gather_extremum_f32(const float *p, const float *q, const int64_t *idx, const float *scale,
+                                  const float *shift, float slope, int b, int n, int k, int co, float *out,
+                                  pdae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

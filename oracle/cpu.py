@@ -270,3 +270,14 @@ def edge_conv_max(x, idx, weight, scale, shift, slope=0.2):
     lib().pdae_oracle_edge_conv_max.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_float] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
     lib().pdae_oracle_edge_conv_max(_p(x), _p(idx), _p(weight), _p(scale), _p(shift), float(slope), b, c, n, k, co, _p(out))
     return out
+
+
+def edge_gather_extremum(p, q, idx, scale, shift, slope=0.2):
+    """The gather half of edge_conv_max in the kernel's operation order: p, q (B,N,Co), idx (B,N,k) -> (B,Co,N)."""
+    p, q, idx, scale, shift = _f32(p), _f32(q), _i64(idx), _f32(scale), _f32(shift)
+    b, n, co = p.shape
+    k = idx.shape[2]
+    out = np.zeros((b, co, n), dtype=np.float32)
+    lib().pdae_oracle_edge_gather_extremum.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_float] + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    lib().pdae_oracle_edge_gather_extremum(_p(p), _p(q), _p(idx), _p(scale), _p(shift), float(slope), b, n, k, co, _p(out))
+    return out

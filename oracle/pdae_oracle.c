@@ -622,3 +622,23 @@ void pdae_oracle_edge_conv_max(const float *x, const int64_t *idx, const float *
     }
   }
 }
+
+/* the gather half alone, with the kernel's operation order (exact): p, q (b,n,co) row-major as the two GEMMs deliver
+ * them; out[b][o][i] = act(fma(scale[o], ext_j p[idx][o] + q[i][o], shift[o])), ext = max / min by the sign of scale. */
+void pdae_oracle_edge_gather_extremum(const float *p, const float *q, const int64_t *idx, const float *scale,
+                                      const float *shift, float slope, int b, int n, int k, int co, float *out) {
+  for (int bi = 0; bi < b; ++bi)
+    for (int i = 0; i < n; ++i)
+      for (int o = 0; o < co; ++o) {
+        const int want_max = scale[o] >= 0.0f;
+        float ext = want_max ? -INFINITY : INFINITY;
+        for (int j = 0; j < k; ++j) {
+          const float v = p[((size_t)bi * n + idx[((size_t)bi * n + i) * k + j]) * co + o];
+          ext = want_max ? (v > ext ? v : ext) : (v < ext ? v : ext);
+        }
+        const float v = ext + q[((size_t)bi * n + i) * co + o];
+        float y = fmaf(scale[o], v, shift[o]);
+        y = y >= 0.0f ? y : y * slope;
+        out[((size_t)bi * co + o) * n + i] = y;
+      }
+}

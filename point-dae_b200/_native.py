@@ -57,6 +57,7 @@ SIGNATURES = {
     "pdae_three_interpolate_grad_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_affine_points_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_group_affine_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pdae_edge_gather_extremum_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

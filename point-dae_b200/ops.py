@@ -594,6 +594,40 @@ class GraphFeatureFunction(torch.autograd.Function):
         return _graph_feature_bwd(g, idx, c, n), None
 
 
+# ---------------------------------------------------------------- EdgeConv, eval mode (stage 1)
+def edge_gather_extremum(p, q, idx, scale, shift, slope=0.2):
+    """p, q (B,N,Co) f32 contiguous, idx (B,N,k) int64, scale / shift (Co) -> (B,Co,N):
+    act(scale * (max|min_j p[idx] + q) + shift), max where scale >= 0, min where scale < 0 (pdae_edge_gather_extremum_f32)."""
+    _require_cuda(p, "edge_conv")
+    for t_, name in ((p, "p"), (q, "q"), (scale, "scale"), (shift, "shift")):
+        _require_f32_contig(t_, name)
+    if idx.dtype != torch.int64 or not idx.is_contiguous():
+        raise RuntimeError("idx must be a contiguous int64 tensor")
+    b, n, co = p.shape
+    k = idx.size(2)
+    if tuple(q.shape) != (b, n, co) or tuple(idx.shape[:2]) != (b, n) or scale.numel() != co or shift.numel() != co:
+        raise RuntimeError("edge_gather_extremum: shapes do not match")
+    with _on(p.device):
+        out = torch.empty((b, co, n), dtype=torch.float32, device=p.device)
+        rc = _native.lib().pdae_edge_gather_extremum_f32(p.data_ptr(), q.data_ptr(), idx.data_ptr(), scale.data_ptr(),
+                                                         shift.data_ptr(), float(slope), b, n, k, co, out.data_ptr(), _stream())
+    _native.check(rc, "pdae_edge_gather_extremum_f32")
+    return out
+
+
+def edge_conv_max(x, idx, weight, scale, shift, slope=0.2):
+    """One eval-mode EdgeConv layer (models/dgcnn_util.py:114-126) without the k-replicated tensors: x (B,C,N), idx (B,N,k)
+    per-cloud int64, weight (Co,2C) of the 1x1 convolution, BatchNorm folded to scale / shift (Co) -> (B,Co,N).
+    Two library GEMMs (x^T W1^T, x^T (W2 - W1)^T) + the gather-extremum kernel.  No gradient (eval only)."""
+    c = x.size(1)
+    with torch.no_grad():
+        xt = x.detach().float().transpose(1, 2)
+        w1, w2 = weight[:, :c].float(), weight[:, c:].float()
+        p = torch.matmul(xt, w1.t()).contiguous()
+        q = torch.matmul(xt, (w2 - w1).t()).contiguous()
+        return edge_gather_extremum(p, q, idx.contiguous(), scale.float().contiguous(), shift.float().contiguous(), slope)
+
+
 # ---------------------------------------------------------------------------- ball query / group
 def ball_query(new_xyz, xyz, radius, nsample):
     """pointnet2._ext.ball_query(new_xyz (B,M,3), xyz (B,N,3), radius, nsample) -> (B,M,nsample) int32."""

@@ -50,4 +50,7 @@ _native.lib().pdae_tune_chamfer_split(0)
 mats = torch.randn(3, 3, 3, 3)
 ops.affine_points(x, cen, mats)
 ops.group_affine(x, cen, 17, mats, want_idx=True); ops.group_affine(x, cen, 40, mats); ops.group_affine(x, cen, 80, mats[:, :0])
+# EdgeConv eval gather (row 4, stage 1): ragged channel / point counts
+ops.edge_gather_extremum(torch.randn(2, 70, 300, device=dev), torch.randn(2, 70, 300, device=dev),
+                         torch.randint(0, 70, (2, 70, 9), device=dev), torch.randn(300, device=dev), torch.randn(300, device=dev))
 torch.cuda.synchronize(); print("sanitize smoke done")

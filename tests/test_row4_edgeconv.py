@@ -37,3 +37,42 @@ def test_two_gemms_plus_gather_extremum_equal_the_layer(layer):
     y = np.where(y >= 0, y, 0.2 * y).astype(np.float32)
     scale = float(np.abs(g["out"]).max())
     assert np.allclose(y, g["out"], rtol=1e-5, atol=2e-5 * scale), float(np.abs(y - g["out"]).max())
+
+
+def test_gather_half_oracle_composes_to_the_layer():
+    g = {k.split("/", 1)[1]: GOLD[k] for k in GOLD.files if k.startswith("l2/")}
+    x, w = g["x"], g["weight"]
+    c = x.shape[1]
+    p = np.einsum("bcn,oc->bno", x, w[:, :c]).astype(np.float32)
+    q = np.einsum("bcn,oc->bno", x, w[:, c:] - w[:, :c]).astype(np.float32)
+    got = oracle.edge_gather_extremum(p, q, g["idx"], g["scale"], g["shift"], 0.2)
+    scale = float(np.abs(g["out"]).max())
+    assert np.allclose(got, g["out"], rtol=1e-5, atol=2e-5 * scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,n,k,co", [(2, 200, 20, 64), (1, 33, 5, 7), (3, 1024, 20, 256), (2, 97, 9, 300), (1, 2048, 20, 128)])
+def test_gpu_gather_extremum_kernel_is_bit_exact_with_its_oracle(b, n, k, co):
+    import torch
+    from pointdae_b200 import ops
+    rng = np.random.default_rng(n + co)
+    p, q = rng.standard_normal((b, n, co)).astype(np.float32), rng.standard_normal((b, n, co)).astype(np.float32)
+    idx = rng.integers(0, n, size=(b, n, k)).astype(np.int64)
+    scale, shift = rng.standard_normal(co).astype(np.float32), rng.standard_normal(co).astype(np.float32)
+    scale[0] = 0.0
+    want = oracle.edge_gather_extremum(p, q, idx, scale, shift, 0.2)
+    dev = "cuda:0"
+    got = ops.edge_gather_extremum(*(torch.from_numpy(a).to(dev) for a in (p, q, idx, scale, shift)), 0.2)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layer", range(4))
+def test_gpu_edge_conv_layer_matches_the_reference_encoder(layer):
+    import torch
+    from pointdae_b200 import ops
+    g = {k.split("/", 1)[1]: GOLD[k] for k in GOLD.files if k.startswith("l%d/" % layer)}
+    dev = "cuda:0"
+    got = ops.edge_conv_max(*(torch.from_numpy(g[k]).to(dev) for k in ("x", "idx", "weight", "scale", "shift")), 0.2)
+    scale = float(np.abs(g["out"]).max())
+    assert np.allclose(got.cpu().numpy(), g["out"], rtol=1e-5, atol=2e-5 * scale)
