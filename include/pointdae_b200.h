@@ -223,7 +223,7 @@ int pdae_group_affine_f32(const float *xyz, const float *center, const float *ma
                           int64_t *idx, float *neighborhood, float *t_neighborhood, float *t_center,
                           pdae_stream_t stream);
 
-/* ---- EdgeConv, eval mode (first stage, NOT YET VERIFIED ON A GPU) ----------------------
+/* ---- EdgeConv, eval mode (first stage: parity verified on B200, not yet timed) ----------------------
  * replaces: the tail of one EdgeConv layer of `dgcnn_encoder`, models/dgcnn_util.py:114-126: Conv2d(2C,Co,1) over the
  *           graph feature -> BatchNorm2d (running statistics) -> LeakyReLU -> max over the k neighbours, once the
  *           convolution has been split into p = x^T W1^T and q = x^T (W2 - W1)^T (two GEMMs, caller's).
