@@ -81,6 +81,13 @@ def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentat
             continue
         for fn in ("knn", "get_graph_feature"):
             rebind(mod, fn, getattr(dgcnn_util, fn), name)
+    try:  # the encoder's forward: fused EdgeConv layers in eval mode, the reference's own sequence otherwise
+        enc = getattr(importlib.import_module("models.dgcnn_util"), "dgcnn_encoder", None)
+        if enc is not None and enc.forward is not dgcnn_util.dgcnn_encoder_forward:
+            enc.forward = dgcnn_util.dgcnn_encoder_forward
+            patched.append("models.dgcnn_util.dgcnn_encoder.forward")
+    except Exception:
+        pass
     try:
         rebind(importlib.import_module("utils.misc"), "fps", group.fps, "utils.misc")
     except Exception:

@@ -109,7 +109,12 @@ class GraphFeatureFunction(torch.autograd.Function):  # same contract as ops.Gra
         return _graph_feature_bwd(grad.permute(0, 2, 3, 1).contiguous().float(), idx, c, n), None
 
 
-NAMES = ("feat_knn", "_graph_feature_fwd", "_graph_feature_bwd", "GraphFeatureFunction", "furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "affine_points", "group_affine",
+def edge_conv_max(x, idx, weight, scale, shift, slope=0.2):
+    return _t(oracle.edge_conv_max(x.detach().float().contiguous().numpy(), idx.numpy(), weight.detach().float().contiguous().numpy(),
+                                   scale.detach().float().numpy(), shift.detach().float().numpy(), float(slope)))
+
+
+NAMES = ("edge_conv_max", "feat_knn", "_graph_feature_fwd", "_graph_feature_bwd", "GraphFeatureFunction", "furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "affine_points", "group_affine",
          "chamfer_forward", "chamfer_backward", "chamfer_mean_loss", "chamfer_loss_backward")
 EXT_NAMES = ("gather_points", "gather_points_grad", "ball_query", "group_points", "group_points_grad", "three_nn",
              "three_interpolate", "three_interpolate_grad")

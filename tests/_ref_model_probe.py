@@ -83,6 +83,19 @@ pts = torch.from_numpy(synth.clouds(2 if MODEL in ("dgcnn", "pointnetv2") else 3
 if MODEL == "masksurf":
     nrm = torch.nn.functional.normalize(torch.randn(pts.shape, generator=torch.Generator().manual_seed(3)), dim=2)
     pts = torch.cat([pts, nrm], dim=2)
+if MODEL == "dgcnn" and os.environ.get("PDAE_PROBE_EVAL"):
+    # feature extraction as the runners do it for the SVM evaluation: eval mode, no autograd, encoder only
+    with torch.no_grad():
+        for m in model.modules():  # trained-looking BatchNorm statistics, some negative scales
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.copy_(torch.randn_like(m.weight)), m.bias.copy_(0.3 * torch.randn_like(m.bias))
+                m.running_mean.copy_(0.2 * torch.randn_like(m.running_mean)), m.running_var.copy_(0.5 + torch.rand_like(m.running_var))
+        model.eval()
+        feat = model.dgcnn_encoder(pts.transpose(1, 2).contiguous())
+    print(json.dumps({"mode": MODE, "feature_shape": list(feat.shape), "feature_abs_sum": float(feat.double().abs().sum()),
+                      "feature_probe": [float(v) for v in feat.reshape(-1)[:6]], "feature_max": float(feat.abs().max()),
+                      "encoder_forward": type(model.dgcnn_encoder).forward.__module__}))
+    sys.exit(0)
 random.seed(1), np.random.seed(1), torch.manual_seed(1)
 model.train()
 if MODEL == "masksurf":
