@@ -9,6 +9,12 @@ shipped to the GPU box by gpurun).  Two extension modules result:
   oracle/_ref/chamfer/chamfer.so        <- extensions/chamfer_dist/{chamfer.cu,chamfer_cuda.cpp}
   oracle/_ref/pointnet2_ext/_ext.so     <- extensions/pointnet2/_ext_src/src/*.{cpp,cu}
 
+  oracle/_ref/pysrc/*.py                <- byte copies of the reference's own Python that sits directly on those
+                                           ops (extensions/pointnet2/pointnet2_utils.py), staged so the GPU box -- which has
+                                           no /root/reference -- can run the reference module over the real _ext.so and
+                                           produce GPU-made golden vectors (tests/golden/make_golden_pointnet2.py --gpu).
+                                           oracle/_ref/ is git-ignored: no reference source enters the history.
+
 They are the *live GPU oracle* (run on the gpurun box by tests/ and by
 tests/golden/make_golden.py) and the "reference CUDA recompiled for B200" speed comparator
 in bench.py's `ref_gpu` block.  They cannot run in the build container (no GPU).
@@ -60,7 +66,25 @@ def build(verbose=False):
         if not os.path.exists(so):
             _load(name, srcs, incs, bdir, verbose)
         built[name] = so
+    built.update(stage_python())
     return built
+
+
+PY_SOURCES = {"pointnet2_utils.py": ("extensions", "pointnet2", "pointnet2_utils.py")}
+
+
+def stage_python():
+    """Copies (never edits) the reference Python listed in PY_SOURCES into oracle/_ref/pysrc/ (git-ignored)."""
+    import shutil
+    out = {}
+    dst_dir = os.path.join(OUT, "pysrc")
+    os.makedirs(dst_dir, exist_ok=True)
+    for name, parts in PY_SOURCES.items():
+        src = os.path.join(REF, *parts)
+        if os.path.exists(src):
+            shutil.copyfile(src, os.path.join(dst_dir, name))
+            out["pysrc/" + name] = os.path.join(dst_dir, name)
+    return out
 
 
 if __name__ == "__main__":

@@ -56,11 +56,12 @@ def install(loss_modules=False):
     return True
 
 
-def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentation.models.dgcnn_util")):
+def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentation.models.dgcnn_util"), edgeconv=False):
     """Rebind the pure-torch hot functions that live inside the reference's own packages: knn / get_graph_feature,
     misc.fps, the corruptions executed inside forward, and every flavour of the `Group` patchifier.  Names that other
     reference modules imported from the defining module (`from .Point_M2AE_modules import *`,
-    `from datasets.corrupt_util_tensor import corrupt_data`) are rebound there too.  Returns what was rebound."""
+    `from datasets.corrupt_util_tensor import corrupt_data`) are rebound there too.  `edgeconv=True` (opt-in) also routes
+    `dgcnn_encoder.forward` through the fused EdgeConv layers.  Returns what was rebound."""
     from . import corrupt_util_tensor, dgcnn_util, group
 
     patched, replaced = [], {}
@@ -81,8 +82,8 @@ def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentat
             continue
         for fn in ("knn", "get_graph_feature"):
             rebind(mod, fn, getattr(dgcnn_util, fn), name)
-    try:  # the encoder's forward: fused EdgeConv layers in eval mode, the reference's own sequence otherwise
-        enc = getattr(importlib.import_module("models.dgcnn_util"), "dgcnn_encoder", None)
+    try:  # the encoder's forward: fused EdgeConv layers where a block qualifies, the reference's own sequence otherwise
+        enc = None if not edgeconv else getattr(importlib.import_module("models.dgcnn_util"), "dgcnn_encoder", None)
         if enc is not None and enc.forward is not dgcnn_util.dgcnn_encoder_forward:
             enc.forward = dgcnn_util.dgcnn_encoder_forward
             patched.append("models.dgcnn_util.dgcnn_encoder.forward")

@@ -6,7 +6,16 @@ Imports the REFERENCE's own `extensions/pointnet2/pointnet2_utils.py` from /root
 by the oracle-backed stand-in tests/_oracle_ext.py (`pytorch_utils` and `ipdb` stubbed: neither is touched on this
 path) and stores what its public functions and modules return on seeded inputs: furthest_point_sample,
 gather_operation (+grad), three_nn, three_interpolate (+grad), ball_query, grouping_operation (+grad), QueryAndGroup in
-five configurations (incl. the seeded `sample_uniformly` resampling), GroupAll."""
+five configurations (incl. the seeded `sample_uniformly` resampling), GroupAll.
+
+    python tests/golden/make_golden_pointnet2.py --gpu      (on the B200 box, via gpurun)
+
+writes gpurun_out/pointnet2_ref_gpu.npz (committed as tests/golden/pointnet2_ref_gpu.npz): the same cases through the
+same reference module, but over the reference's REAL compiled `_ext` (oracle/_ref/pointnet2_ext/_ext.so, its CUDA rebuilt
+unmodified for sm_100a) on cuda:0, the module text read from the copy oracle/build_ref.py stages under oracle/_ref/pysrc/
+(git-ignored; /root/reference does not exist on that box).  These are what the reference produces ON A GPU -- torch-CUDA
+turns `x /= python_scalar` into a multiply by the reciprocal (pointnet2_utils.py:350-351), which the CPU-made file
+cannot show (1 ulp on 2.5 % of the normalised offsets)."""
 import importlib.util
 import os
 import sys
@@ -24,15 +33,21 @@ import _pointnet2_cases as cases  # noqa: E402
 REF = "/root/reference/extensions/pointnet2/pointnet2_utils.py"
 
 
-def load_reference():
+REF_STAGED = os.path.join(ROOT, "oracle", "_ref", "pysrc", "pointnet2_utils.py")
+REF_EXT_SO = os.path.join(ROOT, "oracle", "_ref", "pointnet2_ext", "_ext.so")
+
+
+def load_reference(ext=None, path=None):
+    """The reference module, executed over `ext` as its `pointnet2._ext` (default: the oracle-backed stand-in)."""
+    ext = _oracle_ext if ext is None else ext
     sys.modules.setdefault("ipdb", types.ModuleType("ipdb"))
     sys.modules.setdefault("pytorch_utils", types.ModuleType("pytorch_utils"))
     pkg = types.ModuleType("pointnet2")
     pkg.__path__ = []
-    pkg._ext = _oracle_ext
+    pkg._ext = ext
     sys.modules["pointnet2"] = pkg
-    sys.modules["pointnet2._ext"] = _oracle_ext
-    spec = importlib.util.spec_from_file_location("ref_pointnet2_utils", REF)
+    sys.modules["pointnet2._ext"] = ext
+    spec = importlib.util.spec_from_file_location("ref_pointnet2_utils", path or (REF if os.path.exists(REF) else REF_STAGED))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
@@ -95,7 +110,31 @@ def run_all(p2u, dev="cpu"):
     return out
 
 
+def load_real_ext():
+    """the reference's compiled extension, rebuilt unmodified by oracle/build_ref.py"""
+    spec = importlib.util.spec_from_file_location("_ext", REF_EXT_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main_gpu():
+    assert torch.cuda.is_available(), "--gpu needs the B200 box"
+    out = run_all(load_reference(load_real_ext()), "cuda:0")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", "pointnet2_ref_gpu.npz")
+    np.savez_compressed(path, **out)
+    cpu = np.load(os.path.join(ROOT, "tests", "golden", "pointnet2_ref.npz"))
+    for k in sorted(out):
+        same = cpu[k].shape == out[k].shape and np.array_equal(cpu[k], out[k])
+        print("%-40s %s" % (k, "== cpu-made" if same else "differs from cpu-made: max |d| = %.3g on %d of %d"
+                            % (np.abs(cpu[k].astype(np.float64) - out[k]).max(), (cpu[k] != out[k]).sum(), out[k].size)))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
+    if "--gpu" in sys.argv:
+        return main_gpu()
     out = run_all(load_reference())
     for k, v in out.items():
         print(k, v.shape, v.dtype)

@@ -139,6 +139,32 @@ def test_knn_matches_oracle(b, r, q, dim, k, adv, transpose_mode):
     np.testing.assert_array_equal(D.cpu().numpy(), wd)  # sqrt of identical bits
 
 
+@pytest.mark.parametrize("b,r,q,k", [(128, 2048, 64, 32), (16, 8192, 512, 32), (1, 100000, 2048, 64), (64, 1024, 64, 32)])
+def test_knn_neighbour_sets_against_torch_cdist_topk(b, r, q, k):
+    """Independent cross-check (KNN_CUDA itself is not vendored: its parity is pinned only by the restated algorithm).
+    `torch.cdist` + `topk` on the same GPU rank by a differently-rounded distance, so the *sets* can differ only where
+    the k-th and (k+1)-th neighbours are within rounding noise of each other; every other row must agree exactly."""
+    xyz = synth.clouds(b, r, seed=900 + r)
+    ref = cu(xyz)
+    query = ref[:, torch.randperm(r, generator=torch.Generator().manual_seed(r))[:q].to(DEV)].contiguous()
+    D, I = knn_cuda.KNN(k=k, transpose_mode=True)(ref, query)
+    d_all = torch.cdist(query.double(), ref.double())                       # fp64: the arbiter
+    want = d_all.topk(k, dim=-1, largest=False)[1]
+    got_sorted, want_sorted = I.sort(dim=-1)[0], want.sort(dim=-1)[0]
+    bad = (got_sorted != want_sorted).any(dim=-1)                            # (b, q) rows whose sets differ
+    n_bad = int(bad.sum())
+    if n_bad:
+        # a differing row is legitimate only if the distances (fp64) of what we returned equal the true k smallest up to
+        # fp32 rounding of the squared distance (relative 3 ulp)
+        mine = d_all.gather(-1, I).sort(dim=-1)[0][bad]
+        true = d_all.topk(k, dim=-1, largest=False)[0].sort(dim=-1)[0][bad]
+        assert torch.allclose(mine, true, rtol=4e-7, atol=1e-9), float((mine - true).abs().max())
+    assert n_bad <= max(1, b * q // 2000), (n_bad, b * q)
+    # the returned distances are the Euclidean ones, ascending
+    assert torch.allclose(D.double(), d_all.gather(-1, I), rtol=1e-5, atol=1e-6)
+    assert bool((D[..., 1:] >= D[..., :-1]).all())
+
+
 @pytest.mark.parametrize("b,n,g,m", [(4, 1024, 64, 32), (2, 2048, 64, 32), (2, 1000, 33, 17), (1, 8192, 512, 32)])
 def test_group_matches_oracle(b, n, g, m):
     xyz = synth.adversarial(synth.clouds(b, n, seed=400 + n), seed=n)
