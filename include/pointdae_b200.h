@@ -74,6 +74,16 @@ int pdae_gather_grad_f32(const float *gout, const int *idx, int b, int c, int n,
 int pdae_knn_f32(const float *ref, const float *query, int b, int r, int q, int dim, int k, int out_kq, float *dist,
                  int64_t *idx, pdae_stream_t stream);
 
+/* Same searches with a caller-owned workspace (pdae_knn_workspace_bytes; may return 0): shapes with few queries and a
+ * long reference cloud (scene scale, e.g. 2048 queries x 100 000 points) are cut along the reference cloud into chunks
+ * that fill the GPU; each chunk's k best keys land in the workspace and a merge launch finishes.  Same results bit for
+ * bit; a NULL / too small workspace runs the unchunked form.                                                       */
+size_t pdae_knn_workspace_bytes(int b, int r, int q, int dim, int k);
+int pdae_knn_ws_f32(const float *ref, const float *query, int b, int r, int q, int dim, int k, int out_kq, float *dist,
+                    int64_t *idx, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+int pdae_group_ws_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
+                      float *neighborhood, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+
 /* fused Group.forward tail, models/PointCAE_transformer.py:76-85: kNN of `center` (b,g,3) in
  * xyz (b,n,3) + gather + centre-subtract.  idx (b,g,m) int64 (may be NULL),
  * neighborhood (b,g,m,3).                                                                     */
@@ -154,6 +164,11 @@ int pdae_tune_chamfer_variant(int v);
  * into (ids as the PDAE_CHAMFER_SPLIT environment variable: 0 = automatic, 1 = never split; nc < 0 only queries).
  * Returns the previous setting.  Results do not depend on it.  Not thread-safe.                                 */
 int pdae_tune_chamfer_split(int nc);
+/* kNN / Group (dim 3, k <= 64): impl 4 = multi-query warps + TMA tile prefetch (default), 3 = the first-generation
+ * kernel (kept for A/B measurements); qw queries per warp (1/2/4), nw warps per CTA (4/8), tile points per shared-memory
+ * tile, nz chunks along the reference cloud (needs the workspace), tma 0/1.  -1 = automatic.  Same results for every
+ * setting (tests/test_gpu_parity.py).  Environment: PDAE_KNN_IMPL, PDAE_KNN4_{QW,NW,TILE,NZ,TMA}.                    */
+int pdae_tune_knn(int impl, int qw, int nw, int tile, int nz, int tma);
 
 /* reference-set sharding (scene-scale clouds; new, no reference counterpart):
  * one direction, queries (b,nq,3) against the local slice refs (b,nr,3) whose first point has

@@ -27,6 +27,9 @@ SIGNATURES = {
     "pdae_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_gather_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_knn_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "pdae_knn_ws_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "pdae_group_ws_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "pdae_knn_keys_u64": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _ll, _vp, _vp]),
     "pdae_knn_merge_keys_u64": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -43,6 +46,7 @@ SIGNATURES = {
     "pdae_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_tune_chamfer_variant": (_i, [_i]),
     "pdae_tune_chamfer_split": (_i, [_i]),
+    "pdae_tune_knn": (_i, [_i, _i, _i, _i, _i, _i]),
     "pdae_chamfer_loss_workspace_bytes": (_sz, []),
     "pdae_chamfer_loss_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pdae_chamfer_loss_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -90,6 +90,15 @@ int knn3_points(const float *ref, const float *query, int b, int r, int q, int k
                 float *group, cudaStream_t st, uint64_t *keys = nullptr, uint32_t ref_offset = 0u, int raw_group = 0,
                 const GroupAffine *affine = nullptr);
 int knn3_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st);
+// knn4.cu: second-generation 3-D fast path (multi-query warps, segment-minima threshold, TMA tile prefetch, chunks along
+// the reference cloud through an optional caller-owned workspace); same contract and results as knn3.cu.
+int knn4_points(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
+                float *group, cudaStream_t st, uint64_t *keys = nullptr, uint32_t ref_offset = 0u, int raw_group = 0,
+                const GroupAffine *affine = nullptr, void *ws = nullptr, size_t ws_bytes = 0);
+int knn4_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st, void *ws = nullptr, size_t ws_bytes = 0);
+size_t knn4_workspace_bytes(int b, int r, int q, int k);
+// which generation serves dim-3, k <= 64 searches: 4 (default) or 3 (PDAE_KNN_IMPL=3, kept for A/B measurements)
+int knn3d_impl();
 
 }  // namespace pdae
 

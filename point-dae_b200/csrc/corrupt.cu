@@ -89,7 +89,8 @@ extern "C" int pdae_group_affine_f32(const float *xyz, const float *center, cons
   if (m <= 64) {
     // t == 0 still takes the fused branch (identity chain): point at any valid address, never dereferenced
     const GroupAffine aff{mats ? mats : xyz, t, t_neighborhood, t_center};
-    return knn3_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, st, nullptr, 0u, 0, &aff);
+    return knn3d_impl() == 3 ? knn3_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, st, nullptr, 0u, 0, &aff)
+                             : knn4_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, st, nullptr, 0u, 0, &aff);
   }
   const int rc = pdae_group_f32(xyz, center, b, n, g, m, idx, neighborhood, stream);
   if (rc) return rc;

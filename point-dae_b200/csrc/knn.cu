@@ -17,6 +17,8 @@
 // (distance, lower index first) order and the selection is exact and deterministic.
 #include "knn_select.cuh"
 
+#include <cstdlib>
+
 namespace pdae {
 
 struct KnnArgs {
@@ -171,6 +173,28 @@ static int knn_plan(KnnArgs &a, int b) {
 
 using namespace pdae;
 
+static int knn_dim3(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
+                    float *group, cudaStream_t st, uint64_t *keys, uint32_t off, int raw, void *ws, size_t ws_bytes) {
+  if (knn3d_impl() == 3) return knn3_points(ref, query, b, r, q, k, out_kq, dist, idx, group, st, keys, off, raw);
+  return knn4_points(ref, query, b, r, q, k, out_kq, dist, idx, group, st, keys, off, raw, nullptr, ws, ws_bytes);
+}
+
+extern "C" size_t pdae_knn_workspace_bytes(int b, int r, int q, int dim, int k) {
+  return dim == 3 ? knn4_workspace_bytes(b, r, q, k) : 0;
+}
+
+extern "C" int pdae_knn_ws_f32(const float *ref, const float *query, int b, int r, int q, int dim, int k, int out_kq,
+                               float *dist, int64_t *idx, void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
+  if (b < 0 || r < 0 || q < 0 || dim <= 0 || k <= 0) return PDAE_E_INVALID;
+  if (b == 0 || q == 0) return 0;
+  if (k > r || k > KNN_MAX_K) return PDAE_E_INVALID;
+  if (!ref || !query || (!dist && !idx)) return PDAE_E_INVALID;
+  if (dim == 3 && k <= 64)
+    return knn_dim3(ref, query, b, r, q, k, out_kq ? 1 : 0, dist, idx, nullptr, static_cast<cudaStream_t>(stream), nullptr, 0u,
+                    0, workspace, workspace_bytes);
+  return pdae_knn_f32(ref, query, b, r, q, dim, k, out_kq, dist, idx, stream);
+}
+
 extern "C" int pdae_knn_f32(const float *ref, const float *query, int b, int r, int q, int dim, int k, int out_kq,
                             float *dist, int64_t *idx, pdae_stream_t stream) {
   if (b < 0 || r < 0 || q < 0 || dim <= 0 || k <= 0) return PDAE_E_INVALID;
@@ -178,7 +202,7 @@ extern "C" int pdae_knn_f32(const float *ref, const float *query, int b, int r, 
   if (k > r || k > KNN_MAX_K) return PDAE_E_INVALID;
   if (!ref || !query || (!dist && !idx)) return PDAE_E_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dim == 3 && k <= 64) return knn3_points(ref, query, b, r, q, k, out_kq ? 1 : 0, dist, idx, nullptr, st);
+  if (dim == 3 && k <= 64) return knn_dim3(ref, query, b, r, q, k, out_kq ? 1 : 0, dist, idx, nullptr, st, nullptr, 0u, 0, nullptr, 0);
   KnnArgs a{ref, query, dist, idx, nullptr, nullptr, 0u, 0, r, q, dim, k, 0, 1, out_kq ? 1 : 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
@@ -229,7 +253,7 @@ extern "C" int pdae_knn_keys_u64(const float *ref_local, const float *query, int
     PDAE_CUDA_TRY(cudaMemsetAsync(keys, 0xff, static_cast<size_t>(b) * q * k * sizeof(uint64_t), st));
     return 0;
   }
-  if (dim == 3 && k <= 64) return knn3_points(ref_local, query, b, r_local, q, k, 0, nullptr, nullptr, nullptr, st, keys, off);
+  if (dim == 3 && k <= 64) return knn_dim3(ref_local, query, b, r_local, q, k, 0, nullptr, nullptr, nullptr, st, keys, off, 0, nullptr, 0);
   KnnArgs a{ref_local, query, nullptr, nullptr, nullptr, keys, off, 0, r_local, q, dim, k, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
@@ -251,12 +275,12 @@ extern "C" int pdae_knn_merge_keys_u64(const uint64_t *keys_all, int w, int b, i
 }
 
 static int group_impl(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx, float *neighborhood,
-                      bool raw, cudaStream_t st) {
+                      bool raw, cudaStream_t st, void *ws = nullptr, size_t ws_bytes = 0) {
   if (b < 0 || n < 0 || g < 0 || m <= 0) return PDAE_E_INVALID;
   if (b == 0 || g == 0) return 0;
   if (m > n || m > KNN_MAX_K) return PDAE_E_INVALID;
   if (!xyz || !center || !neighborhood) return PDAE_E_INVALID;
-  if (m <= 64) return knn3_points(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, st, nullptr, 0u, raw ? 1 : 0);
+  if (m <= 64) return knn_dim3(xyz, center, b, n, g, m, 0, nullptr, idx, neighborhood, st, nullptr, 0u, raw ? 1 : 0, ws, ws_bytes);
   KnnArgs a{xyz, center, nullptr, idx, neighborhood, nullptr, 0u, raw ? 1 : 0, n, g, 3, m, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;
@@ -266,6 +290,12 @@ static int group_impl(const float *xyz, const float *center, int b, int n, int g
 extern "C" int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
                               float *neighborhood, pdae_stream_t stream) {
   return group_impl(xyz, center, b, n, g, m, idx, neighborhood, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pdae_group_ws_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
+                                 float *neighborhood, void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
+  return group_impl(xyz, center, b, n, g, m, idx, neighborhood, false, static_cast<cudaStream_t>(stream), workspace,
+                    workspace_bytes);
 }
 
 extern "C" int pdae_group_gather_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
@@ -281,7 +311,7 @@ int pdae::feat_knn_generic(const float *x, int b, int c, int n, int k, int64_t *
   if (b == 0 || n == 0) return 0;
   if (k > n || k > KNN_MAX_K) return PDAE_E_INVALID;
   if (!x || !idx) return PDAE_E_INVALID;
-  if (c == 3 && k <= 64) return knn3_planar(x, b, n, k, idx, st);
+  if (c == 3 && k <= 64) return knn3d_impl() == 3 ? knn3_planar(x, b, n, k, idx, st) : knn4_planar(x, b, n, k, idx, st);
   KnnArgs a{x, nullptr, nullptr, idx, nullptr, nullptr, 0u, 0, n, n, c, k, 0, 1, 0};
   const int rc = knn_plan(a, b);
   if (rc) return rc;

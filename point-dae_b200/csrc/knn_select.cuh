@@ -129,6 +129,54 @@ __device__ __forceinline__ void warp_sort_multi_f32(float (&v)[E], int lane) {
   }
 }
 
+// ---- 32-bit network (knn4.cu) -------------------------------------------------------------------------------------------
+// Directions of the ten compare-exchange stages with k < 32 (k = 2,4,8,16; j = k/2..1) as one bit per stage: they depend
+// on the lane only, so a kernel computes the mask once and every stage costs one bit test instead of three logic ops.
+__device__ __forceinline__ uint32_t warp_sort_dir_mask(int lane) {
+  uint32_t m = 0;
+  int s = 0;
+#pragma unroll
+  for (int k = 2; k <= 16; k <<= 1)
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1, ++s) m |= ((((lane & j) == 0) == ((lane & k) == 0)) ? 1u : 0u) << s;
+  return m;
+}
+// ascending bitonic sort of E unsigned keys per lane (position e*32 + lane): SHFL + one predicated min/max pair per
+// element and stage.  Non-negative floats sort correctly through their bit patterns.
+template <int E>
+__device__ __forceinline__ void warp_sort_u32(uint32_t (&v)[E], int lane, uint32_t dir_mask) {
+  int s = 0;
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int pe = e ^ (j >> 5);
+          if (pe > e) {
+            const bool up = ((e * 32) & k) == 0;
+            const uint32_t lo = min(v[e], v[pe]), hi = max(v[e], v[pe]);
+            v[e] = up ? lo : hi;
+            v[pe] = up ? hi : lo;
+          }
+        }
+      } else {
+        const bool low_lane = (lane & j) == 0;
+        const bool keep_small = k < 32 ? ((dir_mask >> s) & 1u) != 0 : low_lane;  // k >= 32: flipped per element below
+        if (k < 32) ++s;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
+          const bool up = k < 32 ? true : ((e * 32) & k) == 0;  // compile time (k < 32: already folded into the mask)
+          const bool take_min = up ? keep_small : !keep_small;
+          v[e] = take_min ? min(v[e], o) : max(v[e], o);
+        }
+      }
+    }
+  }
+}
+
 // streaming warp-select state: ascending list of 32*NS keys (one per lane per slot), the running
 // k-th key `tau`, and the fill level of the warp's candidate queue (64 entries in shared memory).
 template <int NS>

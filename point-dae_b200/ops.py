@@ -51,6 +51,12 @@ def _require_i32_contig(t, name):
         raise RuntimeError("%s must be a contiguous tensor" % name)
 
 
+def _same_device(dev, **tensors):
+    for name, t in tensors.items():
+        if t is not None and t.device != dev:
+            raise RuntimeError("%s is on %s, expected %s" % (name, t.device, dev))
+
+
 def _dense_storage(t):
     """True when t's elements occupy exactly numel contiguous storage slots (any permutation)."""
     if t.numel() == 0 or t.is_contiguous():
@@ -142,10 +148,23 @@ def gather_points_grad(grad_out, idx, n):
 
 
 # ------------------------------------------------------------------------------------------ kNN
+def _knn_workspace(b, r, q, d, k, dev):
+    """Scratch for the chunked form of scene-scale searches (few queries, long reference cloud); None for every other
+    shape.  Comes from the caching allocator on the current stream, like every other workspace."""
+    nbytes = int(_native.lib().pdae_knn_workspace_bytes(b, r, q, d, k))
+    if nbytes <= 0:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
+
+
 def knn_points(ref, query, k, out_kq=False, want_dist=True):
     """ref (B,R,D), query (B,Q,D) f32 contiguous -> (dist (B,Q,k)|(B,k,Q) f32 or None, idx int64)."""
     _require_cuda(ref, "knn")
     _require_cuda(query, "knn")
+    _require_f32_contig(ref, "ref")      # raw pointers go to the kernel: no silent reinterpretation of strides / dtypes
+    _require_f32_contig(query, "query")
+    if query.device != ref.device:
+        raise RuntimeError("ref is on %s but query is on %s" % (ref.device, query.device))
     b, r, d = ref.shape
     q = query.size(1)
     k = int(k)
@@ -157,9 +176,11 @@ def knn_points(ref, query, k, out_kq=False, want_dist=True):
     with _on(ref.device):
         idx = torch.empty(shape, dtype=torch.int64, device=ref.device)
         dist = torch.empty(shape, dtype=torch.float32, device=ref.device) if want_dist else None
-        rc = _native.lib().pdae_knn_f32(ref.data_ptr(), query.data_ptr(), b, r, q, d, k, 1 if out_kq else 0,
-                                        dist.data_ptr() if want_dist else None, idx.data_ptr(), _stream())
-    _native.check(rc, "pdae_knn_f32")
+        ws, ws_bytes = _knn_workspace(b, r, q, d, k, ref.device)
+        rc = _native.lib().pdae_knn_ws_f32(ref.data_ptr(), query.data_ptr(), b, r, q, d, k, 1 if out_kq else 0,
+                                           dist.data_ptr() if want_dist else None, idx.data_ptr(),
+                                           ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+    _native.check(rc, "pdae_knn_ws_f32")
     return dist, idx
 
 
@@ -213,9 +234,14 @@ def group_points_knn(xyz, center, group_size, want_idx=True, subtract_center=Tru
     with _on(xyz.device):
         nb = torch.empty((b, g, m, 3), dtype=torch.float32, device=xyz.device)
         idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
-        fn = _native.lib().pdae_group_f32 if subtract_center else _native.lib().pdae_group_gather_f32
-        rc = fn(xyz.data_ptr(), center.data_ptr(), b, n, g, m, idx.data_ptr() if want_idx else None, nb.data_ptr(),
-                _stream())
+        if subtract_center:
+            ws, ws_bytes = _knn_workspace(b, n, g, 3, m, xyz.device)
+            rc = _native.lib().pdae_group_ws_f32(xyz.data_ptr(), center.data_ptr(), b, n, g, m,
+                                                 idx.data_ptr() if want_idx else None, nb.data_ptr(),
+                                                 ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+        else:
+            rc = _native.lib().pdae_group_gather_f32(xyz.data_ptr(), center.data_ptr(), b, n, g, m,
+                                                     idx.data_ptr() if want_idx else None, nb.data_ptr(), _stream())
     _native.check(rc, "pdae_group_f32")
     return nb, idx
 
@@ -371,6 +397,7 @@ def chamfer_forward(xyz1, xyz2, symmetric=True, scan_done=None):
     if xyz2.size(0) != b:
         raise RuntimeError("batch sizes differ: %d vs %d" % (b, xyz2.size(0)))
     dev = xyz1.device
+    _same_device(dev, xyz2=xyz2)
     with _on(dev):
         dist1 = torch.empty((b, n), dtype=torch.float32, device=dev)
         dist2 = torch.empty((b, m), dtype=torch.float32, device=dev)
@@ -411,6 +438,7 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
             raise RuntimeError("%s must be a float tensor that densely fills its storage" % name)
     if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
         raise RuntimeError("idx1 / idx2 must be the int tensors returned by chamfer.forward")
+    _same_device(dev, xyz2=xyz2, idx1=idx1, idx2=idx2, grad_dist1=grad_dist1, grad_dist2=grad_dist2)
     idx1, idx2 = idx1.contiguous(), idx2.contiguous()
     if tuple(idx1.shape) != (b, n) or tuple(idx2.shape) != (b, m):
         raise RuntimeError("idx1 / idx2 do not match the clouds' shapes")
@@ -461,6 +489,7 @@ def chamfer_loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, grad_loss, w1, w
             raise RuntimeError("%s must be a float tensor that densely fills its storage" % name)
     if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
         raise RuntimeError("idx1 / idx2 must be the int tensors returned by chamfer.forward")
+    _same_device(dev, xyz2=xyz2, idx1=idx1, idx2=idx2, dist1=dist1, dist2=dist2, grad_loss=grad_loss)
     grad_loss = grad_loss.reshape(-1)
     if grad_loss.numel() != 1 or not grad_loss.is_cuda:
         raise RuntimeError("grad_loss must be a one-element CUDA tensor")
