@@ -176,7 +176,9 @@ using namespace pdae;
 static int knn_dim3(const float *ref, const float *query, int b, int r, int q, int k, int out_kq, float *dist, int64_t *idx,
                     float *group, cudaStream_t st, uint64_t *keys, uint32_t off, int raw, void *ws, size_t ws_bytes) {
   if (knn3d_impl() == 3) return knn3_points(ref, query, b, r, q, k, out_kq, dist, idx, group, st, keys, off, raw);
-  return knn4_points(ref, query, b, r, q, k, out_kq, dist, idx, group, st, keys, off, raw, nullptr, ws, ws_bytes);
+  const int rc = knn4_points(ref, query, b, r, q, k, out_kq, dist, idx, group, st, keys, off, raw, nullptr, ws, ws_bytes);
+  // clouds beyond the 16-bit step numbers of one chunk (> 8 M points without a workspace): first-generation kernel
+  return rc == PDAE_E_UNSUPPORTED ? knn3_points(ref, query, b, r, q, k, out_kq, dist, idx, group, st, keys, off, raw) : rc;
 }
 
 extern "C" size_t pdae_knn_workspace_bytes(int b, int r, int q, int dim, int k) {

@@ -121,15 +121,19 @@ __device__ __forceinline__ void knn4_emit(const Knn4Args &a, const float *__rest
 template <int E>
 struct Knn4Smem {
   static constexpr int CAP = 32 * E;  // keys per query queue
-  static constexpr int LC = 4 * E + 4;  // lane-private step slots per query and tile (+1 slot that absorbs overflow)
-  static constexpr size_t per_query = static_cast<size_t>(CAP) * 8 + static_cast<size_t>(LC + 1) * 32;
-  static constexpr size_t per_warp_extra = static_cast<size_t>(LC) * 32 * 2;  // dense (step, lane) list of one query and tile
-  __host__ __device__ static constexpr size_t per_warp(int qw) { return qw * per_query + per_warp_extra; }
+  static constexpr int LC = 5 * E;    // lane-private step slots per query (+1 slot that absorbs overflow)
+  // a query's step lists ([LC + 1][32] u16) are dead once its dense list is built, and only then is its key queue
+  // ([CAP] u64) written: both live in one region
+  static constexpr size_t lists_bytes = static_cast<size_t>(LC + 1) * 64, queue_bytes = static_cast<size_t>(CAP) * 8;
+  static constexpr size_t per_query = lists_bytes > queue_bytes ? lists_bytes : queue_bytes;
+  static constexpr size_t dense_bytes = static_cast<size_t>(LC) * 32 * 4;  // per warp: (step, lane) entries of one query
+  // with TMA the dense lists sit in the landing zone (no copy is in flight while the rescan runs)
+  __host__ __device__ static constexpr size_t per_warp(int qw, int tma) { return qw * per_query + (tma ? 0 : dense_bytes); }
 };
 
 template <bool PLANAR, int E /*keys per lane in the final sort: 2 (k<=32) or 4 (k<=64)*/, int QW /*queries per warp*/,
           int NW /*warps per CTA*/, bool AFF>
-__global__ void __launch_bounds__(NW * 32) knn4_kernel(const Knn4Args a) {
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Knn4Args a) {
   constexpr int NT = NW * 32;
   constexpr int CAP = Knn4Smem<E>::CAP, LC = Knn4Smem<E>::LC;
   constexpr int NS = E / 2;  // fallback warp-select slots
@@ -140,10 +144,11 @@ __global__ void __launch_bounds__(NW * 32) knn4_kernel(const Knn4Args a) {
   float *stage = planes + 3 * T;                                                    // [3*T] landing zone (tma only)
   unsigned char *warp_area = reinterpret_cast<unsigned char *>(a.tma ? stage + 3 * T : stage);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  unsigned char *my_area = warp_area + static_cast<size_t>(warp) * Knn4Smem<E>::per_warp(QW);
-  uint64_t *queue = reinterpret_cast<uint64_t *>(my_area);                          // [QW][CAP]
-  unsigned char *lists = my_area + static_cast<size_t>(QW) * CAP * 8;               // [QW][LC + 1][32]
-  unsigned short *dense = reinterpret_cast<unsigned short *>(lists + static_cast<size_t>(QW) * (LC + 1) * 32);  // [32 * LC]
+  constexpr size_t PQ = Knn4Smem<E>::per_query;
+  unsigned char *my_area = warp_area + static_cast<size_t>(warp) * Knn4Smem<E>::per_warp(QW, a.tma);
+  // query qi: step lists = [LC + 1][32] u16 at my_area + qi * PQ, later overwritten by its key queue [CAP] u64
+  uint32_t *dense = a.tma ? reinterpret_cast<uint32_t *>(stage) + warp * (32 * LC)
+                          : reinterpret_cast<uint32_t *>(my_area + static_cast<size_t>(QW) * PQ);          // [32 * LC]
   const int cloud = blockIdx.y;
   const int r = a.r, q = a.q, k = a.k;
   const float *__restrict__ R = a.ref + static_cast<size_t>(cloud) * r * 3;
@@ -290,115 +295,139 @@ __global__ void __launch_bounds__(NW * 32) knn4_kernel(const Knn4Args a) {
   // inside the instruction cache.
   const uint32_t dir_mask = warp_sort_dir_mask(lane);
   float tau[QW];
-#pragma unroll 1
-  for (int qi = 0; qi < QW; ++qi) {
-    uint32_t sv[E];  // non-negative floats order like their bit patterns
+  {
+    uint32_t sv[QW][E];  // non-negative floats order like their bit patterns
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      float v = m[0][e];
+    for (int qi = 0; qi < QW; ++qi)
 #pragma unroll
-      for (int j = 1; j < QW; ++j) v = (j == qi) ? m[j][e] : v;
-      sv[e] = __float_as_uint(v);
+      for (int e = 0; e < E; ++e) sv[qi][e] = __float_as_uint(m[qi][e]);
+    warp_sort_u32_multi<QW, E>(sv, lane, dir_mask);
+#pragma unroll
+    for (int qi = 0; qi < QW; ++qi) {
+      uint32_t kth = sv[qi][0];
+#pragma unroll
+      for (int e = 1; e < E; ++e) kth = (e == kslot) ? sv[qi][e] : kth;
+      tau[qi] = __uint_as_float(__shfl_sync(FULL, kth, klane));
     }
-    warp_sort_u32<E>(sv, lane, dir_mask);
-    uint32_t kth = sv[0];
-#pragma unroll
-    for (int e = 1; e < E; ++e) kth = (e == kslot) ? sv[e] : kth;
-    const float t = __uint_as_float(__shfl_sync(FULL, kth, klane));
-#pragma unroll
-    for (int j = 0; j < QW; ++j)
-      if (j == qi) tau[j] = t;
   }
 
-  // ---- pass 2: steps holding a distance <= tau -> per-tile rescan -> key queues --------------------------------------------
-  int qn[QW];
-  bool ovf[QW];
+  // ---- pass 2: which 4-point steps hold a distance <= tau ------------------------------------------------------------------
+  // lp = shared-window address of the lane's next free slot.  The running step number is stored unconditionally; the
+  // address only advances when the step holds a candidate, so a miss is overwritten by the next step (no predicated
+  // store, no branch).  The lists span all tiles of the chunk: tau is final, so they stay ~k entries per query.
+  const uint32_t lbase_s = smem_u32(my_area) + 2 * lane;  // slot LC of a list only absorbs the stores of a full list
+  uint32_t lp[QW], lend[QW];
 #pragma unroll
-  for (int qi = 0; qi < QW; ++qi) qn[qi] = 0, ovf[qi] = !(tau[qi] < INF);
-  unsigned char *lbase = lists + lane;  // [QW][LC + 1][32]: slot LC only absorbs the stores of a full list
-  const uint32_t lbase_s = smem_u32(lbase);
-  uint32_t lend[QW];
-#pragma unroll
-  for (int qi = 0; qi < QW; ++qi) lend[qi] = lbase_s + (qi * (LC + 1) + LC) * 32;
-  const float4 *pl4 = reinterpret_cast<const float4 *>(planes);
-  const int T4 = T >> 2;
+  for (int qi = 0; qi < QW; ++qi) lp[qi] = lbase_s + qi * static_cast<uint32_t>(PQ), lend[qi] = lp[qi] + LC * 64;
   for (int i = 0; i < nt; ++i) {
     const int tl = t_begin + i;
     if (nt > 1) acquire(tl, i + 1 < nt ? tl + 1 : -1);
     const int nsteps = ((tile_n(tl) + 255) & ~255) >> 7;
-    // lp = shared-window address of the lane's next free slot.  The step number is stored unconditionally; the address
-    // only advances when the step holds a candidate, so a miss is overwritten by the next step (no predicated store).
-    uint32_t lp[QW];
-#pragma unroll
-    for (int qi = 0; qi < QW; ++qi) lp[qi] = lbase_s + qi * (LC + 1) * 32;
+    const int gs0 = i * (T >> 7);  // step number inside the chunk
 #pragma unroll 2
     for (int s = 0; s < nsteps; ++s) {
       const float4 X = px[s * 32], Y = py[s * 32], Z = pz[s * 32];
+      const int gs = gs0 + s;
 #pragma unroll
       for (int qi = 0; qi < QW; ++qi) {
         const float2 dA = pair2(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), qi);
         const float2 dB = pair2(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), qi);
         const float mm = min3(dA.x, dA.y, fminf(dB.x, dB.y));
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(lp[qi]), "r"(s) : "memory");
-        if (mm <= tau[qi]) lp[qi] = min(lp[qi] + 32u, lend[qi]);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(lp[qi]), "r"(gs) : "memory");
+        if (mm <= tau[qi]) lp[qi] = min(lp[qi] + 64u, lend[qi]);
       }
     }
-    // rescan: the recorded (lane, step) quads of the tile are compacted across the warp, so that every lane re-evaluates
-    // one quad per round (the lists are short and uneven: ~k entries over 32 lanes)
-    const uint32_t tbase = static_cast<uint32_t>(tl) * static_cast<uint32_t>(T);
+  }
+  __syncwarp();
+
+  // ---- rescan: the recorded quads, compacted across the warp, re-evaluated from global memory -------------------------------
+  // (one quad per lane and round; ~k quads per query, L2 hits).  Qualifying points go to the query's key queue.
+  int qn[QW];
+  bool ovf[QW];
+  const uint32_t chunk_quad0 = static_cast<uint32_t>(t_begin) * static_cast<uint32_t>(T >> 2);
+  const bool vec_ok = (r & 3) == 0 && (reinterpret_cast<uintptr_t>(a.ref) & 15) == 0;
 #pragma unroll 1
-    for (int qi = 0; qi < QW; ++qi) {
-      uint32_t lpq = lp[0];
-      float tq = tau[0], f0 = q0[0], f1 = q1[0], f2 = q2[0];
-      int n = qn[0];
-      bool dead = ovf[0];
+  for (int qi = 0; qi < QW; ++qi) {
+    uint32_t lpq = lp[0];
+    float tq = tau[0], f0 = q0[0], f1 = q1[0], f2 = q2[0];
 #pragma unroll
-      for (int j = 1; j < QW; ++j)
-        if (j == qi) lpq = lp[j], tq = tau[j], f0 = q0[j], f1 = q1[j], f2 = q2[j], n = qn[j], dead = ovf[j];
-      if (dead) continue;  // warp-uniform
-      const int c = static_cast<int>(lpq - lbase_s - qi * (LC + 1) * 32) >> 5;
-      bool over = __any_sync(FULL, c >= LC);  // a lane filled its list: it may have dropped steps
-      int incl = c;
+    for (int j = 1; j < QW; ++j)
+      if (j == qi) lpq = lp[j], tq = tau[j], f0 = q0[j], f1 = q1[j], f2 = q2[j];
+    int n = 0;
+    bool over = !(tq < INF);
+    const int c = static_cast<int>(lpq - lbase_s - qi * static_cast<uint32_t>(PQ)) >> 6;
+    over = over || __any_sync(FULL, c >= LC);  // a lane filled its list: it may have dropped steps
+    int incl = c;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int total = __shfl_sync(FULL, incl, 31);
-      if (!over && total > 0) {
-        const int maxc = __reduce_max_sync(FULL, c);
-        const int off = incl - c;
-        for (int it = 0; it < maxc; ++it)
-          if (it < c) dense[off + it] = static_cast<unsigned short>((lbase[(qi * (LC + 1) + it) * 32] << 5) | lane);
-        __syncwarp();
-        uint64_t *qq = queue + qi * CAP;
-        for (int e0 = 0; e0 < total; e0 += 32) {
-          const bool act = e0 + lane < total;
-          const int quad = act ? dense[e0 + lane] : 0;  // step * 32 + owner lane = quad index inside the tile
-          const float4 X = pl4[quad], Y = pl4[T4 + quad], Z = pl4[2 * T4 + quad];
-          const float2 dxa = sub2(make_float2(X.x, X.y), make_float2(f0, f0)), dxb = sub2(make_float2(X.z, X.w), make_float2(f0, f0));
-          const float2 dya = sub2(make_float2(Y.x, Y.y), make_float2(f1, f1)), dyb = sub2(make_float2(Y.z, Y.w), make_float2(f1, f1));
-          const float2 dza = sub2(make_float2(Z.x, Z.y), make_float2(f2, f2)), dzb = sub2(make_float2(Z.z, Z.w), make_float2(f2, f2));
-          const float2 dA = fma2(dza, dza, fma2(dya, dya, mul2(dxa, dxa)));
-          const float2 dB = fma2(dzb, dzb, fma2(dyb, dyb, mul2(dxb, dxb)));
-          const uint32_t jg = tbase + 4u * static_cast<uint32_t>(quad);
-          const float dv[4] = {dA.x, dA.y, dB.x, dB.y};
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (!over && total > 32 * LC) over = true;
+    if (!over && total > 0) {
+      const int maxc = __reduce_max_sync(FULL, c);
+      const int off = incl - c;
+      for (int it = 0; it < maxc; ++it)
+        if (it < c)
+          dense[off + it] = (static_cast<uint32_t>(reinterpret_cast<const unsigned short *>(my_area + qi * PQ)[it * 32 + lane]) << 5) | lane;
+      __syncwarp();
+      uint64_t *qq = reinterpret_cast<uint64_t *>(my_area + qi * PQ);
+      for (int e0 = 0; e0 < total; e0 += 32) {
+        const bool act = e0 + lane < total;
+        const uint32_t quad = chunk_quad0 + (act ? dense[e0 + lane] : 0u);  // quad index inside the cloud
+        const uint32_t jg = 4u * quad;
+        float4 X, Y, Z;
+        if (PLANAR) {
+          if (vec_ok) {
+            const float4 *P = reinterpret_cast<const float4 *>(R);
+            X = __ldg(P + quad), Y = __ldg(P + (r >> 2) + quad), Z = __ldg(P + 2 * (r >> 2) + quad);
+          } else {
+            float *xs = &X.x, *ys = &Y.x, *zs = &Z.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool in = jg + e < static_cast<uint32_t>(r);
+              xs[e] = in ? __ldg(R + jg + e) : INF, ys[e] = in ? __ldg(R + r + jg + e) : 0.f;
+              zs[e] = in ? __ldg(R + 2 * static_cast<size_t>(r) + jg + e) : 0.f;
+            }
+          }
+        } else if (vec_ok) {
+          const float4 *P = reinterpret_cast<const float4 *>(R) + 3 * static_cast<size_t>(quad);
+          const float4 a0 = __ldg(P), a1 = __ldg(P + 1), a2 = __ldg(P + 2);
+          X = make_float4(a0.x, a0.w, a1.z, a2.y);
+          Y = make_float4(a0.y, a1.x, a1.w, a2.z);
+          Z = make_float4(a0.z, a1.y, a2.x, a2.w);
+        } else {
+          float *xs = &X.x, *ys = &Y.x, *zs = &Z.x;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const bool hit = act && dv[e] <= tq;
-            const unsigned mk = __ballot_sync(FULL, hit);
-            const int pos = n + __popc(mk & lt_mask);
-            if (hit && pos < CAP) qq[pos] = pack_key(dv[e], jg + e);
-            n += __popc(mk);
+            const bool in = jg + e < static_cast<uint32_t>(r);
+            const float *pt = R + 3 * static_cast<size_t>(in ? jg + e : 0u);
+            xs[e] = in ? __ldg(pt) : INF, ys[e] = in ? __ldg(pt + 1) : 0.f, zs[e] = in ? __ldg(pt + 2) : 0.f;
           }
         }
-        __syncwarp();
-        over = n > CAP;
-      }
+        const float2 g0 = make_float2(f0, f0), g1 = make_float2(f1, f1), g2 = make_float2(f2, f2);
+        const float2 dxa = sub2(make_float2(X.x, X.y), g0), dxb = sub2(make_float2(X.z, X.w), g0);
+        const float2 dya = sub2(make_float2(Y.x, Y.y), g1), dyb = sub2(make_float2(Y.z, Y.w), g1);
+        const float2 dza = sub2(make_float2(Z.x, Z.y), g2), dzb = sub2(make_float2(Z.z, Z.w), g2);
+        const float2 dA = fma2(dza, dza, fma2(dya, dya, mul2(dxa, dxa)));
+        const float2 dB = fma2(dzb, dzb, fma2(dyb, dyb, mul2(dxb, dxb)));
+        const float dv[4] = {dA.x, dA.y, dB.x, dB.y};
 #pragma unroll
-      for (int j = 0; j < QW; ++j)
-        if (j == qi) qn[j] = n, ovf[j] = over;
+        for (int e = 0; e < 4; ++e) {
+          const bool hit = act && dv[e] <= tq;
+          const unsigned mk = __ballot_sync(FULL, hit);
+          const int pos = n + __popc(mk & lt_mask);
+          if (hit && pos < CAP) qq[pos] = pack_key(dv[e], jg + e);
+          n += __popc(mk);
+        }
+      }
+      __syncwarp();
+      over = n > CAP;
     }
+#pragma unroll
+    for (int j = 0; j < QW; ++j)
+      if (j == qi) qn[j] = n, ovf[j] = over;
   }
   __syncwarp();
 
@@ -416,45 +445,46 @@ __global__ void __launch_bounds__(NW * 32) knn4_kernel(const Knn4Args a) {
     }
   };
   constexpr int TB = E == 2 ? 6 : 7;  // tag bits: position of the candidate in its queue (CAP = 64 or 128)
-#pragma unroll 1
-  for (int qi = 0; qi < QW; ++qi) {
-    int n = qn[0];
-    bool dead = ovf[0];
-    float f0 = q0[0], f1 = q1[0], f2 = q2[0];
+  // Fast order: sort 32-bit words (distance bits with the low TB bits replaced by the queue position), all queries of
+  // the warp in lockstep.  That order is the exact (distance, index) order unless two of the first k+1 words agree above
+  // the tag -- then, and only then, the full 64-bit keys are sorted.
+  {
+    uint32_t w[QW][E];
 #pragma unroll
-    for (int j = 1; j < QW; ++j)
-      if (j == qi) n = qn[j], dead = ovf[j], f0 = q0[j], f1 = q1[j], f2 = q2[j];
-    const int qidx = qbase + qi;
-    if (dead || qidx >= q) continue;
-    const uint64_t *qq = queue + qi * CAP;
-    // Fast order: sort 32-bit words (distance bits with the low TB bits replaced by the queue position).  That order is
-    // the exact (distance, index) order unless two of the first k+1 words agree above the tag -- then, and only then,
-    // the full 64-bit keys are sorted.
-    uint32_t w[E];
+    for (int qi = 0; qi < QW; ++qi) {
+      const uint64_t *qq = reinterpret_cast<const uint64_t *>(my_area + qi * PQ);
+      const int n = ovf[qi] ? 0 : qn[qi];
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int p = e * 32 + lane;
-      w[e] = p < n ? ((static_cast<uint32_t>(qq[p] >> 32) & ~((1u << TB) - 1u)) | static_cast<uint32_t>(p)) : 0xffffffffu;
+      for (int e = 0; e < E; ++e) {
+        const int p = e * 32 + lane;
+        w[qi][e] = p < n ? ((static_cast<uint32_t>(qq[p] >> 32) & ~((1u << TB) - 1u)) | static_cast<uint32_t>(p)) : 0xffffffffu;
+      }
     }
-    warp_sort_u32<E>(w, lane, dir_mask);
-    bool amb = false;
+    warp_sort_u32_multi<QW, E>(w, lane, dir_mask);
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      uint32_t nxt = __shfl_down_sync(FULL, w[e], 1);
-      const uint32_t head = __shfl_sync(FULL, w[e + 1 < E ? e + 1 : e], 0);
-      if (lane == 31) nxt = e + 1 < E ? head : 0xffffffffu;
-      amb |= (e * 32 + lane < k) && (w[e] >> TB) == (nxt >> TB);
+    for (int qi = 0; qi < QW; ++qi) {
+      const int qidx = qbase + qi;
+      if (ovf[qi] || qidx >= q) continue;  // warp-uniform
+      const uint64_t *qq = reinterpret_cast<const uint64_t *>(my_area + qi * PQ);
+      bool amb = false;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        uint32_t nxt = __shfl_down_sync(FULL, w[qi][e], 1);
+        const uint32_t head = __shfl_sync(FULL, w[qi][e + 1 < E ? e + 1 : e], 0);
+        if (lane == 31) nxt = e + 1 < E ? head : 0xffffffffu;
+        amb |= (e * 32 + lane < k) && (w[qi][e] >> TB) == (nxt >> TB);
+      }
+      uint64_t keys[E];
+      if (!__any_sync(FULL, amb)) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) keys[e] = w[qi][e] == 0xffffffffu ? KEY_INF : qq[w[qi][e] & ((1u << TB) - 1u)];
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) keys[e] = (e * 32 + lane) < qn[qi] ? qq[e * 32 + lane] : KEY_INF;
+        warp_sort_multi<E>(keys, lane);
+      }
+      finish_query(qidx, q0[qi], q1[qi], q2[qi], keys);
     }
-    uint64_t keys[E];
-    if (!__any_sync(FULL, amb)) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) keys[e] = w[e] == 0xffffffffu ? KEY_INF : qq[w[e] & ((1u << TB) - 1u)];
-    } else {
-#pragma unroll
-      for (int e = 0; e < E; ++e) keys[e] = (e * 32 + lane) < n ? qq[e * 32 + lane] : KEY_INF;
-      warp_sort_multi<E>(keys, lane);
-    }
-    finish_query(qidx, f0, f1, f2, keys);
   }
 #pragma unroll 1
   for (int qi = 0; qi < QW; ++qi) {
@@ -467,7 +497,7 @@ __global__ void __launch_bounds__(NW * 32) knn4_kernel(const Knn4Args a) {
     if (!__syncthreads_or(mine)) continue;  // the tiles are re-streamed by the whole CTA
     WarpSelect<NS> sel;
     sel.init();
-    uint64_t *wq = queue;  // 64 entries: this warp's first queue (CAP >= 64)
+    uint64_t *wq = reinterpret_cast<uint64_t *>(my_area);  // 64 entries: the region of the warp's first query (CAP >= 64)
     if (a.tma && nt > 1 && tid == 0) issue_tile(t_begin);
     for (int i = 0; i < nt; ++i) {
       const int tl = t_begin + i;
@@ -544,7 +574,7 @@ static Knn4Tune &knn4_tune() {
 int knn3d_impl() { return knn4_tune().impl == 3 ? 3 : 4; }
 
 static size_t knn4_smem_bytes(int e, int qw, int nw, int tile, int tma) {
-  const size_t per_warp = e == 2 ? Knn4Smem<2>::per_warp(qw) : Knn4Smem<4>::per_warp(qw);
+  const size_t per_warp = e == 2 ? Knn4Smem<2>::per_warp(qw, tma) : Knn4Smem<4>::per_warp(qw, tma);
   return 128 + static_cast<size_t>(tma ? 24 : 12) * tile + static_cast<size_t>(nw) * per_warp;
 }
 
@@ -571,6 +601,7 @@ static Knn4Plan knn4_plan(int b, int r, int q, int k, bool aligned, bool have_ws
   p.tma = aligned && (r & 3) == 0 && ntiles > 1;
   if (tn.tma >= 0) p.tma = tn.tma;
   if (!aligned || (r & 3) != 0) p.tma = 0;
+  if (12 * p.tile < p.nw * 32 * (5 * e) * 4) p.tma = 0;  // the landing zone also holds the warps' dense lists
   // chunks along the reference cloud: waves x (two passes over the chunk's tiles + ~3 tile-passes of selection work)
   p.nz = 1;
   if (have_ws && ntiles > 1) {
@@ -656,6 +687,7 @@ static int knn4_dispatch(Knn4Args a, int b, void *ws, size_t ws_bytes, cudaStrea
   a.tma = p.tma;
   const int ntiles = (a.r + p.tile - 1) / p.tile;
   a.tiles_per_chunk = (ntiles + p.nz - 1) / p.nz;
+  if (static_cast<long long>(a.tiles_per_chunk) * (p.tile >> 7) > 65535) return PDAE_E_UNSUPPORTED;  // 16-bit step numbers
   a.chunk_keys = p.nz > 1 ? static_cast<uint64_t *>(ws) : nullptr;
   if constexpr (!PLANAR) {
     if (a.aff.mats != nullptr)

@@ -177,6 +177,46 @@ __device__ __forceinline__ void warp_sort_u32(uint32_t (&v)[E], int lane, uint32
   }
 }
 
+// NQ independent arrays through the same network in lockstep: the compare-exchange chains of one array are strictly
+// dependent (SHFL -> min/max -> SHFL ...), so interleaving the arrays of a warp's queries hides the shuffle latency.
+template <int NQ, int E>
+__device__ __forceinline__ void warp_sort_u32_multi(uint32_t (&v)[NQ][E], int lane, uint32_t dir_mask) {
+  int s = 0;
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+#pragma unroll
+        for (int a = 0; a < NQ; ++a)
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int pe = e ^ (j >> 5);
+            if (pe > e) {
+              const bool up = ((e * 32) & k) == 0;
+              const uint32_t lo = min(v[a][e], v[a][pe]), hi = max(v[a][e], v[a][pe]);
+              v[a][e] = up ? lo : hi;
+              v[a][pe] = up ? hi : lo;
+            }
+          }
+      } else {
+        const bool low_lane = (lane & j) == 0;
+        const bool keep_small = k < 32 ? ((dir_mask >> s) & 1u) != 0 : low_lane;
+        if (k < 32) ++s;
+#pragma unroll
+        for (int a = 0; a < NQ; ++a)
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, v[a][e], j);
+            const bool up = k < 32 ? true : ((e * 32) & k) == 0;
+            const bool take_min = up ? keep_small : !keep_small;
+            v[a][e] = take_min ? min(v[a][e], o) : max(v[a][e], o);
+          }
+      }
+    }
+  }
+}
+
 // streaming warp-select state: ascending list of 32*NS keys (one per lane per slot), the running
 // k-th key `tau`, and the fill level of the warp's candidate queue (64 entries in shared memory).
 template <int NS>

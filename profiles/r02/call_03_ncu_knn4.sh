@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out/r02
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn4_kernel -o gpurun_out/r02/ncu_knn4_v1 -f python profiles/ncu_knn.py H C4 C5 C3 > gpurun_out/r02/ncu_knn4_v1.log 2>&1
-tail -5 gpurun_out/r02/ncu_knn4_v1.log
-ls -la gpurun_out/r02/
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn4_kernel -o gpurun_out/r02/ncu_knn4_v2 -f python profiles/ncu_knn.py H C4 > gpurun_out/r02/ncu_knn4_v2.log 2>&1
+tail -3 gpurun_out/r02/ncu_knn4_v2.log
