@@ -166,9 +166,10 @@ int pdae_tune_chamfer_variant(int v);
 int pdae_tune_chamfer_split(int nc);
 /* kNN / Group (dim 3, k <= 64): impl 4 = multi-query warps + TMA tile prefetch (default), 3 = the first-generation
  * kernel (kept for A/B measurements); qw queries per warp (1/2/4), nw warps per CTA (4/8), tile points per shared-memory
- * tile, nz chunks along the reference cloud (needs the workspace), tma 0/1.  -1 = automatic.  Same results for every
+ * tile, nz chunks along the reference cloud (needs the workspace), tma 0/1, spec 0/1 (warp-specialised CTAs with a
+ * producer warp; 8-warp CTAs only).  -1 = automatic.  Same results for every
  * setting (tests/test_gpu_parity.py).  Environment: PDAE_KNN_IMPL, PDAE_KNN4_{QW,NW,TILE,NZ,TMA}.                    */
-int pdae_tune_knn(int impl, int qw, int nw, int tile, int nz, int tma);
+int pdae_tune_knn(int impl, int qw, int nw, int tile, int nz, int tma, int spec);
 
 /* reference-set sharding (scene-scale clouds; new, no reference counterpart):
  * one direction, queries (b,nq,3) against the local slice refs (b,nr,3) whose first point has

@@ -46,7 +46,7 @@ SIGNATURES = {
     "pdae_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_tune_chamfer_variant": (_i, [_i]),
     "pdae_tune_chamfer_split": (_i, [_i]),
-    "pdae_tune_knn": (_i, [_i, _i, _i, _i, _i, _i]),
+    "pdae_tune_knn": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "pdae_chamfer_loss_workspace_bytes": (_sz, []),
     "pdae_chamfer_loss_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pdae_chamfer_loss_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -43,6 +43,7 @@ struct Knn4Args {
   int tiles_per_chunk;
   int out_kq;
   int tma;              // 1: tiles arrive through cp.async.bulk + mbarrier
+  int dense_in_stage;   // 1: the rescan's dense lists live in the landing zone (it is idle by then)
 };
 
 // ---- TMA (bulk copy) + mbarrier, PTX ----------------------------------------------------------------------------------
@@ -59,6 +60,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -131,24 +136,30 @@ struct Knn4Smem {
   __host__ __device__ static constexpr size_t per_warp(int qw, int tma) { return qw * per_query + (tma ? 0 : dense_bytes); }
 };
 
+// SPEC (streamed clouds): the CTA's last warp is a PRODUCER -- it waits for the TMA copy of the next tile, transposes it
+// into the free one of two plane buffers and hands it to the NW-1 compute warps through mbarriers (full / empty per
+// buffer); the compute warps never meet at a CTA barrier and never touch the staging, so the FMA pipe keeps running while
+// tiles are converted.  !SPEC (single-tile clouds): all warps stage the tile together, once.
 template <bool PLANAR, int E /*keys per lane in the final sort: 2 (k<=32) or 4 (k<=64)*/, int QW /*queries per warp*/,
-          int NW /*warps per CTA*/, bool AFF>
+          int NW /*warps per CTA*/, bool AFF, bool SPEC>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Knn4Args a) {
-  constexpr int NT = NW * 32;
+  constexpr int CW = SPEC ? NW - 1 : NW;   // compute warps
+  constexpr int NT = SPEC ? 32 : NW * 32;  // threads that stage a tile
   constexpr int CAP = Knn4Smem<E>::CAP, LC = Knn4Smem<E>::LC;
   constexpr int NS = E / 2;  // fallback warp-select slots
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int T = a.tile;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-  float *planes = reinterpret_cast<float *>(smem_raw + 128);                        // [3][T]
-  float *stage = planes + 3 * T;                                                    // [3*T] landing zone (tma only)
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);  // [0] landing zone full, [1..2] planes full, [3..4] planes empty
+  float *planes0 = reinterpret_cast<float *>(smem_raw + 128);                       // [SPEC ? 2 : 1][3][T]
+  float *stage = planes0 + (SPEC ? 6 : 3) * T;                                      // [3*T] landing zone (tma only)
   unsigned char *warp_area = reinterpret_cast<unsigned char *>(a.tma ? stage + 3 * T : stage);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = SPEC ? (threadIdx.x & 31) : threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr size_t PQ = Knn4Smem<E>::per_query;
-  unsigned char *my_area = warp_area + static_cast<size_t>(warp) * Knn4Smem<E>::per_warp(QW, a.tma);
+  unsigned char *my_area = warp_area + static_cast<size_t>(warp) * Knn4Smem<E>::per_warp(QW, a.dense_in_stage);
   // query qi: step lists = [LC + 1][32] u16 at my_area + qi * PQ, later overwritten by its key queue [CAP] u64
-  uint32_t *dense = a.tma ? reinterpret_cast<uint32_t *>(stage) + warp * (32 * LC)
-                          : reinterpret_cast<uint32_t *>(my_area + static_cast<size_t>(QW) * PQ);          // [32 * LC]
+  uint32_t *dense = a.dense_in_stage ? reinterpret_cast<uint32_t *>(stage) + warp * (32 * LC)
+                                     : reinterpret_cast<uint32_t *>(my_area + static_cast<size_t>(QW) * PQ);  // [32 * LC]
+  float *planes = planes0;  // the buffer being filled (producer) / scanned (compute warps)
   const int cloud = blockIdx.y;
   const int r = a.r, q = a.q, k = a.k;
   const float *__restrict__ R = a.ref + static_cast<size_t>(cloud) * r * 3;
@@ -163,8 +174,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
   const unsigned lt_mask = (1u << lane) - 1u;
   uint32_t parity = 0;
 
-  if (a.tma && tid == 0) mbar_init(bar, 1);
-  if (a.tma) __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    if (SPEC) {
+      mbar_init(bar + 1, 1), mbar_init(bar + 2, 1);
+      mbar_init(bar + 3, CW), mbar_init(bar + 4, CW);
+    }
+  }
+  __syncthreads();
 
   auto tile_n = [&](int tl) { return min(T, r - tl * T); };
   auto issue_tile = [&](int tl) {  // one thread
@@ -239,8 +256,62 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
     if (a.tma && next >= 0 && tid == 0) issue_tile(next);
   };
 
+  // SPEC, compute warps: wait for / give back the plane buffer of position cseq in the CTA's tile sequence
+  uint32_t cseq = 0;
+  auto tile_begin = [&](int tl, int next) {
+    if constexpr (SPEC) {
+      const uint32_t buf = cseq & 1u;
+      while (!mbar_try_wait(bar + 1 + buf, (cseq >> 1) & 1u)) {}
+      planes = planes0 + buf * 3 * T;
+    } else {
+      acquire(tl, next);
+    }
+  };
+  auto tile_end = [&]() {
+    if constexpr (SPEC) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + 3 + (cseq & 1u));
+      ++cseq;
+    }
+  };
+  if constexpr (SPEC) {
+    if (warp == CW) {
+      // ---- producer warp --------------------------------------------------------------------------------------------
+      uint32_t pseq = 0;
+      auto produce = [&](int npass) {
+        const int total = npass * nt;
+        if (a.tma && lane == 0 && total > 0) issue_tile(t_begin);
+        int ti = 0;
+        for (int p = 0; p < total; ++p, ++pseq) {
+          const uint32_t buf = pseq & 1u;
+          if (a.tma) {
+            while (!mbar_try_wait(bar, parity)) {}
+            parity ^= 1u;
+          }
+          while (!mbar_try_wait(bar + 3 + buf, ((pseq >> 1) & 1u) ^ 1u)) {}  // the buffer's previous tile is consumed
+          planes = planes0 + buf * 3 * T;
+          fill_planes(t_begin + ti);
+          ti = ti + 1 == nt ? 0 : ti + 1;
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar + 1 + buf);
+            if (a.tma && p + 1 < total) {
+              fence_proxy_async();
+              issue_tile(t_begin + ti);
+            }
+          }
+          __syncwarp();
+        }
+      };
+      produce(2);  // pass 1 and pass 2 stream the chunk's tiles
+      for (int qi = 0; qi < QW; ++qi)
+        if (__syncthreads_or(0)) produce(1);  // exact fallback of some warp's query: one more sweep
+      return;
+    }
+  }
+
   // ---- this warp's queries ------------------------------------------------------------------------------------------
-  const int qbase = (blockIdx.x * NW + warp) * QW;
+  const int qbase = (blockIdx.x * CW + warp) * QW;
   float q0[QW], q1[QW], q2[QW];
   float2 qx2[QW], qy2[QW], qz2[QW];
 #pragma unroll
@@ -256,14 +327,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
     }
     qx2[qi] = make_float2(q0[qi], q0[qi]), qy2[qi] = make_float2(q1[qi], q1[qi]), qz2[qi] = make_float2(q2[qi], q2[qi]);
   }
-  const float4 *px = reinterpret_cast<const float4 *>(planes) + lane;
-  const float4 *py = px + (T >> 2), *pz = px + (T >> 1);
+  const float4 *px, *py, *pz;
+  auto set_planes = [&]() {
+    px = reinterpret_cast<const float4 *>(planes) + lane;
+    py = px + (T >> 2), pz = px + (T >> 1);
+  };
+  set_planes();
   auto pair2 = [&](float2 X, float2 Y, float2 Z, int qi) {
     const float2 dx = sub2(X, qx2[qi]), dy = sub2(Y, qy2[qi]), dz = sub2(Z, qz2[qi]);
     return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
   };
 
-  if (a.tma && tid == 0 && nt > 0) issue_tile(t_begin);
+  if (!SPEC && a.tma && tid == 0 && nt > 0) issue_tile(t_begin);
 
   // ---- pass 1: segment minima -> tau -------------------------------------------------------------------------------------
   float m[QW][E];
@@ -273,7 +348,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
     for (int e = 0; e < E; ++e) m[qi][e] = INF;
   for (int i = 0; i < nt; ++i) {
     const int tl = t_begin + i;
-    acquire(tl, nt > 1 ? (i + 1 < nt ? tl + 1 : t_begin) : -1);
+    tile_begin(tl, nt > 1 ? (i + 1 < nt ? tl + 1 : t_begin) : -1);
+    set_planes();
     const int nsteps = ((tile_n(tl) + 255) & ~255) >> 7;  // even
     for (int s = 0; s < nsteps; s += 2) {
 #pragma unroll
@@ -289,6 +365,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
         }
       }
     }
+    tile_end();
   }
   // The per-query phases below run as ROLLED loops over the warp's queries (values picked out of the register arrays
   // with select chains): the sorting networks appear once in the code instead of QW times, which keeps the kernel
@@ -321,7 +398,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
   for (int qi = 0; qi < QW; ++qi) lp[qi] = lbase_s + qi * static_cast<uint32_t>(PQ), lend[qi] = lp[qi] + LC * 64;
   for (int i = 0; i < nt; ++i) {
     const int tl = t_begin + i;
-    if (nt > 1) acquire(tl, i + 1 < nt ? tl + 1 : -1);
+    if (SPEC || nt > 1) {
+      tile_begin(tl, i + 1 < nt ? tl + 1 : -1);
+      set_planes();
+    }
     const int nsteps = ((tile_n(tl) + 255) & ~255) >> 7;
     const int gs0 = i * (T >> 7);  // step number inside the chunk
 #pragma unroll 2
@@ -337,6 +417,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
         if (mm <= tau[qi]) lp[qi] = min(lp[qi] + 64u, lend[qi]);
       }
     }
+    tile_end();
   }
   __syncwarp();
 
@@ -498,20 +579,22 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 5) knn4_kernel(const Kn
     WarpSelect<NS> sel;
     sel.init();
     uint64_t *wq = reinterpret_cast<uint64_t *>(my_area);  // 64 entries: the region of the warp's first query (CAP >= 64)
-    if (a.tma && nt > 1 && tid == 0) issue_tile(t_begin);
+    if (!SPEC && a.tma && nt > 1 && tid == 0) issue_tile(t_begin);
     for (int i = 0; i < nt; ++i) {
       const int tl = t_begin + i;
-      if (nt > 1) acquire(tl, i + 1 < nt ? tl + 1 : -1);
-      if (!mine) continue;
-      const int tn = tile_n(tl);
-      const float *sx = planes, *sy = planes + T, *sz = planes + 2 * T;
-      for (int j0 = 0; j0 < tn; j0 += 32) {
-        const int j = j0 + lane;
-        const bool in = j < tn;
-        const float d = dist_seq3(__fsub_rn(sx[in ? j : 0], f0), __fsub_rn(sy[in ? j : 0], f1), __fsub_rn(sz[in ? j : 0], f2));
-        const uint64_t key = pack_key(d, static_cast<uint32_t>(tl * T + j));
-        sel.offer(in && key < sel.tau, key, wq, lane, kslot, klane);
+      if (SPEC || nt > 1) tile_begin(tl, i + 1 < nt ? tl + 1 : -1);
+      if (mine) {
+        const int tn = tile_n(tl);
+        const float *sx = planes, *sy = planes + T, *sz = planes + 2 * T;
+        for (int j0 = 0; j0 < tn; j0 += 32) {
+          const int j = j0 + lane;
+          const bool in = j < tn;
+          const float d = dist_seq3(__fsub_rn(sx[in ? j : 0], f0), __fsub_rn(sy[in ? j : 0], f1), __fsub_rn(sz[in ? j : 0], f2));
+          const uint64_t key = pack_key(d, static_cast<uint32_t>(tl * T + j));
+          sel.offer(in && key < sel.tau, key, wq, lane, kslot, klane);
+        }
       }
+      if (SPEC || nt > 1) tile_end();
     }
     if (mine) {
       sel.finish(wq, lane);
@@ -555,12 +638,12 @@ __global__ void __launch_bounds__(128) knn4_merge_kernel(const Knn4Args a, int n
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 struct Knn4Plan {
-  int qw, nw, tile, nz, tma;
+  int qw, nw, tile, nz, tma, spec, dense_in_stage;
 };
 
-// Tuning hooks (profiles/tune_knn.py): pdae_tune_knn / PDAE_KNN4_{QW,NW,TILE,NZ,TMA} override the plan; -1 = automatic.
+// Tuning hooks (profiles/tune_knn.py): pdae_tune_knn / PDAE_KNN4_{QW,NW,TILE,NZ,TMA,SPEC} override the plan; -1 = automatic.
 struct Knn4Tune {
-  int impl, qw, nw, tile, nz, tma;
+  int impl, qw, nw, tile, nz, tma, spec;
 };
 static int env_int(const char *name, int dflt) {
   const char *s = std::getenv(name);
@@ -568,20 +651,30 @@ static int env_int(const char *name, int dflt) {
 }
 static Knn4Tune &knn4_tune() {
   static Knn4Tune t{env_int("PDAE_KNN_IMPL", 4), env_int("PDAE_KNN4_QW", -1), env_int("PDAE_KNN4_NW", -1),
-                    env_int("PDAE_KNN4_TILE", -1), env_int("PDAE_KNN4_NZ", -1), env_int("PDAE_KNN4_TMA", -1)};
+                    env_int("PDAE_KNN4_TILE", -1), env_int("PDAE_KNN4_NZ", -1), env_int("PDAE_KNN4_TMA", -1),
+                    env_int("PDAE_KNN4_SPEC", -1)};
   return t;
 }
 int knn3d_impl() { return knn4_tune().impl == 3 ? 3 : 4; }
 
-static size_t knn4_smem_bytes(int e, int qw, int nw, int tile, int tma) {
-  const size_t per_warp = e == 2 ? Knn4Smem<2>::per_warp(qw, tma) : Knn4Smem<4>::per_warp(qw, tma);
-  return 128 + static_cast<size_t>(tma ? 24 : 12) * tile + static_cast<size_t>(nw) * per_warp;
+static size_t knn4_smem_bytes(int e, const Knn4Plan &p) {
+  const size_t per_warp = e == 2 ? Knn4Smem<2>::per_warp(p.qw, p.dense_in_stage) : Knn4Smem<4>::per_warp(p.qw, p.dense_in_stage);
+  const int cw = p.spec ? p.nw - 1 : p.nw;
+  return 128 + static_cast<size_t>((p.spec ? 24 : 12) + (p.tma ? 12 : 0)) * p.tile + static_cast<size_t>(cw) * per_warp;
 }
 
 static Knn4Plan knn4_plan(int b, int r, int q, int k, bool aligned, bool have_ws) {
   Knn4Plan p;
   const int e = k <= 32 ? 2 : 4;
   const Knn4Tune &tn = knn4_tune();
+  // streamed clouds that cannot fill the GPU with CTAs (scene scale: few queries, long cloud): warp-specialised CTAs
+  // (7 compute warps + 1 producer, two plane buffers) keep the lone CTA of an SM computing while tiles are converted;
+  // with several CTAs per SM the conversions already overlap with other CTAs' scans and the eighth compute warp wins
+  // (measured, profiles/r02/tune_knn_v5.json: C4 611 vs 690 us, C5 161 vs 142 us)
+  const bool streamed = r > 2048;
+  const long long ctas_plain = static_cast<long long>(b) * ((q + 31) / 32);
+  p.spec = streamed && ctas_plain < 148 * 3 ? 1 : 0;
+  if (tn.spec >= 0) p.spec = tn.spec;
   p.tile = tn.tile > 0 ? tn.tile : 2048;
   if (p.tile < 256) p.tile = 256;
   p.tile = (p.tile + 255) & ~255;
@@ -593,32 +686,37 @@ static Knn4Plan knn4_plan(int b, int r, int q, int k, bool aligned, bool have_ws
   p.qw = nq >= 148LL * 4 * 8 ? 4 : 2;
   p.nw = 4;
   if (q >= 256 && nq >= 148LL * 8 * 4 * 2) p.nw = 8;
+  if (streamed) p.qw = 4, p.nw = 8;
   if (tn.qw > 0) p.qw = tn.qw;
   if (tn.nw > 0) p.nw = tn.nw;
   if (p.qw != 1 && p.qw != 2 && p.qw != 4) p.qw = 4;
   if (p.nw != 4 && p.nw != 8) p.nw = 4;
-  // the TMA landing zone doubles the tile's shared memory: worth it only when tiles are streamed
+  if (p.spec) {  // instantiated shapes
+    p.nw = 8;
+    if (p.qw == 1) p.qw = 2;
+  }
+  // the TMA landing zone costs a tile of shared memory: worth it only when tiles are streamed
   p.tma = aligned && (r & 3) == 0 && ntiles > 1;
   if (tn.tma >= 0) p.tma = tn.tma;
   if (!aligned || (r & 3) != 0) p.tma = 0;
-  if (12 * p.tile < p.nw * 32 * (5 * e) * 4) p.tma = 0;  // the landing zone also holds the warps' dense lists
-  // chunks along the reference cloud: waves x (two passes over the chunk's tiles + ~3 tile-passes of selection work)
+  // the idle landing zone holds the rescan's dense lists when they fit
+  const int cw = p.spec ? p.nw - 1 : p.nw;
+  p.dense_in_stage = p.tma && 12 * p.tile >= cw * 32 * (5 * e) * 4;
+  // chunks along the reference cloud: waves x (two passes over the chunk's tiles + the per-chunk selection work)
   p.nz = 1;
+  const int qpc = cw * p.qw;  // queries per CTA
   if (have_ws && ntiles > 1) {
-    const size_t smem = knn4_smem_bytes(e, p.qw, p.nw, p.tile, p.tma);
-    long long occ = static_cast<long long>((227 * 1024) / smem);
-    const long long by_warps = 16 / p.nw;
-    if (occ > by_warps) occ = by_warps;
-    if (occ < 1) occ = 1;
-    const long long slots = 148 * occ;
-    const long long ctas1 = static_cast<long long>(b) * ((q + p.qw * p.nw - 1) / (p.qw * p.nw));
+    // CTAs that share an SM share its issue slots: count waves against the SMs, not against the resident slots
+    const long long slots = 148;
+    const long long ctas1 = static_cast<long long>(b) * ((q + qpc - 1) / qpc);
+    const double tiles2k = p.tile / 2048.0;  // cost unit: one pass over 2048 points
     double best = 1e30;
     for (int nz = 1; nz <= 16 && nz <= ntiles; ++nz) {
       const int tpc = (ntiles + nz - 1) / nz;
       const int nz_eff = (ntiles + tpc - 1) / tpc;
       if (nz_eff != nz) continue;
       const long long waves = (ctas1 * nz + slots - 1) / slots;
-      const double cost = static_cast<double>(waves) * (2.0 * tpc + 3.0) + (nz > 1 ? 0.5 : 0.0);
+      const double cost = static_cast<double>(waves) * (2.0 * tpc * tiles2k + (e == 2 ? 3.0 : 6.0)) + (nz > 1 ? 0.5 : 0.0);
       if (cost < best * 0.97) best = cost, p.nz = nz;
     }
   }
@@ -631,17 +729,17 @@ static Knn4Plan knn4_plan(int b, int r, int q, int k, bool aligned, bool have_ws
   return p;
 }
 
-template <bool PLANAR, int E, int QW, int NW, bool AFF>
+template <bool PLANAR, int E, int QW, int NW, bool AFF, bool SPEC>
 static int knn4_launch_cfg(Knn4Args a, int b, const Knn4Plan &p, cudaStream_t st) {
-  const size_t smem = knn4_smem_bytes(E, QW, NW, a.tile, a.tma);
+  const size_t smem = knn4_smem_bytes(E, p);
   static int configured = 0;  // per instantiation; the attribute is sticky per device function
   if (smem > 48 * 1024 && static_cast<int>(smem) > configured) {
-    PDAE_CUDA_TRY(cudaFuncSetAttribute(knn4_kernel<PLANAR, E, QW, NW, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(knn4_kernel<PLANAR, E, QW, NW, AFF, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     configured = static_cast<int>(smem);
   }
-  const dim3 grid(ceil_div(a.q, NW * QW), b, p.nz);
-  knn4_kernel<PLANAR, E, QW, NW, AFF><<<grid, NW * 32, smem, st>>>(a);
+  const dim3 grid(ceil_div(a.q, (SPEC ? NW - 1 : NW) * QW), b, p.nz);
+  knn4_kernel<PLANAR, E, QW, NW, AFF, SPEC><<<grid, NW * 32, smem, st>>>(a);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   if (p.nz > 1) {
     const long long warps = static_cast<long long>(b) * a.q;
@@ -653,14 +751,18 @@ static int knn4_launch_cfg(Knn4Args a, int b, const Knn4Plan &p, cudaStream_t st
 
 template <bool PLANAR, int E, bool AFF>
 static int knn4_launch_e(const Knn4Args &a, int b, const Knn4Plan &p, cudaStream_t st) {
-  if (p.nw == 8) {
-    if (p.qw == 4) return knn4_launch_cfg<PLANAR, E, 4, 8, AFF>(a, b, p, st);
-    if (p.qw == 2) return knn4_launch_cfg<PLANAR, E, 2, 8, AFF>(a, b, p, st);
-    return knn4_launch_cfg<PLANAR, E, 1, 8, AFF>(a, b, p, st);
+  if (p.spec) {
+    if (p.qw == 4) return knn4_launch_cfg<PLANAR, E, 4, 8, AFF, true>(a, b, p, st);
+    return knn4_launch_cfg<PLANAR, E, 2, 8, AFF, true>(a, b, p, st);
   }
-  if (p.qw == 4) return knn4_launch_cfg<PLANAR, E, 4, 4, AFF>(a, b, p, st);
-  if (p.qw == 2) return knn4_launch_cfg<PLANAR, E, 2, 4, AFF>(a, b, p, st);
-  return knn4_launch_cfg<PLANAR, E, 1, 4, AFF>(a, b, p, st);
+  if (p.nw == 8) {
+    if (p.qw == 4) return knn4_launch_cfg<PLANAR, E, 4, 8, AFF, false>(a, b, p, st);
+    if (p.qw == 2) return knn4_launch_cfg<PLANAR, E, 2, 8, AFF, false>(a, b, p, st);
+    return knn4_launch_cfg<PLANAR, E, 1, 8, AFF, false>(a, b, p, st);
+  }
+  if (p.qw == 4) return knn4_launch_cfg<PLANAR, E, 4, 4, AFF, false>(a, b, p, st);
+  if (p.qw == 2) return knn4_launch_cfg<PLANAR, E, 2, 4, AFF, false>(a, b, p, st);
+  return knn4_launch_cfg<PLANAR, E, 1, 4, AFF, false>(a, b, p, st);
 }
 
 size_t knn4_workspace_bytes(int b, int r, int q, int k) {
@@ -685,6 +787,7 @@ static int knn4_dispatch(Knn4Args a, int b, void *ws, size_t ws_bytes, cudaStrea
   }
   a.tile = p.tile;
   a.tma = p.tma;
+  a.dense_in_stage = p.dense_in_stage;
   const int ntiles = (a.r + p.tile - 1) / p.tile;
   a.tiles_per_chunk = (ntiles + p.nz - 1) / p.nz;
   if (static_cast<long long>(a.tiles_per_chunk) * (p.tile >> 7) > 65535) return PDAE_E_UNSUPPORTED;  // 16-bit step numbers
@@ -700,19 +803,19 @@ int knn4_points(const float *ref, const float *query, int b, int r, int q, int k
                 float *group, cudaStream_t st, uint64_t *keys, uint32_t ref_offset, int raw_group, const GroupAffine *affine,
                 void *ws, size_t ws_bytes) {
   Knn4Args a{ref, query, dist, idx, group, keys, nullptr, ref_offset, raw_group,
-             affine ? *affine : GroupAffine{nullptr, 0, nullptr, nullptr}, r, q, k, 0, 0, out_kq, 0};
+             affine ? *affine : GroupAffine{nullptr, 0, nullptr, nullptr}, r, q, k, 0, 0, out_kq, 0, 0};
   return knn4_dispatch<false>(a, b, ws, ws_bytes, st);
 }
 int knn4_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st, void *ws, size_t ws_bytes) {
   Knn4Args a{x, nullptr, nullptr, idx, nullptr, nullptr, nullptr, 0u, 0, GroupAffine{nullptr, 0, nullptr, nullptr}, n, n, k,
-             0, 0, 0, 0};
+             0, 0, 0, 0, 0};
   return knn4_dispatch<true>(a, b, ws, ws_bytes, st);
 }
 
 }  // namespace pdae
 
-extern "C" int pdae_tune_knn(int impl, int qw, int nw, int tile, int nz, int tma) {
+extern "C" int pdae_tune_knn(int impl, int qw, int nw, int tile, int nz, int tma, int spec) {
   pdae::Knn4Tune &t = pdae::knn4_tune();
-  t.impl = impl, t.qw = qw, t.nw = nw, t.tile = tile, t.nz = nz, t.tma = tma;
+  t.impl = impl, t.qw = qw, t.nw = nw, t.tile = tile, t.nz = nz, t.tma = tma, t.spec = spec;
   return 0;
 }

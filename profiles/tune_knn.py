@@ -45,8 +45,8 @@ def timed(fn, reps=10, rounds=5):
     return best * 1e3  # us
 
 
-def tune(impl=4, qw=-1, nw=-1, tile=-1, nz=-1, tma=-1):
-    _native.lib().pdae_tune_knn(impl, qw, nw, tile, nz, tma)
+def tune(impl=4, qw=-1, nw=-1, tile=-1, nz=-1, tma=-1, spec=-1):
+    _native.lib().pdae_tune_knn(impl, qw, nw, tile, nz, tma, spec)
 
 
 def main():
@@ -81,13 +81,18 @@ def main():
         rec["impl3_us"] = t3
         rec["impl3_fma_frac"] = pairs * 6 / (t3 * 1e-6) / PEAK
         ntiles = (r + 2047) // 2048
-        grid = [dict(qw=-1, nw=-1, tma=-1, nz=-1)]
+        grid = [dict(qw=-1, nw=-1, tma=-1, nz=-1, spec=-1, tile=-1)]
         if not args.quick:
             nzs = [-1] if ntiles == 1 else sorted({1, 2, 3, 4, 6, 8, 12, 16} & set(range(1, ntiles + 1))) + [-1]
             for qw, nw, tma, nz in itertools.product((1, 2, 4), (4, 8), (0, 1), nzs):
                 if b * q > 20000 and (qw == 1 or (nz not in (-1, 1))):
                     continue
-                grid.append(dict(qw=qw, nw=nw, tma=tma, nz=nz))
+                grid.append(dict(qw=qw, nw=nw, tma=tma, nz=nz, spec=0, tile=2048))
+            if ntiles > 1:  # warp-specialised CTAs (7 compute warps + producer)
+                for qw, tma, nz, tile in itertools.product((2, 4), (0, 1), nzs, (1024, 2048)):
+                    if b * q > 20000 and nz not in (-1, 1):
+                        continue
+                    grid.append(dict(qw=qw, nw=8, tma=tma, nz=nz, spec=1, tile=tile))
         for cfg in grid:
             tune(impl=4, **cfg)
             got = run()
@@ -102,7 +107,7 @@ def main():
         rec["auto"] = rec["runs"][0]
         print(name, "impl3 %.1f us | auto %.1f us (%s) | best %.1f us %s" % (
             t3, rec["auto"]["us"], "same" if rec["auto"]["same_as_impl3"] else "DIFFERENT", best["us"],
-            {kk: best[kk] for kk in ("qw", "nw", "tma", "nz")}), flush=True)
+            {kk: best[kk] for kk in ("qw", "nw", "tma", "nz", "spec", "tile")}), flush=True)
         assert all(x["same_as_impl3"] for x in rec["runs"]), [x for x in rec["runs"] if not x["same_as_impl3"]]
         out[name] = rec
     if args.out:
