@@ -31,11 +31,18 @@ B, N, G, M = 128, 2048, 64, 32  # headline shape (per GPU)
 POOL = 48                        # distinct resident batches cycled through: 48 * 6.3 MB = 302 MB > 126 MB L2
 METRIC = "clouds/sec (FPS+Group+Chamfer fwd/bwd, B=128 N=2048)"
 UNIT = "clouds/s"
-REF_STEP_CLOUDS = 8              # clouds per step of the CPU reference arm (bounded sample)
+REF_BUDGET_S = 170.0             # wall-clock budget of the CPU reference arm (it does ~50 clouds/s on 16 cores)
+MIN_TIMED_MS = 60.0              # the timed region is repeated until it is at least this long
 
 
 def workload_name():
     return "H: B=%d/GPU, N=%d, FPS->%d centres, kNN %d (Group), ChamferL2 %dx%d fwd+bwd" % (B, N, G, M, N, N)
+
+
+def config_dict(world):
+    """Identical for both arms (the driver compares it): what is computed, never how."""
+    return {"workload": workload_name(), "sharding": "batch (no collective)" if world > 1 else "single GPU",
+            "l2": "inputs rotate through %d distinct resident batches (%.0f MB > 126 MB L2)" % (POOL, POOL * 2 * B * N * 12 / 1e6)}
 
 
 # ------------------------------------------------------------------------------------ CPU reference
@@ -50,7 +57,18 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cloud = torch.from_numpy(synth.clouds(REF_STEP_CLOUDS, N, seed=1))
+    # one step = the whole B-cloud batch, like the GPU arm, whenever (warmup + steps) of them fit the time budget (they
+    # do for the driver's --steps 20); a longer run times a power-of-two share of the batch per step and says so
+    probe_c = torch.from_numpy(synth.clouds(8, N, seed=3))
+    probe_p = torch.from_numpy(synth.prediction(probe_c.numpy(), seed=3))
+    T.step(probe_c, probe_p, G, M)
+    t0 = time.perf_counter()
+    T.step(probe_c, probe_p, G, M)
+    per_cloud = (time.perf_counter() - t0) / 8
+    nc = B
+    while nc > 8 and nc * per_cloud * (args.steps + args.warmup) > REF_BUDGET_S:
+        nc //= 2
+    cloud = torch.from_numpy(synth.clouds(nc, N, seed=1))
     pred = torch.from_numpy(synth.prediction(cloud.numpy(), seed=1))
     for _ in range(args.warmup):
         T.step(cloud, pred, G, M)
@@ -59,14 +77,16 @@ def run_reference(args):
         T.step(cloud, pred, G, M)
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
-    value = REF_STEP_CLOUDS / (dt / args.steps)
-    sample = "%d clouds per step (of the %d-cloud batch), same N=%d/G=%d/M=%d, pure-PyTorch CPU path" % (
-        REF_STEP_CLOUDS, B, N, G, M)
+    value = nc / (dt / args.steps)
+    sample = "%d of the %d clouds of a batch per step%s, same N=%d/G=%d/M=%d, pure-PyTorch CPU path (torch FPS loop, " \
+             "cdist+topk Group, pairwise ChamferL2 fwd+bwd), %d threads" % (
+                 nc, B, "" if nc < B else " (the whole batch)", N, G, M, torch.get_num_threads())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms * B / nc, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "sample": sample},
+        "config": config_dict(int(os.environ.get("WORLD_SIZE", "1"))),
+        "clouds_per_step": nc,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -91,7 +111,7 @@ def cpu_baseline():
 
 
 # ------------------------------------------------------------------- reference CUDA ops, same GPU
-def ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, our_ms):
+def ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, our_ms, ours_us=None):
     """Times the REFERENCE's own CUDA ops (rebuilt unmodified for sm_100a into oracle/_ref by oracle/build_ref.py)
     on the same resident inputs, outside the timed region: misc.fps (FPS + transposes + gather, utils/misc.py:13-20),
     a KNN_CUDA-like per-cloud loop for the kNN (KNN_CUDA is not vendored: torch cdist+topk per cloud, the launch
@@ -144,10 +164,21 @@ def ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, our_ms):
             acc[k].append(ts[k])
     med = [statistics.median(a) for a in acc]
     total = sum(med)
+    kernels_only = None
+    if ours_us:
+        # the reference's own compiled kernels only (FPS + gather, chamfer.forward + mean, chamfer.backward) against this
+        # repo's kernels for the same three pieces, each timed alone: no stand-in in either term
+        mine_ms = (ours_us["fps"] + ours_us["chamfer_fwd"] + ours_us["loss"] + ours_us["chamfer_bwd"]) * 1e-3
+        kernels_only = {"reference_ms": med[0] + med[2] + med[3], "this_repo_ms": mine_ms,
+                        "speedup": (med[0] + med[2] + med[3]) / mine_ms,
+                        "pieces": {"fps+gather": med[0] / (ours_us["fps"] * 1e-3),
+                                   "chamfer.forward + mean": med[2] / ((ours_us["chamfer_fwd"] + ours_us["loss"]) * 1e-3),
+                                   "chamfer.backward": med[3] / (ours_us["chamfer_bwd"] * 1e-3)}}
     return {"ms_per_step": total, "clouds_per_s": B / (total * 1e-3),
             "ms": {"fps+gather (pointnet2 _ext)": med[0], "knn loop (KNN_CUDA-like torch stand-in) + group": med[1],
                    "chamfer.forward + mean": med[2], "chamfer.backward": med[3]},
-            "speedup_of_this_repo": total / our_ms,
+            "kernels_only_speedup": kernels_only,
+            "speedup_of_this_repo_incl_knn_stand_in": total / our_ms,
             "note": "reference CUDA sources compiled unmodified for sm_100a; eager launches, median of 10"}
 
 
@@ -385,14 +416,25 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    # K steps are ~5 ms at the driver's --steps 20: the K-step region is repeated back to back until the timed region is
+    # at least MIN_TIMED_MS long (same count on every rank), and ms_per_step is the mean over all timed steps
     barrier()
     e0.record(stream)
     for i in range(args.steps):
         run_step(args.warmup + i)
     e1.record(stream)
     barrier()
+    probe_ms = max_over_ranks(e0.elapsed_time(e1))
+    inner = max(1, int(MIN_TIMED_MS / max(probe_ms, 1e-3)) + 1)
+    barrier()
+    e0.record(stream)
+    for rep in range(inner):
+        for i in range(args.steps):
+            run_step(args.warmup + rep * args.steps + i)
+    e1.record(stream)
+    barrier()
     total_ms = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = total_ms / args.steps
+    ms_per_step = total_ms / (args.steps * inner)
     value = world * B / (ms_per_step * 1e-3)
     # dominant kernel, timed live with CUDA events on its launching stream: the Chamfer forward alone (no co-running
     # branch), once per timed step over the same rotating pool.  Launched from Python each forward is three kernels
@@ -449,14 +491,15 @@ def run_ours(args):
     t0 = time.perf_counter()
     e0.record(stream)
     e2e_first = max(args.warmup, 100)
-    for i in range(args.steps):
+    e2e_steps = args.steps * inner
+    for i in range(e2e_steps):
         step_e2e(e2e_first + i, first=(i == 0))
     e1.record(stream)
     barrier()
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / e2e_steps
     # sanity (outside the timed region): the loss the e2e arm read back for its last step equals the loss of the
     # device-resident chain on the same pool slot
-    last = e2e_first + args.steps - 1
+    last = e2e_first + e2e_steps - 1
     loss_ev[last % 2].synchronize()
     e2e_loss = float(loss_h[last % 2])
     dev_loss = float(step_device(last, overlap=False)[0])
@@ -464,6 +507,24 @@ def run_ours(args):
     if not e2e_checked:
         raise RuntimeError("e2e loss %.9g != device-chain loss %.9g" % (e2e_loss, dev_loss))
     clocks = sampler.stop() if rank == 0 else None
+    peaks_all = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks_all = json.load(f)
+    except Exception:
+        pass
+    configs = None
+    sharded_c5 = None
+    if not args.no_configs:
+        try:
+            configs = config_blocks(dev, peaks_all, world, max_over_ranks)
+        except Exception as e:  # evidence only
+            configs = {"error": repr(e)[:300]}
+        if world > 1:
+            try:
+                sharded_c5 = sharded_c5_block(dev, world, rank, max_over_ranks)
+            except Exception as e:
+                sharded_c5 = {"error": repr(e)[:300]}
 
     if rank == 0:
         props = torch.cuda.get_device_properties(local)
@@ -477,25 +538,29 @@ def run_ours(args):
         peak_tflops = props.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # FP32 FMA pipe, FMA = 2
         pairs = 2.0 * B * N * N  # algorithmic: every (query, reference) pair of both directions
         # 6 FMA-pipe lane-ops per point pair (3 FADD, 1 FMUL, 2 FFMA), each counted as one FMA slot = 2 FLOP
-        achieved = pairs * 6 * 2 / (cham_ms * 1e-3) / 1e12
+        achieved = pairs * 6 * 2 / (cham_unsplit_ms * 1e-3) / 1e12      # the form inside the timed step
+        achieved_alone = pairs * 6 * 2 / (cham_ms * 1e-3) / 1e12           # library default for a forward alone
         roofline = {
-            "kernel": "Chamfer forward = fill_keys + chamfer_min_kernel<4,128,1,SYM> (512-row x 1024-column units) + "
-                      "chamfer_col_recover_list_kernel (row-key unpack fused)",
+            "kernel": "Chamfer forward as the timed step launches it = fill_keys + chamfer_min_kernel<4,128,1,SYM> "
+                      "(one CTA per 512-row block) + chamfer_col_recover_list_kernel",
             "bound": "fp32-fma-pipe", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops, "traffic": 8.44e6,
+            "traffic_source": "constant: dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r01/"
+                              "ncu_full_chamfer_symmetric_summary.csv (ncu --set full); not re-measured in this run",
             "note": "achieved = ALGORITHMIC 2*B*N*N pairs x 6 FMA-pipe lane-ops x 2 / CUDA-event time per forward "
                     "(launched alone, 8 forwards per replayed graph); peak = SMs x 128 lanes x 2 x sm_max_mhz (%s). The kernel evaluates each "
                     "unordered pair ONCE for both directions (bit-identical by symmetry), so EXECUTED FMA work is half "
-                    "the algorithmic count: executed_frac is what the FMA pipe actually sustains. traffic = "
-                    "dram__bytes_read+write of one launch from profiles/r01 (ncu); algorithmic bytes 10.5 MB "
-                    "(2 clouds in, 4 arrays out) -- not HBM-bound" % (
+                    "the algorithmic count: executed_frac is what the FMA pipe actually sustains. Algorithmic bytes "
+                    "10.5 MB (2 clouds in, 4 arrays out) -- not HBM-bound" % (
                         "MEASURED_PEAKS.json" if peaks else "fallback 1965 MHz"),
             "executed_frac": 0.5 * achieved / peak_tflops,
-            "ms_per_launch": cham_ms, "ms_per_launch_unsplit": cham_unsplit_ms,
+            "ms_per_launch": cham_unsplit_ms,
             "share_of_step": cham_unsplit_ms / ms_per_step,
-            "split_note": "ms_per_launch: the library default for a forward alone (column-split units even out the "
-                          "SMs' load); the timed step runs the unsplit form (ms_per_launch_unsplit, used for "
-                          "share_of_step) because the patchifier on the second stream fills the wave tail there",
+            "alone_with_column_split": {"ms_per_launch": cham_ms, "frac": achieved_alone / peak_tflops,
+                                        "executed_frac": 0.5 * achieved_alone / peak_tflops,
+                                        "note": "library default when the forward has the GPU to itself (512-row x "
+                                                "column-chunk units even out the SMs); the timed step keeps one CTA per "
+                                                "row block because the patchifier on the second stream fills the tail"},
         }
         try:
             others = other_kernels(dev, clouds_d, preds_d, peaks, props) if world == 1 else None
@@ -505,31 +570,204 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(), "sharding": "batch (no collective)" if world > 1 else "single GPU",
-                       "launch": ("eager, 2 streams" if args.no_graphs else "CUDA graph per pool slot, 2 streams (FPS+Group || Chamfer)") + (
-                           "; kNN gated behind the Chamfer scan" if args.knn_gate == "scan" else ""),
-                       "l2": "inputs rotate through %d distinct resident batches (%.0f MB > 126 MB L2)" % (
-                           POOL, POOL * 2 * B * N * 12 / 1e6)},
+            "config": config_dict(world),
+            "launch": ("eager, 2 streams" if args.no_graphs else "CUDA graph per pool slot, 2 streams (FPS+Group || Chamfer)") + (
+                "; kNN gated behind the Chamfer scan" if args.knn_gate == "scan" else ""),
+            "timed_steps": args.steps * inner, "timed_region_ms": total_ms,
+            "timed_region_note": "the K-step region repeated %d times back to back (>= %.0f ms); ms_per_step = mean over "
+                                 "all timed steps" % (inner, MIN_TIMED_MS),
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * N * 12,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "loss_checked_against_device_chain": e2e_checked,
                     "how": "public modules (Group, ChamferDistanceL2, autograd) on double-buffered inputs; every step "
-                           "copies the next batch from pinned host memory and the loss back to the host" + (
+                           "copies the next batch from pinned host memory and the loss back to the host (a training step: "
+                           "patches and gradients stay on the device)" + (
                                "" if args.no_graphs else "; the step is replayed as a CUDA graph")},
-            "gpu_launches": 9 * args.steps,
+            "gpu_launches": 9 * args.steps * inner,
             "roofline": roofline,
             "other_kernels": others,
+            "configs": configs,
+            "sharded_c5": sharded_c5,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_ref_gpu:
             try:
-                line["ref_gpu"] = ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, ms_per_step)
+                ours_us = None
+                if isinstance(others, dict) and "error" not in others:
+                    ours_us = {"fps": others["fps+centre gather %dx%d->%d" % (B, N, G)]["us"], "chamfer_fwd": cham_unsplit_ms * 1e3,
+                               "loss": others["chamfer mean loss (2 launches)"]["us"],
+                               "chamfer_bwd": others["chamfer backward (2 launches)"]["us"]}
+                line["ref_gpu"] = ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, ms_per_step, ours_us)
             except Exception as e:  # evidence only; never part of the measured arm
                 line["ref_gpu"] = {"unavailable": str(e)[:200]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _median_ms(fn, reps=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def config_blocks(dev, peaks, world, max_over_ranks):
+    """BASELINE.json configs 2-5 at their full per-GPU size, every kernel of the path timed alone on the device (median of
+    5, CUDA events; outside the timed region) with its roofline fraction.  Under torchrun every rank runs its own share
+    (C3 is "batch-sharded over 8 B200": B=128 -> 128/world clouds per rank; C2/C4 keep the per-GPU batch; C5 here is
+    the unsharded single-GPU form, the sharded form is the `sharded_c5` block) and the times are the max over ranks."""
+    import torch
+    from pointdae_b200 import dgcnn_util, ops, synth
+
+    fma = 148 * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6  # lane-ops / s
+    hbm = float(peaks.get("hbm_gbs", 6556.5))
+
+    def cloud(b, n, seed):
+        base = torch.from_numpy(synth.clouds(min(b, 8), n, seed=seed)).to(dev)
+        return (base.repeat((b + base.size(0) - 1) // base.size(0), 1, 1)[:b].contiguous()
+                + 0.001 * torch.randn(b, n, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(seed)))
+
+    def entry(ms, pairs=None, nbytes=None, **kw):
+        ms = max_over_ranks(ms)
+        e = {"ms": ms}
+        if pairs is not None:
+            e["fma_pipe_frac_algorithmic"] = pairs * 6.0 / (ms * 1e-3) / fma
+        if nbytes is not None:
+            e["GBps"] = nbytes / (ms * 1e-3) / 1e9
+            e["hbm_frac"] = e["GBps"] / hbm
+        e.update(kw)
+        return e
+
+    out = {"peaks": {"fma_lane_ops_per_s": fma, "hbm_GBps": hbm, "source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    # ---- C2: transformer pretrain, B=128, N=1024, 64 x 32 groups, ChamferL2 (coarse 64^2 and ~5000 fine clouds of 36 x 32)
+    c = cloud(128, 1024, 2)
+    cen = ops.fps_gather(c, 64)[1]
+    fa, fb = cloud(5000, 36, 3), cloud(5000, 32, 4)
+    p = c + 0.01 * torch.randn_like(c)
+    out["C2 B=128 N=1024 G=64 M=32"] = {
+        "fps 1024->64": entry(_median_ms(lambda: ops.fps_gather(c, 64)), us_per_iteration_note="63 sequential iterations"),
+        "group k=32": entry(_median_ms(lambda: ops.group_points_knn(c, cen, 32, want_idx=False)), pairs=128 * 64 * 1024),
+        "chamfer fwd 128x1024^2": entry(_median_ms(lambda: ops.chamfer_forward(p, c)), pairs=2.0 * 128 * 1024 * 1024),
+        "chamfer fwd fine 5000x36x32": entry(_median_ms(lambda: ops.chamfer_forward(fa, fb)), pairs=2.0 * 5000 * 36 * 32),
+    }
+    del c, cen, fa, fb, p
+    # ---- C3: DGCNN k=20 at N=2048, batch-sharded: 128 clouds / world per rank (16 per GPU on 8)
+    b3 = 16  # the per-GPU share of the 8-GPU configuration, whatever the world size of this run
+    c3 = {"clouds_per_rank": b3, "note": "feature kNN: algorithmic work = C FMA-pipe lane-ops per point pair (the "
+                                         "reference's expanded-form GEMM); C=3 runs the 3-D kernel (6 lane-ops per pair)"}
+    for C in (3, 64, 128):
+        x = torch.from_numpy(synth.features(b3, C, 2048, seed=C)).to(dev)
+        idx = dgcnn_util.knn(x, 20)
+        ms = max_over_ranks(_median_ms(lambda: dgcnn_util.knn(x, 20), reps=3))
+        c3["knn C=%d" % C] = {"ms": ms, "fma_pipe_frac": b3 * 2048.0 * 2048 * (6.0 if C == 3 else C) / (ms * 1e-3) / fma}
+        nbytes = b3 * 2048 * 20 * 2 * C * 4 + b3 * C * 2048 * 4 + b3 * 2048 * 20 * 8
+        c3["graph feature C=%d" % C] = entry(_median_ms(lambda: ops._graph_feature_fwd(x, idx), reps=3), nbytes=nbytes)
+        del x, idx
+    a1, a2 = cloud(b3, 1024, 7), cloud(b3, 1024, 8)
+    c3["chamferL1 fwd %dx1024^2" % b3] = entry(_median_ms(lambda: ops.chamfer_forward(a1, a2)), pairs=2.0 * b3 * 1024 * 1024)
+    out["C3 DGCNN k=20 N=2048 (batch-sharded)"] = c3
+    del a1, a2
+    # ---- C4: B=256, N=8192 -> FPS 512, kNN 32, ChamferL2 8192^2
+    c = cloud(256, 8192, 5)
+    cen = ops.fps_gather(c, 512)[1]
+    p = c + 0.01 * torch.randn_like(c)
+    d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+    g = torch.full_like(d1, 1e-6)
+    out["C4 B=256 N=8192 G=512 M=32"] = {
+        "fps 8192->512": entry(_median_ms(lambda: ops.fps_gather(c, 512), reps=3)),
+        "group k=32": entry(_median_ms(lambda: ops.group_points_knn(c, cen, 32, want_idx=False), reps=3), pairs=256.0 * 512 * 8192),
+        "chamfer fwd 256x8192^2": entry(_median_ms(lambda: ops.chamfer_forward(p, c), reps=3), pairs=2.0 * 256 * 8192 * 8192),
+        "chamfer bwd": entry(_median_ms(lambda: ops.chamfer_backward(p, c, i1, i2, g, g), reps=3), nbytes=2.0 * 256 * 8192 * 56),
+    }
+    del c, cen, p, d1, d2, i1, i2, g
+    # ---- C5: scene scale, one cloud per GPU, unsharded form
+    c = cloud(1, 100000, 6)
+    cen = ops.fps_gather(c, 2048)[1]
+    p = c + 0.01 * torch.randn_like(c)
+    out["C5 N=100000 G=2048 M=64 (one GPU, unsharded)"] = {
+        "fps 100k->2048": entry(_median_ms(lambda: ops.fps_gather(c, 2048), reps=3)),
+        "group k=64": entry(_median_ms(lambda: ops.group_points_knn(c, cen, 64, want_idx=False), reps=3), pairs=2048.0 * 100000),
+        "chamfer fwd 100k^2": entry(_median_ms(lambda: ops.chamfer_forward(p, c), reps=3), pairs=2.0 * 100000 * 100000),
+    }
+    return out
+
+
+def sharded_c5_block(dev, world, rank, max_over_ranks):
+    """BASELINE config 5 with the Chamfer / kNN reference set sharded over the ranks: Chamfer forward +
+    backward and kNN at N = 100 000 over NCCL, bit-exactness against the unsharded kernels on the same GPU, and the
+    share of the sharded time spent outside the local kernels (the collective + its launch)."""
+    import torch
+    import torch.distributed as dist
+    from pointdae_b200 import ops, sharded, synth
+
+    n, q, k = 100000, 2048, 64
+    xyz2 = torch.from_numpy(synth.adversarial(synth.clouds(1, n, seed=5), seed=5, n_small=0, n_dup=200)).to(dev)
+    xyz1 = torch.from_numpy(synth.prediction(synth.clouds(1, n, seed=5), seed=5)).to(dev)
+    lo, hi = sharded.shard_bounds(n, world, rank)
+    local_refs = xyz2[:, lo:hi].contiguous()
+
+    def synced_ms(fn, reps=10):
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return max_over_ranks(a.elapsed_time(b) / reps)
+
+    def all_ok(flag):
+        t = torch.tensor([1 if flag else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    out = {"n_points": n, "world": world, "impl": sharded.exchange_name()}
+    fwd_ms = synced_ms(lambda: sharded.chamfer_forward_sharded(xyz1, local_refs, lo))
+    local_ms = synced_ms(lambda: ops.chamfer_unpack_keys(ops.chamfer_sharded_local(xyz1, local_refs, lo)[0]))
+    unsharded_ms = _median_ms(lambda: ops.chamfer_forward(xyz1, xyz2), reps=5)
+    d1, d2l, i1, i2l = sharded.chamfer_forward_sharded(xyz1, local_refs, lo)
+    fd1, fd2, fi1, fi2 = ops.chamfer_forward(xyz1, xyz2)
+    ok = torch.equal(d1, fd1) and torch.equal(i1, fi1) and torch.equal(d2l, fd2[:, lo:hi]) and torch.equal(i2l, fi2[:, lo:hi])
+    out["chamfer_forward"] = {"sharded_ms": fwd_ms, "local_kernels_only_ms": local_ms,
+                              "exchange_share": max(0.0, 1.0 - local_ms / fwd_ms), "unsharded_1gpu_ms": max_over_ranks(unsharded_ms),
+                              "speedup_vs_1gpu": max_over_ranks(unsharded_ms) / fwd_ms,
+                              "efficiency_vs_1gpu": max_over_ranks(unsharded_ms) / fwd_ms / world,
+                              "bit_exact_vs_unsharded": all_ok(ok),
+                              "fma_pipe_frac_algorithmic_all_gpus": 2.0 * n * n * 6 / (fwd_ms * 1e-3) / (world * 148 * 128 * 1.965e9)}
+    g1 = torch.full_like(fd1, 1.0 / fd1.numel())
+    g2 = torch.full_like(fd2, 1.0 / fd2.numel())
+    g2l = g2[:, lo:hi].contiguous()
+    bwd_ms = synced_ms(lambda: sharded.chamfer_backward_sharded(xyz1, local_refs, lo, i1, i2l, g1, g2l))
+    gx1, gx2l = sharded.chamfer_backward_sharded(xyz1, local_refs, lo, i1, i2l, g1, g2l)
+    w1, w2 = ops.chamfer_backward(xyz1, xyz2, fi1, fi2, g1, g2)
+    ok_b = (torch.allclose(gx1, w1, rtol=1e-5, atol=1e-6 * float(w1.abs().max()))
+            and torch.allclose(gx2l, w2[:, lo:hi], rtol=1e-5, atol=1e-6 * float(w2.abs().max())))
+    out["chamfer_backward"] = {"sharded_ms": bwd_ms, "matches_unsharded_1e-5": all_ok(ok_b)}
+    centers = ops.fps_gather(xyz2, q)[1]
+    knn_ms = synced_ms(lambda: sharded.knn_sharded(local_refs, centers, k, lo))
+    knn_local_ms = synced_ms(lambda: ops.knn_keys(local_refs, centers, k, lo))
+    knn_1gpu = _median_ms(lambda: ops.knn_points(xyz2, centers, k), reps=5)
+    kd, ki = sharded.knn_sharded(local_refs, centers, k, lo)
+    wd, wi = ops.knn_points(xyz2, centers, k)
+    out["knn"] = {"queries": q, "k": k, "sharded_ms": knn_ms, "local_kernel_only_ms": knn_local_ms,
+                  "exchange_share": max(0.0, 1.0 - knn_local_ms / knn_ms), "unsharded_1gpu_ms": max_over_ranks(knn_1gpu),
+                  "speedup_vs_1gpu": max_over_ranks(knn_1gpu) / knn_ms,
+                  "bit_exact_vs_unsharded": all_ok(torch.equal(kd, wd) and torch.equal(ki, wi))}
+    return out
 
 
 def other_kernels(dev, clouds_d, preds_d, peaks, props):
@@ -576,10 +814,13 @@ def other_kernels(dev, clouds_d, preds_d, peaks, props):
     center = ops.fps_gather(c, G)[1]
     t = timed_us(lambda: ops.group_points_knn(c, center, M, want_idx=False))
     out["group kNN %d + gather" % M] = {"us": t, "fma_pipe_frac_algorithmic": B * G * N * 6.0 / (t * 1e-6) / fma,
-                                    "bound": "instruction issue (selection), see DESIGN.md 4.4"}
+                                    "bound": "per-warp latency + instruction issue of the selection at this size (16.8 M pairs = "
+                                             "2.7 us of FMA work); see `configs` for the shapes where the FMA pipe binds"}
     d1, d2, i1, i2 = ops.chamfer_forward(p, c)
     gone = torch.ones(1, device=dev)
     t = timed_us(lambda: ops.chamfer_loss_backward(p, c, i1, i2, d1, d2, gone, 1.0, 1.0))
+    tl = timed_us(lambda: ops.chamfer_mean_loss(d1, d2))
+    out["chamfer mean loss (2 launches)"] = {"us": tl, "bound": "launch latency (128 partial sums + ordered fp64 final sum)"}
     out["chamfer backward (2 launches)"] = {"us": t, "GBps": 2 * B * N * 56 / (t * 1e-6) / 1e9, "hbm_frac": 2 * B * N * 56 / (t * 1e-6) / 1e9 / hbm,
                                            "bound": "L2 atomics / launch latency (56 B per point, L2 resident)"}
     Cf, Bf, kf = 128, 16, 20
@@ -629,6 +870,7 @@ def main():
                          "the Chamfer scan kernel and overlaps the step's tail instead (measured 6 %% slower: the tail "
                          "kernels are issue-bound like the kNN, the FMA-bound scan is the better partner)")
     ap.add_argument("--no-graphs", action="store_true", help="issue the resident chain eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config (C2..C5) and sharded-C5 evidence blocks")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

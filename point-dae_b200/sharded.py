@@ -20,6 +20,11 @@ import torch
 import torch.distributed as dist
 
 
+def exchange_name():
+    """which exchange the sharded forward uses (bench / test reports)"""
+    return "torch.distributed all_reduce(MIN) on packed int64 keys (NCCL over NVLink)"
+
+
 def shard_bounds(n, world, rank):
     """contiguous, balanced partition of range(n): the first n % world ranks get one extra item."""
     base, extra = divmod(int(n), int(world))
