@@ -331,6 +331,12 @@ def run_ours(args):
 
     capturing = [False]
 
+    def pred_source(i):
+        """The cloud is the step's host input (the data loader's batch).  The prediction is the decoder's output and
+        is born on the device in the model (models/PointCAE_transformer.py:1059-1066), so by default it is taken from
+        device memory (a device-to-device copy stands in for the decoder); --e2e-upload both also uploads it."""
+        return preds_h[i % POOL] if args.e2e_upload == "both" else preds_d[i % POOL]
+
     def prefetch(i):
         c_in, p_in = in_bufs[i % 2]
         cur = torch.cuda.current_stream()
@@ -340,12 +346,12 @@ def run_ours(args):
             copy_stream.wait_stream(cur)
             with torch.cuda.stream(copy_stream):
                 c_in.detach().copy_(clouds_h[i % POOL], non_blocking=True)
-                p_in.detach().copy_(preds_h[i % POOL], non_blocking=True)
+                p_in.detach().copy_(pred_source(i), non_blocking=True)
             return
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[i % 2])
             c_in.detach().copy_(clouds_h[i % POOL], non_blocking=True)
-            p_in.detach().copy_(preds_h[i % POOL], non_blocking=True)
+            p_in.detach().copy_(pred_source(i), non_blocking=True)
             ready[i % 2].record(copy_stream)
 
     def e2e_body(i):
@@ -507,6 +513,16 @@ def run_ours(args):
     if not e2e_checked:
         raise RuntimeError("e2e loss %.9g != device-chain loss %.9g" % (e2e_loss, dev_loss))
     clocks = sampler.stop() if rank == 0 else None
+    # PCIe floor: the step's host -> device copy alone, every rank at once
+    barrier()
+    e0.record(stream)
+    for i in range(50):
+        in_bufs[i % 2][0].detach().copy_(clouds_h[i % POOL], non_blocking=True)
+        if args.e2e_upload == "both":
+            in_bufs[i % 2][1].detach().copy_(preds_h[i % POOL], non_blocking=True)
+    e1.record(stream)
+    barrier()
+    h2d_only_ms = max_over_ranks(e0.elapsed_time(e1)) / 50
     peaks_all = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -576,7 +592,13 @@ def run_ours(args):
             "timed_steps": args.steps * inner, "timed_region_ms": total_ms,
             "timed_region_note": "the K-step region repeated %d times back to back (>= %.0f ms); ms_per_step = mean over "
                                  "all timed steps" % (inner, MIN_TIMED_MS),
-            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * N * 12,
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": (2 if args.e2e_upload == "both" else 1) * B * N * 12,
+                    "h2d_only_ms_per_step": h2d_only_ms,
+                    "h2d_note": "h2d_only_ms_per_step = the same pinned-host -> device copy alone, all ranks at once (max "
+                                "over ranks): the PCIe floor of the step on this box; uploads: %s" % (
+                                    "cloud + prediction" if args.e2e_upload == "both" else
+                                    "the cloud (the prediction is a device-side product of the model)"),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "loss_checked_against_device_chain": e2e_checked,
                     "how": "public modules (Group, ChamferDistanceL2, autograd) on double-buffered inputs; every step "
                            "copies the next batch from pinned host memory and the loss back to the host (a training step: "
@@ -870,6 +892,9 @@ def main():
                          "the Chamfer scan kernel and overlaps the step's tail instead (measured 6 %% slower: the tail "
                          "kernels are issue-bound like the kNN, the FMA-bound scan is the better partner)")
     ap.add_argument("--no-graphs", action="store_true", help="issue the resident chain eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--e2e-upload", default="cloud", choices=["cloud", "both"],
+                    help="what the end-to-end arm copies from pinned host memory every step: the cloud (default; the "
+                         "prediction is produced on the device by the model) or cloud + prediction")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config (C2..C5) and sharded-C5 evidence blocks")
     args = ap.parse_args()
     if args.warmup < 3:

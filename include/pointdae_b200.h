@@ -157,6 +157,18 @@ int pdae_chamfer_loss_bwd_f32(const float *xyz1, const float *xyz2, const int *i
                               const float *dist2, const float *gloss, float w1, float w2, int b, int n, int m, int l1,
                               float *gx1, float *gx2, pdae_stream_t stream);
 
+/* ---- "next" rows: the dense consumers on the tensor cores --------------------------------------
+ * replaces: the 1x1 convolutions of `dgcnn_encoder` (nn.Conv2d(2C, Co, 1, bias=False) over the graph feature,
+ *           models/dgcnn_util.py:96-128 -- through the identity W [x_j - x_i ; x_i] = W1 x_j + (W2 - W1) x_i it is
+ *           one Conv1d-shaped product per layer) and of the patch `Encoder` (nn.Conv1d, models/PointCAE_transformer.py:
+ *           24-35).
+ * z[b][j][n] = sum_c w[j][c] * x[b][c][n]:  x (b,c,n), w (j,c), z (b,j,n), fp32 in and out.  tcgen05.mma kind::tf32 with
+ * the 3xTF32 operand split (fp32 accuracy, ~1e-6 relative), accumulator in tensor memory.  The workspace holds the
+ * weights' hi / lo shared-memory images (pdae_conv1x1_workspace_bytes).                                            */
+size_t pdae_conv1x1_workspace_bytes(int c, int j);
+int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, int c, int n, int j, float *z, void *workspace,
+                            size_t workspace_bytes, pdae_stream_t stream);
+
 /* tuning hook, no reference counterpart: select the CTA shape of the large-cloud forward kernel (ids as the
  * PDAE_CHAMFER_CFG environment variable; v < 0 only queries).  Returns the previous id.  Not thread-safe.      */
 int pdae_tune_chamfer_variant(int v);

@@ -123,6 +123,7 @@ def corrupt_stack(batch_size, type=['clean']):
     """The (B,T,3,3) CPU tensor of matrices `corrupt_data(..., type)` would apply, in order (None when it applies
     nothing).  Consumes the host RNGs exactly as the reference's `corrupt_data` does."""
     mats = []
+    level_bound = False  # the reference's `level = 4` (:718) stays bound for later items of the same call
     for corruption_item in type:
         if corruption_item == 'clean' or corruption_item == 'Drop-Patch':
             pass
@@ -130,10 +131,16 @@ def corrupt_stack(batch_size, type=['clean']):
             number = random.choice([1, 2, 3])
             for name in random.sample(affine_corruptions, number):
                 mats.append(affine_matrices[name](batch_size, 4))
+                level_bound = True
+        elif level_bound and corruption_item in affine_matrices:
+            # generic branch (:719-723) after an 'affine_r3' item, e.g. type=['affine_r3', 'rotate_z']: level is 4
+            mats.append(affine_matrices[corruption_item](batch_size, 4))
+        elif level_bound:
+            raise KeyError(corruption_item)  # corruptions[corruption_item] (:723): not an affine corruption of this module
         else:
-            # the reference's generic branch evaluates an unbound `level` (:722): same outcome, stated plainly
+            # the reference's generic branch evaluates an unbound `level` (:723): same outcome, stated plainly
             raise NameError("corrupt_data: corruption %r needs a `level` the reference never defines "
-                            "(datasets/corrupt_util_tensor.py:722)" % (corruption_item,))
+                            "(datasets/corrupt_util_tensor.py:723)" % (corruption_item,))
     return torch.stack(mats, dim=1) if mats else None
 
 

@@ -9,9 +9,19 @@ from . import ops
 from .knn_cuda import KNN
 
 
+def _needs_grad(t):
+    return torch.is_grad_enabled() and t.requires_grad
+
+
 def fps(data, number):
-    """utils/misc.py:13-20.  data (B,N,3|6) -> (fps_idx (B,G) int32, fps_data (B,G,3|6))."""
-    return ops.fps_gather(data, number)
+    """utils/misc.py:13-20.  data (B,N,3|6) -> (fps_idx (B,G) int32, fps_data (B,G,3|6)).
+    The reference gathers the centres with the differentiable `gather_operation`; every call site passes raw data, so
+    the fused kernel (no autograd node) is the normal route, and a tensor that requires grad takes the differentiable
+    gather through the same indices (same values, gradient scattered to the picked rows)."""
+    fps_idx, fps_data = ops.fps_gather(data, number)
+    if _needs_grad(data):
+        fps_data = torch.gather(data, 1, fps_idx.long().unsqueeze(-1).expand(-1, -1, data.size(2)))
+    return fps_idx, fps_data
 
 
 class Group(nn.Module):  # FPS + KNN
@@ -31,6 +41,9 @@ class Group(nn.Module):  # FPS + KNN
         _, center = fps(xyz, self.num_group)  # B G 3
         if knn_after is not None:
             torch.cuda.current_stream().wait_event(knn_after)
+        if _needs_grad(xyz):  # the reference's indexing and subtraction are differentiable (:80-85)
+            _, idx = ops.group_points_knn(xyz.detach(), center.detach(), self.group_size, want_idx=True)
+            return _gather_rows(xyz, idx) - center.unsqueeze(2), center
         neighborhood, _ = ops.group_points_knn(xyz.detach(), center, self.group_size, want_idx=False)
         return neighborhood, center
 
@@ -54,7 +67,9 @@ class Group(nn.Module):  # FPS + KNN
 def _patches_with_idx(xyz_only, num_group, group_size):
     """FPS + centre gather, kNN + gather + centre-subtract with the int64 neighbour indices kept: two launches."""
     fps_idx, center = fps(xyz_only, num_group)
-    neighborhood, idx = ops.group_points_knn(xyz_only.detach(), center, group_size, want_idx=True)
+    neighborhood, idx = ops.group_points_knn(xyz_only.detach(), center.detach(), group_size, want_idx=True)
+    if _needs_grad(xyz_only):  # differentiable like the reference's indexing + subtraction
+        neighborhood = _gather_rows(xyz_only, idx) - center.unsqueeze(2)
     return fps_idx, center, neighborhood, idx
 
 

@@ -624,6 +624,27 @@ class GraphFeatureFunction(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------- EdgeConv, eval mode (stage 1)
+def conv1x1(x, w):
+    """z[b,j,n] = sum_c w[j,c] x[b,c,n] on the tensor cores (tcgen05 kind::tf32, 3xTF32 split: fp32 accuracy).
+    x (B,C,N), w (J,C) f32 contiguous -> (B,J,N)."""
+    _require_cuda(x, "conv1x1")
+    _require_f32_contig(x, "x")
+    _require_f32_contig(w, "w")
+    _same_device(x.device, w=w)
+    b, c, n = x.shape
+    j = w.size(0)
+    if w.dim() != 2 or w.size(1) != c:
+        raise RuntimeError("w must have shape (J, %d), got %s" % (c, tuple(w.shape)))
+    L = _native.lib()
+    with _on(x.device):
+        z = torch.empty((b, j, n), dtype=torch.float32, device=x.device)
+        nbytes = int(L.pdae_conv1x1_workspace_bytes(c, j))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        rc = L.pdae_conv1x1_tf32x3_f32(x.data_ptr(), w.data_ptr(), b, c, n, j, z.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    _native.check(rc, "pdae_conv1x1_tf32x3_f32")
+    return z
+
+
 def edge_gather_extremum(p, q, idx, scale, shift, slope=0.2):
     """p, q (B,N,Co) f32 contiguous, idx (B,N,k) int64, scale / shift (Co) -> (B,Co,N):
     act(scale * (max|min_j p[idx] + q) + shift), max where scale >= 0, min where scale < 0 (pdae_edge_gather_extremum_f32)."""

@@ -190,3 +190,48 @@ def test_column_chunks_merge_through_packed_keys_to_the_unsplit_result(chunks):
     np.testing.assert_array_equal(got_d, want_d)
     np.testing.assert_array_equal(got_i, want_i)
     assert want_i[0, 3] == 7 and want_d[0, 3] == 0.0
+
+
+def test_group_and_fps_are_differentiable_when_the_input_requires_grad(monkeypatch):
+    """The reference's misc.fps gathers with the differentiable GatherOperation and Group indexes / subtracts with plain
+    torch (models/PointCAE_transformer.py:80-85): a tensor that requires grad must get the same gradient here (the fused
+    kernels carry no autograd node; advisor finding, round 1)."""
+    import _oracle_ops
+    for name in ("fps_gather", "group_points_knn"):
+        monkeypatch.setattr(ops, name, getattr(_oracle_ops, name))
+    from pointdae_b200 import synth
+    xyz = torch.from_numpy(synth.clouds(2, 200, seed=3)).requires_grad_(True)
+    nb, center = group.Group(8, 5)(xyz)
+    assert nb.requires_grad and center.requires_grad
+    (nb.sum() * 2.0 + center.sum()).backward()
+    # reference expression on the same indices
+    ref_in = xyz.detach().clone().requires_grad_(True)
+    idx = torch.from_numpy(oracle.fps(ref_in.detach().numpy(), 8)).long()
+    c_ref = torch.gather(ref_in, 1, idx.unsqueeze(-1).expand(-1, -1, 3))
+    _, knn_idx = _oracle_ops.knn_points(ref_in.detach(), c_ref.detach(), 5)
+    flat = (knn_idx + torch.arange(2).view(-1, 1, 1) * 200).view(-1)
+    nb_ref = ref_in.view(400, 3)[flat].view(2, 8, 5, 3) - c_ref.unsqueeze(2)
+    (nb_ref.sum() * 2.0 + c_ref.sum()).backward()
+    assert torch.equal(nb.detach(), nb_ref.detach()) and torch.equal(center.detach(), c_ref.detach())
+    assert torch.allclose(xyz.grad, ref_in.grad)
+    # raw data (every reference call site): fused route, no graph
+    nb2, c2 = group.Group(8, 5)(xyz.detach())
+    assert not nb2.requires_grad and torch.equal(nb2, nb.detach()) and torch.equal(c2, center.detach())
+
+
+def test_corrupt_stack_keeps_level_bound_after_an_affine_r3_item():
+    """datasets/corrupt_util_tensor.py:718-723: `level = 4` assigned inside the 'affine_r3' branch stays bound, so a later
+    generic item of the same list runs at level 4; without a preceding 'affine_r3' the reference raises NameError."""
+    import random
+    from pointdae_b200 import corrupt_util_tensor as cut
+    random.seed(1)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    mats = cut.corrupt_stack(3, ['affine_r3', 'rotate_z'])
+    assert mats.dim() == 4 and mats.shape[0] == 3 and mats.shape[2:] == (3, 3) and 2 <= mats.shape[1] <= 4
+    last = mats[:, -1]  # a rotation about z: third row / column untouched
+    assert torch.allclose(last[:, 2, 2], torch.ones(3, dtype=last.dtype)) and torch.allclose(last[:, 2, :2], torch.zeros(3, 2, dtype=last.dtype))
+    with pytest.raises(NameError):
+        cut.corrupt_stack(3, ['rotate_z'])
+    with pytest.raises(KeyError):
+        cut.corrupt_stack(3, ['affine_r3', 'jitter'])
