@@ -166,8 +166,31 @@ int pdae_chamfer_loss_bwd_f32(const float *xyz1, const float *xyz2, const int *i
  * the 3xTF32 operand split (fp32 accuracy, ~1e-6 relative), accumulator in tensor memory.  The workspace holds the
  * weights' hi / lo shared-memory images (pdae_conv1x1_workspace_bytes).                                            */
 size_t pdae_conv1x1_workspace_bytes(int c, int j);
-int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, int c, int n, int j, float *z, void *workspace,
-                            size_t workspace_bytes, pdae_stream_t stream);
+int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, int c, int n, int j, int in_point_major,
+                            int out_point_major, float *z, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+/* in_point_major / out_point_major: x is (b,n,c) / z is (b,n,j) instead of the channel-major layouts above.
+ *
+ * One EdgeConv layer on the point-major product z = [P | Q] (b,n,ld >= 2*co) of the call above with the stacked weight
+ * [W1 ; W2 - W1] (W = [W1 | W2] the layer's (co,2c) convolution weight): y[i][j] = P[idx(i,j)] + Q[i] is the layer's
+ * convolution output for edge (i,j) without the (b,2c,n,k) graph feature or the (b,co,n,k) tensor ever existing.
+ *   pdae_edge_stats_f64     per-CTA partial sums (pdae_edge_partial_count(b,n), co, 2) of sum y and sum y^2 -> BatchNorm
+ *                           batch statistics (training mode); summed by the caller in a fixed order.
+ *   pdae_edge_forward_f32   out (b,co,n) = LeakyReLU(scale (ext_j P[idx] + Q) + shift), ext = max where scale >= 0, min
+ *                           where scale < 0 (BatchNorm + LeakyReLU is monotone per channel); jstar (b,n,co) uint8 = the
+ *                           neighbour slot selected (NULL: not wanted).
+ *   pdae_edge_backward_f32  partial != NULL: per-CTA partial sums of dbeta / dgamma from g (b,n,co), the upstream
+ *                           gradient point-major.  dz != NULL: dz (b,n,ld) = [dP | dQ], zero-filled by the caller
+ *                           (dP is scatter-added); train = 1 adds the two per-channel terms training-mode BatchNorm
+ *                           spreads over every edge (ca, cb = gamma dbeta / M, gamma dgamma / M, M = b n k).      */
+size_t pdae_edge_partial_count(int b, int n);
+int pdae_edge_stats_f64(const float *z, int ld, const int64_t *idx, int b, int n, int k, int co, double *partial,
+                        pdae_stream_t stream);
+int pdae_edge_forward_f32(const float *z, int ld, const int64_t *idx, const float *scale, const float *shift, float slope,
+                          int b, int n, int k, int co, float *out, unsigned char *jstar, pdae_stream_t stream);
+int pdae_edge_backward_f32(const float *z, int ld, const int64_t *idx, const unsigned char *jstar, const float *g,
+                           const float *scale, const float *shift, const float *mean, const float *invstd,
+                           const float *gamma, const float *ca, const float *cb, float slope, int train, int b, int n, int k,
+                           int co, double *partial, float *dz, pdae_stream_t stream);
 
 /* tuning hook, no reference counterpart: select the CTA shape of the large-cloud forward kernel (ids as the
  * PDAE_CHAMFER_CFG environment variable; v < 0 only queries).  Returns the previous id.  Not thread-safe.      */

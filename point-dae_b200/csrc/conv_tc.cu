@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) conv_pack_weights_kernel(const float *__r
 
 // One CTA = 128 points of one cloud x NT output channels.  128 threads (the four warps own the four 32-lane quarters of the
 // accumulator in the epilogue).
-template <int NT>
+// IN_PM / OUT_PM: the activations / the result are point-major ((b, n, c) / (b, n, j)) instead of channel-major.
+template <int NT, bool IN_PM, bool OUT_PM>
 __global__ void __launch_bounds__(128) conv1x1_tc_kernel(const float *__restrict__ x, const float *__restrict__ wpacked, int c,
                                                         int cpad, int n, int j, float *__restrict__ z) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -156,10 +157,16 @@ __global__ void __launch_bounds__(128) conv1x1_tc_kernel(const float *__restrict
 #pragma unroll 2
       for (int kc16 = 0; kc16 < TC_KC / 4; ++kc16) {
         float v[4];
+        const int ch0 = kch * TC_KC + kc16 * 4;
+        if (IN_PM && in && (c & 3) == 0 && ch0 + 3 < c) {  // a point's channels are contiguous: one 128-bit load
+          const float4 t = __ldg(reinterpret_cast<const float4 *>(X + static_cast<size_t>(p) * c + ch0));
+          v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ch = kch * TC_KC + kc16 * 4 + e;
-          v[e] = (in && ch < c) ? __ldg(X + static_cast<size_t>(ch) * n + p) : 0.f;
+          for (int e = 0; e < 4; ++e) {
+            const int ch = ch0 + e;
+            v[e] = (in && ch < c) ? __ldg(IN_PM ? X + static_cast<size_t>(p) * c + ch : X + static_cast<size_t>(ch) * n + p) : 0.f;
+          }
         }
         float4 hi, lo;
         hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u), lo.x = __fsub_rn(v[0], hi.x);
@@ -208,10 +215,20 @@ __global__ void __launch_bounds__(128) conv1x1_tc_kernel(const float *__restrict
       tc::tmem_ld16(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
       tc::tmem_ld16(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + NT + c0, s);
       if (p < n) {
+        float v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int jj = ntile * NT + c0 + e;
-          if (jj < j) Z[static_cast<size_t>(jj) * n + p] = __fadd_rn(__uint_as_float(r[e]), __uint_as_float(s[e]));
+        for (int e = 0; e < 16; ++e) v[e] = __fadd_rn(__uint_as_float(r[e]), __uint_as_float(s[e]));
+        const int jj0 = ntile * NT + c0;
+        if (OUT_PM && (j & 3) == 0 && jj0 + 15 < j) {  // 64 contiguous bytes of the point's row
+          float4 *dst = reinterpret_cast<float4 *>(Z + static_cast<size_t>(p) * j + jj0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int jj = jj0 + e;
+            if (jj < j) Z[OUT_PM ? static_cast<size_t>(p) * j + jj : static_cast<size_t>(jj) * n + p] = v[e];
+          }
         }
       }
     }
@@ -234,8 +251,25 @@ extern "C" size_t pdae_conv1x1_workspace_bytes(int c, int j) {
   return static_cast<size_t>(ntiles) * nt * cpad * 2 * sizeof(float);
 }
 
-extern "C" int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, int c, int n, int j, float *z, void *workspace,
-                                       size_t workspace_bytes, pdae_stream_t stream) {
+template <int NT, bool IN_PM, bool OUT_PM>
+static int conv_launch(const float *x, const float *packed, int b, int c, int cpad, int n, int j, int ntiles, float *z,
+                       cudaStream_t st) {
+  const dim3 grid(ceil_div(n, TC_M), ntiles, b);
+  const size_t smem = 128 + static_cast<size_t>(2) * TC_M * TC_KC * 4 + static_cast<size_t>(2) * NT * TC_KC * 4;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(conv1x1_tc_kernel<NT, IN_PM, OUT_PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    configured = true;
+  }
+  conv1x1_tc_kernel<NT, IN_PM, OUT_PM><<<grid, 128, smem, st>>>(x, packed, c, cpad, n, j, z);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+extern "C" int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, int c, int n, int j, int in_point_major,
+                                       int out_point_major, float *z, void *workspace, size_t workspace_bytes,
+                                       pdae_stream_t stream) {
   if (b < 0 || c <= 0 || n < 0 || j <= 0) return PDAE_E_INVALID;
   if (b == 0 || n == 0) return 0;
   if (!x || !w || !z || !workspace) return PDAE_E_INVALID;
@@ -249,23 +283,15 @@ extern "C" int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, in
   conv_pack_weights_kernel<<<static_cast<unsigned>((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256), 256, 0, st>>>(
       w, j, c, nt, cpad, packed);
   PDAE_RETURN_IF_LAUNCH_FAILED();
-  const dim3 grid(ceil_div(n, TC_M), ntiles, b);
-  const size_t smem = 128 + static_cast<size_t>(2) * TC_M * TC_KC * 4 + static_cast<size_t>(2) * nt * TC_KC * 4;
-  if (nt == 128) {
-    static bool set128 = false;
-    if (!set128) {
-      PDAE_CUDA_TRY(cudaFuncSetAttribute(conv1x1_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      set128 = true;
-    }
-    conv1x1_tc_kernel<128><<<grid, 128, smem, st>>>(x, packed, c, cpad, n, j, z);
-  } else {
-    static bool set256 = false;
-    if (!set256) {
-      PDAE_CUDA_TRY(cudaFuncSetAttribute(conv1x1_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      set256 = true;
-    }
-    conv1x1_tc_kernel<256><<<grid, 128, smem, st>>>(x, packed, c, cpad, n, j, z);
+  const int sel = (nt == 256 ? 4 : 0) | (in_point_major ? 2 : 0) | (out_point_major ? 1 : 0);
+  switch (sel) {
+    case 0: return conv_launch<128, false, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    case 1: return conv_launch<128, false, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    case 2: return conv_launch<128, true, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    case 3: return conv_launch<128, true, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    case 4: return conv_launch<256, false, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    case 5: return conv_launch<256, false, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    case 6: return conv_launch<256, true, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    default: return conv_launch<256, true, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
   }
-  PDAE_RETURN_IF_LAUNCH_FAILED();
-  return 0;
 }

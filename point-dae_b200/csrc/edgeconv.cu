@@ -98,3 +98,334 @@ extern "C" int pdae_edge_gather_extremum_f32(const float *p, const float *q, con
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
+
+// ======================================================================================================================
+// Second stage (training mode + backward): the same layer on a point-major product Z = [P | Q] (b, n, 2*co) that
+// pdae_conv1x1_tf32x3_f32 writes (tensor cores), with BatchNorm batch statistics from gather sums and the backward pass
+// through the maximum, LeakyReLU, BatchNorm and the gather.  With y[i][j][o] = P[idx(i,j)][o] + Q[i][o]:
+//   statistics   sum_j y = s1 + k q,   sum_j y^2 = s2 + 2 q s1 + k q^2     (s1 = sum_j p_j, s2 = sum_j p_j^2)
+//   forward      out[o][i] = act(scale_o (ext_j p_j + q) + shift_o), jstar = first slot attaining the extremum
+//   backward     dbn = g * act'(bn*) on the selected edge;  dbeta = sum dbn,  dgamma = sum dbn * yhat*;
+//                training-mode BatchNorm spreads two per-channel terms over EVERY edge:
+//                  dy[i][j] = invstd (gamma dbn [j = jstar] - A - Bc yhat[i][j]),  A = gamma dbeta / M, Bc = gamma dgamma / M
+//                (eval-mode BatchNorm: A = Bc = 0, only the selected edges carry gradient);
+//                dP[idx(i,j)] += dy[i][j] (RED.ADD rows, coalesced over the channels), dQ[i] = sum_j dy[i][j].
+// All kernels: one warp per point, lanes over the channels (8 per lane and 256-channel pass), neighbour rows read as
+// coalesced row segments (L2 resident).
+namespace pdae {
+
+struct EdgeArgs {
+  const float *z;        // (b, n, ld): P = z[..., 0:co], Q = z[..., co:2co]
+  const int64_t *idx;    // (b, n, k) per-cloud neighbour indices
+  int ld, n, k, co;
+};
+
+__device__ __forceinline__ void edge_block_sums_to_global(double (&a)[EC_CHUNK / 32], double (&c)[EC_CHUNK / 32], double *sm, int c0,
+                                                          int co, double *__restrict__ partial) {
+  // sm: [2][EC_CHUNK] doubles, zeroed by the caller before the warps add their lanes' sums
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int u = 0; u < EC_CHUNK / 32; ++u) {
+    atomicAdd(sm + u * 32 + lane, a[u]);
+    atomicAdd(sm + EC_CHUNK + u * 32 + lane, c[u]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < EC_CHUNK; e += EC_WARPS * 32) {
+    const int o = c0 + e;
+    if (o < co) {
+      double *dst = partial + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * co * 2 + static_cast<size_t>(o) * 2;
+      dst[0] = sm[e], dst[1] = sm[EC_CHUNK + e];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(EC_WARPS * 32) edge_stats_kernel(const EdgeArgs a, double *__restrict__ partial) {
+  __shared__ double sm[2 * EC_CHUNK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t cloud = blockIdx.y;
+  const int i0 = blockIdx.x * EC_POINTS, n = a.n, k = a.k, co = a.co, ld = a.ld;
+  const float *__restrict__ Z = a.z + cloud * n * ld;
+  const int64_t *__restrict__ Ic = a.idx + cloud * n * k;
+  constexpr int PER_LANE = EC_CHUNK / 32, PER_WARP = EC_POINTS / EC_WARPS;
+  const float kf = static_cast<float>(k);
+  for (int c0 = 0; c0 < co; c0 += EC_CHUNK) {
+    for (int e = threadIdx.x; e < 2 * EC_CHUNK; e += EC_WARPS * 32) sm[e] = 0.0;
+    __syncthreads();
+    double t1[PER_LANE], t2[PER_LANE];
+#pragma unroll
+    for (int u = 0; u < PER_LANE; ++u) t1[u] = 0.0, t2[u] = 0.0;
+    for (int pw = 0; pw < PER_WARP; ++pw) {
+      const int i = i0 + warp * PER_WARP + pw;
+      if (i >= n) continue;  // warp-uniform
+      float s1[PER_LANE], s2[PER_LANE];
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) s1[u] = 0.f, s2[u] = 0.f;
+      for (int j = 0; j < k; ++j) {
+        const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + j)) * ld;
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) {
+          const int o = c0 + u * 32 + lane;
+          if (o < co) {
+            const float p = __ldg(Z + row + o);
+            s1[u] += p;
+            s2[u] = fmaf(p, p, s2[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) {
+        const int o = c0 + u * 32 + lane;
+        if (o < co) {
+          const double q = static_cast<double>(__ldg(Z + static_cast<size_t>(i) * ld + co + o));
+          t1[u] += static_cast<double>(s1[u]) + kf * q;
+          t2[u] += static_cast<double>(s2[u]) + 2.0 * q * static_cast<double>(s1[u]) + kf * q * q;
+        }
+      }
+    }
+    edge_block_sums_to_global(t1, t2, sm, c0, co, partial);
+  }
+}
+
+// forward on point-major Z: out (b, co, n) like the reference, jstar (b, n, co) = neighbour slot of the extremum
+__global__ void __launch_bounds__(EC_WARPS * 32) edge_forward_kernel(const EdgeArgs a, const float *__restrict__ scale,
+                                                                     const float *__restrict__ shift, float slope,
+                                                                     float *__restrict__ out, unsigned char *__restrict__ jstar) {
+  __shared__ float tile[EC_CHUNK][EC_POINTS + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t cloud = blockIdx.y;
+  const int i0 = blockIdx.x * EC_POINTS, n = a.n, k = a.k, co = a.co, ld = a.ld;
+  const float *__restrict__ Z = a.z + cloud * n * ld;
+  const int64_t *__restrict__ Ic = a.idx + cloud * n * k;
+  constexpr int PER_LANE = EC_CHUNK / 32, PER_WARP = EC_POINTS / EC_WARPS;
+  for (int c0 = 0; c0 < co; c0 += EC_CHUNK) {
+    float s[PER_LANE], t[PER_LANE], sgn[PER_LANE];
+#pragma unroll
+    for (int u = 0; u < PER_LANE; ++u) {
+      const int o = c0 + u * 32 + lane;
+      s[u] = o < co ? __ldg(scale + o) : 0.0f;
+      t[u] = o < co ? __ldg(shift + o) : 0.0f;
+      sgn[u] = s[u] >= 0.0f ? 1.0f : -1.0f;
+    }
+    for (int pw = 0; pw < PER_WARP; ++pw) {
+      const int pl = warp * PER_WARP + pw, i = i0 + pl;
+      if (i >= n) continue;
+      float acc[PER_LANE];
+      int js[PER_LANE];
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) acc[u] = -__int_as_float(0x7f800000), js[u] = 0;
+      for (int j = 0; j < k; ++j) {
+        const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + j)) * ld;
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) {
+          const int o = c0 + u * 32 + lane;
+          if (o < co) {
+            const float v = __fmul_rn(sgn[u], __ldg(Z + row + o));
+            if (v > acc[u]) acc[u] = v, js[u] = j;  // strict: the first slot attaining the extremum
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) {
+        const int o = c0 + u * 32 + lane;
+        if (o < co) {
+          const float v = __fadd_rn(__fmul_rn(sgn[u], acc[u]), __ldg(Z + static_cast<size_t>(i) * ld + co + o));
+          float y = __fmaf_rn(s[u], v, t[u]);
+          y = y >= 0.0f ? y : __fmul_rn(y, slope);
+          tile[u * 32 + lane][pl] = y;
+          if (jstar) jstar[(cloud * n + i) * co + o] = static_cast<unsigned char>(js[u]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < EC_CHUNK * EC_POINTS; e += EC_WARPS * 32) {
+      const int ol = e / EC_POINTS, pl = e - ol * EC_POINTS;
+      const int o = c0 + ol, i = i0 + pl;
+      if (o < co && i < n) out[(cloud * co + o) * n + i] = tile[ol][pl];
+    }
+    __syncthreads();
+  }
+}
+
+struct EdgeBwdArgs {
+  const unsigned char *jstar;  // (b, n, co)
+  const float *g;              // (b, n, co): upstream gradient, point-major
+  const float *scale, *shift;  // folded BatchNorm used in the forward
+  const float *mean, *invstd;  // statistics used in the forward
+  const float *gamma;          // BatchNorm weight
+  const float *ca, *cb;        // A, Bc per channel (zeros for eval-mode BatchNorm)
+  float slope;
+  int train;
+};
+
+// per-channel sums of dbn and dbn * yhat* (-> dbeta, dgamma)
+__global__ void __launch_bounds__(EC_WARPS * 32) edge_backward_reduce_kernel(const EdgeArgs a, const EdgeBwdArgs w,
+                                                                             double *__restrict__ partial) {
+  __shared__ double sm[2 * EC_CHUNK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t cloud = blockIdx.y;
+  const int i0 = blockIdx.x * EC_POINTS, n = a.n, k = a.k, co = a.co, ld = a.ld;
+  const float *__restrict__ Z = a.z + cloud * n * ld;
+  const int64_t *__restrict__ Ic = a.idx + cloud * n * k;
+  constexpr int PER_LANE = EC_CHUNK / 32, PER_WARP = EC_POINTS / EC_WARPS;
+  for (int c0 = 0; c0 < co; c0 += EC_CHUNK) {
+    for (int e = threadIdx.x; e < 2 * EC_CHUNK; e += EC_WARPS * 32) sm[e] = 0.0;
+    __syncthreads();
+    double t1[PER_LANE], t2[PER_LANE];
+#pragma unroll
+    for (int u = 0; u < PER_LANE; ++u) t1[u] = 0.0, t2[u] = 0.0;
+    for (int pw = 0; pw < PER_WARP; ++pw) {
+      const int i = i0 + warp * PER_WARP + pw;
+      if (i >= n) continue;
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) {
+        const int o = c0 + u * 32 + lane;
+        if (o < co) {
+          const size_t e = (cloud * n + i) * co + o;
+          const int js = w.jstar[e];
+          const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + js)) * ld;
+          const float y = __fadd_rn(__ldg(Z + row + o), __ldg(Z + static_cast<size_t>(i) * ld + co + o));
+          const float bn = __fmaf_rn(__ldg(w.scale + o), y, __ldg(w.shift + o));
+          const float dbn = __ldg(w.g + e) * (bn >= 0.0f ? 1.0f : w.slope);
+          const float yhat = (y - __ldg(w.mean + o)) * __ldg(w.invstd + o);
+          t1[u] += static_cast<double>(dbn);
+          t2[u] += static_cast<double>(dbn) * static_cast<double>(yhat);
+        }
+      }
+    }
+    edge_block_sums_to_global(t1, t2, sm, c0, co, partial);
+  }
+}
+
+// dZ = [dP | dQ] (b, n, 2*co), zero-filled by the caller
+__global__ void __launch_bounds__(EC_WARPS * 32) edge_backward_kernel(const EdgeArgs a, const EdgeBwdArgs w, float *__restrict__ dz) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t cloud = blockIdx.y;
+  const int i0 = blockIdx.x * EC_POINTS, n = a.n, k = a.k, co = a.co, ld = a.ld;
+  const float *__restrict__ Z = a.z + cloud * n * ld;
+  float *__restrict__ DZ = dz + cloud * n * ld;
+  const int64_t *__restrict__ Ic = a.idx + cloud * n * k;
+  constexpr int PER_LANE = EC_CHUNK / 32, PER_WARP = EC_POINTS / EC_WARPS;
+  for (int c0 = 0; c0 < co; c0 += EC_CHUNK) {
+    float sc[PER_LANE], sh[PER_LANE], mu[PER_LANE], is[PER_LANE], ga[PER_LANE], ca[PER_LANE], cb[PER_LANE];
+#pragma unroll
+    for (int u = 0; u < PER_LANE; ++u) {
+      const int o = c0 + u * 32 + lane;
+      const bool in = o < co;
+      sc[u] = in ? __ldg(w.scale + o) : 0.f, sh[u] = in ? __ldg(w.shift + o) : 0.f;
+      mu[u] = in ? __ldg(w.mean + o) : 0.f, is[u] = in ? __ldg(w.invstd + o) : 0.f;
+      ga[u] = in ? __ldg(w.gamma + o) : 0.f, ca[u] = in ? __ldg(w.ca + o) : 0.f, cb[u] = in ? __ldg(w.cb + o) : 0.f;
+    }
+    for (int pw = 0; pw < PER_WARP; ++pw) {
+      const int i = i0 + warp * PER_WARP + pw;
+      if (i >= n) continue;
+      float q[PER_LANE], dsel[PER_LANE], accq[PER_LANE];
+      int js[PER_LANE];
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) {
+        const int o = c0 + u * 32 + lane;
+        q[u] = 0.f, dsel[u] = 0.f, accq[u] = 0.f, js[u] = 0;
+        if (o < co) {
+          const size_t e = (cloud * n + i) * co + o;
+          js[u] = w.jstar[e];
+          q[u] = __ldg(Z + static_cast<size_t>(i) * ld + co + o);
+          const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + js[u])) * ld;
+          const float y = __fadd_rn(__ldg(Z + row + o), q[u]);
+          const float bn = __fmaf_rn(sc[u], y, sh[u]);
+          dsel[u] = ga[u] * (__ldg(w.g + e) * (bn >= 0.0f ? 1.0f : w.slope));  // gamma * dbn on the selected edge
+        }
+      }
+      if (w.train) {
+        for (int j = 0; j < k; ++j) {
+          const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + j)) * ld;
+#pragma unroll
+          for (int u = 0; u < PER_LANE; ++u) {
+            const int o = c0 + u * 32 + lane;
+            if (o < co) {
+              const float yhat = (__fadd_rn(__ldg(Z + row + o), q[u]) - mu[u]) * is[u];
+              const float val = is[u] * ((j == js[u] ? dsel[u] : 0.f) - ca[u] - cb[u] * yhat);
+              atomicAdd(DZ + row + o, val);
+              accq[u] += val;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) {
+          const int o = c0 + u * 32 + lane;
+          if (o < co) {
+            const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + js[u])) * ld;
+            accq[u] = is[u] * dsel[u];
+            atomicAdd(DZ + row + o, accq[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) {
+        const int o = c0 + u * 32 + lane;
+        if (o < co) DZ[static_cast<size_t>(i) * ld + co + o] = accq[u];
+      }
+    }
+  }
+}
+
+}  // namespace pdae
+
+static int edge_check(const float *z, const int64_t *idx, int b, int n, int k, int co, int ld) {
+  if (b < 0 || n < 0 || k <= 0 || co <= 0 || ld < 2 * co || k > 255) return PDAE_E_INVALID;
+  if (b > 65535) return PDAE_E_UNSUPPORTED;
+  if (b && n && (!z || !idx)) return PDAE_E_INVALID;
+  return 0;
+}
+
+extern "C" size_t pdae_edge_partial_count(int b, int n) {
+  return b <= 0 || n <= 0 ? 0 : static_cast<size_t>(b) * ((n + EC_POINTS - 1) / EC_POINTS);
+}
+
+extern "C" int pdae_edge_stats_f64(const float *z, int ld, const int64_t *idx, int b, int n, int k, int co, double *partial,
+                                   pdae_stream_t stream) {
+  const int rc = edge_check(z, idx, b, n, k, co, ld);
+  if (rc) return rc;
+  if (b == 0 || n == 0) return 0;
+  if (!partial) return PDAE_E_INVALID;
+  const dim3 grid(static_cast<unsigned>((n + EC_POINTS - 1) / EC_POINTS), static_cast<unsigned>(b));
+  edge_stats_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(EdgeArgs{z, idx, ld, n, k, co}, partial);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+extern "C" int pdae_edge_forward_f32(const float *z, int ld, const int64_t *idx, const float *scale, const float *shift,
+                                     float slope, int b, int n, int k, int co, float *out, unsigned char *jstar,
+                                     pdae_stream_t stream) {
+  const int rc = edge_check(z, idx, b, n, k, co, ld);
+  if (rc) return rc;
+  if (b == 0 || n == 0) return 0;
+  if (!scale || !shift || !out) return PDAE_E_INVALID;
+  const dim3 grid(static_cast<unsigned>((n + EC_POINTS - 1) / EC_POINTS), static_cast<unsigned>(b));
+  edge_forward_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(EdgeArgs{z, idx, ld, n, k, co}, scale, shift,
+                                                                                  slope, out, jstar);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+extern "C" int pdae_edge_backward_f32(const float *z, int ld, const int64_t *idx, const unsigned char *jstar, const float *g,
+                                      const float *scale, const float *shift, const float *mean, const float *invstd,
+                                      const float *gamma, const float *ca, const float *cb, float slope, int train, int b, int n,
+                                      int k, int co, double *partial, float *dz, pdae_stream_t stream) {
+  const int rc = edge_check(z, idx, b, n, k, co, ld);
+  if (rc) return rc;
+  if (b == 0 || n == 0) return 0;
+  if (!jstar || !g || !scale || !shift || !mean || !invstd || !gamma) return PDAE_E_INVALID;
+  if ((partial == nullptr) == (dz == nullptr)) return PDAE_E_INVALID;  // one phase per call
+  const dim3 grid(static_cast<unsigned>((n + EC_POINTS - 1) / EC_POINTS), static_cast<unsigned>(b));
+  const EdgeArgs a{z, idx, ld, n, k, co};
+  const EdgeBwdArgs w{jstar, g, scale, shift, mean, invstd, gamma, ca, cb, slope, train};
+  if (partial) {
+    edge_backward_reduce_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(a, w, partial);
+  } else {
+    if (!ca || !cb) return PDAE_E_INVALID;
+    edge_backward_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(a, w, dz);
+  }
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}

@@ -624,25 +624,168 @@ class GraphFeatureFunction(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------- EdgeConv, eval mode (stage 1)
-def conv1x1(x, w):
+def conv1x1(x, w, in_point_major=False, out_point_major=False):
     """z[b,j,n] = sum_c w[j,c] x[b,c,n] on the tensor cores (tcgen05 kind::tf32, 3xTF32 split: fp32 accuracy).
-    x (B,C,N), w (J,C) f32 contiguous -> (B,J,N)."""
+    x (B,C,N) -- or (B,N,C) with in_point_major --, w (J,C) f32 contiguous -> (B,J,N), or (B,N,J) with out_point_major."""
     _require_cuda(x, "conv1x1")
     _require_f32_contig(x, "x")
     _require_f32_contig(w, "w")
     _same_device(x.device, w=w)
-    b, c, n = x.shape
+    if in_point_major:
+        b, n, c = x.shape
+    else:
+        b, c, n = x.shape
     j = w.size(0)
     if w.dim() != 2 or w.size(1) != c:
         raise RuntimeError("w must have shape (J, %d), got %s" % (c, tuple(w.shape)))
     L = _native.lib()
     with _on(x.device):
-        z = torch.empty((b, j, n), dtype=torch.float32, device=x.device)
+        z = torch.empty((b, n, j) if out_point_major else (b, j, n), dtype=torch.float32, device=x.device)
         nbytes = int(L.pdae_conv1x1_workspace_bytes(c, j))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        rc = L.pdae_conv1x1_tf32x3_f32(x.data_ptr(), w.data_ptr(), b, c, n, j, z.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        rc = L.pdae_conv1x1_tf32x3_f32(x.data_ptr(), w.data_ptr(), b, c, n, j, 1 if in_point_major else 0,
+                                       1 if out_point_major else 0, z.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _native.check(rc, "pdae_conv1x1_tf32x3_f32")
     return z
+
+
+def _edge_dims(z, idx, co):
+    _require_cuda(z, "edge_conv")
+    _require_f32_contig(z, "z")
+    if idx.dtype != torch.int64 or not idx.is_contiguous() or idx.device != z.device:
+        raise RuntimeError("idx must be a contiguous int64 tensor on z's device")
+    b, n, ld = z.shape
+    k = idx.size(2)
+    if tuple(idx.shape[:2]) != (b, n) or ld < 2 * co or not (1 <= k <= 255):
+        raise RuntimeError("edge_conv: z %s / idx %s / co=%d do not match" % (tuple(z.shape), tuple(idx.shape), co))
+    return b, n, ld, k
+
+
+def edge_stats(z, idx, co):
+    """Sum and sum of squares per output channel of y[i][j] = P[idx(i,j)] + Q[i] over all edges of the batch, from the
+    point-major product z = [P | Q] (B,N,2*co): float64 (co, 2)."""
+    b, n, ld, k = _edge_dims(z, idx, co)
+    L = _native.lib()
+    with _on(z.device):
+        partial = torch.empty((int(L.pdae_edge_partial_count(b, n)), co, 2), dtype=torch.float64, device=z.device)
+        rc = L.pdae_edge_stats_f64(z.data_ptr(), ld, idx.data_ptr(), b, n, k, co, partial.data_ptr(), _stream())
+    _native.check(rc, "pdae_edge_stats_f64")
+    return partial.sum(dim=0)  # fixed order: deterministic
+
+
+def edge_forward(z, idx, co, scale, shift, slope=0.2, want_jstar=False):
+    """out (B,co,N) = LeakyReLU(scale * (ext_j P[idx] + Q) + shift) (+ the selected neighbour slots (B,N,co) uint8)."""
+    b, n, ld, k = _edge_dims(z, idx, co)
+    _require_f32_contig(scale, "scale")
+    _require_f32_contig(shift, "shift")
+    with _on(z.device):
+        out = torch.empty((b, co, n), dtype=torch.float32, device=z.device)
+        jstar = torch.empty((b, n, co), dtype=torch.uint8, device=z.device) if want_jstar else None
+        rc = _native.lib().pdae_edge_forward_f32(z.data_ptr(), ld, idx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                 float(slope), b, n, k, co, out.data_ptr(),
+                                                 jstar.data_ptr() if want_jstar else None, _stream())
+    _native.check(rc, "pdae_edge_forward_f32")
+    return out, jstar
+
+
+def edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, slope, train):
+    """Backward of edge_forward (+ training-mode BatchNorm when train): g_pm (B,N,co) upstream gradient, point-major ->
+    dz (B,N,ld) = [dP | dQ], dgamma (co), dbeta (co)."""
+    b, n, ld, k = _edge_dims(z, idx, co)
+    L = _native.lib()
+    args = (z.data_ptr(), ld, idx.data_ptr(), jstar.data_ptr(), g_pm.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+            mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr())
+    with _on(z.device):
+        partial = torch.empty((int(L.pdae_edge_partial_count(b, n)), co, 2), dtype=torch.float64, device=z.device)
+        rc = L.pdae_edge_backward_f32(*args, None, None, float(slope), 1 if train else 0, b, n, k, co, partial.data_ptr(), None,
+                                      _stream())
+        _native.check(rc, "pdae_edge_backward_f32 (reduce)")
+        sums = partial.sum(dim=0)
+        dbeta, dgamma = sums[:, 0], sums[:, 1]
+        m = float(b) * n * k
+        if train:
+            ca = (gamma.double() * dbeta / m).float().contiguous()
+            cb = (gamma.double() * dgamma / m).float().contiguous()
+        else:
+            ca = torch.zeros(co, dtype=torch.float32, device=z.device)
+            cb = ca
+        dz = torch.zeros_like(z)
+        rc = L.pdae_edge_backward_f32(*args, ca.data_ptr(), cb.data_ptr(), float(slope), 1 if train else 0, b, n, k, co, None,
+                                      dz.data_ptr(), _stream())
+    _native.check(rc, "pdae_edge_backward_f32")
+    return dz, dgamma.float(), dbeta.float()
+
+
+class EdgeConvFunction(torch.autograd.Function):
+    """One EdgeConv layer of the DGCNN encoder (models/dgcnn_util.py:114-116 and the three after it):
+    get_graph_feature(x, k, idx) -> Conv2d(2C, Co, 1, bias=False) -> BatchNorm2d -> LeakyReLU -> max over k, as
+    tensor-core product + gather kernels; the (B,2C,N,k) and (B,Co,N,k) tensors never exist.  Training-mode BatchNorm
+    takes its batch statistics from gather sums and updates the running buffers like nn.BatchNorm2d."""
+
+    @staticmethod
+    def forward(ctx, x, idx, wz, gamma, beta, running_mean, running_var, training, momentum, eps, slope):
+        co = wz.size(0) // 2
+        b, c, n = x.shape
+        k = idx.size(2)
+        x = x.contiguous()
+        z = conv1x1(x, wz.contiguous(), out_point_major=True)  # (B,N,2co): [W1 x | (W2 - W1) x]
+        if training:
+            sums = edge_stats(z, idx, co)
+            m = float(b) * n * k
+            mean64 = sums[:, 0] / m
+            var64 = (sums[:, 1] / m - mean64 * mean64).clamp_min_(0.0)
+            if running_mean is not None:
+                with torch.no_grad():
+                    running_mean.mul_(1.0 - momentum).add_(mean64.to(running_mean.dtype), alpha=momentum)
+                    running_var.mul_(1.0 - momentum).add_((var64 * (m / max(m - 1.0, 1.0))).to(running_var.dtype), alpha=momentum)
+            mean, var = mean64.float(), var64.float()
+        else:
+            mean, var = running_mean.float(), running_var.float()
+        invstd = torch.rsqrt(var + eps)
+        scale = (gamma * invstd).contiguous()
+        shift = (beta - scale * mean).contiguous()
+        need_grad = any(ctx.needs_input_grad)
+        out, jstar = edge_forward(z, idx, co, scale, shift, slope, want_jstar=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x, idx, wz, z, jstar, scale, shift, mean.contiguous(), invstd.contiguous(), gamma.contiguous())
+            ctx.meta = (co, float(slope), bool(training))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, idx, wz, z, jstar, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        co, slope, training = ctx.meta
+        g_pm = g_out.transpose(1, 2).contiguous()
+        dz, dgamma, dbeta = edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, slope, training)
+        dx = dwz = None
+        if ctx.needs_input_grad[0]:
+            dx = conv1x1(dz, wz.t().contiguous(), in_point_major=True)  # (B,C,N) = Wz^T [dP ; dQ]
+        if ctx.needs_input_grad[2]:
+            b, c, n = x.shape
+            # weight gradient: a (2co x B N) by (B N x C) product with a tiny output -- a plain library GEMM
+            dwz = torch.matmul(dz.reshape(b * n, 2 * co).t(), x.transpose(1, 2).reshape(b * n, c))
+        return dx, None, dwz, dgamma if ctx.needs_input_grad[3] else None, dbeta if ctx.needs_input_grad[4] else None, \
+            None, None, None, None, None, None
+
+
+def edge_conv(x, idx, weight, bn, slope=0.2):
+    """x (B,C,N), idx (B,N,k) per-cloud int64, weight (Co,2C) (the layer's 1x1 convolution, bias-free), bn the layer's
+    BatchNorm2d (its mode decides batch vs running statistics) -> (B,Co,N), differentiable w.r.t. x, weight, bn.weight,
+    bn.bias."""
+    c = x.size(1)
+    w = weight.reshape(weight.size(0), -1).float()
+    wz = torch.cat([w[:, :c], w[:, c:] - w[:, :c]], dim=0)  # differentiable: autograd maps d(wz) back to W1 / W2
+    train_stats = bn.training or bn.running_mean is None
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    gamma = bn.weight if bn.weight is not None else torch.ones(w.size(0), device=x.device)
+    beta = bn.bias if bn.bias is not None else torch.zeros(w.size(0), device=x.device)
+    return EdgeConvFunction.apply(x.float(), idx.contiguous(), wz, gamma.float(), beta.float(),
+                                  bn.running_mean if bn.track_running_stats else None,
+                                  bn.running_var if bn.track_running_stats else None, train_stats, momentum, bn.eps, slope)
 
 
 def edge_gather_extremum(p, q, idx, scale, shift, slope=0.2):
