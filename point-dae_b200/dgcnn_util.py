@@ -35,41 +35,51 @@ def get_graph_feature(x, k=20, idx=None, extra_dim=False):
     return feature  # (batch_size, 2 * num_dims, num_points, k)
 
 
-# ---- eval-mode EdgeConv layers without the k-replicated tensors (stage 1) --------------------------
+# ---- EdgeConv layers without the k-replicated tensors ---------------------------------------------
 def fold_batchnorm(bn):
     """BatchNorm (running statistics) as y * scale + shift."""
     scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
     return scale, bn.bias - scale * bn.running_mean
 
 
-def edge_conv_eval(x, block, k=20, idx=None):
-    """`get_graph_feature(x, k)` -> `block` -> max over k (models/dgcnn_util.py:114-116 and the three layers after it) for a
-    block = Sequential(Conv2d(2C, Co, 1, bias=False), BatchNorm2d, LeakyReLU) in eval mode: x (B,C,N) -> (B,Co,N).
-    Two GEMMs + one gather kernel (ops.edge_conv_max); the (B,2C,N,k) and (B,Co,N,k) tensors are never formed."""
-    conv, bn, act = block[0], block[1], block[2]
-    if bn.training:
-        raise RuntimeError("edge_conv_eval needs BatchNorm in eval mode (running statistics)")
-    if conv.bias is not None or tuple(conv.kernel_size) != (1, 1):
-        raise RuntimeError("edge_conv_eval expects the reference's bias-free 1x1 convolution")
+def _fusable(block):
+    """Sequential(Conv2d(2C, Co, 1, bias=False), BatchNorm2d, LeakyReLU) -- what models/dgcnn_util.py:96-110 builds."""
+    try:
+        conv, bn, act = block[0], block[1], block[2]
+    except (TypeError, IndexError):
+        return False
+    return (isinstance(conv, torch.nn.Conv2d) and conv.bias is None and tuple(conv.kernel_size) == (1, 1)
+            and tuple(conv.stride) == (1, 1) and conv.groups == 1 and isinstance(bn, torch.nn.BatchNorm2d)
+            and isinstance(act, torch.nn.LeakyReLU) and len(block) == 3
+            and (bn.training or bn.running_mean is not None)  # eval mode needs running statistics
+            and not torch.is_autocast_enabled())
+
+
+def edge_conv(x, block, k=20, idx=None):
+    """`get_graph_feature(x, k)` -> `block` -> max over k (models/dgcnn_util.py:114-116 and the three layers after it):
+    x (B,C,N) -> (B,Co,N), differentiable, training or eval BatchNorm (the block's own mode), on the tensor cores
+    (ops.edge_conv); the (B,2C,N,k) and (B,Co,N,k) tensors are never formed.  A block of another shape runs as the
+    reference wrote it."""
+    if not _fusable(block):
+        return block(get_graph_feature(x, k=k, idx=idx)).max(dim=-1, keepdim=False)[0]
     if idx is None:
         idx = knn(x, k)
-    scale, shift = fold_batchnorm(bn)
-    return ops.edge_conv_max(x, idx, conv.weight.view(conv.out_channels, -1), scale, shift, act.negative_slope)
+    return ops.edge_conv(x, idx, block[0].weight, block[1], block[2].negative_slope)
+
+
+def edge_conv_eval(x, block, k=20, idx=None):
+    """round-1 name: the same layer without autograd"""
+    with torch.no_grad():
+        return edge_conv(x, block, k=k, idx=idx)
 
 
 def dgcnn_encoder_forward(self, x):
-    """Drop-in for `dgcnn_encoder.forward` (models/dgcnn_util.py:112-133).  In eval mode without autograd (feature
-    extraction for the SVM / linear evaluation the runners do every epoch) the four EdgeConv layers take the fused
-    route; otherwise -- training needs batch statistics and gradients -- the layers run as the reference wrote them, on
-    this module's knn / get_graph_feature."""
+    """Drop-in for `dgcnn_encoder.forward` (models/dgcnn_util.py:112-133): the four EdgeConv layers take the fused route
+    (training and eval, with or without autograd), decided per block; conv5 and the pooling are the reference's."""
     batch_size = x.size()[0]
-    fused = not self.training and not torch.is_grad_enabled()
     feats = []
     for block in (self.conv1, self.conv2, self.conv3, self.conv4):
-        if fused:
-            x = edge_conv_eval(x, block, k=20)
-        else:
-            x = block(get_graph_feature(x, k=20)).max(dim=-1, keepdim=False)[0]
+        x = edge_conv(x, block, k=20)
         feats.append(x)
     x = self.conv5(torch.cat(feats, dim=1))
     return torch.nn.functional.adaptive_max_pool1d(x, 1).view(batch_size, -1)

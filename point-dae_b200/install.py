@@ -56,12 +56,13 @@ def install(loss_modules=False):
     return True
 
 
-def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentation.models.dgcnn_util"), edgeconv=False):
+def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentation.models.dgcnn_util"), edgeconv=True):
     """Rebind the pure-torch hot functions that live inside the reference's own packages: knn / get_graph_feature,
     misc.fps, the corruptions executed inside forward, and every flavour of the `Group` patchifier.  Names that other
     reference modules imported from the defining module (`from .Point_M2AE_modules import *`,
-    `from datasets.corrupt_util_tensor import corrupt_data`) are rebound there too.  `edgeconv=True` (opt-in) also routes
-    `dgcnn_encoder.forward` through the fused EdgeConv layers.  Returns what was rebound."""
+    `from datasets.corrupt_util_tensor import corrupt_data`) are rebound there too.  `edgeconv=True` (default) also routes
+    `dgcnn_encoder.forward` through the fused tensor-core EdgeConv layers (training and eval, differentiable; GPU parity in
+    tests/test_gpu_edgeconv_tc.py); `edgeconv=False` keeps the reference's layer sequence on this repo's knn / get_graph_feature.  Returns what was rebound."""
     from . import corrupt_util_tensor, dgcnn_util, group
 
     patched, replaced = [], {}

@@ -811,14 +811,15 @@ def edge_gather_extremum(p, q, idx, scale, shift, slope=0.2):
 def edge_conv_max(x, idx, weight, scale, shift, slope=0.2):
     """One eval-mode EdgeConv layer (models/dgcnn_util.py:114-126) without the k-replicated tensors: x (B,C,N), idx (B,N,k)
     per-cloud int64, weight (Co,2C) of the 1x1 convolution, BatchNorm folded to scale / shift (Co) -> (B,Co,N).
-    Two library GEMMs (x^T W1^T, x^T (W2 - W1)^T) + the gather-extremum kernel.  No gradient (eval only)."""
+    The tensor-core product [P | Q] = x^T [W1 ; W2 - W1]^T (conv1x1) + the gather kernel.  No gradient: the
+    differentiable, training-capable form is `edge_conv`."""
     c = x.size(1)
+    co = weight.size(0)
     with torch.no_grad():
-        xt = x.detach().float().transpose(1, 2)
-        w1, w2 = weight[:, :c].float(), weight[:, c:].float()
-        p = torch.matmul(xt, w1.t()).contiguous()
-        q = torch.matmul(xt, (w2 - w1).t()).contiguous()
-        return edge_gather_extremum(p, q, idx.contiguous(), scale.float().contiguous(), shift.float().contiguous(), slope)
+        w = weight.reshape(co, -1).float()
+        wz = torch.cat([w[:, :c], w[:, c:] - w[:, :c]], dim=0).contiguous()
+        z = conv1x1(x.detach().float().contiguous(), wz, out_point_major=True)
+        return edge_forward(z, idx.contiguous(), co, scale.float().contiguous(), shift.float().contiguous(), slope)[0]
 
 
 # ---------------------------------------------------------------------------- ball query / group

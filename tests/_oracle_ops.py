@@ -114,7 +114,23 @@ def edge_conv_max(x, idx, weight, scale, shift, slope=0.2):
                                    scale.detach().float().numpy(), shift.detach().float().numpy(), float(slope)))
 
 
-NAMES = ("edge_conv_max", "feat_knn", "_graph_feature_fwd", "_graph_feature_bwd", "GraphFeatureFunction", "furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "affine_points", "group_affine",
+def edge_conv(x, idx, weight, bn, slope=0.2):
+    """CPU stand-in for ops.edge_conv: the layer spelled out with torch's own differentiable ops (the reference's
+    expression, models/dgcnn_util.py:24-34 + the block + max), so the HOST wiring of dgcnn_util.edge_conv /
+    dgcnn_encoder_forward can run inside the reference's model on CPU tensors."""
+    import torch.nn.functional as F
+    b, c, n = x.shape
+    k = idx.size(2)
+    flat = (idx + torch.arange(b).view(-1, 1, 1) * n).view(-1)
+    xt = x.transpose(2, 1).contiguous()
+    neigh = xt.view(b * n, c)[flat, :].view(b, n, k, c)
+    xi = xt.view(b, n, 1, c).expand(-1, -1, k, -1)
+    feature = torch.cat((neigh - xi, xi), dim=3).permute(0, 3, 1, 2)
+    y = F.conv2d(feature, weight.reshape(weight.size(0), 2 * c, 1, 1))
+    return F.leaky_relu(bn(y), slope).max(dim=-1, keepdim=False)[0]
+
+
+NAMES = ("edge_conv", "edge_conv_max", "feat_knn", "_graph_feature_fwd", "_graph_feature_bwd", "GraphFeatureFunction", "furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "affine_points", "group_affine",
          "chamfer_forward", "chamfer_backward", "chamfer_mean_loss", "chamfer_loss_backward")
 EXT_NAMES = ("gather_points", "gather_points_grad", "ball_query", "group_points", "group_points_grad", "three_nn",
              "three_interpolate", "three_interpolate_grad")

@@ -46,8 +46,7 @@ else:
     _oracle_ops.apply()
 _ref_stubs.install_third_party()
 models, _ = _ref_stubs.import_with_stubs("models")
-patched = (pointdae_b200.patch_models(edgeconv=bool(os.environ.get("PDAE_PROBE_EVAL")))  # the fused EdgeConv route is opt-in
-           if MODE in ("patched", "patched_loss") else [])
+patched = pointdae_b200.patch_models() if MODE in ("patched", "patched_loss") else []
 
 from easydict import EasyDict  # noqa: E402
 from pointdae_b200 import synth  # noqa: E402

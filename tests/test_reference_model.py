@@ -172,8 +172,8 @@ def test_masksurf_v2_attribute_group_inside_the_model():
 
 def test_eval_mode_dgcnn_encoder_takes_the_fused_edgeconv_route():
     """Feature extraction (eval mode, no autograd) through the reference's `Point_CAE_DGCNN.dgcnn_encoder`: after
-    patch_models() the four EdgeConv layers run as two GEMMs + a gather-extremum each (ops.edge_conv_max; here served by
-    the oracle) on this repo's direct-form kNN, and the 1024-d feature equals the reference's own forward.  Tolerance
+    patch_models(edgeconv=True) the four EdgeConv layers take dgcnn_util.edge_conv (ops.edge_conv; here served by a torch
+    stand-in of the same layer) on this repo's direct-form kNN, and the 1024-d feature equals the reference's own forward.  Tolerance
     1e-4: neighbour sets may differ on near-ties of the reference's expanded-form ranking."""
     out = _run_all("dgcnn", modes=("reference", "patched"), evaluate=True)
     ref, got = out["reference"], out["patched"]
