@@ -166,9 +166,11 @@ int pdae_chamfer_loss_bwd_f32(const float *xyz1, const float *xyz2, const int *i
  * the 3xTF32 operand split (fp32 accuracy, ~1e-6 relative), accumulator in tensor memory.  The workspace holds the
  * weights' hi / lo shared-memory images (pdae_conv1x1_workspace_bytes).                                            */
 size_t pdae_conv1x1_workspace_bytes(int c, int j);
-int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, int c, int n, int j, int in_point_major,
-                            int out_point_major, float *z, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
-/* in_point_major / out_point_major: x is (b,n,c) / z is (b,n,j) instead of the channel-major layouts above.
+int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, const float *bias, int b, int c, int n, int j,
+                            int in_point_major, int out_point_major, float *z, void *workspace, size_t workspace_bytes,
+                            pdae_stream_t stream);
+/* bias (j) or NULL is added in the epilogue (nn.Conv1d's bias).  in_point_major / out_point_major: x is (b,n,c) / z is
+ * (b,n,j) instead of the channel-major layouts above.
  *
  * One EdgeConv layer on the point-major product z = [P | Q] (b,n,ld >= 2*co) of the call above with the stacked weight
  * [W1 ; W2 - W1] (W = [W1 | W2] the layer's (co,2c) convolution weight): y[i][j] = P[idx(i,j)] + Q[i] is the layer's

@@ -109,8 +109,9 @@ __global__ void __launch_bounds__(256) conv_pack_weights_kernel(const float *__r
 // accumulator in the epilogue).
 // IN_PM / OUT_PM: the activations / the result are point-major ((b, n, c) / (b, n, j)) instead of channel-major.
 template <int NT, bool IN_PM, bool OUT_PM>
-__global__ void __launch_bounds__(128) conv1x1_tc_kernel(const float *__restrict__ x, const float *__restrict__ wpacked, int c,
-                                                        int cpad, int n, int j, float *__restrict__ z) {
+__global__ void __launch_bounds__(128) conv1x1_tc_kernel(const float *__restrict__ x, const float *__restrict__ wpacked,
+                                                        const float *__restrict__ bias, int c, int cpad, int n, int j,
+                                                        float *__restrict__ z) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem_raw);       // weights landed (TMA)
   uint64_t *bar_mma = bar_w + 1;                                  // MMAs of the chunk retired
@@ -219,6 +220,11 @@ __global__ void __launch_bounds__(128) conv1x1_tc_kernel(const float *__restrict
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = __fadd_rn(__uint_as_float(r[e]), __uint_as_float(s[e]));
         const int jj0 = ntile * NT + c0;
+        if (bias) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (jj0 + e < j) v[e] = __fadd_rn(v[e], __ldg(bias + jj0 + e));
+        }
         if (OUT_PM && (j & 3) == 0 && jj0 + 15 < j) {  // 64 contiguous bytes of the point's row
           float4 *dst = reinterpret_cast<float4 *>(Z + static_cast<size_t>(p) * j + jj0);
 #pragma unroll
@@ -252,8 +258,8 @@ extern "C" size_t pdae_conv1x1_workspace_bytes(int c, int j) {
 }
 
 template <int NT, bool IN_PM, bool OUT_PM>
-static int conv_launch(const float *x, const float *packed, int b, int c, int cpad, int n, int j, int ntiles, float *z,
-                       cudaStream_t st) {
+static int conv_launch(const float *x, const float *packed, const float *bias, int b, int c, int cpad, int n, int j, int ntiles,
+                       float *z, cudaStream_t st) {
   const dim3 grid(ceil_div(n, TC_M), ntiles, b);
   const size_t smem = 128 + static_cast<size_t>(2) * TC_M * TC_KC * 4 + static_cast<size_t>(2) * NT * TC_KC * 4;
   static bool configured = false;  // per instantiation
@@ -262,14 +268,14 @@ static int conv_launch(const float *x, const float *packed, int b, int c, int cp
                                        static_cast<int>(smem)));
     configured = true;
   }
-  conv1x1_tc_kernel<NT, IN_PM, OUT_PM><<<grid, 128, smem, st>>>(x, packed, c, cpad, n, j, z);
+  conv1x1_tc_kernel<NT, IN_PM, OUT_PM><<<grid, 128, smem, st>>>(x, packed, bias, c, cpad, n, j, z);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
 
-extern "C" int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, int c, int n, int j, int in_point_major,
-                                       int out_point_major, float *z, void *workspace, size_t workspace_bytes,
-                                       pdae_stream_t stream) {
+extern "C" int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, const float *bias, int b, int c, int n, int j,
+                                       int in_point_major, int out_point_major, float *z, void *workspace,
+                                       size_t workspace_bytes, pdae_stream_t stream) {
   if (b < 0 || c <= 0 || n < 0 || j <= 0) return PDAE_E_INVALID;
   if (b == 0 || n == 0) return 0;
   if (!x || !w || !z || !workspace) return PDAE_E_INVALID;
@@ -285,13 +291,13 @@ extern "C" int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, int b, in
   PDAE_RETURN_IF_LAUNCH_FAILED();
   const int sel = (nt == 256 ? 4 : 0) | (in_point_major ? 2 : 0) | (out_point_major ? 1 : 0);
   switch (sel) {
-    case 0: return conv_launch<128, false, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
-    case 1: return conv_launch<128, false, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
-    case 2: return conv_launch<128, true, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
-    case 3: return conv_launch<128, true, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
-    case 4: return conv_launch<256, false, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
-    case 5: return conv_launch<256, false, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
-    case 6: return conv_launch<256, true, false>(x, packed, b, c, cpad, n, j, ntiles, z, st);
-    default: return conv_launch<256, true, true>(x, packed, b, c, cpad, n, j, ntiles, z, st);
+    case 0: return conv_launch<128, false, false>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
+    case 1: return conv_launch<128, false, true>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
+    case 2: return conv_launch<128, true, false>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
+    case 3: return conv_launch<128, true, true>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
+    case 4: return conv_launch<256, false, false>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
+    case 5: return conv_launch<256, false, true>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
+    case 6: return conv_launch<256, true, false>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
+    default: return conv_launch<256, true, true>(x, packed, bias, b, c, cpad, n, j, ntiles, z, st);
   }
 }

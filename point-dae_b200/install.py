@@ -90,6 +90,18 @@ def patch_models(names=("models.dgcnn_util", "models.PointCAE_DGCNN", "segmentat
             patched.append("models.dgcnn_util.dgcnn_encoder.forward")
     except Exception:
         pass
+    # the patch Encoder (mini-PointNet) of every transformer model that defines one: forward on the tensor cores
+    if edgeconv:
+        from . import encoder
+        for mname, mod in list(sys.modules.items()):
+            if mod is None or not mname.startswith("models."):
+                continue
+            cls = vars(mod).get("Encoder")
+            if isinstance(cls, type) and getattr(cls, "__module__", None) == mname and hasattr(cls, "forward") \
+                    and cls.forward is not encoder.encoder_forward:
+                cls._pdae_reference_forward = cls.forward
+                cls.forward = encoder.encoder_forward
+                patched.append(mname + ".Encoder.forward")
     try:
         rebind(importlib.import_module("utils.misc"), "fps", group.fps, "utils.misc")
     except Exception:

@@ -624,8 +624,8 @@ class GraphFeatureFunction(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------- EdgeConv, eval mode (stage 1)
-def conv1x1(x, w, in_point_major=False, out_point_major=False):
-    """z[b,j,n] = sum_c w[j,c] x[b,c,n] on the tensor cores (tcgen05 kind::tf32, 3xTF32 split: fp32 accuracy).
+def conv1x1(x, w, in_point_major=False, out_point_major=False, bias=None):
+    """z[b,j,n] = sum_c w[j,c] x[b,c,n] (+ bias[j]) on the tensor cores (tcgen05 kind::tf32, 3xTF32 split: fp32 accuracy).
     x (B,C,N) -- or (B,N,C) with in_point_major --, w (J,C) f32 contiguous -> (B,J,N), or (B,N,J) with out_point_major."""
     _require_cuda(x, "conv1x1")
     _require_f32_contig(x, "x")
@@ -643,10 +643,43 @@ def conv1x1(x, w, in_point_major=False, out_point_major=False):
         z = torch.empty((b, n, j) if out_point_major else (b, j, n), dtype=torch.float32, device=x.device)
         nbytes = int(L.pdae_conv1x1_workspace_bytes(c, j))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        rc = L.pdae_conv1x1_tf32x3_f32(x.data_ptr(), w.data_ptr(), b, c, n, j, 1 if in_point_major else 0,
+        if bias is not None:
+            _require_f32_contig(bias, "bias")
+            _same_device(x.device, bias=bias)
+            if bias.numel() != j:
+                raise RuntimeError("bias must have %d elements" % j)
+        rc = L.pdae_conv1x1_tf32x3_f32(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, b, c, n, j,
+                                       1 if in_point_major else 0,
                                        1 if out_point_major else 0, z.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _native.check(rc, "pdae_conv1x1_tf32x3_f32")
     return z
+
+
+class Conv1x1Function(torch.autograd.Function):
+    """nn.Conv1d(C, J, 1) on point-major activations: x (N,C), weight (J,C), bias (J)|None -> (N,J); forward and the input
+    gradient on the tensor cores, the (J x C) weight gradient as one plain library product."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight = x.contiguous(), weight.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return conv1x1(x.unsqueeze(0), weight, True, True, bias.contiguous() if bias is not None else None).squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        dx = conv1x1(g.unsqueeze(0), weight.t().contiguous(), True, True).squeeze(0) if ctx.needs_input_grad[0] else None
+        dw = torch.matmul(g.t(), x) if ctx.needs_input_grad[1] else None
+        db = g.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def pointwise_conv(x, conv):
+    """x (N,C) point-major through an nn.Conv1d(C, J, kernel_size=1) -> (N,J)"""
+    return Conv1x1Function.apply(x.float(), conv.weight.reshape(conv.out_channels, -1).float(),
+                                 conv.bias.float() if conv.bias is not None else None)
 
 
 def _edge_dims(z, idx, co):
