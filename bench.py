@@ -696,6 +696,34 @@ def config_blocks(dev, peaks, world, max_over_ranks):
         nbytes = b3 * 2048 * 20 * 2 * C * 4 + b3 * C * 2048 * 4 + b3 * 2048 * 20 * 8
         c3["graph feature C=%d" % C] = entry(_median_ms(lambda: ops._graph_feature_fwd(x, idx), reps=3), nbytes=nbytes)
         del x, idx
+    # the EdgeConv layers that consume the graph feature: tensor-core route against the reference's own
+    # layer sequence (get_graph_feature -> Conv2d -> BatchNorm2d -> LeakyReLU -> max, models/dgcnn_util.py:114-128) run by
+    # torch on the same GPU with its defaults, training mode, forward + backward
+    import torch.nn as nn
+
+    def ref_layer(x, idx, block):
+        bb, cc, nn_ = x.shape
+        kk = idx.size(2)
+        flat = (idx + torch.arange(bb, device=x.device).view(-1, 1, 1) * nn_).view(-1)
+        xt = x.transpose(2, 1).contiguous()
+        neigh = xt.view(bb * nn_, cc)[flat, :].view(bb, nn_, kk, cc)
+        xi = xt.view(bb, nn_, 1, cc).repeat(1, 1, kk, 1)
+        return block(torch.cat((neigh - xi, xi), dim=3).permute(0, 3, 1, 2).contiguous()).max(dim=-1, keepdim=False)[0]
+
+    for C, Co in ((3, 64), (64, 64), (64, 128), (128, 256)):
+        x = torch.from_numpy(synth.features(b3, C, 2048, seed=C + Co)).to(dev)
+        idx = dgcnn_util.knn(x, 20)
+        block = nn.Sequential(nn.Conv2d(2 * C, Co, 1, bias=False), nn.BatchNorm2d(Co), nn.LeakyReLU(0.2)).to(dev).train()
+        up = torch.randn(b3, Co, 2048, device=dev)
+
+        def step(fn):
+            xx = x.clone().requires_grad_(True)
+            (fn(xx) * up).sum().backward()
+
+        mine = max_over_ranks(_median_ms(lambda: step(lambda xx: ops.edge_conv(xx, idx, block[0].weight, block[1], 0.2)), reps=3))
+        ref = max_over_ranks(_median_ms(lambda: step(lambda xx: ref_layer(xx, idx, block)), reps=3))
+        c3["edgeconv %d->%d fwd+bwd (train)" % (C, Co)] = {"ms": mine, "reference_torch_sequence_ms": ref, "speedup": ref / mine}
+        del x, idx, block, up
     a1, a2 = cloud(b3, 1024, 7), cloud(b3, 1024, 8)
     c3["chamferL1 fwd %dx1024^2" % b3] = entry(_median_ms(lambda: ops.chamfer_forward(a1, a2)), pairs=2.0 * b3 * 1024 * 1024)
     out["C3 DGCNN k=20 N=2048 (batch-sharded)"] = c3
