@@ -785,11 +785,29 @@ def sharded_c5_block(dev, world, rank, max_over_ranks):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item())
 
-    out = {"n_points": n, "world": world, "impl": sharded.exchange_name()}
-    fwd_ms = synced_ms(lambda: sharded.chamfer_forward_sharded(xyz1, local_refs, lo))
+    # exchange forms: the fused peer-memory kernel (default when symmetric memory is available), its in-switch (NVLS)
+    # variant, and the NCCL all-reduce it replaces
+    forms = {"nccl_all_reduce": None}
+    for nm, mm in (("peer_kernel", False), ("multimem_kernel", True)):
+        ex = sharded.make_exchange(n, dev, use_multimem=mm)
+        if ex is not None and (ex.use_multimem == mm):
+            forms[nm] = ex
+    best = "peer_kernel" if "peer_kernel" in forms else "nccl_all_reduce"
+    exchange = forms[best]
+    out = {"n_points": n, "world": world, "impl": sharded.exchange_name(exchange), "exchange_forms_ms": {}}
+    for nm, ex in forms.items():
+        t = synced_ms(lambda: sharded.chamfer_forward_sharded(xyz1, local_refs, lo, exchange=ex))
+        r = sharded.chamfer_forward_sharded(xyz1, local_refs, lo, exchange=ex)
+        out["exchange_forms_ms"][nm] = {"forward_ms": t, "name": sharded.exchange_name(ex)}
+        out["exchange_forms_ms"][nm]["_res"] = [x.clone() for x in r]
+    ref_res = out["exchange_forms_ms"]["nccl_all_reduce"]["_res"]
+    for nm in list(out["exchange_forms_ms"]):
+        res = out["exchange_forms_ms"][nm].pop("_res")
+        out["exchange_forms_ms"][nm]["same_bits_as_nccl_form"] = all_ok(all(torch.equal(a, bb) for a, bb in zip(res, ref_res)))
+    fwd_ms = out["exchange_forms_ms"][best]["forward_ms"]
     local_ms = synced_ms(lambda: ops.chamfer_unpack_keys(ops.chamfer_sharded_local(xyz1, local_refs, lo)[0]))
     unsharded_ms = _median_ms(lambda: ops.chamfer_forward(xyz1, xyz2), reps=5)
-    d1, d2l, i1, i2l = sharded.chamfer_forward_sharded(xyz1, local_refs, lo)
+    d1, d2l, i1, i2l = [x.clone() for x in sharded.chamfer_forward_sharded(xyz1, local_refs, lo, exchange=exchange)]
     fd1, fd2, fi1, fi2 = ops.chamfer_forward(xyz1, xyz2)
     ok = torch.equal(d1, fd1) and torch.equal(i1, fi1) and torch.equal(d2l, fd2[:, lo:hi]) and torch.equal(i2l, fi2[:, lo:hi])
     out["chamfer_forward"] = {"sharded_ms": fwd_ms, "local_kernels_only_ms": local_ms,

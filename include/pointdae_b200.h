@@ -234,6 +234,17 @@ int pdae_knn_keys_u64(const float *ref_local, const float *query, int b, int r_l
 int pdae_knn_merge_keys_u64(const uint64_t *keys_all, int w, int b, int q, int k, int out_kq, float *dist, int64_t *idx,
                             pdae_stream_t stream);
 
+/* The exchange of the sharded forward as one kernel over NVLink peer memory (no collective call): every rank's packed
+ * row keys live in a symmetric buffer; rank r reduces rows [lo, hi) (its share) over all ranks' buffers and writes the
+ * unpacked (distance, index) pairs into every rank's result buffers.  keys / dist / idx: host arrays of `world` peer-mapped
+ * device pointers.  _multimem: the same through the multicast address of the allocation -- the NVSwitch reduces the keys
+ * (multimem.ld_reduce.min.u64) and broadcasts the results (multimem.st).  The caller brackets the call with cross-rank
+ * barriers.  Results equal pdae_chamfer_unpack_keys of an all-reduce(MIN) bit for bit.                             */
+int pdae_chamfer_exchange_keys_peer(const void *const *keys, void *const *dist, void *const *idx, int world, long long lo,
+                                    long long hi, pdae_stream_t stream);
+int pdae_chamfer_exchange_keys_multimem(const void *mc_keys, void *mc_dist, void *mc_idx, long long lo, long long hi,
+                                        pdae_stream_t stream);
+
 /* ---- "next" rows: ball query + grouping (3DETR / PointNet++ configs) ------------------------
  * replaces: `ball_query` ball_query_gpu.cu:12-57, `group_points` / `_grad`
  *           group_points_gpu.cu:11-78 (bindings.cpp:18-21).                                    */

@@ -27,6 +27,8 @@ SIGNATURES = {
     "pdae_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_gather_grad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_knn_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_chamfer_exchange_keys_peer": (_i, [_vp, _vp, _vp, _i, _ll, _ll, _vp]),
+    "pdae_chamfer_exchange_keys_multimem": (_i, [_vp, _vp, _vp, _ll, _ll, _vp]),
     "pdae_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pdae_knn_ws_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "pdae_group_ws_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -520,9 +520,10 @@ def chamfer_min_keys(queries, refs, ref_offset):
     return keys
 
 
-def chamfer_sharded_local(xyz1, xyz2_local, ref_offset):
+def chamfer_sharded_local(xyz1, xyz2_local, ref_offset, out_keys=None):
     """One rank's share of a reference-set-sharded forward in a single pass (every pair evaluated once):
-    -> (keys1 (B,N) int64 for the MIN all-reduce, dist2_local (B,Ml) f32, idx2_local (B,Ml) int32)."""
+    -> (keys1 (B,N) int64 for the MIN all-reduce, dist2_local (B,Ml) f32, idx2_local (B,Ml) int32).
+    out_keys: an int64 (B,N) buffer to write the keys into (e.g. a view of a symmetric allocation)."""
     _require_f32_contig(xyz1, "xyz1")
     _require_f32_contig(xyz2_local, "xyz2_local")
     _require_cuda(xyz1, "chamfer_sharded_local")
@@ -530,7 +531,12 @@ def chamfer_sharded_local(xyz1, xyz2_local, ref_offset):
     ml = xyz2_local.size(1)
     dev = xyz1.device
     with _on(dev):
-        keys = torch.empty((b, n), dtype=torch.int64, device=dev)
+        if out_keys is not None:
+            if out_keys.dtype != torch.int64 or tuple(out_keys.shape) != (b, n) or not out_keys.is_contiguous() or out_keys.device != dev:
+                raise RuntimeError("out_keys must be a contiguous int64 (B,N) tensor on xyz1's device")
+            keys = out_keys
+        else:
+            keys = torch.empty((b, n), dtype=torch.int64, device=dev)
         d2 = torch.empty((b, ml), dtype=torch.float32, device=dev)
         i2 = torch.empty((b, ml), dtype=torch.int32, device=dev)
         nbytes = b * ml * 8

@@ -20,9 +20,73 @@ import torch
 import torch.distributed as dist
 
 
-def exchange_name():
+def exchange_name(exchange=None):
     """which exchange the sharded forward uses (bench / test reports)"""
-    return "torch.distributed all_reduce(MIN) on packed int64 keys (NCCL over NVLink)"
+    if exchange is None:
+        return "torch.distributed all_reduce(MIN) on packed int64 keys (NCCL over NVLink)"
+    return exchange.name()
+
+
+class PeerExchange:
+    """Symmetric buffers of one rank for the fused exchange of reference-set-sharded Chamfer (csrc/exchange.cu): packed row
+    keys | distances | indices of `rows` rows in ONE symmetric allocation (torch.distributed._symmetric_memory: every
+    rank's copy is mapped into every rank), the peer pointers, and -- when the allocation has one -- the NVSwitch
+    multicast address.  Collective: every rank of `group` constructs it with the same `rows`."""
+
+    def __init__(self, rows, device, group=None, use_multimem=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rows = int(rows)
+        self.buf = symm_mem.empty(self.rows * 16, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        arr = ctypes.c_void_p * self.world
+        self.keys_ptrs = arr(*base)
+        self.dist_ptrs = arr(*[p + self.rows * 8 for p in base])
+        self.idx_ptrs = arr(*[p + self.rows * 12 for p in base])
+        self.keys = self.buf[: self.rows * 8].view(torch.int64)
+        self.dist = self.buf[self.rows * 8: self.rows * 12].view(torch.float32)
+        self.idx = self.buf[self.rows * 12: self.rows * 16].view(torch.int32)
+        mc = 0
+        try:
+            mc = int(self.hdl.multicast_ptr or 0)
+        except Exception:
+            mc = 0
+        self.mc = mc
+        self.use_multimem = bool(mc) if use_multimem is None else (bool(use_multimem) and bool(mc))
+
+    def name(self):
+        return ("one kernel over NVLink peer memory (symmetric buffers): " +
+                ("in-switch reduction, multimem.ld_reduce.min.u64 + multimem.st (NVLS)" if self.use_multimem
+                 else "peer loads + min + peer stores"))
+
+    def run(self):
+        """keys of every rank -> (dist, idx) of all rows on every rank; returns views of this rank's result buffers
+        (valid until the next run)."""
+        from . import _native, ops
+        lo, hi = shard_bounds(self.rows, self.world, self.rank)
+        L = _native.lib()
+        self.hdl.barrier(channel=0)  # every rank's keys are complete
+        with torch.cuda.device(self.buf.device):
+            st = torch.cuda.current_stream().cuda_stream
+            if self.use_multimem:
+                rc = L.pdae_chamfer_exchange_keys_multimem(self.mc, self.mc + self.rows * 8, self.mc + self.rows * 12, lo, hi, st)
+            else:
+                rc = L.pdae_chamfer_exchange_keys_peer(self.keys_ptrs, self.dist_ptrs, self.idx_ptrs, self.world, lo, hi, st)
+        _native.check(rc, "pdae_chamfer_exchange_keys")
+        self.hdl.barrier(channel=1)  # every rank's share has landed everywhere
+        return self.dist, self.idx
+
+
+def make_exchange(rows, device, group=None, use_multimem=None):
+    """PeerExchange, or None where symmetric memory is not available (then the NCCL all-reduce is used)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and torch.device(device).type == "cuda"):
+        return None
+    try:
+        return PeerExchange(rows, device, group, use_multimem)
+    except Exception:
+        return None
 
 
 def shard_bounds(n, world, rank):
@@ -54,7 +118,7 @@ def chamfer_direction_sharded(queries, refs_local, ref_offset, group=None, keys_
     return unpack_fn(keys)
 
 
-def chamfer_forward_sharded(xyz1, xyz2_local, xyz2_offset, group=None, keys_fn=None, unpack_fn=None):
+def chamfer_forward_sharded(xyz1, xyz2_local, xyz2_offset, group=None, keys_fn=None, unpack_fn=None, exchange=None):
     """Chamfer forward with cloud 2 (the big reference / target cloud) sharded along its points.
 
     xyz1 (B,N,3) is replicated; rank r holds xyz2[:, off:off+m_local].  Returns dist1, idx1 for all of
@@ -62,6 +126,15 @@ def chamfer_forward_sharded(xyz1, xyz2_local, xyz2_offset, group=None, keys_fn=N
     nearest neighbours in the replicated xyz1 need no exchange).  On CUDA the rank's whole share is ONE pass
     (pdae_chamfer_sharded_f32: every local pair evaluated once); `keys_fn` / `unpack_fn` let the CPU tests drive
     the same host logic with the oracle."""
+    if keys_fn is None and unpack_fn is None and exchange is not None:
+        # fused exchange over NVLink peer memory: the local pass writes its keys into the symmetric buffer
+        from . import ops
+        b, n = xyz1.shape[:2]
+        if exchange.rows != b * n:
+            raise RuntimeError("exchange was built for %d rows, got %d" % (exchange.rows, b * n))
+        _, dist2_local, idx2_local = ops.chamfer_sharded_local(xyz1, xyz2_local, xyz2_offset, out_keys=exchange.keys.view(b, n))
+        dist1, idx1 = exchange.run()
+        return dist1.view(b, n), dist2_local, idx1.view(b, n), idx2_local
     if keys_fn is None and unpack_fn is None:
         from . import ops
         keys, dist2_local, idx2_local = ops.chamfer_sharded_local(xyz1, xyz2_local, xyz2_offset)
