@@ -519,6 +519,229 @@ __global__ void __launch_bounds__(256) feat_select_kernel(const float *__restric
   if (lane < k) idx[(cloud * n + q) * k + lane] = static_cast<int64_t>(static_cast<uint32_t>(keys[0]));
 }
 
+// ---- symmetric form of the matrix path (default) -------------------------------------------------------------------------
+// The search is a SELF-kNN: d(i,j) and d(j,i) are the same bits (the operands of every subtraction only change sign), so
+// each unordered pair is evaluated once.  A CTA still owns 64 queries but walks only the 128-point reference tiles from
+// its own diagonal tile on; besides its rows it stores the TRANSPOSED block D[r][q] (for every reference four consecutive
+// queries = one 128-bit store; the two 16-row halves of a warp fill whole 32-byte sectors), which is exactly the part of
+// the lower triangle no CTA computes directly.  Executed FMA work: (ntiles + 1) / (2 ntiles) of the full matrix.
+// The threshold tau0 can no longer come from this kernel (a CTA does not see its rows' lower-triangle distances), so the
+// selection kernel takes it from the stored row itself: 64 segment minima per query (one FMNMX3 per two values),
+// k-th smallest by one 32-bit bitonic sort -- the pass 1 of knn4.cu -- then the row is read again (L1 / L2 hit).
+__global__ void __launch_bounds__(FT_THREADS, 2) feat_dist_sym_kernel(const float *__restrict__ x, int c, int n,
+                                                                      float *__restrict__ dmat /*(b, n, n)*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *ops0 = reinterpret_cast<float *>(smem_raw);  // operand stage, 2 buffers
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads: 4 queries x (4 + 4) references each
+  const int cloud = blockIdx.y;
+  const int q0 = blockIdx.x * FT_Q;
+  const float *__restrict__ X = x + static_cast<size_t>(cloud) * c * n;
+  float *__restrict__ D = dmat + static_cast<size_t>(cloud) * n * n;
+  constexpr int LD = FT_K * (FT_Q + FT_R) / FT_THREADS;
+  const int nst = (c + FT_K - 1) / FT_K;
+  const int ntiles = (n + FT_R - 1) / FT_R;
+  const int t_first = q0 / FT_R;  // the diagonal tile of this query block
+  const int total = nst * (ntiles - t_first);
+  float pre[LD];
+  const float *__restrict__ pq = X + static_cast<size_t>(tid >> 6) * n + q0 + (tid & 63);
+  const float *__restrict__ pr = X + static_cast<size_t>(tid >> 7) * n + (tid & 127);
+  const bool q_ok = q0 + (tid & 63) < n;
+  auto fetch = [&](int st) {
+    const int tile_i = t_first + st / nst;
+    const int r0 = tile_i * FT_R, c0 = (st % nst) * FT_K;
+    const int kc = c - c0;
+    const bool r_ok = r0 + (tid & 127) < n;
+    const float *bq = pq + static_cast<size_t>(c0) * n;
+    const float *br = pr + static_cast<size_t>(c0) * n + r0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      pre[i] = (q_ok && (tid >> 6) + 4 * i < kc) ? __ldg(bq + static_cast<size_t>(4 * i) * n) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pre[4 + i] = (r_ok && (tid >> 7) + 2 * i < kc) ? __ldg(br + static_cast<size_t>(2 * i) * n) : 0.f;
+  };
+  auto stash = [&](int buf) {
+    float *dst = ops0 + buf * FT_K * (FT_Q + FT_R);
+#pragma unroll
+    for (int i = 0; i < LD; ++i) dst[tid + i * FT_THREADS] = pre[i];
+  };
+  const bool vec = (n & 3) == 0;
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  float2 acc[4][4];
+  for (int st = 0; st < total; ++st) {
+    const int tile_i = t_first + st / nst, si = st % nst;
+    const int r0 = tile_i * FT_R, c0 = si * FT_K;
+    if (si == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
+    }
+    if (st + 1 < total) fetch(st + 1);
+    const float *qs = ops0 + (st & 1) * FT_K * (FT_Q + FT_R);
+    const float *rs = qs + FT_K * FT_Q;
+    const int kc = (c - c0) < FT_K ? (c - c0) : FT_K;
+#pragma unroll 4
+    for (int cc = 0; cc < kc; ++cc) {
+      const float4 qv = *reinterpret_cast<const float4 *>(qs + cc * FT_Q + ty * 4);
+      const float4 ra = *reinterpret_cast<const float4 *>(rs + cc * FT_R + tx * 4);
+      const float4 rb = *reinterpret_cast<const float4 *>(rs + cc * FT_R + 64 + tx * 4);
+      const float2 rp[4] = {make_float2(ra.x, ra.y), make_float2(ra.z, ra.w), make_float2(rb.x, rb.y), make_float2(rb.z, rb.w)};
+      const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float2 q2 = make_float2(qq[a], qq[a]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float2 t = sub2(rp[b], q2);
+          acc[a][b] = fma2(t, t, acc[a][b]);
+        }
+      }
+    }
+    if (st + 1 < total) stash((st + 1) & 1);
+    if (si == nst - 1) {
+      const int ra0 = r0 + tx * 4, rb0 = r0 + 64 + tx * 4;  // first reference of each half
+      float v[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        v[a][0] = acc[a][0].x, v[a][1] = acc[a][0].y, v[a][2] = acc[a][1].x, v[a][3] = acc[a][1].y;
+        v[a][4] = acc[a][2].x, v[a][5] = acc[a][2].y, v[a][6] = acc[a][3].x, v[a][7] = acc[a][3].y;
+      }
+      // rows of this query block
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int qg = q0 + ty * 4 + a;
+        if (qg < n) {
+          float *row = D + static_cast<size_t>(qg) * n;
+          if (vec) {
+            if (ra0 < n) *reinterpret_cast<float4 *>(row + ra0) = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
+            if (rb0 < n) *reinterpret_cast<float4 *>(row + rb0) = make_float4(v[a][4], v[a][5], v[a][6], v[a][7]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int r = e < 4 ? ra0 + e : rb0 + e - 4;
+              if (r < n) row[r] = v[a][e];
+            }
+          }
+        }
+      }
+      // the transposed block: rows = this tile's references, columns = this block's queries (tiles above the diagonal)
+      if (tile_i > t_first) {
+        const int qa = q0 + ty * 4;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int r = e < 4 ? ra0 + e : rb0 + e - 4;
+          if (r < n) {
+            float *col = D + static_cast<size_t>(r) * n + qa;
+            if (vec && qa + 3 < n) {
+              *reinterpret_cast<float4 *>(col) = make_float4(v[0][e], v[1][e], v[2][e], v[3][e]);
+            } else {
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+                if (qa + a < n) col[a] = v[a][e];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) feat_select2_kernel(const float *__restrict__ dmat, int n, int k, int64_t *__restrict__ idx) {
+  __shared__ uint64_t queue_all[8][64];
+  __shared__ uint64_t lq_all[8][FS_LC * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;
+  const size_t cloud = blockIdx.y;
+  if (q >= n) return;
+  const float *__restrict__ row = dmat + (cloud * n + q) * n;
+  uint64_t *queue = queue_all[warp], *lq = lq_all[warp];
+  const float INF = __int_as_float(0x7f800000);
+  const bool vec = (n & 3) == 0;
+  // ---- pass 1: 64 segment minima (2 per lane) -> tau0 = their k-th smallest (k <= 32) ---------------------------------
+  float ma = INF, mb = INF;
+  if (vec) {
+    for (int j0 = 0; j0 < n; j0 += 128) {
+      const int j = j0 + 4 * lane;
+      if (j < n) {
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(row + j));
+        ma = min3(ma, d.x, d.y);
+        mb = min3(mb, d.z, d.w);
+      }
+    }
+  } else {
+    for (int j = lane; j < n; j += 64) ma = fminf(ma, __ldg(row + j));
+    for (int j = lane + 32; j < n; j += 64) mb = fminf(mb, __ldg(row + j));
+  }
+  uint32_t sv[2] = {__float_as_uint(ma), __float_as_uint(mb)};  // distances are >= 0: bit patterns order like values
+  warp_sort_u32<2>(sv, lane, warp_sort_dir_mask(lane));
+  const float tau0 = __uint_as_float(__shfl_sync(0xffffffffu, sv[0], k - 1));
+  // ---- pass 2: every point with d <= tau0 -> lane-private lists -> exact order ---------------------------------------------
+  const bool degenerate = !(tau0 < INF);
+  int cnt = 0;
+  if (vec) {
+    for (int j0 = 0; j0 < n; j0 += 128) {
+      const int j = j0 + 4 * lane;
+      if (j < n) {
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(row + j));
+        if (min3(d.x, d.y, fminf(d.z, d.w)) <= tau0) {
+          const float v[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool cnd = v[e] <= tau0;
+            if (cnd && cnt < FS_LC) lq[cnt * 32 + lane] = pack_key(v[e], static_cast<uint32_t>(j + e));
+            cnt += cnd;
+          }
+        }
+      }
+    }
+  } else {
+    for (int j = lane; j < n; j += 32) {
+      const float v = __ldg(row + j);
+      const bool cnd = v <= tau0;
+      if (cnd && cnt < FS_LC) lq[cnt * 32 + lane] = pack_key(v, static_cast<uint32_t>(j));
+      cnt += cnd;
+    }
+  }
+  if (degenerate) cnt = FS_LC + 1;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int totalc = __shfl_sync(0xffffffffu, incl, 31);
+  const bool overflow = __any_sync(0xffffffffu, cnt > FS_LC) || totalc > 64;
+  uint64_t keys[2];
+  if (!overflow) {
+    const int off = incl - cnt;
+    for (int i = 0; i < cnt; ++i) queue[off + i] = lq[i * 32 + lane];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 2; ++e) keys[e] = (e * 32 + lane) < totalc ? queue[e * 32 + lane] : KEY_INF;
+    __syncwarp();
+    warp_sort_multi<2>(keys, lane);
+  } else {  // exact fallback: streaming warp-select over the stored row
+    WarpSelect<1> sel;
+    sel.init();
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool in = j < n;
+      const uint64_t key = in ? pack_key(__ldg(row + j), static_cast<uint32_t>(j)) : KEY_INF;
+      sel.offer(in && key < sel.tau, key, queue, lane, 0, k - 1);
+    }
+    sel.finish(queue, lane);
+    keys[0] = sel.L[0];
+    keys[1] = KEY_INF;
+  }
+  if (lane < k) idx[(cloud * n + q) * k + lane] = static_cast<int64_t>(static_cast<uint32_t>(keys[0]));
+}
+
 static size_t feat_matrix_bytes_per_cloud(int n) { return (static_cast<size_t>(n) * n + n) * sizeof(float); }
 
 static int launch_feat_knn_matrix(const float *x, int b, int c, int n, int k, int64_t *idx, void *workspace,
@@ -533,11 +756,19 @@ static int launch_feat_knn_matrix(const float *x, int b, int c, int n, int k, in
     float *dmat = static_cast<float *>(workspace);
     float *tau = dmat + static_cast<size_t>(nb) * n * n;
     const dim3 ga(ceil_div(n, FT_Q), nb);
-    feat_dist_tiled_kernel<<<ga, FT_THREADS, smem, st>>>(x + static_cast<size_t>(b0) * c * n, c, n, k, dmat, tau);
-    PDAE_RETURN_IF_LAUNCH_FAILED();
     const dim3 gb(ceil_div(n, 8), nb);
-    feat_select_kernel<<<gb, 256, 0, st>>>(dmat, tau, n, k, idx + static_cast<size_t>(b0) * n * k);
-    PDAE_RETURN_IF_LAUNCH_FAILED();
+    static const bool full_matrix = getenv("PDAE_FEATKNN_FULL") != nullptr;  // A/B hook: the round-1 form (every pair twice)
+    if (full_matrix) {
+      feat_dist_tiled_kernel<<<ga, FT_THREADS, smem, st>>>(x + static_cast<size_t>(b0) * c * n, c, n, k, dmat, tau);
+      PDAE_RETURN_IF_LAUNCH_FAILED();
+      feat_select_kernel<<<gb, 256, 0, st>>>(dmat, tau, n, k, idx + static_cast<size_t>(b0) * n * k);
+      PDAE_RETURN_IF_LAUNCH_FAILED();
+    } else {
+      feat_dist_sym_kernel<<<ga, FT_THREADS, smem, st>>>(x + static_cast<size_t>(b0) * c * n, c, n, dmat);
+      PDAE_RETURN_IF_LAUNCH_FAILED();
+      feat_select2_kernel<<<gb, 256, 0, st>>>(dmat, n, k, idx + static_cast<size_t>(b0) * n * k);
+      PDAE_RETURN_IF_LAUNCH_FAILED();
+    }
   }
   return 0;
 }
