@@ -534,8 +534,10 @@ __global__ void __launch_bounds__(FT_THREADS, 2) feat_dist_sym_kernel(const floa
   float *ops0 = reinterpret_cast<float *>(smem_raw);  // operand stage, 2 buffers
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads: 4 queries x (4 + 4) references each
-  const int cloud = blockIdx.y;
-  const int q0 = blockIdx.x * FT_Q;
+  // grid (clouds, query blocks): the dispatcher hands out blockIdx.x fastest, so ALL clouds' heaviest query blocks (block 0
+  // walks every tile, the last block one) start first and the light ones fill the tail -- longest-processing-time order
+  const int cloud = blockIdx.x;
+  const int q0 = blockIdx.y * FT_Q;
   const float *__restrict__ X = x + static_cast<size_t>(cloud) * c * n;
   float *__restrict__ D = dmat + static_cast<size_t>(cloud) * n * n;
   constexpr int LD = FT_K * (FT_Q + FT_R) / FT_THREADS;
@@ -764,7 +766,8 @@ static int launch_feat_knn_matrix(const float *x, int b, int c, int n, int k, in
       feat_select_kernel<<<gb, 256, 0, st>>>(dmat, tau, n, k, idx + static_cast<size_t>(b0) * n * k);
       PDAE_RETURN_IF_LAUNCH_FAILED();
     } else {
-      feat_dist_sym_kernel<<<ga, FT_THREADS, smem, st>>>(x + static_cast<size_t>(b0) * c * n, c, n, dmat);
+      if (ga.x > 65535) return PDAE_E_UNSUPPORTED;
+      feat_dist_sym_kernel<<<dim3(ga.y, ga.x), FT_THREADS, smem, st>>>(x + static_cast<size_t>(b0) * c * n, c, n, dmat);
       PDAE_RETURN_IF_LAUNCH_FAILED();
       feat_select2_kernel<<<gb, 256, 0, st>>>(dmat, n, k, idx + static_cast<size_t>(b0) * n * k);
       PDAE_RETURN_IF_LAUNCH_FAILED();
