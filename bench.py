@@ -164,6 +164,40 @@ def ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, our_ms, ours_us=None):
             acc[k].append(ts[k])
     med = [statistics.median(a) for a in acc]
     total = sum(med)
+    # the scene path's radius grouping at 3DETR scale (one block per cloud in the reference,
+    # ball_query_gpu.cu:12-57, a warp per query here), same inputs, same GPU
+    ball = None
+    try:
+        from pointdae_b200 import ops as our_ops, synth as our_synth
+        bq_xyz = torch.from_numpy(our_synth.clouds(8, 20000, seed=21)).to(dev)
+        bq_new = bq_xyz[:, :2048].contiguous()
+
+        def t_us(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) * 1e3)
+            return statistics.median(ts)
+
+        ref_idx = ext.ball_query(bq_new, bq_xyz, 0.2, 64)
+        our_idx = our_ops.ball_query(bq_new, bq_xyz, 0.2, 64)
+        g_feat = torch.randn(8, 128, 20000, device=dev)
+        ball = {"shape": "8 clouds x 20000 points, 2048 centres, radius 0.2, nsample 64",
+                "ball_query_us": {"reference": t_us(lambda: ext.ball_query(bq_new, bq_xyz, 0.2, 64)),
+                                  "this_repo": t_us(lambda: our_ops.ball_query(bq_new, bq_xyz, 0.2, 64))},
+                "group_points_128ch_us": {"reference": t_us(lambda: ext.group_points(g_feat, ref_idx)),
+                                          "this_repo": t_us(lambda: our_ops.group_points(g_feat, our_idx))},
+                "same_indices": bool(torch.equal(ref_idx, our_idx))}
+        ball["ball_query_speedup"] = ball["ball_query_us"]["reference"] / ball["ball_query_us"]["this_repo"]
+        ball["group_points_speedup"] = ball["group_points_128ch_us"]["reference"] / ball["group_points_128ch_us"]["this_repo"]
+    except Exception as e:  # evidence only
+        ball = {"error": repr(e)[:200]}
     kernels_only = None
     if ours_us:
         # the reference's own compiled kernels only (FPS + gather, chamfer.forward + mean, chamfer.backward) against this
@@ -178,6 +212,7 @@ def ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, our_ms, ours_us=None):
             "ms": {"fps+gather (pointnet2 _ext)": med[0], "knn loop (KNN_CUDA-like torch stand-in) + group": med[1],
                    "chamfer.forward + mean": med[2], "chamfer.backward": med[3]},
             "kernels_only_speedup": kernels_only,
+            "ball_query_scene_scale": ball,
             "speedup_of_this_repo_incl_knn_stand_in": total / our_ms,
             "note": "reference CUDA sources compiled unmodified for sm_100a; eager launches, median of 10"}
 
@@ -792,7 +827,7 @@ def sharded_c5_block(dev, world, rank, max_over_ranks):
         ex = sharded.make_exchange(n, dev, use_multimem=mm)
         if ex is not None and (ex.use_multimem == mm):
             forms[nm] = ex
-    best = "peer_kernel" if "peer_kernel" in forms else "nccl_all_reduce"
+    best = "multimem_kernel" if "multimem_kernel" in forms else ("peer_kernel" if "peer_kernel" in forms else "nccl_all_reduce")
     exchange = forms[best]
     out = {"n_points": n, "world": world, "impl": sharded.exchange_name(exchange), "exchange_forms_ms": {}}
     for nm, ex in forms.items():
@@ -824,7 +859,13 @@ def sharded_c5_block(dev, world, rank, max_over_ranks):
     w1, w2 = ops.chamfer_backward(xyz1, xyz2, fi1, fi2, g1, g2)
     ok_b = (torch.allclose(gx1, w1, rtol=1e-5, atol=1e-6 * float(w1.abs().max()))
             and torch.allclose(gx2l, w2[:, lo:hi], rtol=1e-5, atol=1e-6 * float(w2.abs().max())))
-    out["chamfer_backward"] = {"sharded_ms": bwd_ms, "matches_unsharded_1e-5": all_ok(ok_b)}
+    bwd2_ms = synced_ms(lambda: sharded.chamfer_backward_gathered(xyz1, local_refs, lo, n, i1, i2l, g1, g2l))
+    hx1, hx2l = sharded.chamfer_backward_gathered(xyz1, local_refs, lo, n, i1, i2l, g1, g2l)
+    ok_b2 = (torch.allclose(hx1, w1, rtol=1e-5, atol=1e-6 * float(w1.abs().max()))
+             and torch.allclose(hx2l, w2[:, lo:hi], rtol=1e-5, atol=1e-6 * float(w2.abs().max())))
+    out["chamfer_backward"] = {"masked_all_reduce_ms": bwd_ms, "matches_unsharded_1e-5": all_ok(ok_b),
+                               "gathered_ms": bwd2_ms, "gathered_matches_unsharded_1e-5": all_ok(ok_b2),
+                               "unsharded_1gpu_ms": max_over_ranks(_median_ms(lambda: ops.chamfer_backward(xyz1, xyz2, fi1, fi2, g1, g2)))}
     centers = ops.fps_gather(xyz2, q)[1]
     knn_ms = synced_ms(lambda: sharded.knn_sharded(local_refs, centers, k, lo))
     knn_local_ms = synced_ms(lambda: ops.knn_keys(local_refs, centers, k, lo))

@@ -194,6 +194,19 @@ int pdae_edge_backward_f32(const float *z, int ld, const int64_t *idx, const uns
                            const float *gamma, const float *ca, const float *cb, float slope, int train, int b, int n, int k,
                            int co, double *partial, float *dz, pdae_stream_t stream);
 
+/* ---- "next" rows: index consumers of the match ---------------------------------------------------
+ * replaces: the torch.gather / normalize / difference / mean chains of the normal, curvature and position terms of
+ *           ChamferDistanceL2_withnormal* (extensions/chamfer_dist/__init__.py:95-120, 143-165, 206-376).
+ * One term  mean_j metric(a_j, b[idx1[j]]) + mean_j metric(b_j, a[idx2[j]]),  a (bs,n,d), b (bs,m,d), d <= 8, idx from
+ * pdae_chamfer_fwd_f32; metric 0 dis_l2, 1 dis_normalized_l2 (orientation-free), 2 dis_normalized_l1, 3
+ * dis_normalized_l2_strict.  fwd: per-CTA fp64 partial sums (pdae_pair_loss_partial_count(bs,n,m), 2), summed by the
+ * caller in a fixed order.  bwd: ga / gb overwritten with gloss * (w1 d(side 1) + w2 d(side 2)), w = 1/(bs n), 1/(bs m). */
+size_t pdae_pair_loss_partial_count(int bs, int n, int m);
+int pdae_pair_loss_fwd_f64(const float *a, const float *b, const int *idx1, const int *idx2, int bs, int n, int m, int d,
+                           int metric, double *partial, pdae_stream_t stream);
+int pdae_pair_loss_bwd_f32(const float *a, const float *b, const int *idx1, const int *idx2, const float *gloss, float w1,
+                           float w2, int bs, int n, int m, int d, int metric, float *ga, float *gb, pdae_stream_t stream);
+
 /* tuning hook, no reference counterpart: select the CTA shape of the large-cloud forward kernel (ids as the
  * PDAE_CHAMFER_CFG environment variable; v < 0 only queries).  Returns the previous id.  Not thread-safe.      */
 int pdae_tune_chamfer_variant(int v);

@@ -52,6 +52,9 @@ SIGNATURES = {
     "pdae_edge_stats_f64": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_edge_forward_f32": (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_edge_backward_f32": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_pair_loss_partial_count": (_sz, [_i, _i, _i]),
+    "pdae_pair_loss_fwd_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pdae_pair_loss_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_tune_chamfer_variant": (_i, [_i]),
     "pdae_tune_chamfer_split": (_i, [_i]),
     "pdae_tune_knn": (_i, [_i, _i, _i, _i, _i, _i, _i]),

@@ -92,6 +92,11 @@ def _nearest_rows(values, idx, like):
 
 def _two_sided(metric, a, b, idx1, idx2):
     """mean over cloud 1 of metric(a_j, b_{idx1[j]}) + mean over cloud 2 of metric(b_j, a_{idx2[j]})"""
+    if a.is_cuda:
+        from . import ops
+        fused = ops.matched_pair_loss(a, b, idx1, idx2, getattr(metric, "__name__", ""))
+        if fused is not None:  # one launch forward, two backward (csrc/pairloss.cu)
+            return fused
     d1 = metric(a, _nearest_rows(b, idx1, a))
     d2 = metric(b, _nearest_rows(a, idx2, b))
     return torch.mean(d1) + torch.mean(d2)

@@ -243,6 +243,38 @@ __global__ void __launch_bounds__(256) knn_merge_keys_kernel(const uint64_t *__r
   }
 }
 
+// k <= 64: a warp per query keeps the running k best in registers (one key per lane and 32 of k) and folds every rank's
+// ascending list in with the bitonic warp merge -- the thread-per-query walk above is latency-bound (2048 threads for the
+// scene-scale shape)
+template <int E>
+__global__ void __launch_bounds__(128) knn_merge_keys_warp_kernel(const uint64_t *__restrict__ keys /*(w, nq, k)*/, int w,
+                                                                  long long nq, int q, int k, int out_kq,
+                                                                  float *__restrict__ dist, int64_t *__restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (t >= nq) return;
+  uint64_t L[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) L[e] = KEY_INF;
+  for (int s = 0; s < w; ++s) {
+    const uint64_t *src = keys + (static_cast<long long>(s) * nq + t) * k;
+    for (int p0 = 0; p0 < k; p0 += 32) {
+      const uint64_t c = (p0 + lane) < k ? __ldg(src + p0 + lane) : KEY_INF;
+      warp_merge<E>(L, c, lane);
+    }
+  }
+  const long long cloud = t / q, qi = t - cloud * q;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int p = e * 32 + lane;
+    if (p < k) {
+      const long long o = out_kq ? (cloud * k + p) * q + qi : t * k + p;
+      if (idx) idx[o] = static_cast<int64_t>(static_cast<uint32_t>(L[e]));
+      if (dist) dist[o] = __fsqrt_rn(__uint_as_float(static_cast<uint32_t>(L[e] >> 32)));
+    }
+  }
+}
+
 extern "C" int pdae_knn_keys_u64(const float *ref_local, const float *query, int b, int r_local, int q, int dim, int k,
                                  long long ref_offset, uint64_t *keys, pdae_stream_t stream) {
   if (b < 0 || r_local < 0 || q < 0 || dim <= 0 || k <= 0 || ref_offset < 0 || ref_offset + r_local > 0xffffffffLL)
@@ -268,6 +300,15 @@ extern "C" int pdae_knn_merge_keys_u64(const uint64_t *keys_all, int w, int b, i
   const long long nq = static_cast<long long>(b) * q;
   if (nq == 0) return 0;
   if (!keys_all || (!dist && !idx)) return PDAE_E_INVALID;
+  if (k <= 64) {
+    const long long wgrid = (nq + 3) / 4;
+    if (wgrid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (k <= 32) knn_merge_keys_warp_kernel<1><<<static_cast<unsigned>(wgrid), 128, 0, st>>>(keys_all, w, nq, q, k, out_kq ? 1 : 0, dist, idx);
+    else knn_merge_keys_warp_kernel<2><<<static_cast<unsigned>(wgrid), 128, 0, st>>>(keys_all, w, nq, q, k, out_kq ? 1 : 0, dist, idx);
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+  }
   const long long grid = (nq + 255) / 256;
   if (grid > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
   knn_merge_keys_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(

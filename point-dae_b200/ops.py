@@ -505,6 +505,56 @@ def chamfer_loss_backward(xyz1, xyz2, idx1, idx2, dist1, dist2, grad_loss, w1, w
     return [gx1, gx2]
 
 
+PAIR_METRICS = {"dis_l2": 0, "dis_normalized_l2": 1, "dis_normalized_l1": 2, "dis_normalized_l2_strict": 3}
+
+
+class MatchedPairLoss(torch.autograd.Function):
+    """mean_j metric(a_j, b[idx1[j]]) + mean_j metric(b_j, a[idx2[j]]) over the Chamfer match (one forward launch, two
+    backward launches; csrc/pairloss.cu) -- the normal / curvature / position terms of ChamferDistanceL2_withnormal*
+    (extensions/chamfer_dist/__init__.py:143-165) without their gather / normalize / difference / mean chains."""
+
+    @staticmethod
+    def forward(ctx, a, b, idx1, idx2, metric):
+        a, b = a.contiguous(), b.contiguous()
+        idx1, idx2 = idx1.contiguous(), idx2.contiguous()
+        bs, n, d = a.shape
+        m = b.size(1)
+        L = _native.lib()
+        with _on(a.device):
+            partial = torch.empty((int(L.pdae_pair_loss_partial_count(bs, n, m)), 2), dtype=torch.float64, device=a.device)
+            rc = L.pdae_pair_loss_fwd_f64(a.data_ptr(), b.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), bs, n, m, d, int(metric),
+                                          partial.data_ptr(), _stream())
+        _native.check(rc, "pdae_pair_loss_fwd_f64")
+        sums = partial.sum(dim=0)
+        ctx.save_for_backward(a, b, idx1, idx2)
+        ctx.metric = int(metric)
+        return (sums[0] / (bs * n) + sums[1] / (bs * m)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, idx1, idx2 = ctx.saved_tensors
+        bs, n, d = a.shape
+        m = b.size(1)
+        with _on(a.device):
+            ga, gb = torch.empty_like(a), torch.empty_like(b)
+            gl = g.reshape(1).float().contiguous()
+            rc = _native.lib().pdae_pair_loss_bwd_f32(a.data_ptr(), b.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), gl.data_ptr(),
+                                                      1.0 / (bs * n), 1.0 / (bs * m), bs, n, m, d, ctx.metric, ga.data_ptr(),
+                                                      gb.data_ptr(), _stream())
+        _native.check(rc, "pdae_pair_loss_bwd_f32")
+        return ga, gb, None, None, None
+
+
+def matched_pair_loss(a, b, idx1, idx2, metric):
+    """fused form when it applies (CUDA fp32, <= 8 attribute channels, int32 match indices), else None"""
+    code = PAIR_METRICS.get(metric)
+    if (code is None or not a.is_cuda or a.dtype != torch.float32 or b.dtype != torch.float32 or a.dim() != 3 or b.dim() != 3
+            or a.size(2) != b.size(2) or a.size(2) > 8 or idx1.dtype != torch.int32 or idx2.dtype != torch.int32
+            or a.size(1) == 0 or b.size(1) == 0 or tuple(idx1.shape) != tuple(a.shape[:2]) or tuple(idx2.shape) != tuple(b.shape[:2])):
+        return None
+    return MatchedPairLoss.apply(a, b, idx1, idx2, code)
+
+
 def chamfer_min_keys(queries, refs, ref_offset):
     """One Chamfer direction against a local slice of the reference set -> packed int64 keys (B,Nq)."""
     _require_f32_contig(queries, "queries")

@@ -76,3 +76,40 @@ def test_product_path_has_no_cpu_fallback():
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_gpu_losses_match_reference_classes(name):
     _check(name, torch.device("cuda:0"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric", ["dis_l2", "dis_normalized_l2", "dis_normalized_l1", "dis_normalized_l2_strict"])
+@pytest.mark.parametrize("d", [3, 1, 6])
+def test_gpu_fused_matched_pair_loss_equals_the_torch_expression(metric, d):
+    """ops.matched_pair_loss (csrc/pairloss.cu) against the reference's expression -- torch.gather + the metric + mean
+    (extensions/chamfer_dist/__init__.py:95-120, 143-146) -- value and both gradients, incl. a zero vector (F.normalize's
+    eps clamp) and an orthogonal pair (torch.min's tie)."""
+    import torch
+    from pointdae_b200 import chamfer_dist, ops
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(d * 7 + len(metric))
+    bs, n, m = 3, 70, 90
+    a0, b0 = torch.randn(bs, n, d, generator=g), torch.randn(bs, m, d, generator=g)
+    a0[0, 0] = 0.0
+    if d >= 2:
+        a0[1, 1] = 0.0
+        a0[1, 1, 0] = 1.0
+    idx1 = torch.randint(0, m, (bs, n), generator=g, dtype=torch.int32)
+    idx2 = torch.randint(0, n, (bs, m), generator=g, dtype=torch.int32)
+    if d >= 2:
+        b0[1, int(idx1[1, 1])] = 0.0
+        b0[1, int(idx1[1, 1]), 1] = 2.0  # orthogonal to a[1,1]: |u-w|^2 == |u+w|^2
+    fn = getattr(chamfer_dist, metric)
+    ar, br = a0.to(dev).requires_grad_(True), b0.to(dev).requires_grad_(True)
+    i1, i2 = idx1.to(dev), idx2.to(dev)
+    want = (torch.mean(fn(ar, chamfer_dist._nearest_rows(br, i1, ar))) + torch.mean(fn(br, chamfer_dist._nearest_rows(ar, i2, br))))
+    (want * 1.7).backward()
+    ao, bo = a0.to(dev).requires_grad_(True), b0.to(dev).requires_grad_(True)
+    got = ops.matched_pair_loss(ao, bo, i1, i2, metric)
+    assert got is not None
+    (got * 1.7).backward()
+    assert abs(float(got) - float(want)) <= 1e-6 * abs(float(want))
+    for x, y in ((ao.grad, ar.grad), (bo.grad, br.grad)):
+        # (one-channel "normals" normalise to +-1: their gradient is zero up to rounding noise on both sides)
+        assert torch.allclose(x, y, rtol=1e-4, atol=max(1e-6 * float(y.abs().max()), 1e-7)), float((x - y).abs().max())

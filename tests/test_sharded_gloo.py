@@ -119,6 +119,12 @@ def _worker_bwd_knn(rank, world, port, m_total, out):
     wg1, wg2 = oracle.chamfer_bwd(x1.numpy(), x2.numpy(), wi1, wi2, g1, g2)
     ok = (np.allclose(gx1.numpy(), wg1, rtol=1e-5, atol=1e-6 * np.abs(wg1).max())
           and np.allclose(gx2l.numpy(), wg2[:, lo:hi], rtol=1e-5, atol=1e-6 * np.abs(wg2).max()))
+    # the all-gather form (uneven slices are padded to the largest one): same gradients
+    hx1, hx2l = sharded.chamfer_backward_gathered(x1, x2l, lo, m_total, torch.from_numpy(wi1), torch.from_numpy(wi2[:, lo:hi].copy()),
+                                                  torch.from_numpy(g1), torch.from_numpy(g2[:, lo:hi].copy()),
+                                                  backward_fn=_oracle_backward)
+    ok = ok and (np.allclose(hx1.numpy(), wg1, rtol=1e-5, atol=1e-6 * np.abs(wg1).max())
+                 and np.allclose(hx2l.numpy(), wg2[:, lo:hi], rtol=1e-5, atol=1e-6 * np.abs(wg2).max()))
     # kNN: 7 queries, k = 5, reference cloud x2 sharded
     k = min(5, m_total)
     query = x1[:, :7].contiguous()
