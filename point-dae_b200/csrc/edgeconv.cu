@@ -159,18 +159,39 @@ __global__ void __launch_bounds__(EC_WARPS * 32) edge_stats_kernel(const EdgeArg
       const int i = i0 + warp * PER_WARP + pw;
       if (i >= n) continue;  // warp-uniform
       float s1[PER_LANE], s2[PER_LANE];
+      int oc[PER_LANE];
 #pragma unroll
-      for (int u = 0; u < PER_LANE; ++u) s1[u] = 0.f, s2[u] = 0.f;
-      for (int j = 0; j < k; ++j) {
-        const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + j)) * ld;
+      for (int u = 0; u < PER_LANE; ++u) {
+        s1[u] = 0.f, s2[u] = 0.f;
+        const int o = c0 + u * 32 + lane;
+        oc[u] = o < co ? o : co - 1;
+      }
+      const int64_t *ip = Ic + static_cast<size_t>(i) * k;
+      int j = 0;
+      for (; j + 4 <= k; j += 4) {
+        size_t row[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) row[t] = static_cast<size_t>(__ldg(ip + j + t)) * ld;
+        float pv[4][PER_LANE];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int u = 0; u < PER_LANE; ++u) pv[t][u] = __ldg(Z + row[t] + oc[u]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int u = 0; u < PER_LANE; ++u) {
+            s1[u] += pv[t][u];
+            s2[u] = fmaf(pv[t][u], pv[t][u], s2[u]);
+          }
+      }
+      for (; j < k; ++j) {
+        const size_t row = static_cast<size_t>(__ldg(ip + j)) * ld;
 #pragma unroll
         for (int u = 0; u < PER_LANE; ++u) {
-          const int o = c0 + u * 32 + lane;
-          if (o < co) {
-            const float p = __ldg(Z + row + o);
-            s1[u] += p;
-            s2[u] = fmaf(p, p, s2[u]);
-          }
+          const float p = __ldg(Z + row + oc[u]);
+          s1[u] += p;
+          s2[u] = fmaf(p, p, s2[u]);
         }
       }
 #pragma unroll
@@ -212,17 +233,42 @@ __global__ void __launch_bounds__(EC_WARPS * 32) edge_forward_kernel(const EdgeA
       if (i >= n) continue;
       float acc[PER_LANE];
       int js[PER_LANE];
+      int oc[PER_LANE];  // channel, clamped into the row: lanes past co read a valid element and drop the result
 #pragma unroll
-      for (int u = 0; u < PER_LANE; ++u) acc[u] = -__int_as_float(0x7f800000), js[u] = 0;
-      for (int j = 0; j < k; ++j) {
-        const size_t row = static_cast<size_t>(__ldg(Ic + static_cast<size_t>(i) * k + j)) * ld;
+      for (int u = 0; u < PER_LANE; ++u) {
+        acc[u] = -__int_as_float(0x7f800000), js[u] = 0;
+        const int o = c0 + u * 32 + lane;
+        oc[u] = o < co ? o : co - 1;
+      }
+      const int64_t *ip = Ic + static_cast<size_t>(i) * k;
+      int j = 0;
+      for (; j + 4 <= k; j += 4) {  // four neighbour rows in flight
+        size_t row[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) row[t] = static_cast<size_t>(__ldg(ip + j + t)) * ld;
+        float pv[4][PER_LANE];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int u = 0; u < PER_LANE; ++u) pv[t][u] = __ldg(Z + row[t] + oc[u]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int u = 0; u < PER_LANE; ++u) {
+            const float v = __fmul_rn(sgn[u], pv[t][u]);
+            const bool gt = v > acc[u];  // strict: the first slot attaining the extremum
+            acc[u] = gt ? v : acc[u];
+            js[u] = gt ? j + t : js[u];
+          }
+      }
+      for (; j < k; ++j) {
+        const size_t row = static_cast<size_t>(__ldg(ip + j)) * ld;
 #pragma unroll
         for (int u = 0; u < PER_LANE; ++u) {
-          const int o = c0 + u * 32 + lane;
-          if (o < co) {
-            const float v = __fmul_rn(sgn[u], __ldg(Z + row + o));
-            if (v > acc[u]) acc[u] = v, js[u] = j;  // strict: the first slot attaining the extremum
-          }
+          const float v = __fmul_rn(sgn[u], __ldg(Z + row + oc[u]));
+          const bool gt = v > acc[u];
+          acc[u] = gt ? v : acc[u];
+          js[u] = gt ? j : js[u];
         }
       }
 #pragma unroll
