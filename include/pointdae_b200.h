@@ -185,8 +185,8 @@ int pdae_conv1x1_tf32x3_f32(const float *x, const float *w, const float *bias, i
  *                           (dP is scatter-added); train = 1 adds the two per-channel terms training-mode BatchNorm
  *                           spreads over every edge (ca, cb = gamma dbeta / M, gamma dgamma / M, M = b n k).      */
 size_t pdae_edge_partial_count(int b, int n);
-int pdae_edge_stats_f64(const float *z, int ld, const int64_t *idx, int b, int n, int k, int co, double *partial,
-                        pdae_stream_t stream);
+int pdae_edge_stats_f64(const float *z, int ld, const int64_t *idx, int b, int n, int k, int co, double *partial, float *s1,
+                        pdae_stream_t stream);  /* s1 (b,n,co) or NULL: sum_j P[idx(i,j)], kept for the backward */
 int pdae_edge_forward_f32(const float *z, int ld, const int64_t *idx, const float *scale, const float *shift, float slope,
                           int b, int n, int k, int co, float *out, unsigned char *jstar, pdae_stream_t stream);
 int pdae_edge_backward_f32(const float *z, int ld, const int64_t *idx, const unsigned char *jstar, const float *g,
@@ -246,6 +246,22 @@ int pdae_knn_keys_u64(const float *ref_local, const float *query, int b, int r_l
                       long long ref_offset, uint64_t *keys, pdae_stream_t stream);
 int pdae_knn_merge_keys_u64(const uint64_t *keys_all, int w, int b, int q, int k, int out_kq, float *dist, int64_t *idx,
                             pdae_stream_t stream);
+
+/* The same backward in two phases without one float atomic per edge and channel (the default of ops.edge_backward):
+ *   pdae_edge_backward_select_f32  per-CTA partial sums of dbeta / dgamma AND the selected edges' term gamma*dbn stored into
+ *                                  the Q half / scatter-added into the P half of dz (b,n,ld), zero-filled by the caller
+ *                                  (b*n*co atomics); with train = 0 (eval-mode BatchNorm) dz is then complete.
+ *   pdae_edge_backward_dense_f32   training mode: the two per-channel terms BatchNorm spreads over every edge, as a gather
+ *                                  of Q rows along the reversed graph (built here in the int workspace,
+ *                                  pdae_edge_reverse_workspace_ints) + s1 of the forward; dz finished in place.       */
+size_t pdae_edge_reverse_workspace_ints(int b, int n, int k);
+int pdae_edge_backward_select_f32(const float *z, int ld, const int64_t *idx, const unsigned char *jstar, const float *g,
+                                  const float *scale, const float *shift, const float *mean, const float *invstd,
+                                  const float *gamma, float slope, int train, int b, int n, int k, int co, double *partial,
+                                  float *dz, pdae_stream_t stream);
+int pdae_edge_backward_dense_f32(const float *z, int ld, const int64_t *idx, const float *s1, const float *mean,
+                                 const float *invstd, const float *ca, const float *cb, int b, int n, int k, int co,
+                                 int *workspace, size_t workspace_ints, float *dz, pdae_stream_t stream);
 
 /* The exchange of the sharded forward as one kernel over NVLink peer memory (no collective call): every rank's packed
  * row keys live in a symmetric buffer; rank r reduces rows [lo, hi) (its share) over all ranks' buffers and writes the

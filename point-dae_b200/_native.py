@@ -49,7 +49,10 @@ SIGNATURES = {
     "pdae_conv1x1_workspace_bytes": (_sz, [_i, _i]),
     "pdae_conv1x1_tf32x3_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pdae_edge_partial_count": (_sz, [_i, _i]),
-    "pdae_edge_stats_f64": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "pdae_edge_stats_f64": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_edge_reverse_workspace_ints": (_sz, [_i, _i, _i]),
+    "pdae_edge_backward_select_f32": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_edge_backward_dense_f32": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "pdae_edge_forward_f32": (_i, [_vp, _i, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_edge_backward_f32": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_pair_loss_partial_count": (_sz, [_i, _i, _i]),

@@ -140,7 +140,8 @@ __device__ __forceinline__ void edge_block_sums_to_global(double (&a)[EC_CHUNK /
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(EC_WARPS * 32) edge_stats_kernel(const EdgeArgs a, double *__restrict__ partial) {
+__global__ void __launch_bounds__(EC_WARPS * 32) edge_stats_kernel(const EdgeArgs a, double *__restrict__ partial,
+                                                                   float *__restrict__ s1_out /*(b, n, co) or NULL*/) {
   __shared__ double sm[2 * EC_CHUNK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t cloud = blockIdx.y;
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32) edge_stats_kernel(const EdgeArg
       for (int u = 0; u < PER_LANE; ++u) {
         const int o = c0 + u * 32 + lane;
         if (o < co) {
+          if (s1_out) s1_out[(cloud * n + i) * co + o] = s1[u];  // sum_j P[idx(i,j)]: the backward's dQ needs it
           const double q = static_cast<double>(__ldg(Z + static_cast<size_t>(i) * ld + co + o));
           t1[u] += static_cast<double>(s1[u]) + kf * q;
           t2[u] += static_cast<double>(s2[u]) + 2.0 * q * static_cast<double>(s1[u]) + kf * q * q;
@@ -305,8 +307,11 @@ struct EdgeBwdArgs {
 };
 
 // per-channel sums of dbn and dbn * yhat* (-> dbeta, dgamma)
+// dz != NULL (zero-filled by the caller): the selected edges' term gamma * dbn is also stored into the Q half (point i) and
+// scatter-added into the P half (point idx(i, jstar)) -- b*n*co atomics; eval-mode BatchNorm (train = 0) scales by invstd
+// and is then complete, training mode is finished by edge_backward_dense_kernel.
 __global__ void __launch_bounds__(EC_WARPS * 32) edge_backward_reduce_kernel(const EdgeArgs a, const EdgeBwdArgs w,
-                                                                             double *__restrict__ partial) {
+                                                                             double *__restrict__ partial, float *__restrict__ dz) {
   __shared__ double sm[2 * EC_CHUNK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t cloud = blockIdx.y;
@@ -336,6 +341,12 @@ __global__ void __launch_bounds__(EC_WARPS * 32) edge_backward_reduce_kernel(con
           const float yhat = (y - __ldg(w.mean + o)) * __ldg(w.invstd + o);
           t1[u] += static_cast<double>(dbn);
           t2[u] += static_cast<double>(dbn) * static_cast<double>(yhat);
+          if (dz) {
+            const float dsel = __ldg(w.gamma + o) * dbn * (w.train ? 1.0f : __ldg(w.invstd + o));
+            float *DZ = dz + cloud * n * ld;
+            DZ[static_cast<size_t>(i) * ld + co + o] = dsel;
+            atomicAdd(DZ + row + o, dsel);
+          }
         }
       }
     }
@@ -429,13 +440,13 @@ extern "C" size_t pdae_edge_partial_count(int b, int n) {
 }
 
 extern "C" int pdae_edge_stats_f64(const float *z, int ld, const int64_t *idx, int b, int n, int k, int co, double *partial,
-                                   pdae_stream_t stream) {
+                                   float *s1, pdae_stream_t stream) {
   const int rc = edge_check(z, idx, b, n, k, co, ld);
   if (rc) return rc;
   if (b == 0 || n == 0) return 0;
   if (!partial) return PDAE_E_INVALID;
   const dim3 grid(static_cast<unsigned>((n + EC_POINTS - 1) / EC_POINTS), static_cast<unsigned>(b));
-  edge_stats_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(EdgeArgs{z, idx, ld, n, k, co}, partial);
+  edge_stats_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(EdgeArgs{z, idx, ld, n, k, co}, partial, s1);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
@@ -467,11 +478,183 @@ extern "C" int pdae_edge_backward_f32(const float *z, int ld, const int64_t *idx
   const EdgeArgs a{z, idx, ld, n, k, co};
   const EdgeBwdArgs w{jstar, g, scale, shift, mean, invstd, gamma, ca, cb, slope, train};
   if (partial) {
-    edge_backward_reduce_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(a, w, partial);
+    edge_backward_reduce_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(a, w, partial, nullptr);
   } else {
     if (!ca || !cb) return PDAE_E_INVALID;
     edge_backward_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(a, w, dz);
   }
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+// ---- training-mode backward without one atomic per edge and channel -----------------------------------------------------------
+// dy[i][j] = invstd (gamma dbn [j = jstar] - A - Bc yhat[i][j]) sums, per TARGET point p = idx(i,j), to
+//   dP[p] = invstd (selected[p] - deg(p) A - Bc invstd (deg(p) (P[p] - mean) + sum_{(i,j) -> p} Q[i]))
+// and per source point to  dQ[i] = invstd (gamma dbn[i] - k A - Bc invstd (s1[i] + k Q[i] - k mean)).
+// `selected` is the b*n*co-atomic scatter of the reduce kernel above; the only edge-wise work left is the GATHER of Q rows
+// along the reversed graph (CSR by target, built per call by three small kernels) -- coalesced row reads, no atomics on
+// floats: 0.66 ms -> ~0.15 ms at 16 x 2048, k = 20, co = 256.
+namespace pdae {
+
+__global__ void __launch_bounds__(256) edge_rev_count_kernel(const int64_t *__restrict__ idx, int n, int k, long long total,
+                                                             int *__restrict__ cnt) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const long long cloud = e / (static_cast<long long>(n) * k);
+  atomicAdd(cnt + cloud * n + static_cast<int>(__ldg(idx + e)), 1);
+}
+
+// one CTA per cloud: ptr[p] = exclusive prefix sum of cnt (n + 1 entries); cnt is zeroed for its second life as cursor
+__global__ void __launch_bounds__(1024) edge_rev_scan_kernel(int *__restrict__ cnt, int n, int *__restrict__ ptr) {
+  __shared__ int part[1024];
+  int *c = cnt + static_cast<size_t>(blockIdx.x) * n;
+  int *p = ptr + static_cast<size_t>(blockIdx.x) * (n + 1);
+  const int per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+  int s = 0;
+  for (int t = lo; t < hi; ++t) s += c[t];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+    const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+  for (int t = lo; t < hi; ++t) {
+    const int v = c[t];
+    p[t] = run;
+    run += v;
+    c[t] = 0;
+  }
+  if (threadIdx.x == 1023) p[n] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) edge_rev_fill_kernel(const int64_t *__restrict__ idx, int n, int k, long long total,
+                                                            const int *__restrict__ ptr, int *__restrict__ cursor,
+                                                            int *__restrict__ src) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const long long cloud = e / (static_cast<long long>(n) * k);
+  const int within = static_cast<int>(e - cloud * n * k);
+  const int i = within / k;
+  const int tgt = static_cast<int>(__ldg(idx + e));
+  const int pos = atomicAdd(cursor + cloud * n + tgt, 1);
+  src[cloud * n * k + __ldg(ptr + cloud * (n + 1) + tgt) + pos] = i;  // the source point of the edge
+}
+
+__global__ void __launch_bounds__(EC_WARPS * 32) edge_backward_dense_kernel(const EdgeArgs a, const float *__restrict__ s1,
+                                                                            const int *__restrict__ ptr, const int *__restrict__ src,
+                                                                            const float *__restrict__ mean,
+                                                                            const float *__restrict__ invstd,
+                                                                            const float *__restrict__ ca, const float *__restrict__ cb,
+                                                                            float *__restrict__ dz) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t cloud = blockIdx.y;
+  const int i0 = blockIdx.x * EC_POINTS, n = a.n, k = a.k, co = a.co, ld = a.ld;
+  const float *__restrict__ Z = a.z + cloud * n * ld;
+  float *__restrict__ DZ = dz + cloud * n * ld;
+  const int *__restrict__ P = ptr + cloud * (n + 1);
+  const int *__restrict__ S = src + cloud * n * k;
+  constexpr int PER_LANE = EC_CHUNK / 32, PER_WARP = EC_POINTS / EC_WARPS;
+  const float kf = static_cast<float>(k);
+  for (int c0 = 0; c0 < co; c0 += EC_CHUNK) {
+    float mu[PER_LANE], is[PER_LANE], va[PER_LANE], vb[PER_LANE];
+    int oc[PER_LANE];
+#pragma unroll
+    for (int u = 0; u < PER_LANE; ++u) {
+      const int o = c0 + u * 32 + lane;
+      oc[u] = o < co ? o : co - 1;
+      mu[u] = __ldg(mean + oc[u]), is[u] = __ldg(invstd + oc[u]), va[u] = __ldg(ca + oc[u]), vb[u] = __ldg(cb + oc[u]);
+    }
+    for (int pw = 0; pw < PER_WARP; ++pw) {
+      const int p = i0 + warp * PER_WARP + pw;
+      if (p >= n) continue;
+      const int e0 = __ldg(P + p), e1 = __ldg(P + p + 1);
+      float rq[PER_LANE];
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) rq[u] = 0.f;
+      int e = e0;
+      for (; e + 4 <= e1; e += 4) {  // four source rows in flight
+        size_t row[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) row[t] = static_cast<size_t>(__ldg(S + e + t)) * ld + co;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int u = 0; u < PER_LANE; ++u) rq[u] += __ldg(Z + row[t] + oc[u]);
+      }
+      for (; e < e1; ++e) {
+        const size_t row = static_cast<size_t>(__ldg(S + e)) * ld + co;
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) rq[u] += __ldg(Z + row + oc[u]);
+      }
+      const float deg = static_cast<float>(e1 - e0);
+#pragma unroll
+      for (int u = 0; u < PER_LANE; ++u) {
+        const int o = c0 + u * 32 + lane;
+        if (o < co) {
+          const size_t rp = static_cast<size_t>(p) * ld;
+          const float pv = __ldg(Z + rp + o), qv = __ldg(Z + rp + co + o);
+          const float sel = DZ[rp + o], dsel = DZ[rp + co + o];
+          const float s1v = __ldg(s1 + (cloud * n + p) * co + o);
+          DZ[rp + o] = is[u] * (sel - deg * va[u] - vb[u] * is[u] * (deg * (pv - mu[u]) + rq[u]));
+          DZ[rp + co + o] = is[u] * (dsel - kf * va[u] - vb[u] * is[u] * (s1v + kf * (qv - mu[u])));
+        }
+      }
+    }
+  }
+}
+
+}  // namespace pdae
+
+extern "C" size_t pdae_edge_reverse_workspace_ints(int b, int n, int k) {
+  if (b <= 0 || n <= 0 || k <= 0) return 0;
+  return static_cast<size_t>(b) * (2 * static_cast<size_t>(n) + 1 + static_cast<size_t>(n) * k);
+}
+
+// phase 1 of the fused backward: partial sums of dbeta / dgamma AND the selected edges' term into dz (zero-filled)
+extern "C" int pdae_edge_backward_select_f32(const float *z, int ld, const int64_t *idx, const unsigned char *jstar, const float *g,
+                                             const float *scale, const float *shift, const float *mean, const float *invstd,
+                                             const float *gamma, float slope, int train, int b, int n, int k, int co,
+                                             double *partial, float *dz, pdae_stream_t stream) {
+  const int rc = edge_check(z, idx, b, n, k, co, ld);
+  if (rc) return rc;
+  if (b == 0 || n == 0) return 0;
+  if (!jstar || !g || !scale || !shift || !mean || !invstd || !gamma || !partial || !dz) return PDAE_E_INVALID;
+  const dim3 grid(static_cast<unsigned>((n + EC_POINTS - 1) / EC_POINTS), static_cast<unsigned>(b));
+  const EdgeBwdArgs w{jstar, g, scale, shift, mean, invstd, gamma, nullptr, nullptr, slope, train};
+  edge_backward_reduce_kernel<<<grid, EC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(EdgeArgs{z, idx, ld, n, k, co}, w, partial,
+                                                                                          dz);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+// phase 2 (training-mode BatchNorm only): reversed graph + dense terms, dz finished in place
+extern "C" int pdae_edge_backward_dense_f32(const float *z, int ld, const int64_t *idx, const float *s1, const float *mean,
+                                            const float *invstd, const float *ca, const float *cb, int b, int n, int k, int co,
+                                            int *workspace, size_t workspace_ints, float *dz, pdae_stream_t stream) {
+  const int rc = edge_check(z, idx, b, n, k, co, ld);
+  if (rc) return rc;
+  if (b == 0 || n == 0) return 0;
+  if (!s1 || !mean || !invstd || !ca || !cb || !dz || !workspace) return PDAE_E_INVALID;
+  if (workspace_ints < pdae_edge_reverse_workspace_ints(b, n, k)) return PDAE_E_WORKSPACE;
+  if (n > (1 << 24)) return PDAE_E_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int *cnt = workspace;                                  // (b, n): counts, then cursors
+  int *ptr = cnt + static_cast<size_t>(b) * n;           // (b, n + 1)
+  int *src = ptr + static_cast<size_t>(b) * (n + 1);     // (b, n * k)
+  const long long total = static_cast<long long>(b) * n * k;
+  if ((total + 255) / 256 > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  PDAE_CUDA_TRY(cudaMemsetAsync(cnt, 0, static_cast<size_t>(b) * n * sizeof(int), st));
+  edge_rev_count_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(idx, n, k, total, cnt);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  edge_rev_scan_kernel<<<b, 1024, 0, st>>>(cnt, n, ptr);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  edge_rev_fill_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(idx, n, k, total, ptr, cnt, src);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  const dim3 grid(static_cast<unsigned>((n + EC_POINTS - 1) / EC_POINTS), static_cast<unsigned>(b));
+  edge_backward_dense_kernel<<<grid, EC_WARPS * 32, 0, st>>>(EdgeArgs{z, idx, ld, n, k, co}, s1, ptr, src, mean, invstd, ca, cb, dz);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }

@@ -750,16 +750,19 @@ def _edge_dims(z, idx, co):
     return b, n, ld, k
 
 
-def edge_stats(z, idx, co):
+def edge_stats(z, idx, co, want_s1=False):
     """Sum and sum of squares per output channel of y[i][j] = P[idx(i,j)] + Q[i] over all edges of the batch, from the
-    point-major product z = [P | Q] (B,N,2*co): float64 (co, 2)."""
+    point-major product z = [P | Q] (B,N,2*co): float64 (co, 2) (+ s1 (B,N,co) = sum_j P[idx(i,j)] for the backward)."""
     b, n, ld, k = _edge_dims(z, idx, co)
     L = _native.lib()
     with _on(z.device):
         partial = torch.empty((int(L.pdae_edge_partial_count(b, n)), co, 2), dtype=torch.float64, device=z.device)
-        rc = L.pdae_edge_stats_f64(z.data_ptr(), ld, idx.data_ptr(), b, n, k, co, partial.data_ptr(), _stream())
+        s1 = torch.empty((b, n, co), dtype=torch.float32, device=z.device) if want_s1 else None
+        rc = L.pdae_edge_stats_f64(z.data_ptr(), ld, idx.data_ptr(), b, n, k, co, partial.data_ptr(),
+                                   s1.data_ptr() if want_s1 else None, _stream())
     _native.check(rc, "pdae_edge_stats_f64")
-    return partial.sum(dim=0)  # fixed order: deterministic
+    sums = partial.sum(dim=0)  # fixed order: deterministic
+    return (sums, s1) if want_s1 else sums
 
 
 def edge_forward(z, idx, co, scale, shift, slope=0.2, want_jstar=False):
@@ -777,30 +780,43 @@ def edge_forward(z, idx, co, scale, shift, slope=0.2, want_jstar=False):
     return out, jstar
 
 
-def edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, slope, train):
+def edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, slope, train, s1=None):
     """Backward of edge_forward (+ training-mode BatchNorm when train): g_pm (B,N,co) upstream gradient, point-major ->
-    dz (B,N,ld) = [dP | dQ], dgamma (co), dbeta (co)."""
+    dz (B,N,ld) = [dP | dQ], dgamma (co), dbeta (co).  With s1 (sum_j P[idx], kept by the training forward) the dense
+    terms of training-mode BatchNorm are gathered along the reversed graph (no float atomic per edge); without it the
+    edge-parallel kernel of the first version runs."""
     b, n, ld, k = _edge_dims(z, idx, co)
     L = _native.lib()
-    args = (z.data_ptr(), ld, idx.data_ptr(), jstar.data_ptr(), g_pm.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-            mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr())
+    m = float(b) * n * k
     with _on(z.device):
         partial = torch.empty((int(L.pdae_edge_partial_count(b, n)), co, 2), dtype=torch.float64, device=z.device)
-        rc = L.pdae_edge_backward_f32(*args, None, None, float(slope), 1 if train else 0, b, n, k, co, partial.data_ptr(), None,
-                                      _stream())
+        dz = torch.zeros_like(z)
+        if not train or s1 is not None:
+            rc = L.pdae_edge_backward_select_f32(z.data_ptr(), ld, idx.data_ptr(), jstar.data_ptr(), g_pm.data_ptr(), scale.data_ptr(),
+                                                 shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), float(slope),
+                                                 1 if train else 0, b, n, k, co, partial.data_ptr(), dz.data_ptr(), _stream())
+            _native.check(rc, "pdae_edge_backward_select_f32")
+            sums = partial.sum(dim=0)
+            dbeta, dgamma = sums[:, 0], sums[:, 1]
+            if train:
+                ca = (gamma.double() * dbeta / m).float().contiguous()
+                cb = (gamma.double() * dgamma / m).float().contiguous()
+                nints = int(L.pdae_edge_reverse_workspace_ints(b, n, k))
+                ws = torch.empty(nints, dtype=torch.int32, device=z.device)
+                rc = L.pdae_edge_backward_dense_f32(z.data_ptr(), ld, idx.data_ptr(), s1.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                                    ca.data_ptr(), cb.data_ptr(), b, n, k, co, ws.data_ptr(), nints, dz.data_ptr(),
+                                                    _stream())
+                _native.check(rc, "pdae_edge_backward_dense_f32")
+            return dz, dgamma.float(), dbeta.float()
+        args = (z.data_ptr(), ld, idx.data_ptr(), jstar.data_ptr(), g_pm.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr())
+        rc = L.pdae_edge_backward_f32(*args, None, None, float(slope), 1, b, n, k, co, partial.data_ptr(), None, _stream())
         _native.check(rc, "pdae_edge_backward_f32 (reduce)")
         sums = partial.sum(dim=0)
         dbeta, dgamma = sums[:, 0], sums[:, 1]
-        m = float(b) * n * k
-        if train:
-            ca = (gamma.double() * dbeta / m).float().contiguous()
-            cb = (gamma.double() * dgamma / m).float().contiguous()
-        else:
-            ca = torch.zeros(co, dtype=torch.float32, device=z.device)
-            cb = ca
-        dz = torch.zeros_like(z)
-        rc = L.pdae_edge_backward_f32(*args, ca.data_ptr(), cb.data_ptr(), float(slope), 1 if train else 0, b, n, k, co, None,
-                                      dz.data_ptr(), _stream())
+        ca = (gamma.double() * dbeta / m).float().contiguous()
+        cb = (gamma.double() * dgamma / m).float().contiguous()
+        rc = L.pdae_edge_backward_f32(*args, ca.data_ptr(), cb.data_ptr(), float(slope), 1, b, n, k, co, None, dz.data_ptr(), _stream())
     _native.check(rc, "pdae_edge_backward_f32")
     return dz, dgamma.float(), dbeta.float()
 
@@ -818,8 +834,13 @@ class EdgeConvFunction(torch.autograd.Function):
         k = idx.size(2)
         x = x.contiguous()
         z = conv1x1(x, wz.contiguous(), out_point_major=True)  # (B,N,2co): [W1 x | (W2 - W1) x]
+        need_grad = any(ctx.needs_input_grad)
+        s1 = None
         if training:
-            sums = edge_stats(z, idx, co)
+            if need_grad:
+                sums, s1 = edge_stats(z, idx, co, want_s1=True)
+            else:
+                sums = edge_stats(z, idx, co)
             m = float(b) * n * k
             mean64 = sums[:, 0] / m
             var64 = (sums[:, 1] / m - mean64 * mean64).clamp_min_(0.0)
@@ -833,19 +854,18 @@ class EdgeConvFunction(torch.autograd.Function):
         invstd = torch.rsqrt(var + eps)
         scale = (gamma * invstd).contiguous()
         shift = (beta - scale * mean).contiguous()
-        need_grad = any(ctx.needs_input_grad)
         out, jstar = edge_forward(z, idx, co, scale, shift, slope, want_jstar=need_grad)
         if need_grad:
-            ctx.save_for_backward(x, idx, wz, z, jstar, scale, shift, mean.contiguous(), invstd.contiguous(), gamma.contiguous())
+            ctx.save_for_backward(x, idx, wz, z, jstar, scale, shift, mean.contiguous(), invstd.contiguous(), gamma.contiguous(), s1)
             ctx.meta = (co, float(slope), bool(training))
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        x, idx, wz, z, jstar, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        x, idx, wz, z, jstar, scale, shift, mean, invstd, gamma, s1 = ctx.saved_tensors
         co, slope, training = ctx.meta
         g_pm = g_out.transpose(1, 2).contiguous()
-        dz, dgamma, dbeta = edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, slope, training)
+        dz, dgamma, dbeta = edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, slope, training, s1)
         dx = dwz = None
         if ctx.needs_input_grad[0]:
             dx = conv1x1(dz, wz.t().contiguous(), in_point_major=True)  # (B,C,N) = Wz^T [dP ; dQ]

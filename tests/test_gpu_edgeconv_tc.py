@@ -146,3 +146,25 @@ def test_whole_encoder_forward_and_backward(monkeypatch, train):
     if train:
         for (name, br), (_, bo) in zip(ref.named_buffers(), ours.named_buffers()):
             assert torch.allclose(bo.float(), br.float(), rtol=1e-4, atol=1e-5), name
+
+
+def test_both_training_backward_forms_agree():
+    """gather along the reversed graph (default) against the edge-parallel atomic kernel of the first version"""
+    b, c, n, co, k = 2, 64, 300, 128, 20
+    x = torch.randn(b, c, n, device=DEV)
+    idx = dgcnn_util.knn(x, k)
+    wz = torch.randn(2 * co, c, device=DEV) / c ** 0.5
+    z = ops.conv1x1(x, wz, out_point_major=True)
+    sums, s1 = ops.edge_stats(z, idx, co, want_s1=True)
+    m = float(b * n * k)
+    mean = (sums[:, 0] / m).float()
+    invstd = torch.rsqrt((sums[:, 1] / m - (sums[:, 0] / m) ** 2).float() + 1e-5)
+    gamma, beta = torch.randn(co, device=DEV), torch.randn(co, device=DEV)
+    scale = (gamma * invstd).contiguous()
+    shift = (beta - scale * mean).contiguous()
+    _, jstar = ops.edge_forward(z, idx, co, scale, shift, 0.2, want_jstar=True)
+    g = torch.randn(b, n, co, device=DEV)
+    new = ops.edge_backward(z, idx, co, jstar, g, scale, shift, mean, invstd, gamma, 0.2, True, s1)
+    old = ops.edge_backward(z, idx, co, jstar, g, scale, shift, mean, invstd, gamma, 0.2, True, None)
+    for a, w in zip(new, old):
+        assert torch.allclose(a, w, rtol=1e-4, atol=1e-5 * float(w.abs().max())), float((a - w).abs().max())
