@@ -263,6 +263,15 @@ int pdae_edge_backward_dense_f32(const float *z, int ld, const int64_t *idx, con
                                  const float *invstd, const float *ca, const float *cb, int b, int n, int k, int co,
                                  int *workspace, size_t workspace_ints, float *dz, pdae_stream_t stream);
 
+/* The per-channel BatchNorm arithmetic around those kernels, one launch each: partial sums -> batch statistics (training:
+ * running buffers updated like nn.BatchNorm2d; train = 0: the running buffers ARE the statistics) -> invstd and the folded
+ * scale / shift; and the backward's partial sums -> dgamma, dbeta and the two per-channel terms ca, cb.               */
+int pdae_edge_bn_prepare_f32(const double *partial, int np, int co, double m, const float *gamma, const float *beta,
+                             float *running_mean, float *running_var, float momentum, float eps, int train, float *mean,
+                             float *invstd, float *scale, float *shift, pdae_stream_t stream);
+int pdae_edge_bn_backward_f32(const double *partial, int np, int co, double m, const float *gamma, float *dgamma, float *dbeta,
+                              float *ca, float *cb, pdae_stream_t stream);
+
 /* The exchange of the sharded forward as one kernel over NVLink peer memory (no collective call): every rank's packed
  * row keys live in a symmetric buffer; rank r reduces rows [lo, hi) (its share) over all ranks' buffers and writes the
  * unpacked (distance, index) pairs into every rank's result buffers.  keys / dist / idx: host arrays of `world` peer-mapped

@@ -658,3 +658,81 @@ extern "C" int pdae_edge_backward_dense_f32(const float *z, int ld, const int64_
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
+
+// ---- per-channel BatchNorm arithmetic in one launch each (instead of ~15 / ~8 torch micro-ops on (co)-sized tensors) -------
+namespace pdae {
+
+// partial (np, co, 2) fp64 -> batch mean / biased variance -> invstd, folded scale / shift; running buffers updated like
+// nn.BatchNorm2d (momentum, unbiased variance).  train = 0: the statistics are the running buffers.
+__global__ void __launch_bounds__(128) edge_bn_prepare_kernel(const double *__restrict__ partial, int np, int co, double m,
+                                                              const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                              float *running_mean, float *running_var, float momentum, float eps,
+                                                              int train, float *__restrict__ mean, float *__restrict__ invstd,
+                                                              float *__restrict__ scale, float *__restrict__ shift) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= co) return;
+  float mu, var;
+  if (train) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = 0; p < np; ++p) {  // fixed order: deterministic
+      s1 += partial[(static_cast<size_t>(p) * co + o) * 2];
+      s2 += partial[(static_cast<size_t>(p) * co + o) * 2 + 1];
+    }
+    const double mean64 = s1 / m;
+    double var64 = s2 / m - mean64 * mean64;
+    var64 = var64 > 0.0 ? var64 : 0.0;
+    if (running_mean) {
+      running_mean[o] = (1.0f - momentum) * running_mean[o] + momentum * static_cast<float>(mean64);
+      running_var[o] = (1.0f - momentum) * running_var[o] + momentum * static_cast<float>(var64 * (m / (m > 1.0 ? m - 1.0 : 1.0)));
+    }
+    mu = static_cast<float>(mean64), var = static_cast<float>(var64);
+  } else {
+    mu = running_mean[o], var = running_var[o];
+  }
+  const float is = rsqrtf(var + eps);
+  const float g = gamma ? gamma[o] : 1.0f, bta = beta ? beta[o] : 0.0f;
+  const float sc = g * is;
+  mean[o] = mu, invstd[o] = is, scale[o] = sc, shift[o] = bta - sc * mu;
+}
+
+// partial (np, co, 2) fp64 of the backward's reduce phase -> dbeta, dgamma and the two per-channel terms of training-mode
+// BatchNorm's backward
+__global__ void __launch_bounds__(128) edge_bn_backward_kernel(const double *__restrict__ partial, int np, int co, double m,
+                                                               const float *__restrict__ gamma, float *__restrict__ dgamma,
+                                                               float *__restrict__ dbeta, float *__restrict__ ca,
+                                                               float *__restrict__ cb) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= co) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int p = 0; p < np; ++p) {
+    s1 += partial[(static_cast<size_t>(p) * co + o) * 2];
+    s2 += partial[(static_cast<size_t>(p) * co + o) * 2 + 1];
+  }
+  dbeta[o] = static_cast<float>(s1), dgamma[o] = static_cast<float>(s2);
+  const double g = gamma[o];
+  ca[o] = static_cast<float>(g * s1 / m), cb[o] = static_cast<float>(g * s2 / m);
+}
+
+}  // namespace pdae
+
+extern "C" int pdae_edge_bn_prepare_f32(const double *partial, int np, int co, double m, const float *gamma, const float *beta,
+                                        float *running_mean, float *running_var, float momentum, float eps, int train,
+                                        float *mean, float *invstd, float *scale, float *shift, pdae_stream_t stream) {
+  if (co <= 0 || np < 0 || !mean || !invstd || !scale || !shift) return PDAE_E_INVALID;
+  if (train && (!partial || np == 0 || m <= 0)) return PDAE_E_INVALID;
+  if (!train && (!running_mean || !running_var)) return PDAE_E_INVALID;
+  edge_bn_prepare_kernel<<<(co + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, np, co, m, gamma, beta, running_mean,
+                                                                                        running_var, momentum, eps, train, mean,
+                                                                                        invstd, scale, shift);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+extern "C" int pdae_edge_bn_backward_f32(const double *partial, int np, int co, double m, const float *gamma, float *dgamma,
+                                         float *dbeta, float *ca, float *cb, pdae_stream_t stream) {
+  if (co <= 0 || np <= 0 || m <= 0 || !partial || !gamma || !dgamma || !dbeta || !ca || !cb) return PDAE_E_INVALID;
+  edge_bn_backward_kernel<<<(co + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, np, co, m, gamma, dgamma, dbeta, ca,
+                                                                                         cb);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}

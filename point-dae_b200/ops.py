@@ -821,11 +821,24 @@ def edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, sl
     return dz, dgamma.float(), dbeta.float()
 
 
+def _edge_partials(z, idx, co, want_s1):
+    """raw per-CTA partial sums of the statistics kernel (summed inside pdae_edge_bn_prepare_f32)"""
+    b, n, ld, k = _edge_dims(z, idx, co)
+    L = _native.lib()
+    partial = torch.empty((int(L.pdae_edge_partial_count(b, n)), co, 2), dtype=torch.float64, device=z.device)
+    s1 = torch.empty((b, n, co), dtype=torch.float32, device=z.device) if want_s1 else None
+    rc = L.pdae_edge_stats_f64(z.data_ptr(), ld, idx.data_ptr(), b, n, k, co, partial.data_ptr(),
+                               s1.data_ptr() if want_s1 else None, _stream())
+    _native.check(rc, "pdae_edge_stats_f64")
+    return partial, s1
+
+
 class EdgeConvFunction(torch.autograd.Function):
     """One EdgeConv layer of the DGCNN encoder (models/dgcnn_util.py:114-116 and the three after it):
     get_graph_feature(x, k, idx) -> Conv2d(2C, Co, 1, bias=False) -> BatchNorm2d -> LeakyReLU -> max over k, as
     tensor-core product + gather kernels; the (B,2C,N,k) and (B,Co,N,k) tensors never exist.  Training-mode BatchNorm
-    takes its batch statistics from gather sums and updates the running buffers like nn.BatchNorm2d."""
+    takes its batch statistics from gather sums and updates the running buffers like nn.BatchNorm2d.  Host side: five
+    launches forward, six backward, the per-channel arithmetic inside two of them (no torch micro-ops)."""
 
     @staticmethod
     def forward(ctx, x, idx, wz, gamma, beta, running_mean, running_var, training, momentum, eps, slope):
@@ -833,47 +846,63 @@ class EdgeConvFunction(torch.autograd.Function):
         b, c, n = x.shape
         k = idx.size(2)
         x = x.contiguous()
-        z = conv1x1(x, wz.contiguous(), out_point_major=True)  # (B,N,2co): [W1 x | (W2 - W1) x]
+        L = _native.lib()
         need_grad = any(ctx.needs_input_grad)
-        s1 = None
-        if training:
-            if need_grad:
-                sums, s1 = edge_stats(z, idx, co, want_s1=True)
-            else:
-                sums = edge_stats(z, idx, co)
-            m = float(b) * n * k
-            mean64 = sums[:, 0] / m
-            var64 = (sums[:, 1] / m - mean64 * mean64).clamp_min_(0.0)
-            if running_mean is not None:
-                with torch.no_grad():
-                    running_mean.mul_(1.0 - momentum).add_(mean64.to(running_mean.dtype), alpha=momentum)
-                    running_var.mul_(1.0 - momentum).add_((var64 * (m / max(m - 1.0, 1.0))).to(running_var.dtype), alpha=momentum)
-            mean, var = mean64.float(), var64.float()
-        else:
-            mean, var = running_mean.float(), running_var.float()
-        invstd = torch.rsqrt(var + eps)
-        scale = (gamma * invstd).contiguous()
-        shift = (beta - scale * mean).contiguous()
-        out, jstar = edge_forward(z, idx, co, scale, shift, slope, want_jstar=need_grad)
+        with _on(x.device):
+            z = conv1x1(x, wz.contiguous(), out_point_major=True)  # (B,N,2co): [W1 x | (W2 - W1) x]
+            partial = s1 = None
+            if training:
+                partial, s1 = _edge_partials(z, idx, co, need_grad)
+            stats = torch.empty((4, co), dtype=torch.float32, device=x.device)  # mean | invstd | scale | shift
+            gamma_c, beta_c = gamma.contiguous(), beta.contiguous()
+            rc = L.pdae_edge_bn_prepare_f32(partial.data_ptr() if training else None, partial.size(0) if training else 0, co,
+                                            float(b) * n * k, gamma_c.data_ptr(), beta_c.data_ptr(),
+                                            running_mean.data_ptr() if running_mean is not None else None,
+                                            running_var.data_ptr() if running_var is not None else None, float(momentum),
+                                            float(eps), 1 if training else 0, stats[0].data_ptr(), stats[1].data_ptr(),
+                                            stats[2].data_ptr(), stats[3].data_ptr(), _stream())
+            _native.check(rc, "pdae_edge_bn_prepare_f32")
+            out, jstar = edge_forward(z, idx, co, stats[2], stats[3], slope, want_jstar=need_grad)
         if need_grad:
-            ctx.save_for_backward(x, idx, wz, z, jstar, scale, shift, mean.contiguous(), invstd.contiguous(), gamma.contiguous(), s1)
+            ctx.save_for_backward(x, idx, wz, z, jstar, stats, gamma_c, s1)
             ctx.meta = (co, float(slope), bool(training))
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        x, idx, wz, z, jstar, scale, shift, mean, invstd, gamma, s1 = ctx.saved_tensors
+        x, idx, wz, z, jstar, stats, gamma, s1 = ctx.saved_tensors
         co, slope, training = ctx.meta
-        g_pm = g_out.transpose(1, 2).contiguous()
-        dz, dgamma, dbeta = edge_backward(z, idx, co, jstar, g_pm, scale, shift, mean, invstd, gamma, slope, training, s1)
-        dx = dwz = None
-        if ctx.needs_input_grad[0]:
-            dx = conv1x1(dz, wz.t().contiguous(), in_point_major=True)  # (B,C,N) = Wz^T [dP ; dQ]
-        if ctx.needs_input_grad[2]:
-            b, c, n = x.shape
-            # weight gradient: a (2co x B N) by (B N x C) product with a tiny output -- a plain library GEMM
-            dwz = torch.matmul(dz.reshape(b * n, 2 * co).t(), x.transpose(1, 2).reshape(b * n, c))
-        return dx, None, dwz, dgamma if ctx.needs_input_grad[3] else None, dbeta if ctx.needs_input_grad[4] else None, \
+        b, n, ld, k = _edge_dims(z, idx, co)
+        L = _native.lib()
+        with _on(z.device):
+            g_pm = g_out.transpose(1, 2).contiguous()
+            mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+            partial = torch.empty((int(L.pdae_edge_partial_count(b, n)), co, 2), dtype=torch.float64, device=z.device)
+            dz = torch.zeros_like(z)
+            rc = L.pdae_edge_backward_select_f32(z.data_ptr(), ld, idx.data_ptr(), jstar.data_ptr(), g_pm.data_ptr(), scale.data_ptr(),
+                                                 shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), slope,
+                                                 1 if training else 0, b, n, k, co, partial.data_ptr(), dz.data_ptr(), _stream())
+            _native.check(rc, "pdae_edge_backward_select_f32")
+            grads = torch.empty((4, co), dtype=torch.float32, device=z.device)  # dgamma | dbeta | ca | cb
+            rc = L.pdae_edge_bn_backward_f32(partial.data_ptr(), partial.size(0), co, float(b) * n * k, gamma.data_ptr(),
+                                             grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), grads[3].data_ptr(),
+                                             _stream())
+            _native.check(rc, "pdae_edge_bn_backward_f32")
+            if training:
+                nints = int(L.pdae_edge_reverse_workspace_ints(b, n, k))
+                ws = torch.empty(nints, dtype=torch.int32, device=z.device)
+                rc = L.pdae_edge_backward_dense_f32(z.data_ptr(), ld, idx.data_ptr(), s1.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                                    grads[2].data_ptr(), grads[3].data_ptr(), b, n, k, co, ws.data_ptr(), nints,
+                                                    dz.data_ptr(), _stream())
+                _native.check(rc, "pdae_edge_backward_dense_f32")
+            dx = dwz = None
+            if ctx.needs_input_grad[0]:
+                dx = conv1x1(dz, wz.t().contiguous(), in_point_major=True)  # (B,C,N) = Wz^T [dP ; dQ]
+            if ctx.needs_input_grad[2]:
+                c = x.size(1)
+                # weight gradient: a (2co x B N) by (B N x C) product with a tiny output -- a plain library GEMM
+                dwz = torch.matmul(dz.reshape(b * n, 2 * co).t(), x.transpose(1, 2).reshape(b * n, c))
+        return dx, None, dwz, grads[0] if ctx.needs_input_grad[3] else None, grads[1] if ctx.needs_input_grad[4] else None, \
             None, None, None, None, None, None
 
 
