@@ -214,6 +214,18 @@ int pdae_tune_chamfer_variant(int v);
  * into (ids as the PDAE_CHAMFER_SPLIT environment variable: 0 = automatic, 1 = never split; nc < 0 only queries).
  * Returns the previous setting.  Results do not depend on it.  Not thread-safe.                                 */
 int pdae_tune_chamfer_split(int nc);
+/* Chamfer forward, both clouds 512..2048 points: the tensor cores (tcgen05.mma kind::tf32, hi/lo split operands) evaluate
+ * approximate distances, the 32-column groups that can hold a row's minimum within the error bound are re-evaluated with the
+ * reference's exact expression (chamfer.cu:42-79) -- same bits as the FP32-pipe kernels (csrc/chamfer_tc.cu).
+ * Tuning / test hook: mode 0 = FP32-pipe kernels only, 1 / 2 = tensor-core filter with 128- / 256-column accumulators
+ * (default 1; environment PDAE_CHAMFER_TC); eps_rel > 0 sets the filter's error bound relative to
+ * max|a - c|^2 + max|b - c|^2 (default 2^-16; PDAE_CHAMFER_TC_EPS).  mode < 0 only queries.  Returns the previous mode.     */
+int pdae_tune_chamfer_tc(int mode, float eps_rel);
+/* probe: the tensor-core forward regardless of the mode, plus filter statistics in stats4 (4 x uint64, zeroed by the caller):
+ * [0] float bits of the largest |approximate - exact| group minimum relative to the bound's scale, [1] rows decided by the
+ * literal scan (list overflow / no finite candidate), [2] 32-column groups evaluated exactly, [3] rows written.            */
+int pdae_chamfer_tc_probe(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
+                          int *idx2, unsigned long long *stats4, pdae_stream_t stream);
 /* kNN / Group (dim 3, k <= 64): impl 4 = multi-query warps + TMA tile prefetch (default), 3 = the first-generation
  * kernel (kept for A/B measurements); qw queries per warp (1/2/4), nw warps per CTA (4/8), tile points per shared-memory
  * tile, nz chunks along the reference cloud (needs the workspace), tma 0/1, spec 0/1 (warp-specialised CTAs with a

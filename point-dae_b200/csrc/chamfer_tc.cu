@@ -1,0 +1,515 @@
+// chamfer_tc.cu -- Chamfer forward with the 5th-generation tensor cores as an exact FILTER (round 2).
+//
+// The reference (extensions/chamfer_dist/chamfer.cu:15-145) evaluates every pair (a_i, b_j) in fp32 on the CUDA cores and
+// keeps, per point, the minimum distance and its lowest index; chamfer.cu here does the same on the FP32 FMA pipe and is
+// bound by it (6 lane-ops per pair).  This file gets the same bits from ~1/4 of the issue slots:
+//
+//   1. tcgen05.mma (kind::tf32, M128 x N128|256 x K8, accumulators in TENSOR MEMORY) evaluates an APPROXIMATE
+//      D[i][j] = |b'_j|^2 - 2 a'_i . b'_j   (= |a'_i - b'_j|^2 - |a'_i|^2: the row constant does not move a row's argmin)
+//      for centred points a' = a - c, b' = b - c.  Every coordinate is split into tf32 hi + lo; one K = 8 operand row
+//      carries [ah.x ah.y ah.z al.x | al.y al.z 1 1] against [-2bh.x -2bh.y -2bh.z -2bh.x | -2bh.y -2bh.z m_hi m_lo] and a
+//      second MMA adds [.. same A ..] x [-2bl.x -2bl.y -2bl.z -2bl.x | -2bl.y -2bl.z 0 0]: all four hi/lo cross terms, so
+//      |D - exact| <= eps = eps_rel * (max|a'|^2 + max|b'|^2) with eps_rel = 2^-16 by default (measured error: see
+//      DESIGN.md 4.1b; the tune hook lowers eps_rel until results change, which is how the margin is tested).
+//   2. The epilogue warps read D with tcgen05.ld (32 columns per instruction, a thread = a row), reduce every 32-column
+//      group to its minimum g with FMNMX3 and keep, per row, the groups with g <= (running best) + 2 eps -- a superset of
+//      the groups that can hold the exact argmin; a new best more than 2 eps below the old one clears the list, so it
+//      holds one or two entries.
+//   3. The surviving groups (32 columns each, ~1.0 per row) are evaluated EXACTLY -- the reference's own expression
+//      fma(dz,dz, fma(dx,dx, dy*dy)) on the original coordinates -- and the (distance bits, index) minimum is the
+//      reference's result bit for bit (strict `<`: lowest index on ties).  Rows whose list overflowed (mass ties), rows
+//      without a finite candidate and clouds with non-finite bounds are scanned exactly over all columns: the result
+//      never depends on the filter being right, only its speed does.
+//
+// Persistent CTAs (one per SM: a CTA owns all 512 TMEM columns), each walks a contiguous range of 128-row blocks; the
+// operand image of the whole reference cloud (<= 2048 points, 128 KB) is built once per (cloud, direction) and stays in
+// shared memory.  Warp 8 builds the row operands and issues the MMAs; warps 0-7 are the epilogue (warp w reads TMEM lanes
+// 32 (w & 3).., columns of half w >> 2); accumulator buffers cycle through full / empty mbarriers (tcgen05.commit).
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace pdae {
+
+namespace tcc {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = bytes between the two 16-byte K chunks, SBO = between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+#define PDAE_TMEM_LD32(taddr, r)                                                                                          \
+  asm volatile(                                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20," \
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                              \
+      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),       \
+        "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),            \
+        "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),           \
+        "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])                         \
+      : "r"(taddr))
+}  // namespace tcc
+
+constexpr int TCC_M = 128;         // rows of a row block (MMA M, the 128 TMEM lanes)
+constexpr int TCC_MAXCOLS = 2048;  // reference points whose operand image stays in shared memory
+constexpr int TCC_GROUP = 32;      // columns per candidate group (one tcgen05.ld.x32)
+constexpr int TCC_CAP = 8;         // candidate groups kept per (row, column half)
+constexpr int TCC_EPI = 256;       // epilogue threads (warps 0-7)
+constexpr int TCC_THREADS = TCC_EPI + 32;
+constexpr float TCC_BIG = 1.0e30f;  // "distance" of a padded column
+
+struct TccDir {
+  const float *q;  // (b, nq, 3) the points that receive a minimum (rows)
+  const float *r;  // (b, nr, 3) the cloud that is searched (columns)
+  float *dist;     // (b, nq)
+  int *idx;        // (b, nq)
+  int nq, nr, rbs;  // rbs = ceil(nq / 128)
+};
+struct TccArgs {
+  TccDir d[2];
+  long long units;  // b * (d[0].rbs + d[1].rbs) row blocks
+  float eps_rel;
+  unsigned long long *stats;  // optional probe: [0] max |g - (exact group minimum - |a'|^2)| / (max|a'|^2 + max|b'|^2) as float
+                              // bits, [1] rows decided by the literal scan, [2] groups evaluated exactly, [3] rows
+};
+
+// literal reference scan of one row (chamfer.cu:42-79): the fallback that makes the result independent of the filter
+__device__ __forceinline__ void tcc_exact_row(const float *__restrict__ R, int nr, float ax, float ay, float az, float &best,
+                                              int &bi) {
+  best = 0.f;
+  bi = 0;
+  for (int j = 0; j < nr; ++j) {
+    const float d = dist_yxz(__fsub_rn(__ldg(R + 3 * j), ax), __fsub_rn(__ldg(R + 3 * j + 1), ay), __fsub_rn(__ldg(R + 3 * j + 2), az));
+    if (j == 0 || d < best) best = d, bi = j;
+  }
+}
+
+// TN = columns per accumulator buffer (128: four buffers in flight, 256: two)
+template <int TN>
+__global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArgs args) {
+  constexpr int NBUF = 512 / TN;
+  constexpr int CHUNK = TN * 16;          // bytes of one 16-byte-wide K chunk of a B tile
+  constexpr int BTILE = 2 * CHUNK;        // bytes of one B tile image (K = 8 floats)
+  constexpr int ACHUNK = TCC_M * 16;      // 2 KB
+  constexpr int MAXT = TCC_MAXCOLS / TN;
+  constexpr int HALF = TN / 2;            // columns of a tile one epilogue thread reads
+  constexpr int STEPS = HALF / TCC_GROUP; // tcgen05.ld.x32 per tile and thread
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);         // [NBUF] accumulator written (tcgen05.commit)
+  uint64_t *empty = full + NBUF;                               // [NBUF] accumulator read by all 256 epilogue threads
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 64);
+  float *scal = reinterpret_cast<float *>(smem + 128);         // [0..2] centre, [3] eps2, [4] fallback flag
+  float *red = reinterpret_cast<float *>(smem + 256);          // [9 warps][8] reduction scratch
+  unsigned char *b1 = smem + 1024;                             // [MAXT][2 chunks][TN/8][8][16 B]
+  unsigned char *b2 = b1 + MAXT * BTILE;
+  unsigned char *aimg = b2 + MAXT * BTILE;                     // [2][2 chunks][16][8][16 B]
+  uint2 *lists = reinterpret_cast<uint2 *>(aimg + 2 * 2 * ACHUNK);  // [CAP][256]
+  float *sbest = reinterpret_cast<float *>(lists + TCC_CAP * TCC_EPI);  // [256]
+  uint64_t *skey = reinterpret_cast<uint64_t *>(sbest + TCC_EPI);      // [256]
+  int *sovf = reinterpret_cast<int *>(skey + TCC_EPI);                 // [256]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NBUF; ++i) {
+      tcc::mbar_init(full + i, 1);
+      tcc::mbar_init(empty + i, TCC_EPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tcc::smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcc::tc_fence_before();
+  __syncthreads();
+  tcc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t IDESC = tcc::instr_desc_tf32(TCC_M, TN);
+
+  // this CTA's contiguous share of the row blocks
+  const int per_cloud = args.d[0].rbs + args.d[1].rbs;
+  const long long u0 = static_cast<long long>(blockIdx.x) * args.units / gridDim.x;
+  const long long u1 = static_cast<long long>(blockIdx.x + 1) * args.units / gridDim.x;
+  uint32_t k = 0;  // accumulator tiles issued / consumed so far (all roles count alike)
+  long long u = u0;
+  while (u < u1) {
+    // ---- a run of row blocks of one (cloud, direction): build the reference cloud's operand image ----------------------
+    const long long cloud = u / per_cloud;
+    const int t0 = static_cast<int>(u - cloud * per_cloud);
+    const int dir = t0 >= args.d[0].rbs ? 1 : 0;
+    const TccDir &D = args.d[dir];
+    const int rb0 = dir ? t0 - args.d[0].rbs : t0;
+    long long uend = cloud * per_cloud + (dir ? per_cloud : args.d[0].rbs);
+    if (uend > u1) uend = u1;
+    const int nrb = static_cast<int>(uend - u);  // row blocks rb0 .. rb0 + nrb - 1
+    const float *Q = D.q + static_cast<size_t>(cloud) * D.nq * 3, *R = D.r + static_cast<size_t>(cloud) * D.nr * 3;
+    const int nq = D.nq, nr = D.nr;
+    const int ntiles = (nr + TN - 1) / TN;
+
+    {  // centre = middle of the reference cloud's bounding box
+      float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (int j = tid; j < nr; j += TCC_THREADS) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const float v = __ldg(R + 3 * j + e);
+          lo[e] = fminf(lo[e], v), hi[e] = fmaxf(hi[e], v);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          lo[e] = fminf(lo[e], __shfl_xor_sync(0xffffffffu, lo[e], o));
+          hi[e] = fmaxf(hi[e], __shfl_xor_sync(0xffffffffu, hi[e], o));
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) red[warp * 8 + e] = lo[e], red[warp * 8 + 3 + e] = hi[e];
+      }
+      __syncthreads();
+      if (tid < 3) {
+        float l = red[tid], h = red[3 + tid];
+        for (int w = 1; w < TCC_THREADS / 32; ++w) l = fminf(l, red[w * 8 + tid]), h = fmaxf(h, red[w * 8 + 3 + tid]);
+        scal[tid] = 0.5f * l + 0.5f * h;
+      }
+      __syncthreads();
+    }
+    const float cx = scal[0], cy = scal[1], cz = scal[2];
+    float rmax = 0.f;  // max |b'|^2 and max |a'|^2 over the rows of this run
+    float bad = 0.f;   // becomes NaN when any squared norm is NaN or infinite (fmaxf would drop a NaN)
+    for (int j = tid; j < ntiles * TN; j += TCC_THREADS) {
+      float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, TCC_BIG, 0.f), l0 = c0, l1 = c0;
+      if (j < nr) {
+        const float x = __fsub_rn(__ldg(R + 3 * j), cx), y = __fsub_rn(__ldg(R + 3 * j + 1), cy), z = __fsub_rn(__ldg(R + 3 * j + 2), cz);
+        const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+        rmax = fmaxf(rmax, m);
+        bad += m * 0.f;
+        const float hx = tcc::tf32_rn(x), hy = tcc::tf32_rn(y), hz = tcc::tf32_rn(z);
+        const float lx = tcc::tf32_rn(__fsub_rn(x, hx)), ly = tcc::tf32_rn(__fsub_rn(y, hy)), lz = tcc::tf32_rn(__fsub_rn(z, hz));
+        const float mh = tcc::tf32_rn(m), ml = tcc::tf32_rn(__fsub_rn(m, mh));
+        c0 = make_float4(-2.f * hx, -2.f * hy, -2.f * hz, -2.f * hx);
+        c1 = make_float4(-2.f * hy, -2.f * hz, mh, ml);
+        l0 = make_float4(-2.f * lx, -2.f * ly, -2.f * lz, -2.f * lx);
+        l1 = make_float4(-2.f * ly, -2.f * lz, 0.f, 0.f);
+      }
+      const int t = j / TN, r = j - t * TN;
+      const int off = t * BTILE + (r >> 3) * 128 + (r & 7) * 16;
+      *reinterpret_cast<float4 *>(b1 + off) = c0;
+      *reinterpret_cast<float4 *>(b1 + off + CHUNK) = c1;
+      *reinterpret_cast<float4 *>(b2 + off) = l0;
+      *reinterpret_cast<float4 *>(b2 + off + CHUNK) = l1;
+    }
+    float amax = 0.f;
+    {
+      const int r_lo = rb0 * TCC_M, r_hi = min(nq, (rb0 + nrb) * TCC_M);
+      for (int i = r_lo + tid; i < r_hi; i += TCC_THREADS) {
+        const float x = __fsub_rn(__ldg(Q + 3 * i), cx), y = __fsub_rn(__ldg(Q + 3 * i + 1), cy), z = __fsub_rn(__ldg(Q + 3 * i + 2), cz);
+        const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+        amax = fmaxf(amax, m);
+        bad += m * 0.f;
+      }
+    }
+    {
+      float s = bad + (cx + cy + cz) * 0.f;  // NaN when anything above was not finite
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        s = s + __shfl_xor_sync(0xffffffffu, s, o);
+      }
+      if (lane == 0) red[warp * 8] = rmax, red[warp * 8 + 1] = amax, red[warp * 8 + 2] = s;
+    }
+    tcc::fence_proxy_async();  // the operand image was written through the generic proxy
+    __syncthreads();
+    if (tid == 0) {
+      float rm = 0.f, am = 0.f, s = 0.f;
+      for (int w = 0; w < TCC_THREADS / 32; ++w) rm = fmaxf(rm, red[w * 8]), am = fmaxf(am, red[w * 8 + 1]), s += red[w * 8 + 2];
+      const float eps2 = 2.f * args.eps_rel * (rm + am);
+      scal[3] = eps2;
+      scal[4] = (s == 0.f && eps2 < 1.0e25f) ? 0.f : 1.f;  // non-finite or huge coordinates: exact scan of every row
+      scal[5] = rm + am;
+    }
+    __syncthreads();
+    const float eps2 = scal[3];
+    const bool fallback_all = scal[4] != 0.f;
+
+    if (fallback_all) {
+      for (int i = rb0 * TCC_M + tid; i < min(nq, (rb0 + nrb) * TCC_M); i += TCC_THREADS) {
+        float best;
+        int bi;
+        tcc_exact_row(R, nr, __ldg(Q + 3 * i), __ldg(Q + 3 * i + 1), __ldg(Q + 3 * i + 2), best, bi);
+        D.dist[cloud * nq + i] = best;
+        D.idx[cloud * nq + i] = bi;
+      }
+    } else if (warp == TCC_EPI / 32) {
+      // ================= producer warp: row operands + MMA issue ====================================================
+      for (int rbl = 0; rbl < nrb; ++rbl) {
+        unsigned char *A = aimg + (rbl & 1) * 2 * ACHUNK;
+#pragma unroll
+        for (int t = 0; t < TCC_M / 32; ++t) {
+          const int r = lane + 32 * t;
+          int i = (rb0 + rbl) * TCC_M + r;
+          i = i < nq ? i : nq - 1;
+          const float x = __fsub_rn(__ldg(Q + 3 * i), cx), y = __fsub_rn(__ldg(Q + 3 * i + 1), cy), z = __fsub_rn(__ldg(Q + 3 * i + 2), cz);
+          const float hx = tcc::tf32_rn(x), hy = tcc::tf32_rn(y), hz = tcc::tf32_rn(z);
+          const float lx = tcc::tf32_rn(__fsub_rn(x, hx)), ly = tcc::tf32_rn(__fsub_rn(y, hy)), lz = tcc::tf32_rn(__fsub_rn(z, hz));
+          const int off = (r >> 3) * 128 + (r & 7) * 16;
+          *reinterpret_cast<float4 *>(A + off) = make_float4(hx, hy, hz, lx);
+          *reinterpret_cast<float4 *>(A + off + ACHUNK) = make_float4(ly, lz, 1.f, 1.f);
+        }
+        tcc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const uint64_t ad = tcc::smem_desc(tcc::smem_u32(A), ACHUNK, 128);
+          for (int t = 0; t < ntiles; ++t, ++k) {
+            const uint32_t buf = k % NBUF, use = k / NBUF;
+            tcc::mbar_wait(empty + buf, (use & 1u) ^ 1u);  // the epilogue has read this accumulator's previous tile
+            tcc::tc_fence_after();
+            const uint64_t bd1 = tcc::smem_desc(tcc::smem_u32(b1 + t * BTILE), CHUNK, 128);
+            const uint64_t bd2 = tcc::smem_desc(tcc::smem_u32(b2 + t * BTILE), CHUNK, 128);
+            tcc::mma_tf32(tmem + buf * TN, ad, bd1, IDESC, 0u);
+            tcc::mma_tf32(tmem + buf * TN, ad, bd2, IDESC, 1u);
+            tcc::mma_commit(full + buf);
+          }
+        }
+        k = __shfl_sync(0xffffffffu, k, 0);
+      }
+    } else {
+      // ================= epilogue warps: group minima, candidate lists, exact evaluation ===========================
+      const int quarter = warp & 3, half = warp >> 2;
+      const int row = quarter * 32 + lane;  // TMEM lane = row of the block
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * HALF;
+      uint2 *mylist = lists + tid;
+      for (int rbl = 0; rbl < nrb; ++rbl) {
+        float best = INFINITY, thr = INFINITY, low = INFINITY;
+        int cnt = 0;
+        for (int t = 0; t < ntiles; ++t, ++k) {
+          const uint32_t buf = k % NBUF, use = k / NBUF;
+          tcc::mbar_wait(full + buf, use & 1u);
+          tcc::tc_fence_after();
+          float v[STEPS][32];
+#pragma unroll
+          for (int s = 0; s < STEPS; ++s) PDAE_TMEM_LD32(tbase + buf * TN + s * TCC_GROUP, v[s]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tcc::tc_fence_before();
+          tcc::mbar_arrive(empty + buf);  // the values are in registers: the accumulator may be overwritten
+#pragma unroll
+          for (int s = 0; s < STEPS; ++s) {
+            float m0 = min3(v[s][0], v[s][1], v[s][2]), m1 = min3(v[s][3], v[s][4], v[s][5]);
+            float m2 = min3(v[s][6], v[s][7], v[s][8]), m3 = min3(v[s][9], v[s][10], v[s][11]);
+            m0 = min3(m0, v[s][12], v[s][13]), m1 = min3(m1, v[s][14], v[s][15]);
+            m2 = min3(m2, v[s][16], v[s][17]), m3 = min3(m3, v[s][18], v[s][19]);
+            m0 = min3(m0, v[s][20], v[s][21]), m1 = min3(m1, v[s][22], v[s][23]);
+            m2 = min3(m2, v[s][24], v[s][25]), m3 = min3(m3, v[s][26], v[s][27]);
+            m0 = min3(m0, v[s][28], v[s][29]), m1 = min3(m1, v[s][30], v[s][31]);
+            const float g = fminf(min3(m0, m1, m2), m3);
+            const int gid = (t * TN + half * HALF + s * TCC_GROUP) / TCC_GROUP;
+            cnt = g < low ? 0 : cnt;  // everything kept so far is more than 2 eps above this group
+            if (g <= thr) {
+              if (cnt < TCC_CAP) mylist[cnt * TCC_EPI] = make_uint2(__float_as_uint(g), static_cast<uint32_t>(gid));
+              ++cnt;
+            }
+            best = fminf(best, g);
+            thr = best + eps2;
+            low = best - eps2;
+          }
+        }
+        // ---- the row's two halves agree on the approximate minimum, then evaluate their surviving groups exactly --------
+        sbest[tid] = best;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float limit = fminf(best, sbest[tid ^ 128]) + eps2;
+        const int i = (rb0 + rbl) * TCC_M + row;
+        const bool live = i < nq;
+        const int ic = live ? i : nq - 1;
+        const float ax = __ldg(Q + 3 * ic), ay = __ldg(Q + 3 * ic + 1), az = __ldg(Q + 3 * ic + 2);
+        uint64_t key = ~0ull;
+        const int nlist = cnt < TCC_CAP ? cnt : TCC_CAP;
+        const bool vec_ok = (nr & 3) == 0;
+        for (int e = 0; e < nlist; ++e) {
+          const uint2 ent = mylist[e * TCC_EPI];
+          if (!(__uint_as_float(ent.x) <= limit)) continue;
+          const int base = static_cast<int>(ent.y) * TCC_GROUP;
+          uint64_t gk = ~0ull;
+          if (vec_ok && base + TCC_GROUP <= nr) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(R + 3 * static_cast<size_t>(base));
+#pragma unroll
+            for (int c4 = 0; c4 < TCC_GROUP / 4; ++c4) {  // four points = three float4
+              const float4 w0 = __ldg(p4 + 3 * c4), w1 = __ldg(p4 + 3 * c4 + 1), w2 = __ldg(p4 + 3 * c4 + 2);
+              const float d0 = dist_yxz(__fsub_rn(w0.x, ax), __fsub_rn(w0.y, ay), __fsub_rn(w0.z, az));
+              const float d1 = dist_yxz(__fsub_rn(w0.w, ax), __fsub_rn(w1.x, ay), __fsub_rn(w1.y, az));
+              const float d2 = dist_yxz(__fsub_rn(w1.z, ax), __fsub_rn(w1.w, ay), __fsub_rn(w2.x, az));
+              const float d3 = dist_yxz(__fsub_rn(w2.y, ax), __fsub_rn(w2.z, ay), __fsub_rn(w2.w, az));
+              const int j = base + 4 * c4;
+              uint64_t k0 = pack_key(d0, j), k1 = pack_key(d1, j + 1), k2 = pack_key(d2, j + 2), k3 = pack_key(d3, j + 3);
+              k0 = k0 < k1 ? k0 : k1;
+              k2 = k2 < k3 ? k2 : k3;
+              k0 = k0 < k2 ? k0 : k2;
+              gk = gk < k0 ? gk : k0;
+            }
+          } else {
+            for (int c = 0; c < TCC_GROUP; ++c) {
+              const int j = base + c;
+              if (j < nr) {
+                const float d = dist_yxz(__fsub_rn(__ldg(R + 3 * j), ax), __fsub_rn(__ldg(R + 3 * j + 1), ay), __fsub_rn(__ldg(R + 3 * j + 2), az));
+                const uint64_t kk = pack_key(d, j);
+                gk = gk < kk ? gk : kk;
+              }
+            }
+          }
+          key = key < gk ? key : gk;
+          if (args.stats && live) {
+            const float x = __fsub_rn(ax, cx), y = __fsub_rn(ay, cy), z = __fsub_rn(az, cz);
+            const float na = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+            const float err = fabsf(__uint_as_float(ent.x) - (__uint_as_float(static_cast<uint32_t>(gk >> 32)) - na)) / scal[5];
+            atomicMax(args.stats, static_cast<unsigned long long>(__float_as_uint(err)));
+            atomicAdd(args.stats + 2, 1ull);
+          }
+        }
+        skey[tid] = key;
+        sovf[tid] = cnt > TCC_CAP ? 1 : 0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && live) {
+          const uint64_t other = skey[tid + 128];
+          key = key < other ? key : other;
+          float dbest = __uint_as_float(static_cast<uint32_t>(key >> 32));
+          int ibest = static_cast<int>(static_cast<uint32_t>(key));
+          // overflowed list, no candidate at all, or a non-finite winner: the literal scan decides
+          if (cnt > TCC_CAP || sovf[tid + 128] || key == ~0ull || !(dbest < INFINITY)) {
+            tcc_exact_row(R, nr, ax, ay, az, dbest, ibest);
+            if (args.stats) atomicAdd(args.stats + 1, 1ull);
+          }
+          if (args.stats) atomicAdd(args.stats + 3, 1ull);
+          D.dist[cloud * nq + i] = dbest;
+          D.idx[cloud * nq + i] = ibest;
+        }
+      }
+    }
+    u = uend;
+    k = __shfl_sync(0xffffffffu, k, 0);
+    __syncthreads();  // every MMA of this run has been consumed: the operand image may be rebuilt
+  }
+  tcc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+template <int TN>
+static size_t tcc_smem_bytes() {
+  return 1024 + static_cast<size_t>(2) * (TCC_MAXCOLS / TN) * (2 * TN * 16) + 2 * 2 * TCC_M * 16 + TCC_CAP * TCC_EPI * 8 +
+         TCC_EPI * (4 + 8 + 4);
+}
+
+// tuning / test hook state: mode 0 = off, 1 = on with 128-column accumulators, 2 = on with 256-column accumulators
+static int g_tcc_mode = -1;
+static float g_tcc_eps_rel = 0.f;
+static int tcc_mode() {
+  if (g_tcc_mode < 0) {
+    const char *e = getenv("PDAE_CHAMFER_TC");
+    g_tcc_mode = e ? atoi(e) : 1;
+    const char *x = getenv("PDAE_CHAMFER_TC_EPS");
+    g_tcc_eps_rel = x ? static_cast<float>(atof(x)) : 1.52587890625e-5f;  // 2^-16
+  }
+  return g_tcc_mode;
+}
+
+// true when chamfer_tc_forward serves this shape (both clouds are searched, so both must fit the resident image)
+bool chamfer_tc_applies(int b, int n, int m) {
+  if (tcc_mode() <= 0) return false;
+  const int lo = n < m ? n : m, hi = n < m ? m : n;
+  return b > 0 && lo >= 512 && hi <= TCC_MAXCOLS;
+}
+
+template <int TN>
+static int tcc_launch(const TccArgs &a, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = tcc_smem_bytes<TN>();
+  if (!configured) {
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(chamfer_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    PDAE_CUDA_TRY(cudaGetDevice(&dev));
+    PDAE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long grid = a.units < sms ? a.units : sms;
+  chamfer_tc_kernel<TN><<<static_cast<unsigned>(grid), TCC_THREADS, smem, st>>>(a);
+  PDAE_RETURN_IF_LAUNCH_FAILED();
+  return 0;
+}
+
+int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
+                       int *idx2, cudaStream_t st, unsigned long long *stats) {
+  TccArgs a;
+  a.stats = stats;
+  a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, n, m, (n + TCC_M - 1) / TCC_M};
+  a.d[1] = TccDir{xyz2, xyz1, dist2, idx2, m, n, (m + TCC_M - 1) / TCC_M};
+  a.units = static_cast<long long>(b) * (a.d[0].rbs + a.d[1].rbs);
+  a.eps_rel = g_tcc_eps_rel;
+  return tcc_mode() == 2 ? tcc_launch<256>(a, st) : tcc_launch<128>(a, st);
+}
+
+}  // namespace pdae
+
+// tuning / test hook: mode 0 = FP32-pipe kernels only, 1 / 2 = tensor-core filter with 128- / 256-column accumulators;
+// eps_rel > 0 sets the filter's error bound relative to max|a'|^2 + max|b'|^2 (default 2^-16).  Negative mode only queries.
+// Returns the previous mode.
+extern "C" int pdae_tune_chamfer_tc(int mode, float eps_rel) {
+  const int old = pdae::tcc_mode();
+  if (mode >= 0) pdae::g_tcc_mode = mode;
+  if (eps_rel > 0.f) pdae::g_tcc_eps_rel = eps_rel;
+  return old;
+}
+
+// probe: the tensor-core forward regardless of the mode switch, plus filter statistics (4 x uint64, zeroed by the caller):
+// [0] float bits of the largest observed |approximate - exact| group minimum relative to max|a'|^2 + max|b'|^2,
+// [1] rows decided by the literal scan, [2] 32-column groups evaluated exactly, [3] rows written.
+extern "C" int pdae_chamfer_tc_probe(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
+                                     int *idx1, int *idx2, unsigned long long *stats4, pdae_stream_t stream) {
+  if (b <= 0 || !xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return PDAE_E_INVALID;
+  const int lo = n < m ? n : m, hi = n < m ? m : n;
+  if (lo < 512 || hi > pdae::TCC_MAXCOLS) return PDAE_E_UNSUPPORTED;
+  (void)pdae::tcc_mode();
+  return pdae::chamfer_tc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, static_cast<cudaStream_t>(stream), stats4);
+}

@@ -25,9 +25,10 @@ struct PairVal {
 __device__ __forceinline__ void pl_normalize(const float *x, int d, float *u, float &inv) {
   float s = 0.f;
   for (int e = 0; e < d; ++e) s = fmaf(x[e], x[e], s);
-  const float nrm = sqrtf(s);
-  inv = 1.0f / fmaxf(nrm, 1e-12f);
-  for (int e = 0; e < d; ++e) u[e] = x[e] * inv;
+  const float den = fmaxf(sqrtf(s), 1e-12f);
+  inv = 1.0f / den;
+  // true division like torch's x / norm.clamp_min(eps): a one-channel row normalises to exactly +-1 whenever sqrt(x*x) == |x|
+  for (int e = 0; e < d; ++e) u[e] = __fdiv_rn(x[e], den);
 }
 
 // gradient of f(u(x)) w.r.t. x given g = df/du, u = x * inv (inv = 1 / max(|x|, eps)); below eps the map is linear
