@@ -223,9 +223,10 @@ int pdae_tune_chamfer_split(int nc);
 int pdae_tune_chamfer_tc(int mode, float eps_rel);
 /* probe: the tensor-core forward regardless of the mode, plus filter statistics in stats4 (4 x uint64, zeroed by the caller):
  * [0] float bits of the largest |approximate - exact| group minimum relative to the bound's scale, [1] rows decided by the
- * literal scan (list overflow / no finite candidate), [2] 32-column groups evaluated exactly, [3] rows written.            */
+ * literal scan (list overflow / no finite candidate), [2] 32-column groups evaluated exactly, [3] rows written.
+ * trace: optional 256 x 6 int64 of clock64 stamps of CTA 0's first tiles (pipeline timeline), or NULL.                     */
 int pdae_chamfer_tc_probe(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
-                          int *idx2, unsigned long long *stats4, pdae_stream_t stream);
+                          int *idx2, unsigned long long *stats4, long long *trace, pdae_stream_t stream);
 /* kNN / Group (dim 3, k <= 64): impl 4 = multi-query warps + TMA tile prefetch (default), 3 = the first-generation
  * kernel (kept for A/B measurements); qw queries per warp (1/2/4), nw warps per CTA (4/8), tile points per shared-memory
  * tile, nz chunks along the reference cloud (needs the workspace), tma 0/1, spec 0/1 (warp-specialised CTAs with a

@@ -49,6 +49,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                  : "memory");
   }
 }
+// busy poll (no suspended wait): the MMA issuer and the accumulator consumers sit on the pipeline's critical path
+__device__ __forceinline__ void mbar_poll(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -94,7 +104,10 @@ constexpr int TCC_MAXCOLS = 2048;  // reference points whose operand image stays
 constexpr int TCC_GROUP = 32;      // columns per candidate group (one tcgen05.ld.x32)
 constexpr int TCC_CAP = 8;         // candidate groups kept per (row, column half)
 constexpr int TCC_EPI = 256;       // epilogue threads (warps 0-7)
-constexpr int TCC_THREADS = TCC_EPI + 32;
+constexpr int TCC_VER_WARPS = 3;   // verifier warps (exact evaluation of the surviving groups)
+constexpr int TCC_PROD_WARPS = 1;  // MMA issuer warps (two are supported: tile k goes to issuer k & 1; one keeps up with two accumulators)
+constexpr int TCC_THREADS = TCC_EPI + 32 * TCC_PROD_WARPS + 32 * TCC_VER_WARPS;
+constexpr int TCC_RSTRIDE = 36;    // floats per 32-column group in the shared-memory copy of the searched cloud
 constexpr float TCC_BIG = 1.0e30f;  // "distance" of a padded column
 
 struct TccDir {
@@ -109,10 +122,11 @@ struct TccArgs {
   long long units;  // b * (d[0].rbs + d[1].rbs) row blocks
   float eps_rel;
   unsigned long long *stats;  // optional probe: [0] max |g - (exact group minimum - |a'|^2)| / (max|a'|^2 + max|b'|^2) as float
-                              // bits, [1] rows decided by the literal scan, [2] groups evaluated exactly, [3] rows
+                              // bits, [1] rows decided by the full scan, [2] groups evaluated exactly, [3] rows
+  long long *trace;           // optional (probe): clock64 of CTA 0's first 256 tiles, 6 stamps each (see pdae_chamfer_tc_probe)
 };
 
-// literal reference scan of one row (chamfer.cu:42-79): the fallback that makes the result independent of the filter
+// literal reference scan of one row (chamfer.cu:42-79), for clouds with non-finite coordinates
 __device__ __forceinline__ void tcc_exact_row(const float *__restrict__ R, int nr, float ax, float ay, float az, float &best,
                                               int &bi) {
   best = 0.f;
@@ -123,7 +137,7 @@ __device__ __forceinline__ void tcc_exact_row(const float *__restrict__ R, int n
   }
 }
 
-// TN = columns per accumulator buffer (128: four buffers in flight, 256: two)
+// TN = columns per accumulator buffer (256: two buffers, 128: four)
 template <int TN>
 __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArgs args) {
   constexpr int NBUF = 512 / TN;
@@ -133,26 +147,43 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   constexpr int MAXT = TCC_MAXCOLS / TN;
   constexpr int HALF = TN / 2;            // columns of a tile one epilogue thread reads
   constexpr int STEPS = HALF / TCC_GROUP; // tcgen05.ld.x32 per tile and thread
+  static_assert(STEPS % 2 == 0, "the epilogue reads two groups at a time");
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);         // [NBUF] accumulator written (tcgen05.commit)
   uint64_t *empty = full + NBUF;                               // [NBUF] accumulator read by all 256 epilogue threads
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 64);
-  float *scal = reinterpret_cast<float *>(smem + 128);         // [0..2] centre, [3] eps2, [4] fallback flag
-  float *red = reinterpret_cast<float *>(smem + 256);          // [9 warps][8] reduction scratch
+  uint64_t *lfull = empty + NBUF;                              // [2] candidate lists of a row block complete
+  uint64_t *lempty = lfull + 2;                                // [2] ... and consumed by the verifier warps
+  uint64_t *aready = lempty + 2;                               // [3] row operand image written (first issuer -> second)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 128);
+  float *scal = reinterpret_cast<float *>(smem + 160);         // [0..2] centre, [3] eps2, [4] fallback flag, [5] bound scale
+  float *red = reinterpret_cast<float *>(smem + 256);          // [13 warps][8] reduction scratch
   unsigned char *b1 = smem + 1024;                             // [MAXT][2 chunks][TN/8][8][16 B]
   unsigned char *b2 = b1 + MAXT * BTILE;
-  unsigned char *aimg = b2 + MAXT * BTILE;                     // [2][2 chunks][16][8][16 B]
-  uint2 *lists = reinterpret_cast<uint2 *>(aimg + 2 * 2 * ACHUNK);  // [CAP][256]
-  float *sbest = reinterpret_cast<float *>(lists + TCC_CAP * TCC_EPI);  // [256]
-  uint64_t *skey = reinterpret_cast<uint64_t *>(sbest + TCC_EPI);      // [256]
-  int *sovf = reinterpret_cast<int *>(skey + TCC_EPI);                 // [256]
+  unsigned char *aimg = b2 + MAXT * BTILE;                     // [3][2 chunks][16][8][16 B]
+  // the searched cloud as given, planar, every 32-column group padded to 36 floats (16-byte aligned rows whose starts
+  // fall on different banks); padded columns hold x = +inf, so their distance is +inf
+  float *rpx = reinterpret_cast<float *>(aimg + 3 * 2 * ACHUNK);         // [3][TCC_MAXCOLS / 32][36]
+  constexpr int RPLANE = TCC_MAXCOLS / TCC_GROUP * TCC_RSTRIDE;
+  uint2 *lists = reinterpret_cast<uint2 *>(rpx + 3 * RPLANE);            // [2][CAP][256]
+  float *sbest = reinterpret_cast<float *>(lists + 2 * TCC_CAP * TCC_EPI);  // [2][256]
+  int *scnt = reinterpret_cast<int *>(sbest + 2 * TCC_EPI);              // [2][256]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // roles: warps [0, VER) verify, [VER, VER + PROD) issue MMAs, the last eight are the epilogue (their TMEM lane quarter is
+  // warp % 4, so the block of eight must start at a multiple of four)
+  constexpr int W_ISS = TCC_VER_WARPS, W_EPI = TCC_VER_WARPS + TCC_PROD_WARPS;
+  static_assert(W_EPI % 4 == 0, "epilogue warps must start at a multiple of four");
+  const int etid = tid - W_EPI * 32;  // index among the epilogue threads
   if (tid == 0) {
     for (int i = 0; i < NBUF; ++i) {
       tcc::mbar_init(full + i, 1);
       tcc::mbar_init(empty + i, TCC_EPI);
     }
+    for (int i = 0; i < 2; ++i) {
+      tcc::mbar_init(lfull + i, TCC_EPI);
+      tcc::mbar_init(lempty + i, 32 * TCC_VER_WARPS);
+    }
+    for (int i = 0; i < 3; ++i) tcc::mbar_init(aready + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -169,42 +200,63 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   const int per_cloud = args.d[0].rbs + args.d[1].rbs;
   const long long u0 = static_cast<long long>(blockIdx.x) * args.units / gridDim.x;
   const long long u1 = static_cast<long long>(blockIdx.x + 1) * args.units / gridDim.x;
-  uint32_t k = 0;  // accumulator tiles issued / consumed so far (all roles count alike)
+  uint32_t k = 0;   // accumulator tiles issued / consumed so far (producer and epilogue count alike)
+  uint32_t kb = 0;  // row blocks handed from the epilogue to the verifier so far
   long long u = u0;
   while (u < u1) {
-    // ---- a run of row blocks of one (cloud, direction): build the reference cloud's operand image ----------------------
+    // ---- a run of row blocks of one (cloud, direction): build the searched cloud's operand image ----------------------
     const long long cloud = u / per_cloud;
     const int t0 = static_cast<int>(u - cloud * per_cloud);
     const int dir = t0 >= args.d[0].rbs ? 1 : 0;
-    const TccDir &D = args.d[dir];
+    const float *Q = (dir ? args.d[1].q : args.d[0].q), *R = (dir ? args.d[1].r : args.d[0].r);
+    float *odist = dir ? args.d[1].dist : args.d[0].dist;
+    int *oidx = dir ? args.d[1].idx : args.d[0].idx;
+    const int nq = dir ? args.d[1].nq : args.d[0].nq, nr = dir ? args.d[1].nr : args.d[0].nr;
     const int rb0 = dir ? t0 - args.d[0].rbs : t0;
     long long uend = cloud * per_cloud + (dir ? per_cloud : args.d[0].rbs);
     if (uend > u1) uend = u1;
     const int nrb = static_cast<int>(uend - u);  // row blocks rb0 .. rb0 + nrb - 1
-    const float *Q = D.q + static_cast<size_t>(cloud) * D.nq * 3, *R = D.r + static_cast<size_t>(cloud) * D.nr * 3;
-    const int nq = D.nq, nr = D.nr;
+    Q += static_cast<size_t>(cloud) * nq * 3;
+    R += static_cast<size_t>(cloud) * nr * 3;
+    odist += cloud * nq;
+    oidx += cloud * nq;
     const int ntiles = (nr + TN - 1) / TN;
 
-    {  // centre = middle of the reference cloud's bounding box
-      float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-      for (int j = tid; j < nr; j += TCC_THREADS) {
+    {  // centre = middle of the searched cloud's bounding box; raw copy for the exact evaluation
+      float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+      constexpr int NIT = (TCC_MAXCOLS + TCC_THREADS - 1) / TCC_THREADS;
+      float vx[NIT], vy[NIT], vz[NIT];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          const float v = __ldg(R + 3 * j + e);
-          lo[e] = fminf(lo[e], v), hi[e] = fmaxf(hi[e], v);
+      for (int it = 0; it < NIT; ++it) {  // all loads in flight before the first use
+        const int j = tid + it * TCC_THREADS;
+        const int jc = j < nr ? j : nr - 1;
+        vx[it] = __ldg(R + 3 * jc), vy[it] = __ldg(R + 3 * jc + 1), vz[it] = __ldg(R + 3 * jc + 2);
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int j = tid + it * TCC_THREADS;
+        if (j < ntiles * TN) {
+          const int o = (j >> 5) * TCC_RSTRIDE + (j & 31);
+          if (j < nr) {
+            const float x = vx[it], y = vy[it], z = vz[it];
+            rpx[o] = x, rpx[RPLANE + o] = y, rpx[2 * RPLANE + o] = z;
+            lx = fminf(lx, x), hx = fmaxf(hx, x);
+            ly = fminf(ly, y), hy = fmaxf(hy, y);
+            lz = fminf(lz, z), hz = fmaxf(hz, z);
+          } else {
+            rpx[o] = INFINITY, rpx[RPLANE + o] = 0.f, rpx[2 * RPLANE + o] = 0.f;
+          }
         }
       }
 #pragma unroll
-      for (int e = 0; e < 3; ++e) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          lo[e] = fminf(lo[e], __shfl_xor_sync(0xffffffffu, lo[e], o));
-          hi[e] = fmaxf(hi[e], __shfl_xor_sync(0xffffffffu, hi[e], o));
-        }
+      for (int o = 16; o; o >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)), hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+        ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)), hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+        lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)), hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
       }
       if (lane == 0) {
-#pragma unroll
-        for (int e = 0; e < 3; ++e) red[warp * 8 + e] = lo[e], red[warp * 8 + 3 + e] = hi[e];
+        float *w = red + warp * 8;
+        w[0] = lx, w[1] = ly, w[2] = lz, w[3] = hx, w[4] = hy, w[5] = hz;
       }
       __syncthreads();
       if (tid < 3) {
@@ -220,7 +272,8 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
     for (int j = tid; j < ntiles * TN; j += TCC_THREADS) {
       float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, TCC_BIG, 0.f), l0 = c0, l1 = c0;
       if (j < nr) {
-        const float x = __fsub_rn(__ldg(R + 3 * j), cx), y = __fsub_rn(__ldg(R + 3 * j + 1), cy), z = __fsub_rn(__ldg(R + 3 * j + 2), cz);
+        const int o = (j >> 5) * TCC_RSTRIDE + (j & 31);
+        const float x = __fsub_rn(rpx[o], cx), y = __fsub_rn(rpx[RPLANE + o], cy), z = __fsub_rn(rpx[2 * RPLANE + o], cz);
         const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
         rmax = fmaxf(rmax, m);
         bad += m * 0.f;
@@ -242,11 +295,22 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
     float amax = 0.f;
     {
       const int r_lo = rb0 * TCC_M, r_hi = min(nq, (rb0 + nrb) * TCC_M);
-      for (int i = r_lo + tid; i < r_hi; i += TCC_THREADS) {
-        const float x = __fsub_rn(__ldg(Q + 3 * i), cx), y = __fsub_rn(__ldg(Q + 3 * i + 1), cy), z = __fsub_rn(__ldg(Q + 3 * i + 2), cz);
-        const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-        amax = fmaxf(amax, m);
-        bad += m * 0.f;
+      constexpr int NIT = (TCC_MAXCOLS + TCC_THREADS - 1) / TCC_THREADS;
+      for (int base = r_lo; base < r_hi; base += NIT * TCC_THREADS) {
+        float vx[NIT], vy[NIT], vz[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int i = base + tid + it * TCC_THREADS;
+          const int ic = i < r_hi ? i : r_hi - 1;
+          vx[it] = __ldg(Q + 3 * ic), vy[it] = __ldg(Q + 3 * ic + 1), vz[it] = __ldg(Q + 3 * ic + 2);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const float x = __fsub_rn(vx[it], cx), y = __fsub_rn(vy[it], cy), z = __fsub_rn(vz[it], cz);
+          const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+          amax = fmaxf(amax, m);
+          bad += m * 0.f;
+        }
       }
     }
     {
@@ -266,7 +330,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
       for (int w = 0; w < TCC_THREADS / 32; ++w) rm = fmaxf(rm, red[w * 8]), am = fmaxf(am, red[w * 8 + 1]), s += red[w * 8 + 2];
       const float eps2 = 2.f * args.eps_rel * (rm + am);
       scal[3] = eps2;
-      scal[4] = (s == 0.f && eps2 < 1.0e25f) ? 0.f : 1.f;  // non-finite or huge coordinates: exact scan of every row
+      scal[4] = (s == 0.f && eps2 < 1.0e25f) ? 0.f : 1.f;  // non-finite or huge coordinates: literal scan of every row
       scal[5] = rm + am;
     }
     __syncthreads();
@@ -278,19 +342,30 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
         float best;
         int bi;
         tcc_exact_row(R, nr, __ldg(Q + 3 * i), __ldg(Q + 3 * i + 1), __ldg(Q + 3 * i + 2), best, bi);
-        D.dist[cloud * nq + i] = best;
-        D.idx[cloud * nq + i] = bi;
+        odist[i] = best;
+        oidx[i] = bi;
       }
-    } else if (warp == TCC_EPI / 32) {
-      // ================= producer warp: row operands + MMA issue ====================================================
-      for (int rbl = 0; rbl < nrb; ++rbl) {
-        unsigned char *A = aimg + (rbl & 1) * 2 * ACHUNK;
+    } else if (warp >= W_ISS && warp < W_EPI) {
+      // ================= issuer warps: row operands + MMA issue =======================================================
+      // Tiles alternate between the two issuers (tile k belongs to issuer k & 1).  The first issuer also fetches the rows
+      // of block rbl + 1 while block rbl's tiles are issued and writes their operand image (one of three buffers: the
+      // MMAs of block rbl - 1 may still be reading theirs) half way through; `aready` hands it to the second issuer.
+      const int p = warp - W_ISS;
+      float qx[TCC_M / 32], qy[TCC_M / 32], qz[TCC_M / 32];
+      auto fetch_rows = [&](int rbl) {
+#pragma unroll
+        for (int t = 0; t < TCC_M / 32; ++t) {
+          int i = (rb0 + rbl) * TCC_M + lane + 32 * t;
+          i = i < nq ? i : nq - 1;
+          qx[t] = __ldg(Q + 3 * i), qy[t] = __ldg(Q + 3 * i + 1), qz[t] = __ldg(Q + 3 * i + 2);
+        }
+      };
+      auto build_rows = [&](uint32_t kbn) {  // kbn = running number of the row block
+        unsigned char *A = aimg + (kbn % 3) * 2 * ACHUNK;
 #pragma unroll
         for (int t = 0; t < TCC_M / 32; ++t) {
           const int r = lane + 32 * t;
-          int i = (rb0 + rbl) * TCC_M + r;
-          i = i < nq ? i : nq - 1;
-          const float x = __fsub_rn(__ldg(Q + 3 * i), cx), y = __fsub_rn(__ldg(Q + 3 * i + 1), cy), z = __fsub_rn(__ldg(Q + 3 * i + 2), cz);
+          const float x = __fsub_rn(qx[t], cx), y = __fsub_rn(qy[t], cy), z = __fsub_rn(qz[t], cz);
           const float hx = tcc::tf32_rn(x), hy = tcc::tf32_rn(y), hz = tcc::tf32_rn(z);
           const float lx = tcc::tf32_rn(__fsub_rn(x, hx)), ly = tcc::tf32_rn(__fsub_rn(y, hy)), lz = tcc::tf32_rn(__fsub_rn(z, hz));
           const int off = (r >> 3) * 128 + (r & 7) * 16;
@@ -299,40 +374,61 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
         }
         tcc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          const uint64_t ad = tcc::smem_desc(tcc::smem_u32(A), ACHUNK, 128);
-          for (int t = 0; t < ntiles; ++t, ++k) {
+        if (lane == 0) tcc::mbar_arrive(aready + kbn % 3);
+      };
+      if (p == 0) {
+        fetch_rows(0);
+        build_rows(kb);
+      }
+      for (int rbl = 0; rbl < nrb; ++rbl, ++kb) {
+        const bool next = rbl + 1 < nrb;
+        if (p == 0) {
+          if (next) fetch_rows(rbl + 1);
+        } else if (lane == 0) {
+          tcc::mbar_wait(aready + kb % 3, (kb / 3) & 1u);
+        }
+        const uint64_t ad = tcc::smem_desc(tcc::smem_u32(aimg + (kb % 3) * 2 * ACHUNK), ACHUNK, 128);
+        for (int t = 0; t < ntiles; ++t, ++k) {
+          if (lane == 0 && static_cast<int>(k % TCC_PROD_WARPS) == p) {
             const uint32_t buf = k % NBUF, use = k / NBUF;
             tcc::mbar_wait(empty + buf, (use & 1u) ^ 1u);  // the epilogue has read this accumulator's previous tile
             tcc::tc_fence_after();
+            if (args.trace && blockIdx.x == 0 && k < 256) args.trace[k * 6 + 0] = clock64();
             const uint64_t bd1 = tcc::smem_desc(tcc::smem_u32(b1 + t * BTILE), CHUNK, 128);
             const uint64_t bd2 = tcc::smem_desc(tcc::smem_u32(b2 + t * BTILE), CHUNK, 128);
             tcc::mma_tf32(tmem + buf * TN, ad, bd1, IDESC, 0u);
             tcc::mma_tf32(tmem + buf * TN, ad, bd2, IDESC, 1u);
             tcc::mma_commit(full + buf);
+            if (args.trace && blockIdx.x == 0 && k < 256) args.trace[k * 6 + 1] = clock64();
           }
+          __syncwarp();
+          if (p == 0 && next && t == (ntiles - 1) / 2) build_rows(kb + 1);
         }
-        k = __shfl_sync(0xffffffffu, k, 0);
       }
-    } else {
-      // ================= epilogue warps: group minima, candidate lists, exact evaluation ===========================
-      const int quarter = warp & 3, half = warp >> 2;
-      const int row = quarter * 32 + lane;  // TMEM lane = row of the block
+    } else if (warp >= W_EPI) {
+      // ================= epilogue warps: group minima and candidate lists ===========================================
+      const int quarter = warp & 3, half = (warp - W_EPI) >> 2;
       const uint32_t tbase = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + half * HALF;
-      uint2 *mylist = lists + tid;
-      for (int rbl = 0; rbl < nrb; ++rbl) {
+      for (int rbl = 0; rbl < nrb; ++rbl, ++kb) {
+        const uint32_t slot = kb & 1u;
+        tcc::mbar_wait(lempty + slot, ((kb >> 1) & 1u) ^ 1u);  // the verifier is done with this slot's previous row block
+        uint2 *mylist = lists + slot * (TCC_CAP * TCC_EPI) + etid;
         float best = INFINITY, thr = INFINITY, low = INFINITY;
         int cnt = 0;
         for (int t = 0; t < ntiles; ++t, ++k) {
           const uint32_t buf = k % NBUF, use = k / NBUF;
+          const bool tr = args.trace && blockIdx.x == 0 && k < 256 && etid == 0;
+          if (tr) args.trace[k * 6 + 2] = clock64();
           tcc::mbar_wait(full + buf, use & 1u);
           tcc::tc_fence_after();
+          if (tr) args.trace[k * 6 + 3] = clock64();
           float v[STEPS][32];
 #pragma unroll
           for (int s = 0; s < STEPS; ++s) PDAE_TMEM_LD32(tbase + buf * TN + s * TCC_GROUP, v[s]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tcc::tc_fence_before();
-          tcc::mbar_arrive(empty + buf);  // the values are in registers: the accumulator may be overwritten
+          tcc::mbar_arrive(empty + buf);  // the tile is in registers: the accumulator may be overwritten
+          if (tr) args.trace[k * 6 + 4] = clock64();
 #pragma unroll
           for (int s = 0; s < STEPS; ++s) {
             float m0 = min3(v[s][0], v[s][1], v[s][2]), m1 = min3(v[s][3], v[s][4], v[s][5]);
@@ -345,88 +441,159 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
             const float g = fminf(min3(m0, m1, m2), m3);
             const int gid = (t * TN + half * HALF + s * TCC_GROUP) / TCC_GROUP;
             cnt = g < low ? 0 : cnt;  // everything kept so far is more than 2 eps above this group
-            if (g <= thr) {
-              if (cnt < TCC_CAP) mylist[cnt * TCC_EPI] = make_uint2(__float_as_uint(g), static_cast<uint32_t>(gid));
-              ++cnt;
-            }
+            const bool take = g <= thr;
+            const int pos = cnt < TCC_CAP ? cnt : TCC_CAP - 1;  // an overflowing list is flagged by cnt > CAP
+            if (take) mylist[pos * TCC_EPI] = make_uint2(__float_as_uint(g), static_cast<uint32_t>(gid));
+            cnt += take ? 1 : 0;
             best = fminf(best, g);
             thr = best + eps2;
             low = best - eps2;
           }
+          if (tr) args.trace[k * 6 + 5] = clock64();
         }
-        // ---- the row's two halves agree on the approximate minimum, then evaluate their surviving groups exactly --------
-        sbest[tid] = best;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float limit = fminf(best, sbest[tid ^ 128]) + eps2;
+        sbest[slot * TCC_EPI + etid] = best;
+        scnt[slot * TCC_EPI + etid] = cnt;
+        tcc::mbar_arrive(lfull + slot);
+      }
+    } else {
+      // ================= verifier warps: exact evaluation of the surviving groups ====================================
+      // a warp owns 32 rows of the block: every lane filters its own row's lists, then the warp evaluates the surviving
+      // (row, group) items one after the other with a lane per column
+      const int vw = warp;
+      // the four 32-row quarters of a block rotate over the verifier warps: a warp owns one lane per row
+      for (int rbl = 0; rbl < nrb; ++rbl, ++kb) {
+        const uint32_t slot = kb & 1u;
+        const int first = (vw + TCC_VER_WARPS - static_cast<int>(kb % TCC_VER_WARPS)) % TCC_VER_WARPS;  // (sub + kb) % VER == vw
+        float nx, ny, nz;  // the next quarter's rows, fetched one quarter ahead
+        {
+          const int i = (rb0 + rbl) * TCC_M + first * 32 + lane;
+          const int ic = i < nq ? i : nq - 1;
+          nx = __ldg(Q + 3 * ic), ny = __ldg(Q + 3 * ic + 1), nz = __ldg(Q + 3 * ic + 2);
+        }
+        const bool vtr = args.trace && blockIdx.x == 0 && kb < 64 && vw == 0 && lane == 0;
+        if (vtr) args.trace[1536 + kb * 4 + 0] = clock64();
+        tcc::mbar_wait(lfull + slot, (kb >> 1) & 1u);
+        if (vtr) args.trace[1536 + kb * 4 + 1] = clock64();
+#pragma unroll 1
+       for (int sub = first; sub < TCC_M / 32; sub += TCC_VER_WARPS) {
+        const bool last = sub + TCC_VER_WARPS >= TCC_M / 32;
+        const int row = sub * 32 + lane;
         const int i = (rb0 + rbl) * TCC_M + row;
         const bool live = i < nq;
-        const int ic = live ? i : nq - 1;
-        const float ax = __ldg(Q + 3 * ic), ay = __ldg(Q + 3 * ic + 1), az = __ldg(Q + 3 * ic + 2);
-        uint64_t key = ~0ull;
-        const int nlist = cnt < TCC_CAP ? cnt : TCC_CAP;
-        const bool vec_ok = (nr & 3) == 0;
-        for (int e = 0; e < nlist; ++e) {
-          const uint2 ent = mylist[e * TCC_EPI];
-          if (!(__uint_as_float(ent.x) <= limit)) continue;
-          const int base = static_cast<int>(ent.y) * TCC_GROUP;
-          uint64_t gk = ~0ull;
-          if (vec_ok && base + TCC_GROUP <= nr) {
-            const float4 *p4 = reinterpret_cast<const float4 *>(R + 3 * static_cast<size_t>(base));
+        const float ax = nx, ay = ny, az = nz;
+        if (!last) {
+          const int i2 = i + 32 * TCC_VER_WARPS;
+          const int ic = i2 < nq ? i2 : nq - 1;
+          nx = __ldg(Q + 3 * ic), ny = __ldg(Q + 3 * ic + 1), nz = __ldg(Q + 3 * ic + 2);
+        }
+        const uint2 *L = lists + slot * (TCC_CAP * TCC_EPI);
+        const float limit = fminf(sbest[slot * TCC_EPI + row], sbest[slot * TCC_EPI + row + 128]) + eps2;
+        int g0 = 0, g1 = 0, g2 = 0, g3 = 0, nmine = 0;  // this row's surviving groups
+        float a0 = 0.f;                                  // approximate minimum of the first (probe only)
+        bool full_scan = false;
 #pragma unroll
-            for (int c4 = 0; c4 < TCC_GROUP / 4; ++c4) {  // four points = three float4
-              const float4 w0 = __ldg(p4 + 3 * c4), w1 = __ldg(p4 + 3 * c4 + 1), w2 = __ldg(p4 + 3 * c4 + 2);
-              const float d0 = dist_yxz(__fsub_rn(w0.x, ax), __fsub_rn(w0.y, ay), __fsub_rn(w0.z, az));
-              const float d1 = dist_yxz(__fsub_rn(w0.w, ax), __fsub_rn(w1.x, ay), __fsub_rn(w1.y, az));
-              const float d2 = dist_yxz(__fsub_rn(w1.z, ax), __fsub_rn(w1.w, ay), __fsub_rn(w2.x, az));
-              const float d3 = dist_yxz(__fsub_rn(w2.y, ax), __fsub_rn(w2.z, ay), __fsub_rn(w2.w, az));
-              const int j = base + 4 * c4;
-              uint64_t k0 = pack_key(d0, j), k1 = pack_key(d1, j + 1), k2 = pack_key(d2, j + 2), k3 = pack_key(d3, j + 3);
-              k0 = k0 < k1 ? k0 : k1;
-              k2 = k2 < k3 ? k2 : k3;
-              k0 = k0 < k2 ? k0 : k2;
-              gk = gk < k0 ? gk : k0;
-            }
-          } else {
-            for (int c = 0; c < TCC_GROUP; ++c) {
-              const int j = base + c;
-              if (j < nr) {
-                const float d = dist_yxz(__fsub_rn(__ldg(R + 3 * j), ax), __fsub_rn(__ldg(R + 3 * j + 1), ay), __fsub_rn(__ldg(R + 3 * j + 2), az));
-                const uint64_t kk = pack_key(d, j);
-                gk = gk < kk ? gk : kk;
-              }
-            }
-          }
-          key = key < gk ? key : gk;
-          if (args.stats && live) {
-            const float x = __fsub_rn(ax, cx), y = __fsub_rn(ay, cy), z = __fsub_rn(az, cz);
-            const float na = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-            const float err = fabsf(__uint_as_float(ent.x) - (__uint_as_float(static_cast<uint32_t>(gk >> 32)) - na)) / scal[5];
-            atomicMax(args.stats, static_cast<unsigned long long>(__float_as_uint(err)));
-            atomicAdd(args.stats + 2, 1ull);
+        for (int h = 0; h < 2; ++h) {
+          const int cnt = scnt[slot * TCC_EPI + row + 128 * h];
+          full_scan |= cnt > TCC_CAP;
+          const int nl = cnt < TCC_CAP ? cnt : TCC_CAP;
+          const int nlmax = __reduce_max_sync(0xffffffffu, nl);  // warp-uniform trip count, no divergent loop
+          for (int e = 0; e < nlmax; ++e) {
+            const uint2 ent = L[e * TCC_EPI + row + 128 * h];
+            const bool ok = e < nl && __uint_as_float(ent.x) <= limit;
+            const int g = static_cast<int>(ent.y);
+            a0 = (ok && nmine == 0) ? __uint_as_float(ent.x) : a0;
+            g0 = (ok && nmine == 0) ? g : g0;
+            g1 = (ok && nmine == 1) ? g : g1;
+            g2 = (ok && nmine == 2) ? g : g2;
+            g3 = (ok && nmine == 3) ? g : g3;
+            nmine += ok ? 1 : 0;
           }
         }
-        skey[tid] = key;
-        sovf[tid] = cnt > TCC_CAP ? 1 : 0;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && live) {
-          const uint64_t other = skey[tid + 128];
-          key = key < other ? key : other;
-          float dbest = __uint_as_float(static_cast<uint32_t>(key >> 32));
-          int ibest = static_cast<int>(static_cast<uint32_t>(key));
-          // overflowed list, no candidate at all, or a non-finite winner: the literal scan decides
-          if (cnt > TCC_CAP || sovf[tid + 128] || key == ~0ull || !(dbest < INFINITY)) {
-            tcc_exact_row(R, nr, ax, ay, az, dbest, ibest);
+        full_scan |= nmine > 4 || nmine == 0;
+        __syncwarp();
+        if (last) tcc::mbar_arrive(lempty + slot);  // this warp's last lists are in registers
+        uint64_t key = ~0ull;
+        auto probe_err = [&](float approx, uint32_t exact_bits) {
+          const float x = __fsub_rn(ax, cx), y = __fsub_rn(ay, cy), z = __fsub_rn(az, cz);
+          const float na = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+          const float err = fabsf(approx - (__uint_as_float(exact_bits) - na)) / scal[5];
+          atomicMax(args.stats, static_cast<unsigned long long>(__float_as_uint(err)));
+          atomicAdd(args.stats + 2, 1ull);
+        };
+        {  // nearly every row has exactly one surviving group: every lane walks its own group's 32 columns
+          const float *px = rpx + g0 * TCC_RSTRIDE;
+          float d[TCC_GROUP];
+#pragma unroll
+          for (int c4 = 0; c4 < TCC_GROUP / 4; ++c4) {
+            const float4 X = *reinterpret_cast<const float4 *>(px + 4 * c4);
+            const float4 Y = *reinterpret_cast<const float4 *>(px + RPLANE + 4 * c4);
+            const float4 Z = *reinterpret_cast<const float4 *>(px + 2 * RPLANE + 4 * c4);
+            d[4 * c4] = dist_yxz(__fsub_rn(X.x, ax), __fsub_rn(Y.x, ay), __fsub_rn(Z.x, az));
+            d[4 * c4 + 1] = dist_yxz(__fsub_rn(X.y, ax), __fsub_rn(Y.y, ay), __fsub_rn(Z.y, az));
+            d[4 * c4 + 2] = dist_yxz(__fsub_rn(X.z, ax), __fsub_rn(Y.z, ay), __fsub_rn(Z.z, az));
+            d[4 * c4 + 3] = dist_yxz(__fsub_rn(X.w, ax), __fsub_rn(Y.w, ay), __fsub_rn(Z.w, az));
+          }
+          float m0 = min3(d[0], d[1], d[2]), m1 = min3(d[3], d[4], d[5]), m2 = min3(d[6], d[7], d[8]), m3 = min3(d[9], d[10], d[11]);
+          m0 = min3(m0, d[12], d[13]), m1 = min3(m1, d[14], d[15]), m2 = min3(m2, d[16], d[17]), m3 = min3(m3, d[18], d[19]);
+          m0 = min3(m0, d[20], d[21]), m1 = min3(m1, d[22], d[23]), m2 = min3(m2, d[24], d[25]), m3 = min3(m3, d[26], d[27]);
+          m0 = min3(m0, d[28], d[29]), m1 = min3(m1, d[30], d[31]);
+          const float dm = fminf(min3(m0, m1, m2), m3);
+          int found = 0;
+#pragma unroll
+          for (int c = TCC_GROUP - 1; c >= 0; --c) found = (d[c] == dm) ? c : found;  // the lowest column attaining it
+          if (nmine >= 1) {
+            key = pack_key(dm, static_cast<uint32_t>(g0 * TCC_GROUP + found));
+            if (args.stats && live) probe_err(a0, __float_as_uint(dm));
+          }
+        }
+        auto eval = [&](int r, int gsel) {  // lane r's further item: every lane takes one column of the group
+          const int g = __shfl_sync(0xffffffffu, gsel, r);
+          const float bx = __shfl_sync(0xffffffffu, ax, r), by = __shfl_sync(0xffffffffu, ay, r), bz = __shfl_sync(0xffffffffu, az, r);
+          const int o = g * TCC_RSTRIDE + lane;
+          const float d = dist_yxz(__fsub_rn(rpx[o], bx), __fsub_rn(rpx[RPLANE + o], by), __fsub_rn(rpx[2 * RPLANE + o], bz));
+          const uint32_t kd = __float_as_uint(d);
+          const uint32_t m = __reduce_min_sync(0xffffffffu, kd);
+          const uint32_t who = __ballot_sync(0xffffffffu, kd == m);
+          const uint64_t cand = (static_cast<uint64_t>(m) << 32) | static_cast<uint32_t>(g * TCC_GROUP + (__ffs(who) - 1));
+          if (lane == r) key = key < cand ? key : cand;
+        };
+        for (uint32_t mask = __ballot_sync(0xffffffffu, nmine >= 2); mask; mask &= mask - 1) eval(__ffs(mask) - 1, g1);
+        for (uint32_t mask = __ballot_sync(0xffffffffu, nmine >= 3); mask; mask &= mask - 1) eval(__ffs(mask) - 1, g2);
+        for (uint32_t mask = __ballot_sync(0xffffffffu, nmine >= 4); mask; mask &= mask - 1) eval(__ffs(mask) - 1, g3);
+        // overflowed list, too many survivors, none, or a non-finite winner: the whole row, the lanes striding the columns
+        full_scan |= !(__uint_as_float(static_cast<uint32_t>(key >> 32)) < INFINITY);
+        for (uint32_t mask = __ballot_sync(0xffffffffu, full_scan && live); mask; mask &= mask - 1) {
+          const int r = __ffs(mask) - 1;
+          const float bx = __shfl_sync(0xffffffffu, ax, r), by = __shfl_sync(0xffffffffu, ay, r), bz = __shfl_sync(0xffffffffu, az, r);
+          uint64_t mine = ~0ull;
+          for (int j = lane; j < nr; j += 32) {
+            const int o = (j >> 5) * TCC_RSTRIDE + lane;
+            const float d = dist_yxz(__fsub_rn(rpx[o], bx), __fsub_rn(rpx[RPLANE + o], by), __fsub_rn(rpx[2 * RPLANE + o], bz));
+            const uint64_t c = pack_key(d, static_cast<uint32_t>(j));
+            mine = mine < c ? mine : c;
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, o);
+            mine = mine < other ? mine : other;
+          }
+          if (lane == r) {
+            key = mine;
             if (args.stats) atomicAdd(args.stats + 1, 1ull);
           }
-          if (args.stats) atomicAdd(args.stats + 3, 1ull);
-          D.dist[cloud * nq + i] = dbest;
-          D.idx[cloud * nq + i] = ibest;
         }
+        if (live) {
+          odist[i] = __uint_as_float(static_cast<uint32_t>(key >> 32));
+          oidx[i] = static_cast<int>(static_cast<uint32_t>(key));
+          if (args.stats) atomicAdd(args.stats + 3, 1ull);
+        }
+        if (vtr) args.trace[1536 + kb * 4 + 2 + (sub == first ? 0 : 1)] = clock64();
+       }
       }
     }
     u = uend;
     k = __shfl_sync(0xffffffffu, k, 0);
-    __syncthreads();  // every MMA of this run has been consumed: the operand image may be rebuilt
+    __syncthreads();  // every MMA of this run has been consumed and verified: the operand image may be rebuilt
   }
   tcc::tc_fence_before();
   __syncthreads();
@@ -435,8 +602,8 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
 
 template <int TN>
 static size_t tcc_smem_bytes() {
-  return 1024 + static_cast<size_t>(2) * (TCC_MAXCOLS / TN) * (2 * TN * 16) + 2 * 2 * TCC_M * 16 + TCC_CAP * TCC_EPI * 8 +
-         TCC_EPI * (4 + 8 + 4);
+  return 1024 + static_cast<size_t>(2) * (TCC_MAXCOLS / TN) * (2 * TN * 16) + 3 * 2 * TCC_M * 16 + 3 * (TCC_MAXCOLS / TCC_GROUP) * TCC_RSTRIDE * 4 +
+         2 * TCC_CAP * TCC_EPI * 8 + 2 * TCC_EPI * (4 + 4);
 }
 
 // tuning / test hook state: mode 0 = off, 1 = on with 128-column accumulators, 2 = on with 256-column accumulators
@@ -445,7 +612,7 @@ static float g_tcc_eps_rel = 0.f;
 static int tcc_mode() {
   if (g_tcc_mode < 0) {
     const char *e = getenv("PDAE_CHAMFER_TC");
-    g_tcc_mode = e ? atoi(e) : 1;
+    g_tcc_mode = e ? atoi(e) : 2;
     const char *x = getenv("PDAE_CHAMFER_TC_EPS");
     g_tcc_eps_rel = x ? static_cast<float>(atof(x)) : 1.52587890625e-5f;  // 2^-16
   }
@@ -480,14 +647,15 @@ static int tcc_launch(const TccArgs &a, cudaStream_t st) {
 }
 
 int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
-                       int *idx2, cudaStream_t st, unsigned long long *stats) {
+                       int *idx2, cudaStream_t st, unsigned long long *stats, long long *trace) {
   TccArgs a;
   a.stats = stats;
+  a.trace = trace;
   a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, n, m, (n + TCC_M - 1) / TCC_M};
   a.d[1] = TccDir{xyz2, xyz1, dist2, idx2, m, n, (m + TCC_M - 1) / TCC_M};
   a.units = static_cast<long long>(b) * (a.d[0].rbs + a.d[1].rbs);
   a.eps_rel = g_tcc_eps_rel;
-  return tcc_mode() == 2 ? tcc_launch<256>(a, st) : tcc_launch<128>(a, st);
+  return tcc_mode() == 1 ? tcc_launch<128>(a, st) : tcc_launch<256>(a, st);
 }
 
 }  // namespace pdae
@@ -505,11 +673,14 @@ extern "C" int pdae_tune_chamfer_tc(int mode, float eps_rel) {
 // probe: the tensor-core forward regardless of the mode switch, plus filter statistics (4 x uint64, zeroed by the caller):
 // [0] float bits of the largest observed |approximate - exact| group minimum relative to max|a'|^2 + max|b'|^2,
 // [1] rows decided by the literal scan, [2] 32-column groups evaluated exactly, [3] rows written.
+// trace (optional, 256 x 6 int64): clock64 of CTA 0's first 256 accumulator tiles -- producer: accumulator free, MMAs
+// committed; epilogue thread 0: starts waiting, accumulator ready, accumulator released, tile processed.
 extern "C" int pdae_chamfer_tc_probe(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
-                                     int *idx1, int *idx2, unsigned long long *stats4, pdae_stream_t stream) {
+                                     int *idx1, int *idx2, unsigned long long *stats4, long long *trace,
+                                     pdae_stream_t stream) {
   if (b <= 0 || !xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return PDAE_E_INVALID;
   const int lo = n < m ? n : m, hi = n < m ? m : n;
   if (lo < 512 || hi > pdae::TCC_MAXCOLS) return PDAE_E_UNSUPPORTED;
   (void)pdae::tcc_mode();
-  return pdae::chamfer_tc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, static_cast<cudaStream_t>(stream), stats4);
+  return pdae::chamfer_tc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, static_cast<cudaStream_t>(stream), stats4, trace);
 }

@@ -100,7 +100,7 @@ size_t knn4_workspace_bytes(int b, int r, int q, int k);
 // chamfer_tc.cu: Chamfer forward with the tensor cores as an exact filter (both clouds 512..2048 points)
 bool chamfer_tc_applies(int b, int n, int m);
 int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
-                       int *idx2, cudaStream_t st, unsigned long long *stats = nullptr);
+                       int *idx2, cudaStream_t st, unsigned long long *stats = nullptr, long long *trace = nullptr);
 // which generation serves dim-3, k <= 64 searches: 4 (default) or 3 (PDAE_KNN_IMPL=3, kept for A/B measurements)
 int knn3d_impl();
 

@@ -124,6 +124,57 @@ __global__ void k_mma(float *out, int tiles, int per) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "n"(512));
 }
 
+// MMA issue throughput without any wait in the loop: commit every `every` tiles to a barrier nobody waits on
+template <int N>
+__global__ void k_mma_nowait(float *out, int tiles, int per, int every) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t slot;
+  __shared__ __align__(8) uint64_t bar[2];
+  float *a = reinterpret_cast<float *>(smem);
+  float *b = a + 128 * 8;
+  for (int i = threadIdx.x; i < (128 + N) * 8; i += blockDim.x) a[i] = 1.0f;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[0])), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[1])), "r"(every < 0 ? 2 : 1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int issuers = every < 0 ? 2 : 1;
+  if (every < 0) every = 0;
+  if ((threadIdx.x & 31) == 0 && warp < issuers) {
+    const uint64_t ad = smem_desc(smem_u32(a), 16 * 128, 128), bd = smem_desc(smem_u32(b), (N / 8) * 128, 128);
+    constexpr uint32_t idesc = instr_desc_tf32(128, N);
+    for (int t = warp; t < tiles; t += issuers) {
+      const uint32_t d = slot + (t % (512 / N)) * N;
+      for (int m = 0; m < per; ++m)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d),
+                     "l"(ad), "l"(bd), "r"(idesc), "r"(m)
+                     : "memory");
+      if (every > 0 && (t % every) == every - 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[0])) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[1])) : "memory");
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(ok)
+                   : "r"(smem_u32(&bar[1])), "r"(0)
+                   : "memory");
+    out[blockIdx.x * 2 + warp] = 1.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "n"(512));
+}
+
 template <typename F> float timeit(F f) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   f(); cudaDeviceSynchronize(); float best = 1e30f;
@@ -154,7 +205,15 @@ int main() {
            "\"cycles_per_tile\": %.1f, \"cycles_per_mma\": %.1f}\n", N, DEPTH, per, t * 1e-3 * clk / tiles,                    \
            t * 1e-3 * clk / tiles / per);                                                                                \
   }
-  RUN(256, 2) RUN(256, 1) RUN(128, 4) RUN(128, 2) RUN(64, 8) RUN(64, 4)
+  RUN(256, 2)
+#define RUNNW(N, EVERY)                                                                                                   \
+  for (int per = 1; per <= 4; per += 1) {                                                                                \
+    const float t = timeit([&] { k_mma_nowait<N><<<sms, 128, (128 + N) * 8 * 4>>>(out, tiles, per, EVERY); });           \
+    printf("{\"bench\": \"tcgen05.mma tf32 m128 k8, no wait in the loop\", \"n\": %d, \"commit_every_tiles\": %d, "                \
+           "\"mmas_per_tile\": %d, \"cycles_per_tile\": %.1f, \"cycles_per_mma\": %.1f}\n", N, EVERY, per,                     \
+           t * 1e-3 * clk / tiles, t * 1e-3 * clk / tiles / per);                                                       \
+  }
+  RUNNW(256, 1) RUNNW(256, -1) RUNNW(128, -1)
   e = cudaDeviceSynchronize(); if (e != cudaSuccess) printf("error %s\n", cudaGetErrorString(e));
   return 0;
 }
