@@ -311,18 +311,30 @@ def run_ours(args):
         c, p = clouds_d[i % POOL], preds_d[i % POOL]
         main = torch.cuda.current_stream()
         br = side if overlap else main
-        br.wait_stream(main)
-        with torch.cuda.stream(br):
-            _, center = ops.fps_gather(c, G)  # latency-bound, one CTA per cloud: starts at once, costs the scan little
-        gate = torch.cuda.Event() if (overlap and args.knn_gate == "scan") else None
-        with ops.chamfer_column_split(not overlap):  # the patchifier branch already fills the scan's wave tail
-            d1, d2, i1, i2 = ops.chamfer_forward(p, c, scan_done=gate)
-        with torch.cuda.stream(br):
-            if gate is not None:
-                # the issue-bound kNN shares the GPU with the latency-bound tail of the loss branch (column recovery,
-                # loss, backward) instead of with the FMA-bound scan, which it would only slow down
-                br.wait_event(gate)
+        mode = args.patchifier if overlap else "first"
+        if mode == "overlap":  # round 1 / FP32-pipe scan: FPS starts with the forward, the kNN fills its wave tail
+            br.wait_stream(main)
+            with torch.cuda.stream(br):
+                _, center = ops.fps_gather(c, G)  # latency-bound, one CTA per cloud: starts at once, costs the scan little
+            gate = torch.cuda.Event() if args.knn_gate == "scan" else None
+            with ops.chamfer_column_split(False):  # the patchifier branch already fills the scan's wave tail
+                d1, d2, i1, i2 = ops.chamfer_forward(p, c, scan_done=gate)
+            with torch.cuda.stream(br):
+                if gate is not None:
+                    br.wait_event(gate)
+                nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
+        elif mode == "first":  # the model's order: patchify, then (encoder / decoder, not part of this path) the loss
+            br = main
+            _, center = ops.fps_gather(c, G)
             nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
+            d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+        else:  # "tail": the forward has the GPU to itself (the tensor-core kernel owns every SM's shared memory and tensor
+            # memory, nothing can share an SM with it); the patchifier runs beside the light loss / backward kernels
+            d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+            br.wait_stream(main)
+            with torch.cuda.stream(br):
+                _, center = ops.fps_gather(c, G)
+                nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
         # the loss value and the gradients are independent consumers of the match (the gradient needs the upstream scalar,
         # not the loss): the reduction runs on a third stream beside the backward kernels
         lst = aux if overlap else main
@@ -401,14 +413,24 @@ def run_ours(args):
         the public modules + autograd on THIS batch, the loss copied to pinned host memory."""
         prefetch(i + 1)
         c_in, p_in = in_bufs[i % 2]
-        side.wait_stream(torch.cuda.current_stream())
-        if args.knn_gate == "scan":
+        if args.patchifier == "first":
+            nb, center = grouper(c_in)
+            loss = cd_l2(p_in, c_in)
+            side.wait_stream(torch.cuda.current_stream())  # (keeps the join below valid inside a capture)
+        elif args.patchifier == "tail":
+            loss = cd_l2(p_in, c_in)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                nb, center = grouper(c_in)
+        elif args.knn_gate == "scan":
+            side.wait_stream(torch.cuda.current_stream())
             gate = torch.cuda.Event()
             with ops.chamfer_scan_event(gate):  # recorded between the Chamfer scan and its column recovery
                 loss = cd_l2(p_in, c_in)
             with torch.cuda.stream(side):
                 nb, center = grouper(c_in, knn_after=gate)  # FPS at once, kNN once the scan is done
         else:
+            side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 nb, center = grouper(c_in)
             with ops.chamfer_column_split(False):  # the patchifier on `side` already fills the scan's wave tail
@@ -981,6 +1003,9 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA ops (oracle/_ref)")
     ap.add_argument("--sched", default="torch", choices=["torch", "priority"],
                     help="priority: graphs instantiated with per-node launch priorities (Chamfer branch first)")
+    ap.add_argument("--patchifier", default="tail", choices=["tail", "first", "overlap"],
+                    help="where FPS + Group run relative to the Chamfer forward: beside the loss / backward kernels after it "
+                         "(default), before it (the model's order), or from the start on a second stream (round 1)")
     ap.add_argument("--knn-gate", default="none", choices=["scan", "none"],
                     help="none: both branches start together (default, fastest); scan: the patchifier's kNN waits for "
                          "the Chamfer scan kernel and overlaps the step's tail instead (measured 6 %% slower: the tail "
