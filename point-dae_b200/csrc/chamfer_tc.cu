@@ -25,6 +25,7 @@
 // operand image of the whole reference cloud (<= 2048 points, 128 KB) is built once per (cloud, direction) and stays in
 // shared memory.  Warp 8 builds the row operands and issues the MMAs; warps 0-7 are the epilogue (warp w reads TMEM lanes
 // 32 (w & 3).., columns of half w >> 2); accumulator buffers cycle through full / empty mbarriers (tcgen05.commit).
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -80,6 +81,22 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D fp32, A / B fp16 (K = 16 per instruction), both K-major
+__host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// v = hi + lo + r with hi, lo fp16 and |r| <= 2^-24 for |v| <= 1 (fp16 subnormals carry the small lo parts)
+__device__ __forceinline__ void split_h(float v, uint32_t &hi, uint32_t &lo) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(__fsub_rn(v, __half2float(h)));
+  hi = __half_as_ushort(h), lo = __half_as_ushort(l);
+}
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -108,6 +125,9 @@ constexpr int TCC_VER_WARPS = 3;   // verifier warps (exact evaluation of the su
 constexpr int TCC_PROD_WARPS = 1;  // MMA issuer warps (two are supported: tile k goes to issuer k & 1; one keeps up with two accumulators)
 constexpr int TCC_THREADS = TCC_EPI + 32 * TCC_PROD_WARPS + 32 * TCC_VER_WARPS;
 constexpr int TCC_RSTRIDE = 36;    // floats per 32-column group in the shared-memory copy of the searched cloud
+constexpr float TCC_EPS_TF32 = 7.62939453125e-6f;  // 2^-17: default error bound of the tf32 filter relative to the scale
+                                                   // (largest observed error 2^-21.9, results change below 2^-26)
+constexpr float TCC_EPS_F16 = 1.52587890625e-5f;   // 2^-16: ... of the fp16 filter (observed 2^-21.0, results change below 2^-23)
 constexpr float TCC_BIG = 1.0e30f;  // "distance" of a padded column
 
 struct TccDir {
@@ -137,17 +157,20 @@ __device__ __forceinline__ void tcc_exact_row(const float *__restrict__ R, int n
   }
 }
 
-// TN = columns per accumulator buffer (256: two buffers, 128: four)
-template <int TN>
+// TN = columns per accumulator buffer (256: two buffers, 128: four).
+// F16: the operands are fp16 hi/lo pairs of the coordinates scaled by a power of two into [-1/2, 1/2] and ONE
+// kind::f16 MMA (K = 16: ah.bh + al.bh + ah.bl + al.bl + three pieces of |b|^2) makes a tile, instead of two kind::tf32
+// MMAs (K = 8 each): half the tensor time and half the issue work per tile for a 4x wider error bound.
+template <int TN, bool F16>
 __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArgs args) {
   constexpr int NBUF = 512 / TN;
   constexpr int CHUNK = TN * 16;          // bytes of one 16-byte-wide K chunk of a B tile
   constexpr int BTILE = 2 * CHUNK;        // bytes of one B tile image (K = 8 floats)
   constexpr int ACHUNK = TCC_M * 16;      // 2 KB
   constexpr int MAXT = TCC_MAXCOLS / TN;
+  constexpr int NIMG = F16 ? 1 : 2;       // operand images of the searched cloud
   constexpr int HALF = TN / 2;            // columns of a tile one epilogue thread reads
   constexpr int STEPS = HALF / TCC_GROUP; // tcgen05.ld.x32 per tile and thread
-  static_assert(STEPS % 2 == 0, "the epilogue reads two groups at a time");
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem);         // [NBUF] accumulator written (tcgen05.commit)
   uint64_t *empty = full + NBUF;                               // [NBUF] accumulator read by all 256 epilogue threads
@@ -158,8 +181,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   float *scal = reinterpret_cast<float *>(smem + 160);         // [0..2] centre, [3] eps2, [4] fallback flag, [5] bound scale
   float *red = reinterpret_cast<float *>(smem + 256);          // [13 warps][8] reduction scratch
   unsigned char *b1 = smem + 1024;                             // [MAXT][2 chunks][TN/8][8][16 B]
-  unsigned char *b2 = b1 + MAXT * BTILE;
-  unsigned char *aimg = b2 + MAXT * BTILE;                     // [3][2 chunks][16][8][16 B]
+  unsigned char *aimg = b1 + NIMG * MAXT * BTILE;              // [3][2 chunks][16][8][16 B]
   // the searched cloud as given, planar, every 32-column group padded to 36 floats (16-byte aligned rows whose starts
   // fall on different banks); padded columns hold x = +inf, so their distance is +inf
   float *rpx = reinterpret_cast<float *>(aimg + 3 * 2 * ACHUNK);         // [3][TCC_MAXCOLS / 32][36]
@@ -194,7 +216,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   __syncthreads();
   tcc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t IDESC = tcc::instr_desc_tf32(TCC_M, TN);
+  constexpr uint32_t IDESC = F16 ? tcc::instr_desc_f16(TCC_M, TN) : tcc::instr_desc_tf32(TCC_M, TN);
 
   // this CTA's contiguous share of the row blocks
   const int per_cloud = args.d[0].rbs + args.d[1].rbs;
@@ -269,28 +291,12 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
     const float cx = scal[0], cy = scal[1], cz = scal[2];
     float rmax = 0.f;  // max |b'|^2 and max |a'|^2 over the rows of this run
     float bad = 0.f;   // becomes NaN when any squared norm is NaN or infinite (fmaxf would drop a NaN)
-    for (int j = tid; j < ntiles * TN; j += TCC_THREADS) {
-      float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, TCC_BIG, 0.f), l0 = c0, l1 = c0;
-      if (j < nr) {
-        const int o = (j >> 5) * TCC_RSTRIDE + (j & 31);
-        const float x = __fsub_rn(rpx[o], cx), y = __fsub_rn(rpx[RPLANE + o], cy), z = __fsub_rn(rpx[2 * RPLANE + o], cz);
-        const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-        rmax = fmaxf(rmax, m);
-        bad += m * 0.f;
-        const float hx = tcc::tf32_rn(x), hy = tcc::tf32_rn(y), hz = tcc::tf32_rn(z);
-        const float lx = tcc::tf32_rn(__fsub_rn(x, hx)), ly = tcc::tf32_rn(__fsub_rn(y, hy)), lz = tcc::tf32_rn(__fsub_rn(z, hz));
-        const float mh = tcc::tf32_rn(m), ml = tcc::tf32_rn(__fsub_rn(m, mh));
-        c0 = make_float4(-2.f * hx, -2.f * hy, -2.f * hz, -2.f * hx);
-        c1 = make_float4(-2.f * hy, -2.f * hz, mh, ml);
-        l0 = make_float4(-2.f * lx, -2.f * ly, -2.f * lz, -2.f * lx);
-        l1 = make_float4(-2.f * ly, -2.f * lz, 0.f, 0.f);
-      }
-      const int t = j / TN, r = j - t * TN;
-      const int off = t * BTILE + (r >> 3) * 128 + (r & 7) * 16;
-      *reinterpret_cast<float4 *>(b1 + off) = c0;
-      *reinterpret_cast<float4 *>(b1 + off + CHUNK) = c1;
-      *reinterpret_cast<float4 *>(b2 + off) = l0;
-      *reinterpret_cast<float4 *>(b2 + off + CHUNK) = l1;
+    for (int j = tid; j < nr; j += TCC_THREADS) {
+      const int o = (j >> 5) * TCC_RSTRIDE + (j & 31);
+      const float x = __fsub_rn(rpx[o], cx), y = __fsub_rn(rpx[RPLANE + o], cy), z = __fsub_rn(rpx[2 * RPLANE + o], cz);
+      const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+      rmax = fmaxf(rmax, m);
+      bad += m * 0.f;
     }
     float amax = 0.f;
     {
@@ -323,16 +329,62 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
       }
       if (lane == 0) red[warp * 8] = rmax, red[warp * 8 + 1] = amax, red[warp * 8 + 2] = s;
     }
-    tcc::fence_proxy_async();  // the operand image was written through the generic proxy
     __syncthreads();
     if (tid == 0) {
       float rm = 0.f, am = 0.f, s = 0.f;
       for (int w = 0; w < TCC_THREADS / 32; ++w) rm = fmaxf(rm, red[w * 8]), am = fmaxf(am, red[w * 8 + 1]), s += red[w * 8 + 2];
+      // F16: the power of two that brings every centred coordinate into [-1/2, 1/2] (so that -2 b fits [-1, 1])
+      float sc = 1.f;
+      if (F16) {
+        int e = 0;
+        (void)frexpf(sqrtf(fmaxf(rm, am)), &e);  // largest norm = f * 2^e, f in [1/2, 1)
+        sc = (rm + am > 0.f && rm + am < 1.0e30f) ? ldexpf(1.f, -(e + 1)) : 1.f;
+      }
       const float eps2 = 2.f * args.eps_rel * (rm + am);
-      scal[3] = eps2;
+      scal[3] = eps2 * sc * sc;  // the accumulators hold (scaled) distances minus the row's own squared norm
       scal[4] = (s == 0.f && eps2 < 1.0e25f) ? 0.f : 1.f;  // non-finite or huge coordinates: literal scan of every row
       scal[5] = rm + am;
+      scal[6] = sc;
     }
+    __syncthreads();
+    const float sc = scal[6];
+    for (int j = tid; j < ntiles * TN; j += TCC_THREADS) {
+      const int t = j / TN, r = j - t * TN;
+      const int off = t * BTILE + (r >> 3) * 128 + (r & 7) * 16;
+      const int o = (j >> 5) * TCC_RSTRIDE + (j & 31);
+      const float x = __fsub_rn(rpx[o], cx) * sc, y = __fsub_rn(rpx[RPLANE + o], cy) * sc, z = __fsub_rn(rpx[2 * RPLANE + o], cz) * sc;
+      const float m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+      if (F16) {
+        uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0x7b53u /* 60000: a padded column */, 0u);
+        if (j < nr) {
+          uint32_t hx, lx, hy, ly, hz, lz, m1, m2, m3, m4;
+          tcc::split_h(-2.f * x, hx, lx), tcc::split_h(-2.f * y, hy, ly), tcc::split_h(-2.f * z, hz, lz);
+          tcc::split_h(m, m1, m2);
+          tcc::split_h(__fsub_rn(__fsub_rn(m, __half2float(__ushort_as_half(m1))), __half2float(__ushort_as_half(m2))), m3, m4);
+          c0 = make_uint4(hx | (hy << 16), hz | (hx << 16), hy | (hz << 16), lx | (ly << 16));
+          c1 = make_uint4(lz | (lx << 16), ly | (lz << 16), m1 | (m2 << 16), m3);
+        }
+        *reinterpret_cast<uint4 *>(b1 + off) = c0;
+        *reinterpret_cast<uint4 *>(b1 + off + CHUNK) = c1;
+      } else {
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = make_float4(0.f, 0.f, TCC_BIG, 0.f), l0 = c0, l1 = c0;
+        if (j < nr) {
+          const float hx = tcc::tf32_rn(x), hy = tcc::tf32_rn(y), hz = tcc::tf32_rn(z);
+          const float lx = tcc::tf32_rn(__fsub_rn(x, hx)), ly = tcc::tf32_rn(__fsub_rn(y, hy)), lz = tcc::tf32_rn(__fsub_rn(z, hz));
+          const float mh = tcc::tf32_rn(m), ml = tcc::tf32_rn(__fsub_rn(m, mh));
+          c0 = make_float4(-2.f * hx, -2.f * hy, -2.f * hz, -2.f * hx);
+          c1 = make_float4(-2.f * hy, -2.f * hz, mh, ml);
+          l0 = make_float4(-2.f * lx, -2.f * ly, -2.f * lz, -2.f * lx);
+          l1 = make_float4(-2.f * ly, -2.f * lz, 0.f, 0.f);
+        }
+        unsigned char *b2 = b1 + MAXT * BTILE;
+        *reinterpret_cast<float4 *>(b1 + off) = c0;
+        *reinterpret_cast<float4 *>(b1 + off + CHUNK) = c1;
+        *reinterpret_cast<float4 *>(b2 + off) = l0;
+        *reinterpret_cast<float4 *>(b2 + off + CHUNK) = l1;
+      }
+    }
+    tcc::fence_proxy_async();  // the operand image was written through the generic proxy
     __syncthreads();
     const float eps2 = scal[3];
     const bool fallback_all = scal[4] != 0.f;
@@ -365,12 +417,20 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
 #pragma unroll
         for (int t = 0; t < TCC_M / 32; ++t) {
           const int r = lane + 32 * t;
-          const float x = __fsub_rn(qx[t], cx), y = __fsub_rn(qy[t], cy), z = __fsub_rn(qz[t], cz);
-          const float hx = tcc::tf32_rn(x), hy = tcc::tf32_rn(y), hz = tcc::tf32_rn(z);
-          const float lx = tcc::tf32_rn(__fsub_rn(x, hx)), ly = tcc::tf32_rn(__fsub_rn(y, hy)), lz = tcc::tf32_rn(__fsub_rn(z, hz));
+          const float x = __fsub_rn(qx[t], cx) * sc, y = __fsub_rn(qy[t], cy) * sc, z = __fsub_rn(qz[t], cz) * sc;
           const int off = (r >> 3) * 128 + (r & 7) * 16;
-          *reinterpret_cast<float4 *>(A + off) = make_float4(hx, hy, hz, lx);
-          *reinterpret_cast<float4 *>(A + off + ACHUNK) = make_float4(ly, lz, 1.f, 1.f);
+          if (F16) {
+            uint32_t hx, lx, hy, ly, hz, lz;
+            tcc::split_h(x, hx, lx), tcc::split_h(y, hy, ly), tcc::split_h(z, hz, lz);
+            constexpr uint32_t ONE = 0x3c00u;
+            *reinterpret_cast<uint4 *>(A + off) = make_uint4(hx | (hy << 16), hz | (lx << 16), ly | (lz << 16), hx | (hy << 16));
+            *reinterpret_cast<uint4 *>(A + off + ACHUNK) = make_uint4(hz | (lx << 16), ly | (lz << 16), ONE | (ONE << 16), ONE);
+          } else {
+            const float hx = tcc::tf32_rn(x), hy = tcc::tf32_rn(y), hz = tcc::tf32_rn(z);
+            const float lx = tcc::tf32_rn(__fsub_rn(x, hx)), ly = tcc::tf32_rn(__fsub_rn(y, hy)), lz = tcc::tf32_rn(__fsub_rn(z, hz));
+            *reinterpret_cast<float4 *>(A + off) = make_float4(hx, hy, hz, lx);
+            *reinterpret_cast<float4 *>(A + off + ACHUNK) = make_float4(ly, lz, 1.f, 1.f);
+          }
         }
         tcc::fence_proxy_async();
         __syncwarp();
@@ -395,9 +455,13 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
             tcc::tc_fence_after();
             if (args.trace && blockIdx.x == 0 && k < 256) args.trace[k * 6 + 0] = clock64();
             const uint64_t bd1 = tcc::smem_desc(tcc::smem_u32(b1 + t * BTILE), CHUNK, 128);
-            const uint64_t bd2 = tcc::smem_desc(tcc::smem_u32(b2 + t * BTILE), CHUNK, 128);
-            tcc::mma_tf32(tmem + buf * TN, ad, bd1, IDESC, 0u);
-            tcc::mma_tf32(tmem + buf * TN, ad, bd2, IDESC, 1u);
+            if (F16) {
+              tcc::mma_f16(tmem + buf * TN, ad, bd1, IDESC, 0u);
+            } else {
+              const uint64_t bd2 = tcc::smem_desc(tcc::smem_u32(b1 + (MAXT + t) * BTILE), CHUNK, 128);
+              tcc::mma_tf32(tmem + buf * TN, ad, bd1, IDESC, 0u);
+              tcc::mma_tf32(tmem + buf * TN, ad, bd2, IDESC, 1u);
+            }
             tcc::mma_commit(full + buf);
             if (args.trace && blockIdx.x == 0 && k < 256) args.trace[k * 6 + 1] = clock64();
           }
@@ -422,13 +486,16 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
           tcc::mbar_wait(full + buf, use & 1u);
           tcc::tc_fence_after();
           if (tr) args.trace[k * 6 + 3] = clock64();
+          // the whole 128-column share in registers at once: the accumulator is released before any of it is processed
+          // (loading it in two halves keeps the kernel under 128 registers but releases later: 131 vs 122 us)
           float v[STEPS][32];
 #pragma unroll
           for (int s = 0; s < STEPS; ++s) PDAE_TMEM_LD32(tbase + buf * TN + s * TCC_GROUP, v[s]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tcc::tc_fence_before();
-          tcc::mbar_arrive(empty + buf);  // the tile is in registers: the accumulator may be overwritten
-          if (tr) args.trace[k * 6 + 4] = clock64();
+          tcc::mbar_arrive(empty + buf);
+          if (args.trace && blockIdx.x == 0 && k < 256 && lane == 0)  // the last warp's release is the one that counts
+            atomicMax(reinterpret_cast<unsigned long long *>(args.trace + k * 6 + 4), static_cast<unsigned long long>(clock64()));
 #pragma unroll
           for (int s = 0; s < STEPS; ++s) {
             float m0 = min3(v[s][0], v[s][1], v[s][2]), m1 = min3(v[s][3], v[s][4], v[s][5]);
@@ -439,7 +506,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
             m2 = min3(m2, v[s][24], v[s][25]), m3 = min3(m3, v[s][26], v[s][27]);
             m0 = min3(m0, v[s][28], v[s][29]), m1 = min3(m1, v[s][30], v[s][31]);
             const float g = fminf(min3(m0, m1, m2), m3);
-            const int gid = (t * TN + half * HALF + s * TCC_GROUP) / TCC_GROUP;
+            const int gid = t * (TN / TCC_GROUP) + half * (HALF / TCC_GROUP) + s;
             cnt = g < low ? 0 : cnt;  // everything kept so far is more than 2 eps above this group
             const bool take = g <= thr;
             const int pos = cnt < TCC_CAP ? cnt : TCC_CAP - 1;  // an overflowing list is flagged by cnt > CAP
@@ -516,7 +583,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
         auto probe_err = [&](float approx, uint32_t exact_bits) {
           const float x = __fsub_rn(ax, cx), y = __fsub_rn(ay, cy), z = __fsub_rn(az, cz);
           const float na = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-          const float err = fabsf(approx - (__uint_as_float(exact_bits) - na)) / scal[5];
+          const float err = fabsf(approx / (scal[6] * scal[6]) - (__uint_as_float(exact_bits) - na)) / scal[5];
           atomicMax(args.stats, static_cast<unsigned long long>(__float_as_uint(err)));
           atomicAdd(args.stats + 2, 1ull);
         };
@@ -600,9 +667,9 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
-template <int TN>
+template <int TN, bool F16>
 static size_t tcc_smem_bytes() {
-  return 1024 + static_cast<size_t>(2) * (TCC_MAXCOLS / TN) * (2 * TN * 16) + 3 * 2 * TCC_M * 16 + 3 * (TCC_MAXCOLS / TCC_GROUP) * TCC_RSTRIDE * 4 +
+  return 1024 + static_cast<size_t>(F16 ? 1 : 2) * (TCC_MAXCOLS / TN) * (2 * TN * 16) + 3 * 2 * TCC_M * 16 + 3 * (TCC_MAXCOLS / TCC_GROUP) * TCC_RSTRIDE * 4 +
          2 * TCC_CAP * TCC_EPI * 8 + 2 * TCC_EPI * (4 + 4);
 }
 
@@ -614,7 +681,7 @@ static int tcc_mode() {
     const char *e = getenv("PDAE_CHAMFER_TC");
     g_tcc_mode = e ? atoi(e) : 2;
     const char *x = getenv("PDAE_CHAMFER_TC_EPS");
-    g_tcc_eps_rel = x ? static_cast<float>(atof(x)) : 1.52587890625e-5f;  // 2^-16
+    g_tcc_eps_rel = x ? static_cast<float>(atof(x)) : 0.f;  // 0 = the mode's default bound
   }
   return g_tcc_mode;
 }
@@ -626,12 +693,12 @@ bool chamfer_tc_applies(int b, int n, int m) {
   return b > 0 && lo >= 512 && hi <= TCC_MAXCOLS;
 }
 
-template <int TN>
+template <int TN, bool F16>
 static int tcc_launch(const TccArgs &a, cudaStream_t st) {
   static bool configured = false;
-  const size_t smem = tcc_smem_bytes<TN>();
+  const size_t smem = tcc_smem_bytes<TN, F16>();
   if (!configured) {
-    PDAE_CUDA_TRY(cudaFuncSetAttribute(chamfer_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    PDAE_CUDA_TRY(cudaFuncSetAttribute(chamfer_tc_kernel<TN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   static int sms = 0;
@@ -641,7 +708,7 @@ static int tcc_launch(const TccArgs &a, cudaStream_t st) {
     PDAE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const long long grid = a.units < sms ? a.units : sms;
-  chamfer_tc_kernel<TN><<<static_cast<unsigned>(grid), TCC_THREADS, smem, st>>>(a);
+  chamfer_tc_kernel<TN, F16><<<static_cast<unsigned>(grid), TCC_THREADS, smem, st>>>(a);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
@@ -654,8 +721,11 @@ int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m
   a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, n, m, (n + TCC_M - 1) / TCC_M};
   a.d[1] = TccDir{xyz2, xyz1, dist2, idx2, m, n, (m + TCC_M - 1) / TCC_M};
   a.units = static_cast<long long>(b) * (a.d[0].rbs + a.d[1].rbs);
-  a.eps_rel = g_tcc_eps_rel;
-  return tcc_mode() == 1 ? tcc_launch<128>(a, st) : tcc_launch<256>(a, st);
+  const int mode = tcc_mode();
+  a.eps_rel = g_tcc_eps_rel > 0.f ? g_tcc_eps_rel : (mode == 3 ? TCC_EPS_F16 : TCC_EPS_TF32);
+  if (mode == 1) return tcc_launch<128, false>(a, st);
+  if (mode == 3) return tcc_launch<256, true>(a, st);
+  return tcc_launch<256, false>(a, st);
 }
 
 }  // namespace pdae
@@ -667,6 +737,7 @@ extern "C" int pdae_tune_chamfer_tc(int mode, float eps_rel) {
   const int old = pdae::tcc_mode();
   if (mode >= 0) pdae::g_tcc_mode = mode;
   if (eps_rel > 0.f) pdae::g_tcc_eps_rel = eps_rel;
+  if (eps_rel < 0.f) pdae::g_tcc_eps_rel = 0.f;  // back to the mode's default
   return old;
 }
 

@@ -78,14 +78,15 @@ for kind in ("bench", "adversarial", "blob", "offset", "grid", "same"):
         L.pdae_tune_chamfer_tc(0, 0.0)
         want = fwd(a, b)
         row = {"kind": kind, "shape": [bs, n, m]}
-        for mode in (1, 2):
-            L.pdae_tune_chamfer_tc(mode, 0.0)
+        for mode in (1, 2, 3):
+            L.pdae_tune_chamfer_tc(mode, -1.0)
             got = fwd(a, b)
             row["mode%d_mismatches" % mode] = mismatches(got, want)
-        L.pdae_tune_chamfer_tc(1, 0.0)
-        got, st = probe(a, b)
-        row["probe_mismatches"] = mismatches(got, want)
-        row.update(st)
+        for mode in (2, 3):
+            L.pdae_tune_chamfer_tc(mode, -1.0)
+            got, st = probe(a, b)
+            row["probe%d_mismatches" % mode] = mismatches(got, want)
+            row.update({"%s_mode%d" % (k, mode): v for k, v in st.items()})
         out["exactness"].append(row)
         print(json.dumps(row), flush=True)
 
@@ -94,14 +95,15 @@ a_np, b_np = data("bench", 32, 2048, 2048, seed=11)
 a, b = torch.from_numpy(a_np).to(dev), torch.from_numpy(b_np).to(dev)
 L.pdae_tune_chamfer_tc(0, 0.0)
 want = fwd(a, b)
-for e in range(16, 31):
-    L.pdae_tune_chamfer_tc(1, 2.0 ** -e)
-    got, st = probe(a, b)
-    row = {"eps_rel": "2^-%d" % e, "mismatches": mismatches(got, want), "groups_per_row": st["groups_per_row"],
-           "fallback_rows": st["fallback_rows"], "max_rel_err_log2": float(np.log2(max(st["max_rel_err"], 1e-30)))}
-    out["eps_sweep"].append(row)
-    print(json.dumps(row), flush=True)
-L.pdae_tune_chamfer_tc(1, 2.0 ** -16)
+for mode in (2, 3):
+    for e in range(13, 31):
+        L.pdae_tune_chamfer_tc(mode, 2.0 ** -e)
+        got, st = probe(a, b)
+        row = {"mode": mode, "eps_rel": "2^-%d" % e, "mismatches": mismatches(got, want), "groups_per_row": st["groups_per_row"],
+               "fallback_rows": st["fallback_rows"], "max_rel_err_log2": float(np.log2(max(st["max_rel_err"], 1e-30)))}
+        out["eps_sweep"].append(row)
+        print(json.dumps(row), flush=True)
+L.pdae_tune_chamfer_tc(old, -1.0)
 
 
 def timeit(f, reps=20):
@@ -130,11 +132,11 @@ for (bs, n, m) in ((128, 2048, 2048), (128, 1024, 1024)):
         fwd(a, b)
 
     row = {}
-    for mode in (0, 1, 2):
-        L.pdae_tune_chamfer_tc(mode, 0.0)
+    for mode in (0, 1, 2, 3):
+        L.pdae_tune_chamfer_tc(mode, -1.0)
         row["mode%d_us" % mode] = timeit(step)
     out["timing"]["%dx%dx%d" % (bs, n, m)] = row
     print(json.dumps(row), flush=True)
-L.pdae_tune_chamfer_tc(old, 0.0)
+L.pdae_tune_chamfer_tc(old, -1.0)
 if len(sys.argv) > 1:
     json.dump(out, open(sys.argv[1], "w"), indent=1)

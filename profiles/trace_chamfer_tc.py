@@ -14,8 +14,8 @@ c = synth.clouds(128, 2048, seed=1)
 a, b = torch.from_numpy(synth.prediction(c, seed=1)).to(dev), torch.from_numpy(c).to(dev)
 d1 = torch.empty((128, 2048), device=dev); d2 = torch.empty_like(d1)
 i1 = torch.empty((128, 2048), dtype=torch.int32, device=dev); i2 = torch.empty_like(i1)
-for mode in (2, 1):
-    L.pdae_tune_chamfer_tc(mode, 0.0)
+for mode in (3, 2):
+    L.pdae_tune_chamfer_tc(mode, 2.0 ** -16)
     for rep in range(2):
         st = torch.zeros(4, dtype=torch.int64, device=dev)
         tr = torch.zeros(256 * 6 + 64 * 4, dtype=torch.int64, device=dev)
@@ -44,8 +44,8 @@ pool = []
 for s in range(6):
     cc = synth.clouds(128, 2048, seed=100 + s)
     pool.append((torch.from_numpy(synth.prediction(cc, seed=100 + s)).to(dev), torch.from_numpy(cc).to(dev)))
-for mode in (0, 1, 2):
-    L.pdae_tune_chamfer_tc(mode, 0.0)
+for mode in (0, 2, 3):
+    L.pdae_tune_chamfer_tc(mode, 2.0 ** -16)
     for i in range(3):
         ops.chamfer_forward(*pool[i])
     torch.cuda.synchronize()
