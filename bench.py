@@ -11,8 +11,10 @@ One "step" = one pass of the hot path over one batch of synthetic ShapeNet-shape
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM),
 `e2e` the same chain through the public module API (Group, ChamferDistanceL2, autograd) with inputs
 copied from pinned host memory and the loss read back every step.  `roofline` is the dominant
-kernel (chamfer_min_kernel) against the FP32 FMA pipe; `cpu_baseline` is the reference's
-pure-PyTorch CPU path on a bounded sample (oracle/torch_cpu_path.py).
+kernel -- the Chamfer forward, since round 2 the tensor-core filter + exact verification of
+csrc/chamfer_tc.cu -- in the survey's unit (algorithmic pairs x 6 FMA-pipe lane-ops against the FP32
+FMA-pipe peak) with the FP32-pipe kernels of csrc/chamfer.cu timed beside it; `cpu_baseline` is the
+reference's pure-PyTorch CPU path on a bounded sample (oracle/torch_cpu_path.py).
 Multi-GPU: batch sharding, one process per GPU, no data-path collective (weak scaling).
 """
 import argparse
@@ -536,8 +538,15 @@ def run_ours(args):
                 torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n_fwd
 
-    cham_unsplit_ms = time_forward(False)
-    cham_ms = time_forward(True)
+    from pointdae_b200 import _native as _nat
+    tc_mode = _nat.lib().pdae_tune_chamfer_tc(-1, 0.0)  # 0: FP32-pipe kernels only; 1-3: tensor-core filter (default 2)
+    cham_ms = time_forward(True)                        # the forward as the timed step launches it (library default)
+    _nat.lib().pdae_tune_chamfer_tc(0, 0.0)
+    cham_fp32_unsplit_ms = time_forward(False)          # FP32-pipe symmetric kernel, one CTA per 512-row block (round 1)
+    cham_fp32_ms = time_forward(True)                   # ... with column-split units
+    _nat.lib().pdae_tune_chamfer_tc(tc_mode, 0.0)
+    if tc_mode == 0:
+        cham_ms = cham_fp32_unsplit_ms
 
     # ---- end-to-end timing (host buffers, public API) -----------------------------------------------
     for i in range(3):  # eager warm-up (also what --no-graphs measures)
@@ -618,30 +627,65 @@ def run_ours(args):
         peak_tflops = props.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # FP32 FMA pipe, FMA = 2
         pairs = 2.0 * B * N * N  # algorithmic: every (query, reference) pair of both directions
         # 6 FMA-pipe lane-ops per point pair (3 FADD, 1 FMUL, 2 FFMA), each counted as one FMA slot = 2 FLOP
-        achieved = pairs * 6 * 2 / (cham_unsplit_ms * 1e-3) / 1e12      # the form inside the timed step
-        achieved_alone = pairs * 6 * 2 / (cham_ms * 1e-3) / 1e12           # library default for a forward alone
-        roofline = {
-            "kernel": "Chamfer forward as the timed step launches it = fill_keys + chamfer_min_kernel<4,128,1,SYM> "
-                      "(one CTA per 512-row block) + chamfer_col_recover_list_kernel",
-            "bound": "fp32-fma-pipe", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-            "frac": achieved / peak_tflops, "traffic": 8.44e6,
-            "traffic_source": "constant: dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r01/"
-                              "ncu_full_chamfer_symmetric_summary.csv (ncu --set full); not re-measured in this run",
-            "note": "achieved = ALGORITHMIC 2*B*N*N pairs x 6 FMA-pipe lane-ops x 2 / CUDA-event time per forward "
-                    "(launched alone, 8 forwards per replayed graph); peak = SMs x 128 lanes x 2 x sm_max_mhz (%s). The kernel evaluates each "
-                    "unordered pair ONCE for both directions (bit-identical by symmetry), so EXECUTED FMA work is half "
-                    "the algorithmic count: executed_frac is what the FMA pipe actually sustains. Algorithmic bytes "
-                    "10.5 MB (2 clouds in, 4 arrays out) -- not HBM-bound" % (
-                        "MEASURED_PEAKS.json" if peaks else "fallback 1965 MHz"),
-            "executed_frac": 0.5 * achieved / peak_tflops,
-            "ms_per_launch": cham_unsplit_ms,
-            "share_of_step": cham_unsplit_ms / ms_per_step,
-            "alone_with_column_split": {"ms_per_launch": cham_ms, "frac": achieved_alone / peak_tflops,
-                                        "executed_frac": 0.5 * achieved_alone / peak_tflops,
-                                        "note": "library default when the forward has the GPU to itself (512-row x "
-                                                "column-chunk units even out the SMs); the timed step keeps one CTA per "
-                                                "row block because the patchifier on the second stream fills the tail"},
+        achieved = pairs * 6 * 2 / (cham_ms * 1e-3) / 1e12                     # the form inside the timed step
+        ach_fp32_unsplit = pairs * 6 * 2 / (cham_fp32_unsplit_ms * 1e-3) / 1e12
+        ach_fp32 = pairs * 6 * 2 / (cham_fp32_ms * 1e-3) / 1e12
+        fp32_forms = {
+            "one_cta_per_row_block": {"ms_per_launch": cham_fp32_unsplit_ms, "frac": ach_fp32_unsplit / peak_tflops,
+                                      "executed_frac": 0.5 * ach_fp32_unsplit / peak_tflops},
+            "column_split_units": {"ms_per_launch": cham_fp32_ms, "frac": ach_fp32 / peak_tflops,
+                                   "executed_frac": 0.5 * ach_fp32 / peak_tflops},
+            "note": "fill_keys + chamfer_min_kernel<4,128,1,SYM> + chamfer_col_recover_list_kernel (csrc/chamfer.cu): every "
+                    "unordered pair evaluated once on the FP32 FMA pipe for both directions, so the pipe executes half the "
+                    "algorithmic count (executed_frac); still the path of clouds outside 512..2048 points and of the "
+                    "sharded entry points",
         }
+        if tc_mode > 0:
+            ntile = 2 * B * (N // 128) * (N // 256)  # 128-row x 256-column accumulator tiles of one forward
+            mmas = 1 if tc_mode == 3 else 2
+            tensor_tflops = ntile * mmas * 2.0 * 128 * 256 * (16 if tc_mode == 3 else 8) / (cham_ms * 1e-3) / 1e12
+            roofline = {
+                "kernel": "Chamfer forward as the timed step launches it = chamfer_tc_kernel<256,%s> (csrc/chamfer_tc.cu): "
+                          "tcgen05 %s products of hi/lo split coordinates into tensor memory, 32-column group minima + "
+                          "candidate lists in the epilogue warps, exact FP32 re-evaluation of the surviving groups (bit-"
+                          "identical results); one launch" % ("fp16" if tc_mode == 3 else "tf32",
+                                                            "kind::f16" if tc_mode == 3 else "kind::tf32"),
+                "bound": "fp32-fma-pipe (the survey's unit for this op; the kernel itself is bound by the ALU pipe's FMNMX3 "
+                         "rate and by tensor-memory capacity x MMA latency, see tensor_filter)",
+                "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                "traffic": 6.35e6,
+                "traffic_source": "constant: dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r02/"
+                                  "ncu_chamfer_tc_summary.csv (ncu --set full: 6.35 MB read = both clouds once, 0 written -- the 4 MB "
+                                  "of results are still in L2 when the kernel ends); not re-measured in this run",
+                "note": "achieved = ALGORITHMIC 2*B*N*N pairs x 6 FMA-pipe lane-ops x 2 / CUDA-event time per forward "
+                        "(launched alone, 8 forwards per replayed graph); peak = SMs x 128 lanes x 2 x sm_max_mhz (%s). frac "
+                        "> 1: the pair distances are evaluated on the tensor cores (approximately) and only ~1.03 groups of "
+                        "32 columns per row are evaluated exactly on the FP32 pipe, so the FP32 pipe executes ~1.6 %% of the "
+                        "algorithmic count. Algorithmic bytes 10.5 MB (2 clouds in, 4 arrays out) -- not HBM-bound" % (
+                            "MEASURED_PEAKS.json" if peaks else "fallback 1965 MHz"),
+                "ms_per_launch": cham_ms,
+                "share_of_step": cham_ms / ms_per_step,
+                "tensor_filter": {
+                    "tiles_128x256": ntile, "mma_per_tile": mmas, "tensor_tflops_executed": tensor_tflops,
+                    "cycles_per_tile_per_sm": cham_ms * 1e-3 * sm_max_mhz * 1e6 / (ntile / props.multi_processor_count),
+                    "ncu": "profiles/r02/ncu_chamfer_tc_summary.csv: ALU pipe ~50 %% active (18 FMNMX3 per 32 values at "
+                           "half rate are the floor: ~290 of the ~690 cycles a tile takes on a scheduler), tensor pipe ~25 %%, "
+                           "issue ~45 %%",
+                    "pipeline": "profiles/r02/trace_chamfer_tc.txt: accumulator free -> MMAs committed -> ready -> read "
+                                "-> released, per tile (clock64 stamps)"},
+                "fp32_pipe_forms": fp32_forms,
+            }
+        else:
+            roofline = {
+                "kernel": "Chamfer forward (PDAE_CHAMFER_TC=0) = fill_keys + chamfer_min_kernel<4,128,1,SYM> + "
+                          "chamfer_col_recover_list_kernel",
+                "bound": "fp32-fma-pipe", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved / peak_tflops, "traffic": 8.44e6,
+                "traffic_source": "constant: profiles/r01/ncu_full_chamfer_symmetric_summary.csv",
+                "executed_frac": 0.5 * achieved / peak_tflops, "ms_per_launch": cham_ms,
+                "share_of_step": cham_ms / ms_per_step, "fp32_pipe_forms": fp32_forms,
+            }
+        launches_per_step = 7 if tc_mode > 0 else 9  # fps, knn, chamfer forward (1 or 3), loss x2, backward x2
         try:
             others = other_kernels(dev, clouds_d, preds_d, peaks, props) if world == 1 else None
         except Exception as e:  # evidence only
@@ -651,7 +695,10 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": config_dict(world),
-            "launch": ("eager, 3 streams" if args.no_graphs else "CUDA graph per pool slot, 3 streams (FPS+Group || Chamfer forward -> (loss || backward))") + (
+            "launch": ("eager, 3 streams" if args.no_graphs else "CUDA graph per pool slot, 3 streams") + {
+                "tail": ": Chamfer forward -> (FPS+Group || loss || backward)",
+                "first": ": FPS+Group -> Chamfer forward -> (loss || backward)",
+                "overlap": ": FPS+Group || Chamfer forward -> (loss || backward)"}[args.patchifier] + (
                 "; kNN gated behind the Chamfer scan" if args.knn_gate == "scan" else ""),
             "timed_steps": args.steps * inner, "timed_region_ms": total_ms,
             "timed_region_note": "the K-step region repeated %d times back to back (>= %.0f ms); ms_per_step = mean over "
@@ -668,7 +715,7 @@ def run_ours(args):
                            "copies the next batch from pinned host memory and the loss back to the host (a training step: "
                            "patches and gradients stay on the device)" + (
                                "" if args.no_graphs else "; the step is replayed as a CUDA graph")},
-            "gpu_launches": 9 * args.steps * inner,
+            "gpu_launches": launches_per_step * args.steps * inner,
             "roofline": roofline,
             "other_kernels": others,
             "configs": configs,
@@ -681,7 +728,7 @@ def run_ours(args):
             try:
                 ours_us = None
                 if isinstance(others, dict) and "error" not in others:
-                    ours_us = {"fps": others["fps+centre gather %dx%d->%d" % (B, N, G)]["us"], "chamfer_fwd": cham_unsplit_ms * 1e3,
+                    ours_us = {"fps": others["fps+centre gather %dx%d->%d" % (B, N, G)]["us"], "chamfer_fwd": cham_ms * 1e3,
                                "loss": others["chamfer mean loss (2 launches)"]["us"],
                                "chamfer_bwd": others["chamfer backward (2 launches)"]["us"]}
                 line["ref_gpu"] = ref_gpu_chain(dev, clouds_d, preds_d, gd1, gd2, ms_per_step, ours_us)
