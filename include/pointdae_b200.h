@@ -217,9 +217,10 @@ int pdae_tune_chamfer_split(int nc);
 /* Chamfer forward, both clouds 512..2048 points: the tensor cores (tcgen05.mma kind::tf32, hi/lo split operands) evaluate
  * approximate distances, the 32-column groups that can hold a row's minimum within the error bound are re-evaluated with the
  * reference's exact expression (chamfer.cu:42-79) -- same bits as the FP32-pipe kernels (csrc/chamfer_tc.cu).
- * Tuning / test hook: mode 0 = FP32-pipe kernels only, 1 / 2 = tensor-core filter with 128- / 256-column accumulators
- * (default 1; environment PDAE_CHAMFER_TC); eps_rel > 0 sets the filter's error bound relative to
- * max|a - c|^2 + max|b - c|^2 (default 2^-16; PDAE_CHAMFER_TC_EPS).  mode < 0 only queries.  Returns the previous mode.     */
+ * Tuning / test hook: mode 0 = FP32-pipe kernels only, 1 / 2 = tf32 operands (two K = 8 MMAs per tile) with 128- / 256-column
+ * accumulators, 3 = fp16 operands of power-of-two scaled coordinates (one K = 16 MMA per tile; the default; environment
+ * PDAE_CHAMFER_TC); eps_rel > 0 sets the filter's error bound relative to max|a - c|^2 + max|b - c|^2, eps_rel < 0 restores
+ * the mode's default (2^-17 tf32, 2^-16 fp16; PDAE_CHAMFER_TC_EPS).  mode < 0 only queries.  Returns the previous mode.    */
 int pdae_tune_chamfer_tc(int mode, float eps_rel);
 /* probe: the tensor-core forward regardless of the mode, plus filter statistics in stats4 (4 x uint64, zeroed by the caller):
  * [0] float bits of the largest |approximate - exact| group minimum relative to the bound's scale, [1] rows decided by the

@@ -558,26 +558,41 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
         int g0 = 0, g1 = 0, g2 = 0, g3 = 0, nmine = 0;  // this row's surviving groups
         float a0 = 0.f;                                  // approximate minimum of the first (probe only)
         bool full_scan = false;
+        {
+          // the first four entries of both halves are fetched unconditionally (independent loads, no loop-carried
+          // latency); longer lists are rare and walked by a warp-uniform loop
+          const int cnt0 = scnt[slot * TCC_EPI + row], cnt1 = scnt[slot * TCC_EPI + row + 128];
+          full_scan |= cnt0 > TCC_CAP || cnt1 > TCC_CAP;
+          const int nl0 = cnt0 < TCC_CAP ? cnt0 : TCC_CAP, nl1 = cnt1 < TCC_CAP ? cnt1 : TCC_CAP;
+          uint2 ent[2][4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cnt = scnt[slot * TCC_EPI + row + 128 * h];
-          full_scan |= cnt > TCC_CAP;
-          const int nl = cnt < TCC_CAP ? cnt : TCC_CAP;
-          const int nlmax = __reduce_max_sync(0xffffffffu, nl);  // warp-uniform trip count, no divergent loop
-          for (int e = 0; e < nlmax; ++e) {
-            const uint2 ent = L[e * TCC_EPI + row + 128 * h];
-            const bool ok = e < nl && __uint_as_float(ent.x) <= limit;
-            const int g = static_cast<int>(ent.y);
-            a0 = (ok && nmine == 0) ? __uint_as_float(ent.x) : a0;
+          for (int e = 0; e < 4; ++e) {
+            ent[0][e] = L[e * TCC_EPI + row];
+            ent[1][e] = L[e * TCC_EPI + row + 128];
+          }
+          auto consider = [&](uint2 en, bool valid) {
+            const bool ok = valid && __uint_as_float(en.x) <= limit;
+            const int g = static_cast<int>(en.y);
+            a0 = (ok && nmine == 0) ? __uint_as_float(en.x) : a0;
             g0 = (ok && nmine == 0) ? g : g0;
             g1 = (ok && nmine == 1) ? g : g1;
             g2 = (ok && nmine == 2) ? g : g2;
             g3 = (ok && nmine == 3) ? g : g3;
             nmine += ok ? 1 : 0;
+          };
+#pragma unroll
+          for (int e = 0; e < 4; ++e) consider(ent[0][e], e < nl0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) consider(ent[1][e], e < nl1);
+          const int nlmax = __reduce_max_sync(0xffffffffu, nl0 > nl1 ? nl0 : nl1);
+          for (int e = 4; e < nlmax; ++e) {
+            consider(L[e * TCC_EPI + row], e < nl0);
+            consider(L[e * TCC_EPI + row + 128], e < nl1);
           }
         }
         full_scan |= nmine > 4 || nmine == 0;
         __syncwarp();
+        if (vtr && sub == first) args.trace[1792 + kb * 4 + 0] = clock64();
         if (last) tcc::mbar_arrive(lempty + slot);  // this warp's last lists are in registers
         uint64_t key = ~0ull;
         auto probe_err = [&](float approx, uint32_t exact_bits) {
@@ -605,9 +620,16 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
           m0 = min3(m0, d[20], d[21]), m1 = min3(m1, d[22], d[23]), m2 = min3(m2, d[24], d[25]), m3 = min3(m3, d[26], d[27]);
           m0 = min3(m0, d[28], d[29]), m1 = min3(m1, d[30], d[31]);
           const float dm = fminf(min3(m0, m1, m2), m3);
-          int found = 0;
+          int f0 = TCC_GROUP, f1 = TCC_GROUP, f2 = TCC_GROUP, f3 = TCC_GROUP;  // four short chains instead of one of 32
 #pragma unroll
-          for (int c = TCC_GROUP - 1; c >= 0; --c) found = (d[c] == dm) ? c : found;  // the lowest column attaining it
+          for (int c = TCC_GROUP / 4 - 1; c >= 0; --c) {
+            f0 = (d[c] == dm) ? c : f0;
+            f1 = (d[c + 8] == dm) ? c + 8 : f1;
+            f2 = (d[c + 16] == dm) ? c + 16 : f2;
+            f3 = (d[c + 24] == dm) ? c + 24 : f3;
+          }
+          int found = min(min(f0, f1), min(f2, f3));  // the lowest column attaining it
+          found = found < TCC_GROUP ? found : 0;
           if (nmine >= 1) {
             key = pack_key(dm, static_cast<uint32_t>(g0 * TCC_GROUP + found));
             if (args.stats && live) probe_err(a0, __float_as_uint(dm));
@@ -624,9 +646,11 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
           const uint64_t cand = (static_cast<uint64_t>(m) << 32) | static_cast<uint32_t>(g * TCC_GROUP + (__ffs(who) - 1));
           if (lane == r) key = key < cand ? key : cand;
         };
+        if (vtr && sub == first) args.trace[1792 + kb * 4 + 1] = clock64();
         for (uint32_t mask = __ballot_sync(0xffffffffu, nmine >= 2); mask; mask &= mask - 1) eval(__ffs(mask) - 1, g1);
         for (uint32_t mask = __ballot_sync(0xffffffffu, nmine >= 3); mask; mask &= mask - 1) eval(__ffs(mask) - 1, g2);
         for (uint32_t mask = __ballot_sync(0xffffffffu, nmine >= 4); mask; mask &= mask - 1) eval(__ffs(mask) - 1, g3);
+        if (vtr && sub == first) args.trace[1792 + kb * 4 + 2] = clock64();
         // overflowed list, too many survivors, none, or a non-finite winner: the whole row, the lanes striding the columns
         full_scan |= !(__uint_as_float(static_cast<uint32_t>(key >> 32)) < INFINITY);
         for (uint32_t mask = __ballot_sync(0xffffffffu, full_scan && live); mask; mask &= mask - 1) {
@@ -673,13 +697,13 @@ static size_t tcc_smem_bytes() {
          2 * TCC_CAP * TCC_EPI * 8 + 2 * TCC_EPI * (4 + 4);
 }
 
-// tuning / test hook state: mode 0 = off, 1 = on with 128-column accumulators, 2 = on with 256-column accumulators
+// tuning / test hook state: mode 0 = off, 1 / 2 = tf32 filter with 128- / 256-column accumulators, 3 = fp16 filter (default)
 static int g_tcc_mode = -1;
 static float g_tcc_eps_rel = 0.f;
 static int tcc_mode() {
   if (g_tcc_mode < 0) {
     const char *e = getenv("PDAE_CHAMFER_TC");
-    g_tcc_mode = e ? atoi(e) : 2;
+    g_tcc_mode = e ? atoi(e) : 3;
     const char *x = getenv("PDAE_CHAMFER_TC_EPS");
     g_tcc_eps_rel = x ? static_cast<float>(atof(x)) : 0.f;  // 0 = the mode's default bound
   }
@@ -730,8 +754,9 @@ int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m
 
 }  // namespace pdae
 
-// tuning / test hook: mode 0 = FP32-pipe kernels only, 1 / 2 = tensor-core filter with 128- / 256-column accumulators;
-// eps_rel > 0 sets the filter's error bound relative to max|a'|^2 + max|b'|^2 (default 2^-16).  Negative mode only queries.
+// tuning / test hook: mode 0 = FP32-pipe kernels only, 1 / 2 = tf32 filter with 128- / 256-column accumulators, 3 = fp16
+// filter (default); eps_rel > 0 sets the filter's error bound relative to max|a'|^2 + max|b'|^2, < 0 restores the mode's
+// default (2^-17 tf32, 2^-16 fp16).  Negative mode only queries.
 // Returns the previous mode.
 extern "C" int pdae_tune_chamfer_tc(int mode, float eps_rel) {
   const int old = pdae::tcc_mode();

@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 c = synth.clouds(128, 2048, seed=1)
 a, b = torch.from_numpy(synth.prediction(c, seed=1)).to(dev), torch.from_numpy(c).to(dev)
 for mode in [int(x) for x in sys.argv[1:]] or [1, 2]:
-    _native.lib().pdae_tune_chamfer_tc(mode, 0.0)
+    _native.lib().pdae_tune_chamfer_tc(mode, -1.0)
     for _ in range(3):
         ops.chamfer_forward(a, b)
     torch.cuda.synchronize()

@@ -18,12 +18,13 @@ for mode in (3, 2):
     L.pdae_tune_chamfer_tc(mode, 2.0 ** -16)
     for rep in range(2):
         st = torch.zeros(4, dtype=torch.int64, device=dev)
-        tr = torch.zeros(256 * 6 + 64 * 4, dtype=torch.int64, device=dev)
+        tr = torch.zeros(256 * 6 + 64 * 4 + 64 * 4, dtype=torch.int64, device=dev)
         rc = L.pdae_chamfer_tc_probe(a.data_ptr(), b.data_ptr(), 128, 2048, 2048, d1.data_ptr(), d2.data_ptr(), i1.data_ptr(),
                                      i2.data_ptr(), None, tr.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _native.check(rc, "probe")
         torch.cuda.synchronize()
-    tv = tr.cpu()[1536:].view(64, 4)
+    tv = tr.cpu()[1536:1792].view(64, 4)
+    tw = tr.cpu()[1792:].view(64, 4)
     t = tr.cpu()[:1536].view(256, 6)
     t0 = int(t[0, 0])
     print("mode", mode, "tile: prod_free prod_committed | epi_wait_start epi_ready epi_released epi_done  (cycles from the first)")
@@ -35,7 +36,7 @@ for mode in (3, 2):
             print("gap before tile", k, gap, [int(x) - t0 for x in t[k]])
     print("verifier warp 0, row block: start, lists ready, sub 0 done, sub 1 done; epilogue's last tile of that block done")
     for r in range(0, 20):
-        print(r, [int(x) - t0 for x in tv[r]], int(t[min(255, r * 8 + 7), 5]) - t0)
+        print(r, [int(x) - t0 for x in tv[r]], int(t[min(255, r * 8 + 7), 5]) - t0, 'first sub: filtered, main eval, extra rounds:', [int(x) - int(tv[r][1]) for x in tw[r][:3]])
     per = (int(t[200, 5]) - int(t[40, 5])) / 160.0
     print("cycles per tile (tiles 40..200):", per)
 

@@ -26,11 +26,11 @@ def tc_mode():
     lib = _native.lib()
     old = lib.pdae_tune_chamfer_tc(-1, 0.0)
 
-    def set_mode(mode, eps_rel=2.0 ** -16):
+    def set_mode(mode, eps_rel=-1.0):  # eps_rel < 0: the mode's default bound
         lib.pdae_tune_chamfer_tc(mode, eps_rel)
 
     yield set_mode
-    lib.pdae_tune_chamfer_tc(old, 2.0 ** -16)
+    lib.pdae_tune_chamfer_tc(old, -1.0)
 
 
 def probe(a, b):
@@ -75,7 +75,7 @@ ORACLE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("kind,bs,n,m", ORACLE_CASES)
 def test_tc_forward_matches_oracle(tc_mode, mode, kind, bs, n, m):
     tc_mode(mode)
@@ -97,7 +97,7 @@ def test_tc_forward_equals_the_fp32_pipe_kernels_at_full_size(tc_mode, kind, bs,
         a = a + 1e-3 * torch.randn(a.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(n))
     tc_mode(0)
     want = ops.chamfer_forward(a, b)
-    for mode in (2, 1):
+    for mode in (3, 2, 1):
         tc_mode(mode)
         got = ops.chamfer_forward(a, b)
         assert all(torch.equal(g, w) for g, w in zip(got, want)), (mode, kind)
@@ -113,17 +113,18 @@ def test_fp32_pipe_kernels_still_match_reference_cuda(tc_mode, b, n, m):
     a, c = clouds_pair("prediction", min(b, 8), n, m, seed=n)
     x1, x2 = cu(np.tile(a, (-(-b // a.shape[0]), 1, 1))[:b]), cu(np.tile(c, (-(-b // c.shape[0]), 1, 1))[:b])
     want = ref.forward(x1, x2)
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         tc_mode(mode)
         got = ops.chamfer_forward(x1, x2)
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), mode
         assert torch.equal(got[2], want[2]) and torch.equal(got[3], want[3]), mode
 
 
-def test_tc_mass_ties_take_the_full_scan_and_stay_exact(tc_mode):
+@pytest.mark.parametrize("mode", [2, 3])
+def test_tc_mass_ties_take_the_full_scan_and_stay_exact(tc_mode, mode):
     """every point identical (and a cloud of only two distinct points): every group ties, the candidate lists overflow and
     the rows are decided by the exact scan over all columns -- lowest index, like the reference's strict `<`"""
-    tc_mode(2)
+    tc_mode(mode)
     a = np.zeros((2, 1024, 3), dtype=np.float32)
     b = np.zeros((2, 2048, 3), dtype=np.float32)
     a[0] += np.float32(0.25)
@@ -138,10 +139,11 @@ def test_tc_mass_ties_take_the_full_scan_and_stay_exact(tc_mode):
     assert (got[2].cpu().numpy()[0] == 0).all() and (got[3].cpu().numpy()[0] == 0).all()
 
 
-def test_tc_non_finite_and_huge_coordinates_fall_back_to_the_literal_scan(tc_mode):
+@pytest.mark.parametrize("mode", [2, 3])
+def test_tc_non_finite_and_huge_coordinates_fall_back_to_the_literal_scan(tc_mode, mode):
     """a NaN, an infinity, or coordinates too large for the filter's bound: the cloud is scanned literally
     (`k == 0 || d < best`, chamfer.cu:47-79) -- the oracle's semantics"""
-    tc_mode(2)
+    tc_mode(mode)
     a, b = clouds_pair("prediction", 4, 1024, 1024, seed=3)
     b[0, 5, 1] = np.nan
     a[1, 17, 0] = np.inf
@@ -153,19 +155,20 @@ def test_tc_non_finite_and_huge_coordinates_fall_back_to_the_literal_scan(tc_mod
         np.testing.assert_array_equal(g.cpu().numpy(), w)
 
 
-def test_tc_filter_error_and_margin(tc_mode):
-    """the observed error of the approximate group minima stays 8x under the default bound (2^-16 of the scale), the
-    result does not change with a bound 64x tighter, and about one group per row is evaluated exactly"""
+@pytest.mark.parametrize("mode,tight", [(2, 2.0 ** -23), (3, 2.0 ** -21)])
+def test_tc_filter_error_and_margin(tc_mode, mode, tight):
+    """the observed error of the approximate group minima stays 8x under the default bound (2^-17 / 2^-16 of the scale), the
+    result does not change with a bound 32-64x tighter, and about one group per row is evaluated exactly"""
     a, b = clouds_pair("prediction", 32, 2048, 2048, seed=11)
     ta, tb = cu(a), cu(b)
     tc_mode(0)
     want = ops.chamfer_forward(ta, tb)
-    tc_mode(2)
+    tc_mode(mode)
     got, st = probe(ta, tb)
     assert all(torch.equal(g, w) for g, w in zip(got, want))
-    assert st["max_rel_err"] < 2.0 ** -19, st
-    assert st["rows"] == 2 * 32 * 2048 and st["groups"] < 1.2 * st["rows"], st
-    tc_mode(2, 2.0 ** -22)
+    assert st["max_rel_err"] < 2.0 ** -20, st
+    assert st["rows"] == 2 * 32 * 2048 and st["groups"] <= st["rows"], st
+    tc_mode(mode, tight)
     got, st = probe(ta, tb)
     assert all(torch.equal(g, w) for g, w in zip(got, want))
 
@@ -175,11 +178,11 @@ def test_public_modules_run_on_the_tensor_core_path(tc_mode):
     gradient as with the FP32-pipe kernels"""
     a, b = clouds_pair("prediction", 6, 2048, 2048, seed=21)
     out = {}
-    for mode in (0, 2):
+    for mode in (0, 3):
         tc_mode(mode)
         p = cu(a).requires_grad_(True)
         loss = chamfer_dist.ChamferDistanceL2()(p, cu(b))
         loss.backward()
         out[mode] = (float(loss.detach()), p.grad.clone())
-    assert out[0][0] == out[2][0]
-    assert torch.allclose(out[0][1], out[2][1], rtol=1e-5, atol=1e-5 * float(out[0][1].abs().max()))
+    assert out[0][0] == out[3][0]
+    assert torch.allclose(out[0][1], out[3][1], rtol=1e-5, atol=1e-5 * float(out[0][1].abs().max()))
