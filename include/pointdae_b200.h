@@ -214,7 +214,7 @@ int pdae_tune_chamfer_variant(int v);
  * into (ids as the PDAE_CHAMFER_SPLIT environment variable: 0 = automatic, 1 = never split; nc < 0 only queries).
  * Returns the previous setting.  Results do not depend on it.  Not thread-safe.                                 */
 int pdae_tune_chamfer_split(int nc);
-/* Chamfer forward, both clouds 512..2048 points: the tensor cores (tcgen05.mma kind::tf32, hi/lo split operands) evaluate
+/* Chamfer forward, both clouds >= 512 points (above 2048 points: with the workspace, column chunks merged through keys): the tensor cores (tcgen05.mma kind::tf32, hi/lo split operands) evaluate
  * approximate distances, the 32-column groups that can hold a row's minimum within the error bound are re-evaluated with the
  * reference's exact expression (chamfer.cu:42-79) -- same bits as the FP32-pipe kernels (csrc/chamfer_tc.cu).
  * Tuning / test hook: mode 0 = FP32-pipe kernels only, 1 / 2 = tf32 operands (two K = 8 MMAs per tile) with 128- / 256-column

@@ -1022,9 +1022,9 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int b, int n, 
     PDAE_RETURN_IF_LAUNCH_FAILED();
     return 0;
   }
-  if (chamfer_tc_applies(b, n, m)) {  // tensor-core filter + exact evaluation of the surviving groups (chamfer_tc.cu)
+  if (chamfer_tc_applies(b, n, m, workspace ? workspace_bytes : 0)) {  // tensor-core filter + exact evaluation (chamfer_tc.cu)
     if (phase == 2) return 0;
-    return chamfer_tc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, st);
+    return chamfer_tc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, workspace, workspace_bytes, st);
   }
   if (sym) {
     // rows (register-resident queries) = the larger cloud, columns = the smaller one

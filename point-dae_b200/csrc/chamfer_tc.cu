@@ -135,11 +135,13 @@ struct TccDir {
   const float *r;  // (b, nr, 3) the cloud that is searched (columns)
   float *dist;     // (b, nq)
   int *idx;        // (b, nq)
+  uint64_t *keys;  // (b, nq) when the searched cloud is cut into column chunks: (distance bits << 32 | index), RED.MIN target
   int nq, nr, rbs;  // rbs = ceil(nq / 128)
+  int nch, chunk;   // column chunks of the searched cloud (each <= 2048 points, a multiple of 256 but the last) and their size
 };
 struct TccArgs {
   TccDir d[2];
-  long long units;  // b * (d[0].rbs + d[1].rbs) row blocks
+  long long units;  // b * (d[0].rbs * d[0].nch + d[1].rbs * d[1].nch) row blocks x column chunks
   float eps_rel;
   unsigned long long *stats;  // optional probe: [0] max |g - (exact group minimum - |a'|^2)| / (max|a'|^2 + max|b'|^2) as float
                               // bits, [1] rows decided by the full scan, [2] groups evaluated exactly, [3] rows
@@ -219,29 +221,36 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   constexpr uint32_t IDESC = F16 ? tcc::instr_desc_f16(TCC_M, TN) : tcc::instr_desc_tf32(TCC_M, TN);
 
   // this CTA's contiguous share of the row blocks
-  const int per_cloud = args.d[0].rbs + args.d[1].rbs;
+  const int units0 = args.d[0].rbs * args.d[0].nch;
+  const int per_cloud = units0 + args.d[1].rbs * args.d[1].nch;
   const long long u0 = static_cast<long long>(blockIdx.x) * args.units / gridDim.x;
   const long long u1 = static_cast<long long>(blockIdx.x + 1) * args.units / gridDim.x;
   uint32_t k = 0;   // accumulator tiles issued / consumed so far (producer and epilogue count alike)
   uint32_t kb = 0;  // row blocks handed from the epilogue to the verifier so far
   long long u = u0;
   while (u < u1) {
-    // ---- a run of row blocks of one (cloud, direction): build the searched cloud's operand image ----------------------
+    // ---- a run of row blocks of one (cloud, direction, column chunk): build the chunk's operand image ------------------
     const long long cloud = u / per_cloud;
     const int t0 = static_cast<int>(u - cloud * per_cloud);
-    const int dir = t0 >= args.d[0].rbs ? 1 : 0;
+    const int dir = t0 >= units0 ? 1 : 0;
     const float *Q = (dir ? args.d[1].q : args.d[0].q), *R = (dir ? args.d[1].r : args.d[0].r);
     float *odist = dir ? args.d[1].dist : args.d[0].dist;
     int *oidx = dir ? args.d[1].idx : args.d[0].idx;
-    const int nq = dir ? args.d[1].nq : args.d[0].nq, nr = dir ? args.d[1].nr : args.d[0].nr;
-    const int rb0 = dir ? t0 - args.d[0].rbs : t0;
-    long long uend = cloud * per_cloud + (dir ? per_cloud : args.d[0].rbs);
+    uint64_t *okeys = dir ? args.d[1].keys : args.d[0].keys;
+    const int nq = dir ? args.d[1].nq : args.d[0].nq, nr_all = dir ? args.d[1].nr : args.d[0].nr;
+    const int rbs = dir ? args.d[1].rbs : args.d[0].rbs, chunk = dir ? args.d[1].chunk : args.d[0].chunk;
+    const int tt = dir ? t0 - units0 : t0;
+    const int cc = tt / rbs, rb0 = tt - cc * rbs;
+    const int col_off = cc * chunk;                                  // index of the chunk's first column in the cloud
+    const int nr = min(chunk, nr_all - col_off);                     // columns of this chunk
+    long long uend = cloud * per_cloud + (dir ? units0 : 0) + static_cast<long long>(cc + 1) * rbs;
     if (uend > u1) uend = u1;
     const int nrb = static_cast<int>(uend - u);  // row blocks rb0 .. rb0 + nrb - 1
     Q += static_cast<size_t>(cloud) * nq * 3;
-    R += static_cast<size_t>(cloud) * nr * 3;
+    R += (static_cast<size_t>(cloud) * nr_all + col_off) * 3;
     odist += cloud * nq;
     oidx += cloud * nq;
+    if (okeys) okeys += cloud * nq;
     const int ntiles = (nr + TN - 1) / TN;
 
     {  // centre = middle of the searched cloud's bounding box; raw copy for the exact evaluation
@@ -394,8 +403,12 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
         float best;
         int bi;
         tcc_exact_row(R, nr, __ldg(Q + 3 * i), __ldg(Q + 3 * i + 1), __ldg(Q + 3 * i + 2), best, bi);
-        odist[i] = best;
-        oidx[i] = bi;
+        if (okeys) {
+          atomicMin(reinterpret_cast<unsigned long long *>(okeys + i), pack_key(best, static_cast<uint32_t>(bi + col_off)));
+        } else {
+          odist[i] = best;
+          oidx[i] = bi;
+        }
       }
     } else if (warp >= W_ISS && warp < W_EPI) {
       // ================= issuer warps: row operands + MMA issue =======================================================
@@ -674,8 +687,12 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
           }
         }
         if (live) {
-          odist[i] = __uint_as_float(static_cast<uint32_t>(key >> 32));
-          oidx[i] = static_cast<int>(static_cast<uint32_t>(key));
+          if (okeys) {  // one of several column chunks: the (distance, index) order of the key is the reference's tie rule
+            atomicMin(reinterpret_cast<unsigned long long *>(okeys + i), key + static_cast<uint32_t>(col_off));
+          } else {
+            odist[i] = __uint_as_float(static_cast<uint32_t>(key >> 32));
+            oidx[i] = static_cast<int>(static_cast<uint32_t>(key));
+          }
           if (args.stats) atomicAdd(args.stats + 3, 1ull);
         }
         if (vtr) args.trace[1536 + kb * 4 + 2 + (sub == first ? 0 : 1)] = clock64();
@@ -710,11 +727,37 @@ static int tcc_mode() {
   return g_tcc_mode;
 }
 
-// true when chamfer_tc_forward serves this shape (both clouds are searched, so both must fit the resident image)
-bool chamfer_tc_applies(int b, int n, int m) {
+// column chunks of a searched cloud of nr points: as few as fit the resident image, of (nearly) equal size, a multiple of 256
+static void tcc_chunks(int nr, int &nch, int &chunk) {
+  nch = (nr + TCC_MAXCOLS - 1) / TCC_MAXCOLS;
+  chunk = ((nr + nch - 1) / nch + 255) / 256 * 256;
+  nch = (nr + chunk - 1) / chunk;
+}
+
+// workspace of chamfer_tc_forward: merged (distance, index) keys of the rows whose searched cloud is cut into chunks
+static size_t tcc_workspace_bytes(int b, int n, int m) {
+  return (static_cast<size_t>(m > TCC_MAXCOLS ? n : 0) + static_cast<size_t>(n > TCC_MAXCOLS ? m : 0)) * b * sizeof(uint64_t);
+}
+
+// true when chamfer_tc_forward serves this shape: both clouds at least 512 points; clouds above 2048 points are searched
+// in column chunks whose results merge through keys in the caller's workspace
+bool chamfer_tc_applies(int b, int n, int m, size_t workspace_bytes) {
   if (tcc_mode() <= 0) return false;
-  const int lo = n < m ? n : m, hi = n < m ? m : n;
-  return b > 0 && lo >= 512 && hi <= TCC_MAXCOLS;
+  const int lo = n < m ? n : m;
+  return b > 0 && lo >= 512 && workspace_bytes >= tcc_workspace_bytes(b, n, m);
+}
+
+__global__ void __launch_bounds__(256) tcc_fill_keys_kernel(uint64_t *__restrict__ keys, long long count) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) keys[i] = ~0ull;
+}
+__global__ void __launch_bounds__(256) tcc_unpack_keys_kernel(const uint64_t *__restrict__ keys, long long count,
+                                                              float *__restrict__ dist, int *__restrict__ idx) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint64_t k = keys[i];
+  dist[i] = __uint_as_float(static_cast<uint32_t>(k >> 32));
+  idx[i] = static_cast<int>(static_cast<uint32_t>(k));
 }
 
 template <int TN, bool F16>
@@ -738,18 +781,44 @@ static int tcc_launch(const TccArgs &a, cudaStream_t st) {
 }
 
 int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
-                       int *idx2, cudaStream_t st, unsigned long long *stats, long long *trace) {
+                       int *idx2, void *workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long *stats,
+                       long long *trace) {
+  if (workspace_bytes < tcc_workspace_bytes(b, n, m) || (tcc_workspace_bytes(b, n, m) && !workspace)) return PDAE_E_WORKSPACE;
   TccArgs a;
   a.stats = stats;
   a.trace = trace;
-  a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, n, m, (n + TCC_M - 1) / TCC_M};
-  a.d[1] = TccDir{xyz2, xyz1, dist2, idx2, m, n, (m + TCC_M - 1) / TCC_M};
-  a.units = static_cast<long long>(b) * (a.d[0].rbs + a.d[1].rbs);
+  a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, nullptr, n, m, (n + TCC_M - 1) / TCC_M, 1, TCC_MAXCOLS};
+  a.d[1] = TccDir{xyz2, xyz1, dist2, idx2, nullptr, m, n, (m + TCC_M - 1) / TCC_M, 1, TCC_MAXCOLS};
+  uint64_t *ws = static_cast<uint64_t *>(workspace);
+  long long nkeys = 0;
+  for (int d = 0; d < 2; ++d) {
+    tcc_chunks(a.d[d].nr, a.d[d].nch, a.d[d].chunk);
+    if (a.d[d].nch > 1) {
+      a.d[d].keys = ws + nkeys;
+      nkeys += static_cast<long long>(b) * a.d[d].nq;
+    }
+  }
+  const long long per_cloud = static_cast<long long>(a.d[0].rbs) * a.d[0].nch + static_cast<long long>(a.d[1].rbs) * a.d[1].nch;
+  if (per_cloud > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
+  a.units = static_cast<long long>(b) * per_cloud;
+  if (nkeys) {
+    tcc_fill_keys_kernel<<<static_cast<unsigned>((nkeys + 255) / 256), 256, 0, st>>>(ws, nkeys);
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+  }
   const int mode = tcc_mode();
   a.eps_rel = g_tcc_eps_rel > 0.f ? g_tcc_eps_rel : (mode == 3 ? TCC_EPS_F16 : TCC_EPS_TF32);
-  if (mode == 1) return tcc_launch<128, false>(a, st);
-  if (mode == 3) return tcc_launch<256, true>(a, st);
-  return tcc_launch<256, false>(a, st);
+  int rc;
+  if (mode == 1) rc = tcc_launch<128, false>(a, st);
+  else if (mode == 3) rc = tcc_launch<256, true>(a, st);
+  else rc = tcc_launch<256, false>(a, st);
+  if (rc) return rc;
+  for (int d = 0; d < 2; ++d) {
+    if (!a.d[d].keys) continue;
+    const long long cnt = static_cast<long long>(b) * a.d[d].nq;
+    tcc_unpack_keys_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(a.d[d].keys, cnt, a.d[d].dist, a.d[d].idx);
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+  }
+  return 0;
 }
 
 }  // namespace pdae
@@ -776,7 +845,8 @@ extern "C" int pdae_chamfer_tc_probe(const float *xyz1, const float *xyz2, int b
                                      pdae_stream_t stream) {
   if (b <= 0 || !xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return PDAE_E_INVALID;
   const int lo = n < m ? n : m, hi = n < m ? m : n;
-  if (lo < 512 || hi > pdae::TCC_MAXCOLS) return PDAE_E_UNSUPPORTED;
+  if (lo < 512 || hi > pdae::TCC_MAXCOLS) return PDAE_E_UNSUPPORTED;  // (the probe takes no workspace: single-chunk clouds)
   (void)pdae::tcc_mode();
-  return pdae::chamfer_tc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, static_cast<cudaStream_t>(stream), stats4, trace);
+  return pdae::chamfer_tc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, nullptr, 0, static_cast<cudaStream_t>(stream),
+                                  stats4, trace);
 }

@@ -97,10 +97,12 @@ int knn4_points(const float *ref, const float *query, int b, int r, int q, int k
                 const GroupAffine *affine = nullptr, void *ws = nullptr, size_t ws_bytes = 0);
 int knn4_planar(const float *x, int b, int n, int k, int64_t *idx, cudaStream_t st, void *ws = nullptr, size_t ws_bytes = 0);
 size_t knn4_workspace_bytes(int b, int r, int q, int k);
-// chamfer_tc.cu: Chamfer forward with the tensor cores as an exact filter (both clouds 512..2048 points)
-bool chamfer_tc_applies(int b, int n, int m);
+// chamfer_tc.cu: Chamfer forward with the tensor cores as an exact filter (both clouds >= 512 points; clouds above 2048
+// points are searched in column chunks and need the forward's workspace for the merged keys)
+bool chamfer_tc_applies(int b, int n, int m, size_t workspace_bytes);
 int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
-                       int *idx2, cudaStream_t st, unsigned long long *stats = nullptr, long long *trace = nullptr);
+                       int *idx2, void *workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long *stats = nullptr,
+                       long long *trace = nullptr);
 // which generation serves dim-3, k <= 64 searches: 4 (default) or 3 (PDAE_KNN_IMPL=3, kept for A/B measurements)
 int knn3d_impl();
 

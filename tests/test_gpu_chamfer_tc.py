@@ -103,6 +103,35 @@ def test_tc_forward_equals_the_fp32_pipe_kernels_at_full_size(tc_mode, kind, bs,
         assert all(torch.equal(g, w) for g, w in zip(got, want)), (mode, kind)
 
 
+CHUNKED = [("prediction", 2, 4096, 4096), ("ties", 1, 8192, 3000), ("prediction", 2, 2049, 5000), ("lattice", 1, 20000, 777),
+           ("offset", 1, 6000, 6000), ("blob", 3, 1000, 4100)]
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("kind,bs,n,m", CHUNKED)
+def test_tc_forward_in_column_chunks_matches_oracle(tc_mode, mode, kind, bs, n, m):
+    """clouds above 2048 points: the searched cloud is cut into column chunks whose (distance, index) keys merge with
+    RED.MIN in the forward's workspace -- same bits as the oracle, lowest index on ties across chunk boundaries"""
+    tc_mode(mode)
+    a, b = clouds_pair(kind, bs, n, m, seed=n + m)
+    want = oracle.chamfer_fwd(a, b)
+    got = ops.chamfer_forward(cu(a), cu(b))
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g.cpu().numpy(), w)
+
+
+@pytest.mark.parametrize("bs,n,m", [(16, 8192, 8192), (1, 100000, 100000), (2, 30000, 2048)])
+def test_tc_forward_in_column_chunks_equals_the_fp32_pipe_kernels(tc_mode, bs, n, m):
+    a, b = clouds_pair("prediction", bs, n, m, seed=n)
+    ta, tb = cu(a), cu(b)
+    tc_mode(0)
+    want = ops.chamfer_forward(ta, tb)
+    for mode in (3, 2):
+        tc_mode(mode)
+        got = ops.chamfer_forward(ta, tb)
+        assert all(torch.equal(g, w) for g, w in zip(got, want)), mode
+
+
 @pytest.mark.parametrize("b,n,m", [(8, 1024, 1024), (128, 2048, 2048), (6, 2000, 1500)])
 def test_fp32_pipe_kernels_still_match_reference_cuda(tc_mode, b, n, m):
     """the tensor-core path is the default for these shapes; the FP32-pipe kernels (every other shape, the sharded entry
