@@ -1161,6 +1161,9 @@ extern "C" int pdae_chamfer_sharded_f32(const float *xyz1, const float *xyz2_loc
     return 0;
   }
   if (!workspace || workspace_bytes < bm * sizeof(uint64_t)) return PDAE_E_WORKSPACE;
+  if (chamfer_tc_sharded_applies(b, n, m_local))  // tensor-core filter in column chunks; same keys (chamfer_tc.cu)
+    return chamfer_tc_sharded(xyz1, xyz2_local, b, n, m_local, ref_offset, keys1, dist2_local, idx2_local, workspace,
+                              workspace_bytes, st);
   uint64_t *ck = static_cast<uint64_t *>(workspace);
   fill_keys_kernel<<<static_cast<unsigned>((bm + 255) / 256), 256, 0, st>>>(ck, static_cast<long long>(bm));
   PDAE_RETURN_IF_LAUNCH_FAILED();

@@ -138,6 +138,7 @@ struct TccDir {
   uint64_t *keys;  // (b, nq) when the searched cloud is cut into column chunks: (distance bits << 32 | index), RED.MIN target
   int nq, nr, rbs;  // rbs = ceil(nq / 128)
   int nch, chunk;   // column chunks of the searched cloud (each <= 2048 points, a multiple of 256 but the last) and their size
+  int idx_off;      // added to the indices in the keys (reference-set sharding: global index of r[0])
 };
 struct TccArgs {
   TccDir d[2];
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
     const int tt = dir ? t0 - units0 : t0;
     const int cc = tt / rbs, rb0 = tt - cc * rbs;
     const int col_off = cc * chunk;                                  // index of the chunk's first column in the cloud
+    const int idx_base = col_off + (dir ? args.d[1].idx_off : args.d[0].idx_off);  // ... in the indices of the keys
     const int nr = min(chunk, nr_all - col_off);                     // columns of this chunk
     long long uend = cloud * per_cloud + (dir ? units0 : 0) + static_cast<long long>(cc + 1) * rbs;
     if (uend > u1) uend = u1;
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
         int bi;
         tcc_exact_row(R, nr, __ldg(Q + 3 * i), __ldg(Q + 3 * i + 1), __ldg(Q + 3 * i + 2), best, bi);
         if (okeys) {
-          atomicMin(reinterpret_cast<unsigned long long *>(okeys + i), pack_key(best, static_cast<uint32_t>(bi + col_off)));
+          atomicMin(reinterpret_cast<unsigned long long *>(okeys + i), pack_key(best, static_cast<uint32_t>(bi + idx_base)));
         } else {
           odist[i] = best;
           oidx[i] = bi;
@@ -688,7 +690,7 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
         }
         if (live) {
           if (okeys) {  // one of several column chunks: the (distance, index) order of the key is the reference's tie rule
-            atomicMin(reinterpret_cast<unsigned long long *>(okeys + i), key + static_cast<uint32_t>(col_off));
+            atomicMin(reinterpret_cast<unsigned long long *>(okeys + i), key + static_cast<uint32_t>(idx_base));
           } else {
             odist[i] = __uint_as_float(static_cast<uint32_t>(key >> 32));
             oidx[i] = static_cast<int>(static_cast<uint32_t>(key));
@@ -780,30 +782,39 @@ static int tcc_launch(const TccArgs &a, cudaStream_t st) {
   return 0;
 }
 
-int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
-                       int *idx2, void *workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long *stats,
-                       long long *trace) {
-  if (workspace_bytes < tcc_workspace_bytes(b, n, m) || (tcc_workspace_bytes(b, n, m) && !workspace)) return PDAE_E_WORKSPACE;
+// keys1 != nullptr (reference-set sharding): the rows of xyz1 leave as packed keys with ref_offset added to the indices
+// (dist1 / idx1 unused), xyz2 being one rank's slice of the searched cloud
+static int tcc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
+                       int *idx2, uint64_t *keys1, int ref_offset, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                       unsigned long long *stats, long long *trace) {
   TccArgs a;
   a.stats = stats;
   a.trace = trace;
-  a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, nullptr, n, m, (n + TCC_M - 1) / TCC_M, 1, TCC_MAXCOLS};
-  a.d[1] = TccDir{xyz2, xyz1, dist2, idx2, nullptr, m, n, (m + TCC_M - 1) / TCC_M, 1, TCC_MAXCOLS};
+  a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, nullptr, n, m, (n + TCC_M - 1) / TCC_M, 1, TCC_MAXCOLS, ref_offset};
+  a.d[1] = TccDir{xyz2, xyz1, dist2, idx2, nullptr, m, n, (m + TCC_M - 1) / TCC_M, 1, TCC_MAXCOLS, 0};
   uint64_t *ws = static_cast<uint64_t *>(workspace);
   long long nkeys = 0;
   for (int d = 0; d < 2; ++d) {
     tcc_chunks(a.d[d].nr, a.d[d].nch, a.d[d].chunk);
+    if (d == 0 && keys1) continue;
     if (a.d[d].nch > 1) {
       a.d[d].keys = ws + nkeys;
       nkeys += static_cast<long long>(b) * a.d[d].nq;
     }
   }
+  if (static_cast<size_t>(nkeys) * sizeof(uint64_t) > workspace_bytes || (nkeys && !workspace)) return PDAE_E_WORKSPACE;
   const long long per_cloud = static_cast<long long>(a.d[0].rbs) * a.d[0].nch + static_cast<long long>(a.d[1].rbs) * a.d[1].nch;
   if (per_cloud > 0x7fffffffLL) return PDAE_E_UNSUPPORTED;
   a.units = static_cast<long long>(b) * per_cloud;
   if (nkeys) {
     tcc_fill_keys_kernel<<<static_cast<unsigned>((nkeys + 255) / 256), 256, 0, st>>>(ws, nkeys);
     PDAE_RETURN_IF_LAUNCH_FAILED();
+  }
+  if (keys1) {
+    const long long cnt = static_cast<long long>(b) * n;
+    tcc_fill_keys_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(keys1, cnt);
+    PDAE_RETURN_IF_LAUNCH_FAILED();
+    a.d[0].keys = keys1;
   }
   const int mode = tcc_mode();
   a.eps_rel = g_tcc_eps_rel > 0.f ? g_tcc_eps_rel : (mode == 3 ? TCC_EPS_F16 : TCC_EPS_TF32);
@@ -813,12 +824,30 @@ int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m
   else rc = tcc_launch<256, false>(a, st);
   if (rc) return rc;
   for (int d = 0; d < 2; ++d) {
-    if (!a.d[d].keys) continue;
+    if (!a.d[d].keys || (d == 0 && keys1)) continue;
     const long long cnt = static_cast<long long>(b) * a.d[d].nq;
     tcc_unpack_keys_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(a.d[d].keys, cnt, a.d[d].dist, a.d[d].idx);
     PDAE_RETURN_IF_LAUNCH_FAILED();
   }
   return 0;
+}
+
+int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
+                       int *idx2, void *workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long *stats,
+                       long long *trace) {
+  return tcc_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, nullptr, 0, workspace, workspace_bytes, st, stats, trace);
+}
+
+// one rank's share of a reference-set-sharded forward (pdae_chamfer_sharded_f32): true when the tensor-core path serves it
+// (workspace: b * m_local keys, the entry point's own requirement, covers the merged keys of the slice's rows)
+bool chamfer_tc_sharded_applies(int b, int n, int m_local) {
+  if (tcc_mode() <= 0) return false;
+  return b > 0 && n >= 512 && m_local >= 512;
+}
+int chamfer_tc_sharded(const float *xyz1, const float *xyz2_local, int b, int n, int m_local, int ref_offset, uint64_t *keys1,
+                       float *dist2_local, int *idx2_local, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+  return tcc_forward(xyz1, xyz2_local, b, n, m_local, nullptr, dist2_local, nullptr, idx2_local, keys1, ref_offset, workspace,
+                     workspace_bytes, st, nullptr, nullptr);
 }
 
 }  // namespace pdae

@@ -103,6 +103,9 @@ bool chamfer_tc_applies(int b, int n, int m, size_t workspace_bytes);
 int chamfer_tc_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
                        int *idx2, void *workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long *stats = nullptr,
                        long long *trace = nullptr);
+bool chamfer_tc_sharded_applies(int b, int n, int m_local);
+int chamfer_tc_sharded(const float *xyz1, const float *xyz2_local, int b, int n, int m_local, int ref_offset, uint64_t *keys1,
+                       float *dist2_local, int *idx2_local, void *workspace, size_t workspace_bytes, cudaStream_t st);
 // which generation serves dim-3, k <= 64 searches: 4 (default) or 3 (PDAE_KNN_IMPL=3, kept for A/B measurements)
 int knn3d_impl();
 

@@ -37,3 +37,24 @@ for name, (bs, n) in {"C4 32x8192^2": (32, 8192), "C4 256x8192^2": (256, 8192), 
     out[name] = row
     print(name, json.dumps(row), flush=True)
 L.pdae_tune_chamfer_tc(3, -1.0)
+
+# one rank's share of the reference-set-sharded C5 forward (world 8 and 2): all 100 000 rows against a slice
+c = synth.clouds(1, 100000, seed=5)
+a, b = torch.from_numpy(synth.prediction(c, seed=5)).to(dev), torch.from_numpy(c).to(dev)
+for world in (8, 2):
+    sl = b[:, : 100000 // world].contiguous()
+    row = {}
+    for mode in (0, 3):
+        L.pdae_tune_chamfer_tc(mode, -1.0)
+        for _ in range(2):
+            ops.chamfer_sharded_local(a, sl, 0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.chamfer_sharded_local(a, sl, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        row["mode%d_ms" % mode] = e0.elapsed_time(e1) / 10
+    print("sharded C5 share, world", world, json.dumps(row), flush=True)
+L.pdae_tune_chamfer_tc(3, -1.0)

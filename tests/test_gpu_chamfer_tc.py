@@ -132,6 +132,26 @@ def test_tc_forward_in_column_chunks_equals_the_fp32_pipe_kernels(tc_mode, bs, n
         assert all(torch.equal(g, w) for g, w in zip(got, want)), mode
 
 
+@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("n,m,world", [(100000, 100000, 8), (5000, 3000, 3), (1500, 40000, 5)])
+def test_reference_set_sharded_share_through_the_tensor_cores(tc_mode, mode, n, m, world):
+    """pdae_chamfer_sharded_f32 rank by rank in one process: MIN over the ranks' row keys and the slices'
+    final column results equal the unsharded forward, whichever kernel family serves the rank's share"""
+    a, b = clouds_pair("prediction", 1, n, m, seed=n + world)
+    t1, t2 = cu(a), cu(b)
+    tc_mode(0)
+    d1, d2, i1, i2 = ops.chamfer_forward(t1, t2)
+    tc_mode(mode)
+    keys = None
+    for r in range(world):
+        lo, hi = r * m // world, (r + 1) * m // world
+        k, d2l, i2l = ops.chamfer_sharded_local(t1, t2[:, lo:hi].contiguous(), lo)
+        keys = k if keys is None else torch.minimum(keys, k)
+        assert torch.equal(d2l, d2[:, lo:hi]) and torch.equal(i2l, i2[:, lo:hi]), r
+    sd, si = ops.chamfer_unpack_keys(keys)
+    assert torch.equal(sd, d1) and torch.equal(si, i1)
+
+
 @pytest.mark.parametrize("b,n,m", [(8, 1024, 1024), (128, 2048, 2048), (6, 2000, 1500)])
 def test_fp32_pipe_kernels_still_match_reference_cuda(tc_mode, b, n, m):
     """the tensor-core path is the default for these shapes; the FP32-pipe kernels (every other shape, the sharded entry
