@@ -330,6 +330,12 @@ def run_ours(args):
             _, center = ops.fps_gather(c, G)
             nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
             d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+        elif mode == "split":  # FPS alone first (latency-bound, 18 us), the forward, then the kNN beside loss / backward
+            _, center = ops.fps_gather(c, G)
+            d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+            br.wait_stream(main)
+            with torch.cuda.stream(br):
+                nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
         else:  # "tail": the forward has the GPU to itself (the tensor-core kernel owns every SM's shared memory and tensor
             # memory, nothing can share an SM with it); the patchifier runs beside the light loss / backward kernels
             d1, d2, i1, i2 = ops.chamfer_forward(p, c)
@@ -419,7 +425,7 @@ def run_ours(args):
             nb, center = grouper(c_in)
             loss = cd_l2(p_in, c_in)
             side.wait_stream(torch.cuda.current_stream())  # (keeps the join below valid inside a capture)
-        elif args.patchifier == "tail":
+        elif args.patchifier in ("tail", "split"):  # (the Group module runs FPS and kNN back to back: no split here)
             loss = cd_l2(p_in, c_in)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -697,6 +703,7 @@ def run_ours(args):
             "config": config_dict(world),
             "launch": ("eager, 3 streams" if args.no_graphs else "CUDA graph per pool slot, 3 streams") + {
                 "tail": ": Chamfer forward -> (FPS+Group || loss || backward)",
+                "split": ": FPS -> Chamfer forward -> (Group || loss || backward)",
                 "first": ": FPS+Group -> Chamfer forward -> (loss || backward)",
                 "overlap": ": FPS+Group || Chamfer forward -> (loss || backward)"}[args.patchifier] + (
                 "; kNN gated behind the Chamfer scan" if args.knn_gate == "scan" else ""),
@@ -1050,7 +1057,7 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA ops (oracle/_ref)")
     ap.add_argument("--sched", default="torch", choices=["torch", "priority"],
                     help="priority: graphs instantiated with per-node launch priorities (Chamfer branch first)")
-    ap.add_argument("--patchifier", default="tail", choices=["tail", "first", "overlap"],
+    ap.add_argument("--patchifier", default="tail", choices=["tail", "split", "first", "overlap"],
                     help="where FPS + Group run relative to the Chamfer forward: beside the loss / backward kernels after it "
                          "(default), before it (the model's order), or from the start on a second stream (round 1)")
     ap.add_argument("--knn-gate", default="none", choices=["scan", "none"],
