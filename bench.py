@@ -336,6 +336,12 @@ def run_ours(args):
             br.wait_stream(main)
             with torch.cuda.stream(br):
                 nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
+        elif mode == "tail2":  # the forward, then FPS alone, then the kNN beside loss / backward
+            d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+            _, center = ops.fps_gather(c, G)
+            br.wait_stream(main)
+            with torch.cuda.stream(br):
+                nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
         else:  # "tail": the forward has the GPU to itself (the tensor-core kernel owns every SM's shared memory and tensor
             # memory, nothing can share an SM with it); the patchifier runs beside the light loss / backward kernels
             d1, d2, i1, i2 = ops.chamfer_forward(p, c)
@@ -425,7 +431,7 @@ def run_ours(args):
             nb, center = grouper(c_in)
             loss = cd_l2(p_in, c_in)
             side.wait_stream(torch.cuda.current_stream())  # (keeps the join below valid inside a capture)
-        elif args.patchifier in ("tail", "split"):  # (the Group module runs FPS and kNN back to back: no split here)
+        elif args.patchifier in ("tail", "split", "tail2"):  # (the Group module runs FPS and kNN back to back: no split here)
             loss = cd_l2(p_in, c_in)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -704,6 +710,7 @@ def run_ours(args):
             "launch": ("eager, 3 streams" if args.no_graphs else "CUDA graph per pool slot, 3 streams") + {
                 "tail": ": Chamfer forward -> (FPS+Group || loss || backward)",
                 "split": ": FPS -> Chamfer forward -> (Group || loss || backward)",
+                "tail2": ": Chamfer forward -> FPS -> (Group || loss || backward)",
                 "first": ": FPS+Group -> Chamfer forward -> (loss || backward)",
                 "overlap": ": FPS+Group || Chamfer forward -> (loss || backward)"}[args.patchifier] + (
                 "; kNN gated behind the Chamfer scan" if args.knn_gate == "scan" else ""),
@@ -1057,7 +1064,7 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA ops (oracle/_ref)")
     ap.add_argument("--sched", default="torch", choices=["torch", "priority"],
                     help="priority: graphs instantiated with per-node launch priorities (Chamfer branch first)")
-    ap.add_argument("--patchifier", default="tail", choices=["tail", "split", "first", "overlap"],
+    ap.add_argument("--patchifier", default="tail", choices=["tail", "tail2", "split", "first", "overlap"],
                     help="where FPS + Group run relative to the Chamfer forward: beside the loss / backward kernels after it "
                          "(default), before it (the model's order), or from the start on a second stream (round 1)")
     ap.add_argument("--knn-gate", default="none", choices=["scan", "none"],

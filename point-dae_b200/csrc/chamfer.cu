@@ -471,9 +471,14 @@ __global__ void __launch_bounds__(256) chamfer_loss_partial_kernel(const float *
   for (int side = 0; side < 2; ++side) {
     const float *__restrict__ d = side ? dist2 : dist1;
     const long long cnt = side ? c2 : c1;
-    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < cnt; i += 256LL * LOSS_BLOCKS) {
-      const float v = __ldg(d + i);
-      acc[side] += l1 ? __fsqrt_rn(v) : v;
+    // four strided loads in flight per round (the sum is latency-bound: 8 values per thread at the headline shape)
+    constexpr long long STRIDE = 256LL * LOSS_BLOCKS;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < cnt; i += 4 * STRIDE) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = i + u * STRIDE < cnt ? __ldg(d + i + u * STRIDE) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[side] += l1 ? __fsqrt_rn(v[u]) : v[u];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc[side] += __shfl_xor_sync(0xffffffffu, acc[side], o);
@@ -490,13 +495,17 @@ __global__ void __launch_bounds__(256) chamfer_loss_partial_kernel(const float *
 
 __global__ void __launch_bounds__(32) chamfer_loss_final_kernel(const float *__restrict__ partial, long long c1, long long c2,
                                                                 int l1, float *__restrict__ out /*[3]*/) {
-  if (threadIdx.x >= 2) return;
+  // lanes 0-15 sum the first term's partials, lanes 16-31 the second's: 8 each, then a fixed shuffle tree (deterministic)
+  const int side = threadIdx.x >> 4, l = threadIdx.x & 15;
   double t = 0.0;
-  for (int i = 0; i < LOSS_BLOCKS; ++i) t += static_cast<double>(partial[threadIdx.x * LOSS_BLOCKS + i]);
-  const long long cnt = threadIdx.x ? c2 : c1;
+#pragma unroll
+  for (int i = 0; i < LOSS_BLOCKS / 16; ++i) t += static_cast<double>(partial[side * LOSS_BLOCKS + l * (LOSS_BLOCKS / 16) + i]);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  const long long cnt = side ? c2 : c1;
   const float mean = static_cast<float>(t / static_cast<double>(cnt));  // 0/0 = NaN like torch.mean of an empty tensor
-  out[1 + threadIdx.x] = mean;
-  const float other = __shfl_xor_sync(0x3u, mean, 1);
+  const float other = __shfl_xor_sync(0xffffffffu, mean, 16);
+  if (l == 0) out[1 + side] = mean;
   if (threadIdx.x == 0) out[0] = l1 ? __fmul_rn(__fadd_rn(mean, other), 0.5f) : __fadd_rn(mean, other);
 }
 

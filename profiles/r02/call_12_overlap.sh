@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out/r02
 timeout 100 python profiles/trace_chamfer_tc.py 2>&1 | grep "forward us"
-for cfg in "3 tail" "3 split"; do
+for cfg in "3 tail2" "3 tail"; do
   set -- $cfg
   PDAE_CHAMFER_TC=$1 timeout 280 python bench.py --steps 20 --warmup 5 --patchifier $2 --no-configs --no-cpu-baseline --no-ref-gpu > gpurun_out/r02/bench_q_$1_$2.json 2> gpurun_out/r02/bench_q_$1_$2.err; echo "mode $1 patchifier $2 rc=$?"
   tail -2 gpurun_out/r02/bench_q_$1_$2.err
