@@ -764,12 +764,10 @@ __global__ void __launch_bounds__(256) tcc_unpack_keys_kernel(const uint64_t *__
 
 template <int TN, bool F16>
 static int tcc_launch(const TccArgs &a, cudaStream_t st) {
-  static bool configured = false;
   const size_t smem = tcc_smem_bytes<TN, F16>();
-  if (!configured) {
-    PDAE_CUDA_TRY(cudaFuncSetAttribute(chamfer_tc_kernel<TN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
-  }
+  // per launch, not once per process: the attribute belongs to the current device's instance of the kernel (one process may
+  // drive several GPUs, e.g. the reference's nn.DataParallel threads)
+  PDAE_CUDA_TRY(cudaFuncSetAttribute(chamfer_tc_kernel<TN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   static int sms = 0;
   if (!sms) {
     int dev = 0;

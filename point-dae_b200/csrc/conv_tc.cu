@@ -262,12 +262,9 @@ static int conv_launch(const float *x, const float *packed, const float *bias, i
                        float *z, cudaStream_t st) {
   const dim3 grid(ceil_div(n, TC_M), ntiles, b);
   const size_t smem = 128 + static_cast<size_t>(2) * TC_M * TC_KC * 4 + static_cast<size_t>(2) * NT * TC_KC * 4;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    PDAE_CUDA_TRY(cudaFuncSetAttribute(conv1x1_tc_kernel<NT, IN_PM, OUT_PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    configured = true;
-  }
+  // per launch: the attribute belongs to the current device's instance of the kernel (a process may drive several GPUs)
+  PDAE_CUDA_TRY(cudaFuncSetAttribute(conv1x1_tc_kernel<NT, IN_PM, OUT_PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
   conv1x1_tc_kernel<NT, IN_PM, OUT_PM><<<grid, 128, smem, st>>>(x, packed, bias, c, cpad, n, j, z);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
