@@ -282,6 +282,9 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
+    if args.patchify == "two":  # the public Group module then also takes the two-launch form (end-to-end arm)
+        from pointdae_b200 import _native
+        _native.lib().pdae_tune_patchify(0, 1, 8)
 
     # ---- synthetic inputs: POOL distinct batches resident in HBM (rotated so no step re-reads L2-hot data)
     base_c = synth.clouds(B, N, seed=1000 * 1 + rank)
@@ -305,6 +308,13 @@ def run_ours(args):
     side = torch.cuda.Stream(device=dev)
     aux = torch.cuda.Stream(device=dev)
 
+    def patchify(c):
+        """FPS + centre gather + kNN + gather + centre-subtract: one launch (csrc/patchify.cu) or the two-launch form"""
+        if args.patchify == "fused":
+            return ops.fps_group(c, G, M, want_idx=False)[2]
+        _, center = ops.fps_gather(c, G)
+        return ops.group_points_knn(c, center, M, want_idx=False)[0]
+
     def step_device(i, overlap=True):
         """the chain on resident inputs, straight through the op layer (9 of our kernels: fps, knn3,
         fill_keys, chamfer_min, chamfer_col_recover, loss partial + final, chamfer_bwd own + scatter).  The patchifier
@@ -327,8 +337,7 @@ def run_ours(args):
                 nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
         elif mode == "first":  # the model's order: patchify, then (encoder / decoder, not part of this path) the loss
             br = main
-            _, center = ops.fps_gather(c, G)
-            nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
+            nb = patchify(c)
             d1, d2, i1, i2 = ops.chamfer_forward(p, c)
         elif mode == "split":  # FPS alone first (latency-bound, 18 us), the forward, then the kNN beside loss / backward
             _, center = ops.fps_gather(c, G)
@@ -347,8 +356,7 @@ def run_ours(args):
             d1, d2, i1, i2 = ops.chamfer_forward(p, c)
             br.wait_stream(main)
             with torch.cuda.stream(br):
-                _, center = ops.fps_gather(c, G)
-                nb, _ = ops.group_points_knn(c, center, M, want_idx=False)
+                nb = patchify(c)
         # the loss value and the gradients are independent consumers of the match (the gradient needs the upstream scalar,
         # not the loss): the reduction runs on a third stream beside the backward kernels
         lst = aux if overlap else main
@@ -697,7 +705,9 @@ def run_ours(args):
                 "executed_frac": 0.5 * achieved / peak_tflops, "ms_per_launch": cham_ms,
                 "share_of_step": cham_ms / ms_per_step, "fp32_pipe_forms": fp32_forms,
             }
-        launches_per_step = 7 if tc_mode > 0 else 9  # fps, knn, chamfer forward (1 or 3), loss x2, backward x2
+        # patchifier (1 fused launch, or fps + knn), chamfer forward (1 or 3), loss x2, backward x2
+        fused_patchifier = args.patchify == "fused" and args.patchifier in ("tail", "first")
+        launches_per_step = (7 if tc_mode > 0 else 9) - (1 if fused_patchifier else 0)
         try:
             others = other_kernels(dev, clouds_d, preds_d, peaks, props) if world == 1 else None
         except Exception as e:  # evidence only
@@ -713,7 +723,8 @@ def run_ours(args):
                 "tail2": ": Chamfer forward -> FPS -> (Group || loss || backward)",
                 "first": ": FPS+Group -> Chamfer forward -> (loss || backward)",
                 "overlap": ": FPS+Group || Chamfer forward -> (loss || backward)"}[args.patchifier] + (
-                "; kNN gated behind the Chamfer scan" if args.knn_gate == "scan" else ""),
+                "; kNN gated behind the Chamfer scan" if args.knn_gate == "scan" else "") + (
+                "; FPS+Group = one launch (FPS warps + kNN consumer warps per cloud)" if fused_patchifier else ""),
             "timed_steps": args.steps * inner, "timed_region_ms": total_ms,
             "timed_region_note": "the K-step region repeated %d times back to back (>= %.0f ms); ms_per_step = mean over "
                                  "all timed steps" % (inner, MIN_TIMED_MS),
@@ -1033,6 +1044,12 @@ def other_kernels(dev, clouds_d, preds_d, peaks, props):
     out["group kNN %d + gather" % M] = {"us": t, "fma_pipe_frac_algorithmic": B * G * N * 6.0 / (t * 1e-6) / fma,
                                     "bound": "per-warp latency + instruction issue of the selection at this size (16.8 M pairs = "
                                              "2.7 us of FMA work); see `configs` for the shapes where the FMA pipe binds"}
+    t = timed_us(lambda: ops.fps_group(c, G, M, want_idx=False))
+    t_fps = out["fps+centre gather %dx%d->%d" % (B, N, G)]["us"]
+    out["patchifier, one launch (fps + group kNN %d)" % M] = {
+        "us": t, "us_after_the_last_fps_iteration": t - t_fps,
+        "bound": "FPS latency: the search of centre j runs on consumer warps of the same CTA beside FPS iterations j+1.. "
+                 "(csrc/patchify.cu); the two-launch form costs the sum of the two entries above"}
     d1, d2, i1, i2 = ops.chamfer_forward(p, c)
     gone = torch.ones(1, device=dev)
     t = timed_us(lambda: ops.chamfer_loss_backward(p, c, i1, i2, d1, d2, gone, 1.0, 1.0))
@@ -1082,6 +1099,8 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA ops (oracle/_ref)")
     ap.add_argument("--sched", default="torch", choices=["torch", "priority"],
                     help="priority: graphs instantiated with per-node launch priorities (Chamfer branch first)")
+    ap.add_argument("--patchify", default="fused", choices=["fused", "two"],
+                    help="fused: FPS + Group as one launch (pdae_fps_group_f32); two: pdae_fps_gather_f32 + pdae_group_ws_f32")
     ap.add_argument("--patchifier", default="tail", choices=["tail", "tail2", "split", "first", "overlap"],
                     help="where FPS + Group run relative to the Chamfer forward: beside the loss / backward kernels after it "
                          "(default), before it (the model's order), or from the start on a second stream (round 1)")

@@ -95,6 +95,22 @@ int pdae_group_f32(const float *xyz, const float *center, int b, int n, int g, i
 int pdae_group_gather_f32(const float *xyz, const float *center, int b, int n, int g, int m, int64_t *idx,
                           float *patches, pdae_stream_t stream);
 
+/* the whole patchifier of `Group.forward` (models/PointCAE_transformer.py:61-86) in one call: utils/misc.py:13-20 `fps`
+ * (FPS + centre gather) followed by the Group tail above.  xyz (b,n,3); fps_idx (b,g) int32; center (b,g,3);
+ * idx (b,g,m) int64 (may be NULL); neighborhood (b,g,m,3).  Batches of >= 48 clouds of 512..2048 points with m <= 32 and g <= 1024 run as
+ * ONE launch (a CTA per cloud: four FPS warps post each centre to shared memory, consumer warps search it while the
+ * sampling goes on); other shapes run pdae_fps_gather_f32 + pdae_group_ws_f32 (workspace: pdae_fps_group_workspace_bytes,
+ * may be 0).  Same results bit for bit either way.  pdae_tune_patchify(enabled, centres per consumer task, consumer warps)
+ * is the A/B hook (enabled = 0: always the two-launch form, 1: automatic, 2: one launch for every eligible shape).                                                        */
+size_t pdae_fps_group_workspace_bytes(int b, int n, int g, int m);
+int pdae_fps_group_f32(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx,
+                       float *neighborhood, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+int pdae_tune_patchify(int enabled, int qw, int ncw);
+/* diagnostics: while `device_buffer` (>= 1 + g + 8 * g int64, caller-zeroed) is set, CTA 0 of every single-launch
+ * patchifier call stamps clock64 there: [0] start, [1 + j] centre j posted, [1 + g + 8 t + p] phases of search task t.
+ * NULL switches the stamps off (the default).                                                                       */
+int pdae_patchify_trace(long long *device_buffer);
+
 /* ---- DGCNN kNN + graph feature --------------------------------------------------------------
  * replaces: models/dgcnn_util.py:7-12 `knn(x, k)` and :15-36 `get_graph_feature`.
  * x (b,c,n) channel-major.  idx (b,n,k) int64 nearest-first, self included, direct-form

@@ -35,6 +35,10 @@ SIGNATURES = {
     "pdae_knn_keys_u64": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _ll, _vp, _vp]),
     "pdae_knn_merge_keys_u64": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pdae_fps_group_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pdae_fps_group_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pdae_tune_patchify": (_i, [_i, _i, _i]),
+    "pdae_patchify_trace": (_i, [_vp]),
     "pdae_group_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_feat_knn_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_feat_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),

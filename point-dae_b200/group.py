@@ -1,7 +1,7 @@
 """Drop-in for the Point-MAE-style patchifier `Group(num_group, group_size)`
 (models/PointCAE_transformer.py:54-86, byte-identical copies in models/Point_MAE.py:51-83 etc.)
 and for `utils/misc.py:13-20 fps`.  Two launches (FPS+centre gather, kNN+gather+centre-subtract)
-replace the reference's ~1500."""
+replace the reference's ~1500; clouds of 512..2048 points take ONE (csrc/patchify.cu)."""
 import torch
 import torch.nn as nn
 
@@ -38,6 +38,10 @@ class Group(nn.Module):  # FPS + KNN
         an FMA-bound kernel (ops.chamfer_scan_event); FPS is latency-bound and starts at once."""
         batch_size, num_points, _ = xyz.shape
         xyz = xyz.float().contiguous()
+        if knn_after is None and not _needs_grad(xyz) and xyz.size(2) == 3:
+            # one launch: the kNN of every centre runs beside the sampling of the next ones (ops.fps_group)
+            _, center, neighborhood, _ = ops.fps_group(xyz.detach(), self.num_group, self.group_size)
+            return neighborhood, center
         _, center = fps(xyz, self.num_group)  # B G 3
         if knn_after is not None:
             torch.cuda.current_stream().wait_event(knn_after)
@@ -66,6 +70,8 @@ class Group(nn.Module):  # FPS + KNN
 
 def _patches_with_idx(xyz_only, num_group, group_size):
     """FPS + centre gather, kNN + gather + centre-subtract with the int64 neighbour indices kept: two launches."""
+    if not _needs_grad(xyz_only) and xyz_only.dim() == 3 and xyz_only.size(2) == 3:
+        return ops.fps_group(xyz_only.detach().float().contiguous(), num_group, group_size, want_idx=True)
     fps_idx, center = fps(xyz_only, num_group)
     neighborhood, idx = ops.group_points_knn(xyz_only.detach(), center.detach(), group_size, want_idx=True)
     if _needs_grad(xyz_only):  # differentiable like the reference's indexing + subtraction

@@ -246,6 +246,33 @@ def group_points_knn(xyz, center, group_size, want_idx=True, subtract_center=Tru
     return nb, idx
 
 
+def fps_group(xyz, num_group, group_size, want_idx=False):
+    """The whole patchifier of `Group.forward` (models/PointCAE_transformer.py:61-86) in one call / one launch:
+    xyz (B,N,3) -> (fps_idx (B,G) int32, center (B,G,3), neighborhood (B,G,M,3) centre-subtracted, idx (B,G,M) int64|None).
+    Bit-identical with fps_gather + group_points_knn (the form shapes outside 512..2048 points / M <= 32 still take)."""
+    _require_cuda(xyz, "fps_group")
+    _require_f32_contig(xyz, "xyz")
+    if xyz.dim() != 3 or xyz.size(2) != 3:
+        raise RuntimeError("xyz must have shape (B, N, 3)")
+    b, n, _ = xyz.shape
+    g, m = int(num_group), int(group_size)
+    if n < 1 or not (1 <= m <= n):
+        raise RuntimeError("group_size=%d must satisfy 1 <= group_size <= %d points" % (m, n))
+    L = _native.lib()
+    with _on(xyz.device):
+        fps_idx = torch.empty((b, g), dtype=torch.int32, device=xyz.device)
+        center = torch.empty((b, g, 3), dtype=torch.float32, device=xyz.device)
+        nb = torch.empty((b, g, m, 3), dtype=torch.float32, device=xyz.device)
+        idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
+        nbytes = int(L.pdae_fps_group_workspace_bytes(b, n, g, m))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device) if nbytes else None
+        rc = L.pdae_fps_group_f32(xyz.data_ptr(), b, n, g, m, fps_idx.data_ptr(), center.data_ptr(),
+                                  idx.data_ptr() if want_idx else None, nb.data_ptr(),
+                                  ws.data_ptr() if nbytes else None, nbytes, _stream())
+    _native.check(rc, "pdae_fps_group_f32")
+    return fps_idx, center, nb, idx
+
+
 # -------------------------------------------------------------------- affine corruptions (SURVEY.md 8f row 3)
 def _affine_mats(mats, b, dev):
     """(B,T,3,3) matrices, any device -> contiguous fp32 on `dev` (one small H2D copy when they come from the host,
