@@ -324,7 +324,12 @@ def run_ours(args):
         main = torch.cuda.current_stream()
         br = side if overlap else main
         mode = args.patchifier if overlap else "first"
-        if mode == "overlap":  # round 1 / FP32-pipe scan: FPS starts with the forward, the kNN fills its wave tail
+        if mode == "overlap" and args.patchify == "fused":  # both branches start together (priorities decide who gets the SMs)
+            br.wait_stream(main)
+            d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+            with torch.cuda.stream(br):
+                nb = patchify(c)
+        elif mode == "overlap":  # round 1 / FP32-pipe scan: FPS starts with the forward, the kNN fills its wave tail
             br.wait_stream(main)
             with torch.cuda.stream(br):
                 _, center = ops.fps_gather(c, G)  # latency-bound, one CTA per cloud: starts at once, costs the scan little
@@ -706,7 +711,7 @@ def run_ours(args):
                 "share_of_step": cham_ms / ms_per_step, "fp32_pipe_forms": fp32_forms,
             }
         # patchifier (1 fused launch, or fps + knn), chamfer forward (1 or 3), loss x2, backward x2
-        fused_patchifier = args.patchify == "fused" and args.patchifier in ("tail", "first")
+        fused_patchifier = args.patchify == "fused" and args.patchifier in ("tail", "first", "overlap")
         launches_per_step = (7 if tc_mode > 0 else 9) - (1 if fused_patchifier else 0)
         try:
             others = other_kernels(dev, clouds_d, preds_d, peaks, props) if world == 1 else None

@@ -8,7 +8,8 @@ from torch.profiler import profile, ProfilerActivity
 from pointdae_b200 import graphs, ops, synth
 
 PRIO = len(sys.argv) > 1 and sys.argv[1] == "prio"
-DEFER = len(sys.argv) > 1 and sys.argv[1] == "defer"  # patchifier branch forked after the forward instead of before
+DEFER = len(sys.argv) > 1 and sys.argv[1] in ("defer", "fused")  # patchifier branch forked after the forward instead of before
+FUSED = len(sys.argv) > 1 and sys.argv[1] == "fused"  # bench.py's default step: single-launch patchifier, loss on a third stream
 
 dev = torch.device("cuda:0")
 B, N, G, M, POOL = 128, 2048, 64, 32, 8
@@ -18,9 +19,22 @@ clouds = [base[torch.randperm(B, generator=gen).to(dev)][:, torch.randperm(N, ge
 preds = [c + 0.02 * torch.randn_like(c) for c in clouds]
 gone = torch.ones(1, device=dev)
 side = torch.cuda.Stream()
+aux = torch.cuda.Stream()
 
 def step(i):
     main = torch.cuda.current_stream()
+    if FUSED:
+        d1, d2, i1, i2 = ops.chamfer_forward(preds[i], clouds[i])
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            nb = ops.fps_group(clouds[i], G, M)[2]
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            l = ops.chamfer_mean_loss(d1, d2)
+        g = ops.chamfer_loss_backward(preds[i], clouds[i], i1, i2, d1, d2, gone, 1.0, 1.0)
+        main.wait_stream(side)
+        main.wait_stream(aux)
+        return nb, l, g
     if not DEFER:
         side.wait_stream(main)
         with torch.cuda.stream(side):
