@@ -354,6 +354,11 @@ int pdae_affine_points_f32(const float *points, const float *center, const float
 int pdae_group_affine_f32(const float *xyz, const float *center, const float *mats, int b, int n, int g, int m, int t,
                           int64_t *idx, float *neighborhood, float *t_neighborhood, float *t_center,
                           pdae_stream_t stream);
+/* FPS + centre gather + the call above in one call (one launch for the shapes of pdae_fps_group_f32): the first seven
+ * lines of the reference model's forward, models/PointCAE_transformer.py:1010-1017.  fps_idx (b,g) int32, center (b,g,3). */
+int pdae_fps_group_affine_f32(const float *xyz, const float *mats, int b, int n, int g, int m, int t, int *fps_idx,
+                              float *center, int64_t *idx, float *neighborhood, float *t_neighborhood, float *t_center,
+                              void *workspace, size_t workspace_bytes, pdae_stream_t stream);
 
 /* ---- EdgeConv, eval mode (first stage: parity verified on B200, not yet timed) ----------------------
  * replaces: the tail of one EdgeConv layer of `dgcnn_encoder`, models/dgcnn_util.py:114-126: Conv2d(2C,Co,1) over the

@@ -39,6 +39,7 @@ SIGNATURES = {
     "pdae_fps_group_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_tune_patchify": (_i, [_i, _i, _i]),
     "pdae_patchify_trace": (_i, [_vp]),
+    "pdae_fps_group_affine_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_group_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_feat_knn_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "pdae_feat_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -37,6 +37,7 @@ struct PatchArgs {
   int64_t *idx;       // optional (b, g, k)
   float *group;       // (b, g, k, 3)
   int raw_group;
+  GroupAffine aff;    // AFF instances: the corrupted copy of every patch and centre (corrupt.cu / knn4.cu epilogue)
   int n, g, k;
   int npb;   // ceil(n / 512): points per reference slot
   int nbuf;  // distance buffers in the ring (power of two, >= 2 QW)
@@ -77,8 +78,9 @@ __host__ __device__ constexpr size_t pf_align16(size_t v) { return (v + 15) & ~s
 
 }  // namespace
 
-// P = points per FPS thread (n <= 128 * P), QW = centres per consumer task, NCW = consumer warps
-template <int P, int QW, int NCW>
+// P = points per FPS thread (n <= 128 * P), QW = centres per consumer task, NCW = consumer warps, AFF = the epilogue
+// also emits the affinely corrupted patches and centres (models/PointCAE_transformer.py:1011-1017)
+template <int P, int QW, int NCW, bool AFF>
 __global__ void __launch_bounds__(PF_FPS_T + NCW * 32, 1) fps_group_kernel(const PatchArgs a) {
   constexpr int E = PF_E, CAP = PF_CAP, LC = PF_LC;
   constexpr size_t PQ = PF_PQ;
@@ -407,9 +409,26 @@ __global__ void __launch_bounds__(PF_FPS_T + NCW * 32, 1) fps_group_kernel(const
           const int f = ((reg >> 2) << 9) + ((ji & (PF_FPS_T - 1)) << 2) + (reg & 3);
           const float x = planes[f], y = planes[NP + f], z = planes[2 * NP + f];
           float *g = a.group + (bq * k + p) * 3;
-          g[0] = raw ? x : __fsub_rn(x, f0);
-          g[1] = raw ? y : __fsub_rn(y, f1);
-          g[2] = raw ? z : __fsub_rn(z, f2);
+          if constexpr (!AFF) {
+            g[0] = raw ? x : __fsub_rn(x, f0);
+            g[1] = raw ? y : __fsub_rn(y, f1);
+            g[2] = raw ? z : __fsub_rn(z, f2);
+          } else {
+            // the reference re-adds the centre to the centred patch, transforms patch and centre with the same matrices
+            // and subtracts the centres again (same rounding steps as knn4_emit)
+            const float *mats = a.aff.mats + static_cast<size_t>(cloud_id) * a.aff.t * 9;
+            float ax = __fadd_rn(__fsub_rn(x, f0), f0), ay = __fadd_rn(__fsub_rn(y, f1), f1), az = __fadd_rn(__fsub_rn(z, f2), f2);
+            g[0] = __fsub_rn(ax, f0), g[1] = __fsub_rn(ay, f1), g[2] = __fsub_rn(az, f2);
+            float cx = f0, cy = f1, cz = f2;
+            affine_seq(mats, a.aff.t, ax, ay, az);
+            affine_seq(mats, a.aff.t, cx, cy, cz);
+            float *tg = a.aff.tgroup + (bq * k + p) * 3;
+            tg[0] = __fsub_rn(ax, cx), tg[1] = __fsub_rn(ay, cy), tg[2] = __fsub_rn(az, cz);
+            if (p == 0) {
+              float *tc = a.aff.tcenter + bq * 3;
+              tc[0] = cx, tc[1] = cy, tc[2] = cz;
+            }
+          }
         }
       }
     };
@@ -507,7 +526,7 @@ static size_t patch_smem_bytes(const PatchArgs &a, int p, int qw, int ncw, int n
          static_cast<size_t>(ntask + nbuf + ((ntask + nbuf) & 1)) * 8 + static_cast<size_t>(ncw) * (qw * PF_PQ + PF_DENSE);
 }
 
-template <int P, int QW, int NCW>
+template <int P, int QW, int NCW, bool AFF>
 static int patch_launch(PatchArgs a, int b, cudaStream_t st) {
   // ring of distance buffers: as many as fit (a consumer gives a buffer back after its second pass, ~10 FPS iterations
   // after the centre was posted when the SM is busy); at least 2 QW so that the FPS warps never wait for their own task
@@ -518,23 +537,21 @@ static int patch_launch(PatchArgs a, int b, cudaStream_t st) {
   }
   for (a.lg_nbuf = 0; (1 << a.lg_nbuf) < a.nbuf; ++a.lg_nbuf) {}
   if (a.nbuf < 2 * QW || a.nbuf < 2 || smem > 220 * 1024) return PDAE_E_UNSUPPORTED;
-  PDAE_CUDA_TRY(cudaFuncSetAttribute(fps_group_kernel<P, QW, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  fps_group_kernel<P, QW, NCW><<<b, PF_FPS_T + NCW * 32, smem, st>>>(a);
+  PDAE_CUDA_TRY(cudaFuncSetAttribute(fps_group_kernel<P, QW, NCW, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  fps_group_kernel<P, QW, NCW, AFF><<<b, PF_FPS_T + NCW * 32, smem, st>>>(a);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
 }
 
-template <int P>
+template <int P, bool AFF>
 static int patch_launch_p(const PatchArgs &a, int b, int qw, int ncw, cudaStream_t st) {
   // instantiated shapes: one or two centres per task; 4, 6, 8 or 12 consumer warps
-  if (ncw <= 4) return qw == 2 ? patch_launch<P, 2, 4>(a, b, st) : patch_launch<P, 1, 4>(a, b, st);
-  if (ncw <= 6) return qw == 2 ? patch_launch<P, 2, 6>(a, b, st) : patch_launch<P, 1, 6>(a, b, st);
-  if (ncw <= 8) return qw == 2 ? patch_launch<P, 2, 8>(a, b, st) : patch_launch<P, 1, 8>(a, b, st);
-  return qw == 2 ? patch_launch<P, 2, 12>(a, b, st) : patch_launch<P, 1, 12>(a, b, st);
+  if (ncw <= 4) return qw == 2 ? patch_launch<P, 2, 4, AFF>(a, b, st) : patch_launch<P, 1, 4, AFF>(a, b, st);
+  if (ncw <= 6) return qw == 2 ? patch_launch<P, 2, 6, AFF>(a, b, st) : patch_launch<P, 1, 6, AFF>(a, b, st);
+  if (ncw <= 8) return qw == 2 ? patch_launch<P, 2, 8, AFF>(a, b, st) : patch_launch<P, 1, 8, AFF>(a, b, st);
+  return qw == 2 ? patch_launch<P, 2, 12, AFF>(a, b, st) : patch_launch<P, 1, 12, AFF>(a, b, st);
 }
 
-// single-launch form: clouds of 512..2048 points (reference block size 512, the cloud and its planar copy resident in
-// one CTA's shared memory), up to 32 neighbours, up to 1024 centres
 // Below ~48 clouds the stand-alone kNN kernel is short (it spreads the few queries over all SMs) and the FPS warps lose
 // more to the consumers beside them than the overlap saves (measured, profiles/r02/time_patchify.json: 16 clouds 57 vs
 // 48 us, 128 clouds 32 vs 50 us, 256 clouds 61 vs 65 us); enabled = 2 forces the single launch for every eligible shape.
@@ -544,11 +561,12 @@ bool patchify_fused_applies(int b, int n, int g, int m) {
 }
 
 int patchify_fused(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx, float *neighborhood,
-                   int raw, cudaStream_t st) {
-  PatchArgs a{xyz, fps_idx, center, idx, neighborhood, raw, n, g, m, (n + 511) >> 9, 0, 0, patch_tune().trace, pf_env_int("PDAE_PATCHIFY_DBG", 0)};
+                   int raw, const GroupAffine *affine, cudaStream_t st) {
+  PatchArgs a{xyz, fps_idx, center, idx, neighborhood, raw, affine ? *affine : GroupAffine{nullptr, 0, nullptr, nullptr},
+              n, g, m, (n + 511) >> 9, 0, 0, patch_tune().trace, pf_env_int("PDAE_PATCHIFY_DBG", 0)};
   const PatchTune &t = patch_tune();
-  if (n <= 1024) return patch_launch_p<8>(a, b, t.qw, t.ncw, st);
-  return patch_launch_p<16>(a, b, t.qw, t.ncw, st);
+  if (affine) return n <= 1024 ? patch_launch_p<8, true>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, true>(a, b, t.qw, t.ncw, st);
+  return n <= 1024 ? patch_launch_p<8, false>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, false>(a, b, t.qw, t.ncw, st);
 }
 
 }  // namespace pdae
@@ -579,8 +597,25 @@ extern "C" int pdae_fps_group_f32(const float *xyz, int b, int n, int g, int m, 
   if (n == 0 || m > n) return PDAE_E_INVALID;
   if (!xyz || !fps_idx || !center || !neighborhood) return PDAE_E_INVALID;
   if (patchify_fused_applies(b, n, g, m))
-    return patchify_fused(xyz, b, n, g, m, fps_idx, center, idx, neighborhood, 0, static_cast<cudaStream_t>(stream));
+    return patchify_fused(xyz, b, n, g, m, fps_idx, center, idx, neighborhood, 0, nullptr, static_cast<cudaStream_t>(stream));
   const int rc = pdae_fps_gather_f32(xyz, b, n, 3, g, fps_idx, center, workspace, workspace_bytes, stream);
   if (rc) return rc;
   return pdae_group_ws_f32(xyz, center, b, n, g, m, idx, neighborhood, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pdae_fps_group_affine_f32(const float *xyz, const float *mats, int b, int n, int g, int m, int t, int *fps_idx,
+                                         float *center, int64_t *idx, float *neighborhood, float *t_neighborhood, float *t_center,
+                                         void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
+  if (b < 0 || n < 0 || g < 0 || m <= 0 || t < 0 || t > PDAE_AFFINE_MAX_CHAIN) return PDAE_E_INVALID;
+  if (b == 0 || g == 0) return 0;
+  if (n == 0 || m > n) return PDAE_E_INVALID;
+  if (!xyz || !fps_idx || !center || !neighborhood || !t_neighborhood || !t_center || (t > 0 && !mats)) return PDAE_E_INVALID;
+  if (patchify_fused_applies(b, n, g, m)) {
+    // t == 0 is the identity chain: point at any valid address, never dereferenced
+    const GroupAffine aff{mats ? mats : xyz, t, t_neighborhood, t_center};
+    return patchify_fused(xyz, b, n, g, m, fps_idx, center, idx, neighborhood, 0, &aff, static_cast<cudaStream_t>(stream));
+  }
+  const int rc = pdae_fps_gather_f32(xyz, b, n, 3, g, fps_idx, center, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return pdae_group_affine_f32(xyz, center, mats, b, n, g, m, t, idx, neighborhood, t_neighborhood, t_center, stream);
 }

@@ -59,11 +59,14 @@ class Group(nn.Module):  # FPS + KNN
         consumes the host RNGs exactly as the reference's `corrupt_data` does."""
         from . import corrupt_util_tensor
         xyz = xyz.float().contiguous()
-        _, center = fps(xyz, self.num_group)
         if mats is None:
             mats = corrupt_util_tensor.corrupt_stack(xyz.size(0), list(corrupt_type))
         if mats is None:  # clean / Drop-Patch only: the transformed copies are the clean ones, round trip included
             mats = torch.zeros((xyz.size(0), 0, 3, 3))
+        if xyz.size(2) == 3:  # one call: the matrices come from the host RNGs and do not depend on the sampling
+            _, center, nb, tnb, tc, _ = ops.fps_group_affine(xyz.detach(), self.num_group, self.group_size, mats)
+            return nb, center, tnb, tc
+        _, center = fps(xyz, self.num_group)
         nb, tnb, tc, _ = ops.group_affine(xyz.detach(), center, self.group_size, mats)
         return nb, center, tnb, tc
 

@@ -354,6 +354,38 @@ def group_affine(xyz, center, group_size, mats, want_idx=False):
     return nb, tnb, tc, idx
 
 
+def fps_group_affine(xyz, num_group, group_size, mats, want_idx=False):
+    """FPS + centre gather + `group_affine` in one call (one launch for batches of >= 48 clouds of 512..2048 points):
+    xyz (B,N,3), mats (B,T,3,3) -> (fps_idx, center, neighborhood, t_neighborhood, t_center, idx|None); the values of
+    fps_gather followed by group_affine bit for bit."""
+    _require_cuda(xyz, "fps_group_affine")
+    _require_f32_contig(xyz, "xyz")
+    if xyz.dim() != 3 or xyz.size(2) != 3:
+        raise RuntimeError("xyz must have shape (B, N, 3)")
+    b, n, _ = xyz.shape
+    g, m = int(num_group), int(group_size)
+    if n < 1 or not (1 <= m <= n):
+        raise RuntimeError("group_size=%d must satisfy 1 <= group_size <= %d points" % (m, n))
+    if mats.size(1) > 8:
+        raise RuntimeError("at most 8 chained matrices")
+    mats = _affine_mats(mats, b, xyz.device)
+    L = _native.lib()
+    with _on(xyz.device):
+        fps_idx = torch.empty((b, g), dtype=torch.int32, device=xyz.device)
+        center = torch.empty((b, g, 3), dtype=torch.float32, device=xyz.device)
+        nb = torch.empty((b, g, m, 3), dtype=torch.float32, device=xyz.device)
+        tnb = torch.empty_like(nb)
+        tc = torch.empty_like(center)
+        idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
+        nbytes = int(L.pdae_fps_group_workspace_bytes(b, n, g, m))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device) if nbytes else None
+        rc = L.pdae_fps_group_affine_f32(xyz.data_ptr(), mats.data_ptr(), b, n, g, m, mats.size(1), fps_idx.data_ptr(),
+                                         center.data_ptr(), idx.data_ptr() if want_idx else None, nb.data_ptr(),
+                                         tnb.data_ptr(), tc.data_ptr(), ws.data_ptr() if nbytes else None, nbytes, _stream())
+    _native.check(rc, "pdae_fps_group_affine_f32")
+    return fps_idx, center, nb, tnb, tc, idx
+
+
 # -------------------------------------------------------------------------------------- Chamfer
 _scan_events = threading.local()
 

@@ -133,6 +133,38 @@ def test_group_modules_use_the_fused_launch_and_keep_their_outputs(tune):
     assert nbg.requires_grad and torch.equal(nbg.detach(), nb) and torch.equal(cg.detach(), c)
 
 
+@pytest.mark.parametrize("b,n,g,m,t", [(4, 1024, 64, 32, 3), (2, 2048, 64, 32, 1), (3, 777, 20, 17, 2), (2, 512, 8, 16, 0),
+                                       (2, 300, 5, 16, 2), (1, 4096, 16, 32, 3)])
+def test_fused_affine_patchifier_matches_the_oracle(tune, b, n, g, m, t):
+    """`pdae_fps_group_affine_f32` = the first seven lines of the reference model's forward
+    (models/PointCAE_transformer.py:1010-1017): clean patches, centres, corrupted patches and centres, bit for bit, in the
+    single-launch form (forced on these small batches) and, outside its range, in the two-launch form."""
+    xyz = synth.adversarial(synth.clouds(b, n, seed=b * 1000 + n), seed=n)
+    mats = np.random.default_rng(n).standard_normal((b, t, 3, 3)).astype(np.float32)
+    want_nb, want_c, want_tnb, want_tc, want_idx = oracle.group_affine(xyz, g, m, mats)
+    for cfg in CONFIGS[:1] + CONFIGS[4:6] + [dict(enabled=0)]:
+        tune(**cfg)
+        fps_idx, c, nb, tnb, tc, idx = ops.fps_group_affine(cu(xyz), g, m, torch.from_numpy(mats), want_idx=True)
+        np.testing.assert_array_equal(fps_idx.cpu().numpy(), oracle.fps(xyz, g), err_msg=str(cfg))
+        np.testing.assert_array_equal(c.cpu().numpy(), want_c, err_msg=str(cfg))
+        np.testing.assert_array_equal(idx.cpu().numpy(), want_idx, err_msg=str(cfg))
+        np.testing.assert_array_equal(nb.cpu().numpy(), want_nb, err_msg=str(cfg))
+        np.testing.assert_array_equal(tc.cpu().numpy(), want_tc, err_msg=str(cfg))
+        np.testing.assert_array_equal(tnb.cpu().numpy(), want_tnb, err_msg=str(cfg))
+
+
+def test_forward_corrupted_at_full_batch_equals_the_two_launch_form(tune):
+    b, n, g, m = 128, 2048, 64, 32
+    X = cu(synth.clouds(b, n, seed=5))
+    mats = torch.from_numpy(np.random.default_rng(1).standard_normal((b, 3, 3, 3)).astype(np.float32))
+    tune(enabled=0)
+    want = group.Group(g, m).forward_corrupted(X, mats=mats)
+    tune(enabled=1)
+    got = group.Group(g, m).forward_corrupted(X, mats=mats)
+    for a_, b_ in zip(got, want):
+        assert torch.equal(a_, b_)
+
+
 def test_invalid_arguments_are_rejected():
     X = cu(synth.clouds(1, 600, seed=1))
     with pytest.raises(RuntimeError):
