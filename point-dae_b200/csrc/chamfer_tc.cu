@@ -29,6 +29,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pdae {
@@ -140,6 +142,7 @@ struct TccDir {
   int nch, chunk;   // column chunks of the searched cloud (each <= 2048 points, a multiple of 256 but the last) and their size
   int idx_off;      // added to the indices in the keys (reference-set sharding: global index of r[0])
 };
+constexpr int TCC_MAX_BOUNDS = 160;  // CTAs + 1 of a cost-balanced launch (148 SMs on B200)
 struct TccArgs {
   TccDir d[2];
   long long units;  // b * (d[0].rbs * d[0].nch + d[1].rbs * d[1].nch) row blocks x column chunks
@@ -147,6 +150,8 @@ struct TccArgs {
   unsigned long long *stats;  // optional probe: [0] max |g - (exact group minimum - |a'|^2)| / (max|a'|^2 + max|b'|^2) as float
                               // bits, [1] rows decided by the full scan, [2] groups evaluated exactly, [3] rows
   long long *trace;           // optional (probe): clock64 of CTA 0's first 256 tiles, 6 stamps each (see pdae_chamfer_tc_probe)
+  int nbounds;                // > 0: CTA c walks units [bounds[c], bounds[c + 1]) (cost-balanced shares, tcc_partition)
+  long long bounds[TCC_MAX_BOUNDS];
 };
 
 // literal reference scan of one row (chamfer.cu:42-79), for clouds with non-finite coordinates
@@ -224,8 +229,8 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   // this CTA's contiguous share of the row blocks
   const int units0 = args.d[0].rbs * args.d[0].nch;
   const int per_cloud = units0 + args.d[1].rbs * args.d[1].nch;
-  const long long u0 = static_cast<long long>(blockIdx.x) * args.units / gridDim.x;
-  const long long u1 = static_cast<long long>(blockIdx.x + 1) * args.units / gridDim.x;
+  const long long u0 = args.nbounds ? args.bounds[blockIdx.x] : static_cast<long long>(blockIdx.x) * args.units / gridDim.x;
+  const long long u1 = args.nbounds ? args.bounds[blockIdx.x + 1] : static_cast<long long>(blockIdx.x + 1) * args.units / gridDim.x;
   uint32_t k = 0;   // accumulator tiles issued / consumed so far (producer and epilogue count alike)
   uint32_t kb = 0;  // row blocks handed from the epilogue to the verifier so far
   long long u = u0;
@@ -762,8 +767,113 @@ __global__ void __launch_bounds__(256) tcc_unpack_keys_kernel(const uint64_t *__
   idx[i] = static_cast<int>(static_cast<uint32_t>(k));
 }
 
+// Cost-balanced shares.  A CTA pays for every row block (its accumulator tiles) AND for every operand image it has to
+// build (pipeline drain + bounding box + 64 KB image: 13.8 k cycles at 2048 columns = 2.5 row blocks of eight tiles), and
+// equal block counts give the CTAs whose range touches three (cloud, direction, chunk) runs 7 % more work than those that
+// touch two.  The shares are the contiguous partition with the smallest maximum cost (binary search on the cost, greedy
+// fill -- every CTA pays a build for its first run wherever it starts, so the longest feasible prefix is optimal);
+// walked run by run, so the host work is O(runs) per probe.  PDAE_TCC_BUILD_COST = cost of a 2048-column build in
+// tiles (default 20; 0 = equal block counts).
+static double tcc_build_cost() {
+  static double c = -1.0;
+  if (c < 0.0) {
+    const char *e = getenv("PDAE_TCC_BUILD_COST");
+    c = e && *e ? atof(e) : 20.0;
+    if (c < 0.0) c = 0.0;
+  }
+  return c;
+}
+
+template <int TN>
+static void tcc_partition(TccArgs &a, int b, int grid) {
+  a.nbounds = 0;
+  const double bc = tcc_build_cost();
+  if (bc <= 0.0 || grid + 1 > TCC_MAX_BOUNDS || grid < 2 || a.units <= grid) return;
+  // the runs of one cloud: (row blocks, tiles per block, build cost), in unit order
+  struct Run { long long rbs; double w, build; };
+  Run runs[2 * 64];
+  int nruns = 0;
+  for (int d = 0; d < 2; ++d) {
+    if (a.d[d].nch > 64) return;
+    for (int c = 0; c < a.d[d].nch; ++c) {
+      const int cols = a.d[d].nr - c * a.d[d].chunk < a.d[d].chunk ? a.d[d].nr - c * a.d[d].chunk : a.d[d].chunk;
+      runs[nruns++] = Run{a.d[d].rbs, static_cast<double>((cols + TN - 1) / TN), bc * (0.4 + 0.6 * cols / TCC_MAXCOLS)};
+    }
+  }
+  // the shares of the last shape are kept (a training loop repeats one shape); several host threads may launch at once
+  static std::mutex mu;
+  static TccArgs cached;
+  static int cached_b = -1, cached_grid = -1, cached_tn = -1;
+  static double cached_bc = -1.0;
+  auto same = [&](const TccDir &x, const TccDir &y) { return x.nq == y.nq && x.nr == y.nr && x.rbs == y.rbs && x.nch == y.nch && x.chunk == y.chunk; };
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached_b == b && cached_grid == grid && cached_tn == TN && cached_bc == bc && same(cached.d[0], a.d[0]) &&
+      same(cached.d[1], a.d[1])) {
+    a.nbounds = cached.nbounds;
+    for (int i = 0; i <= grid; ++i) a.bounds[i] = cached.bounds[i];
+    return;
+  }
+  double per_cloud_cost = 0.0;
+  for (int r = 0; r < nruns; ++r) per_cloud_cost += runs[r].rbs * runs[r].w + runs[r].build;
+  // fill CTAs up to cost T in unit order; returns the number of CTAs used (their first units go to out[], when given)
+  auto fill = [&](double T, long long *out) -> long long {
+    long long ctas = 1, u = 0;
+    double acc = 0.0;
+    if (out) out[0] = 0;
+    for (int cl = 0; cl < b; ++cl) {
+      for (int r = 0; r < nruns; ++r) {
+        long long left = runs[r].rbs;
+        bool paid = false;  // has the current CTA built this run's image?
+        while (left > 0) {
+          const double need = paid ? 0.0 : runs[r].build;
+          long long fit = static_cast<long long>((T - acc - need) / runs[r].w + 1e-9);
+          if (fit <= 0) {
+            if (acc > 0.0) {  // close this CTA, the next one goes on with the run (and builds its image again)
+              if (out && ctas <= grid) out[ctas] = u;
+              ++ctas, acc = 0.0, paid = false;
+              continue;
+            }
+            fit = 1;  // an empty CTA always takes at least one block
+          }
+          const long long take = fit < left ? fit : left;
+          acc += need + take * runs[r].w;
+          paid = true, left -= take, u += take;
+        }
+      }
+    }
+    if (out && ctas <= grid) out[ctas] = u;
+    return ctas;
+  };
+  double lo = per_cloud_cost * b / grid * 0.5, hi = per_cloud_cost * b / grid * 2.0 + per_cloud_cost;
+  for (int it = 0; it < 48; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (fill(mid, nullptr) <= grid) hi = mid; else lo = mid;
+  }
+  long long bounds[TCC_MAX_BOUNDS];
+  long long used = fill(hi, bounds);
+  // costs are discrete, so the cheapest feasible limit may need fewer CTAs than there are: halve the longest shares until
+  // every CTA has one (a half never costs more than the whole)
+  while (used >= 1 && used < grid) {
+    int big = 0;
+    for (int i = 1; i < used; ++i)
+      if (bounds[i + 1] - bounds[i] > bounds[big + 1] - bounds[big]) big = i;
+    if (bounds[big + 1] - bounds[big] < 2) break;
+    for (long long i = used; i > big; --i) bounds[i + 1] = bounds[i];
+    bounds[big + 1] = bounds[big] + (bounds[big + 2] - bounds[big]) / 2;
+    ++used;
+  }
+  cached = a, cached_b = b, cached_grid = grid, cached_tn = TN, cached_bc = bc;
+  cached.nbounds = 0;
+  // every CTA must own at least one unit (the kernel's roles assume a non-empty share): otherwise equal block counts
+  bool ok = used == grid && bounds[grid] == a.units;
+  for (int i = 0; ok && i < grid; ++i) ok = bounds[i + 1] > bounds[i];
+  if (!ok) return;
+  for (int i = 0; i <= grid; ++i) a.bounds[i] = cached.bounds[i] = bounds[i];
+  a.nbounds = cached.nbounds = grid + 1;
+}
+
 template <int TN, bool F16>
-static int tcc_launch(const TccArgs &a, cudaStream_t st) {
+static int tcc_launch(TccArgs &a, int b, cudaStream_t st) {
   const size_t smem = tcc_smem_bytes<TN, F16>();
   // per launch, not once per process: the attribute belongs to the current device's instance of the kernel (one process may
   // drive several GPUs, e.g. the reference's nn.DataParallel threads)
@@ -775,6 +885,7 @@ static int tcc_launch(const TccArgs &a, cudaStream_t st) {
     PDAE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const long long grid = a.units < sms ? a.units : sms;
+  tcc_partition<TN>(a, b, static_cast<int>(grid));
   chamfer_tc_kernel<TN, F16><<<static_cast<unsigned>(grid), TCC_THREADS, smem, st>>>(a);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
@@ -786,6 +897,7 @@ static int tcc_forward(const float *xyz1, const float *xyz2, int b, int n, int m
                        int *idx2, uint64_t *keys1, int ref_offset, void *workspace, size_t workspace_bytes, cudaStream_t st,
                        unsigned long long *stats, long long *trace) {
   TccArgs a;
+  a.nbounds = 0;
   a.stats = stats;
   a.trace = trace;
   a.d[0] = TccDir{xyz1, xyz2, dist1, idx1, nullptr, n, m, (n + TCC_M - 1) / TCC_M, 1, TCC_MAXCOLS, ref_offset};
@@ -817,9 +929,9 @@ static int tcc_forward(const float *xyz1, const float *xyz2, int b, int n, int m
   const int mode = tcc_mode();
   a.eps_rel = g_tcc_eps_rel > 0.f ? g_tcc_eps_rel : (mode == 3 ? TCC_EPS_F16 : TCC_EPS_TF32);
   int rc;
-  if (mode == 1) rc = tcc_launch<128, false>(a, st);
-  else if (mode == 3) rc = tcc_launch<256, true>(a, st);
-  else rc = tcc_launch<256, false>(a, st);
+  if (mode == 1) rc = tcc_launch<128, false>(a, b, st);
+  else if (mode == 3) rc = tcc_launch<256, true>(a, b, st);
+  else rc = tcc_launch<256, false>(a, b, st);
   if (rc) return rc;
   for (int d = 0; d < 2; ++d) {
     if (!a.d[d].keys || (d == 0 && keys1)) continue;
