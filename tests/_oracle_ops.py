@@ -45,6 +45,19 @@ def group_points_knn(xyz, center, group_size, want_idx=True, subtract_center=Tru
     return _t(nb), (_t(idx) if want_idx else None)
 
 
+def fps_group(xyz, num_group, group_size, want_idx=False):
+    """stand-in of the single-launch patchifier: the same values as fps_gather + group_points_knn (bit for bit on the GPU)"""
+    fps_idx, center = fps_gather(xyz, num_group)
+    nb, idx = group_points_knn(xyz, center, group_size, want_idx=want_idx)
+    return fps_idx, center, nb, idx
+
+
+def fps_group_affine(xyz, num_group, group_size, mats, want_idx=False):
+    fps_idx, center = fps_gather(xyz, num_group)
+    nb, tnb, tc, idx = group_affine(xyz, center, group_size, mats, want_idx=want_idx)
+    return fps_idx, center, nb, tnb, tc, idx
+
+
 def affine_points(points, center, mats):
     p, c = oracle.affine_points(points.detach().float().contiguous().numpy(), center.detach().float().contiguous().numpy(),
                                 mats.float().numpy())
@@ -130,7 +143,7 @@ def edge_conv(x, idx, weight, bn, slope=0.2):
     return F.leaky_relu(bn(y), slope).max(dim=-1, keepdim=False)[0]
 
 
-NAMES = ("edge_conv", "edge_conv_max", "feat_knn", "_graph_feature_fwd", "_graph_feature_bwd", "GraphFeatureFunction", "furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "affine_points", "group_affine",
+NAMES = ("edge_conv", "edge_conv_max", "feat_knn", "_graph_feature_fwd", "_graph_feature_bwd", "GraphFeatureFunction", "furthest_point_sample", "fps_gather", "knn_points", "group_points_knn", "fps_group", "fps_group_affine", "affine_points", "group_affine",
          "chamfer_forward", "chamfer_backward", "chamfer_mean_loss", "chamfer_loss_backward")
 EXT_NAMES = ("gather_points", "gather_points_grad", "ball_query", "group_points", "group_points_grad", "three_nn",
              "three_interpolate", "three_interpolate_grad")

@@ -197,7 +197,7 @@ def test_group_and_fps_are_differentiable_when_the_input_requires_grad(monkeypat
     torch (models/PointCAE_transformer.py:80-85): a tensor that requires grad must get the same gradient here (the fused
     kernels carry no autograd node; advisor finding, round 1)."""
     import _oracle_ops
-    for name in ("fps_gather", "group_points_knn"):
+    for name in ("fps_gather", "group_points_knn", "fps_group"):
         monkeypatch.setattr(ops, name, getattr(_oracle_ops, name))
     from pointdae_b200 import synth
     xyz = torch.from_numpy(synth.clouds(2, 200, seed=3)).requires_grad_(True)
