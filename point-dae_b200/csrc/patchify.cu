@@ -361,28 +361,42 @@ __global__ void __launch_bounds__(PF_FPS_T + NCW * 32, 1) fps_group_kernel(const
         __syncwarp();
         uint64_t *qq = reinterpret_cast<uint64_t *>(my_area + qi * PQ);
         const float2 g0 = make_float2(f0, f0), g1 = make_float2(f1, f1), g2 = make_float2(f2, f2);
-        for (int e0 = 0; e0 < total; e0 += 32) {
-          const bool act = e0 + lane < total;
-          const uint32_t quad = act ? dense[e0 + lane] : 0u;  // = q4 * 128 + FPS thread
-          const float4 X = pl4[quad], Y = pl4[NQ4 + quad], Z = pl4[2 * NQ4 + quad];
-          const float2 dxa = sub2(make_float2(X.x, X.y), g0), dxb = sub2(make_float2(X.z, X.w), g0);
-          const float2 dya = sub2(make_float2(Y.x, Y.y), g1), dyb = sub2(make_float2(Y.z, Y.w), g1);
-          const float2 dza = sub2(make_float2(Z.x, Z.y), g2), dzb = sub2(make_float2(Z.z, Z.w), g2);
-          const float2 dA = fma2(dza, dza, fma2(dya, dya, mul2(dxa, dxa)));
-          const float2 dB = fma2(dzb, dzb, fma2(dyb, dyb, mul2(dxb, dxb)));
-          const float dv[4] = {dA.x, dA.y, dB.x, dB.y};
-          // cloud index of slot e of the group: FPS thread + 128 * fps_point_of_reg(4 q4 + e) = base + a constant per e
-          // (PG = 4: brev2(q4) + 4 e;  PG = 2: q4 + 2 (e >> 1) + 4 (e & 1))
-          const int q4 = static_cast<int>(quad >> 7);
-          const int kbase = static_cast<int>(quad & (PF_FPS_T - 1)) + PF_FPS_T * (PG == 4 ? ((q4 & 1) << 1 | (q4 >> 1)) : q4);
+        // two groups per lane and round (the ~40 recorded groups of a query are one round): all six LDS.128 and both
+        // distance chains are in flight before the first ballot
+        for (int e0 = 0; e0 < total; e0 += 64) {
+          bool act[2];
+          uint32_t quad[2];
+          float dv[2][4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const bool hit = act && dv[e] <= tq;
-            const unsigned mk = __ballot_sync(FULL, hit);
-            const int pos = cnt + __popc(mk & lt_mask);
-            if (hit && pos < CAP)
-              qq[pos] = pack_key(dv[e], static_cast<uint32_t>(kbase + PF_FPS_T * (PG == 4 ? 4 * e : 2 * (e >> 1) + 4 * (e & 1))));
-            cnt += __popc(mk);
+          for (int h = 0; h < 2; ++h) {
+            act[h] = e0 + 32 * h + lane < total;
+            quad[h] = act[h] ? dense[e0 + 32 * h + lane] : 0u;  // = q4 * 128 + FPS thread
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 X = pl4[quad[h]], Y = pl4[NQ4 + quad[h]], Z = pl4[2 * NQ4 + quad[h]];
+            const float2 dxa = sub2(make_float2(X.x, X.y), g0), dxb = sub2(make_float2(X.z, X.w), g0);
+            const float2 dya = sub2(make_float2(Y.x, Y.y), g1), dyb = sub2(make_float2(Y.z, Y.w), g1);
+            const float2 dza = sub2(make_float2(Z.x, Z.y), g2), dzb = sub2(make_float2(Z.z, Z.w), g2);
+            const float2 dA = fma2(dza, dza, fma2(dya, dya, mul2(dxa, dxa)));
+            const float2 dB = fma2(dzb, dzb, fma2(dyb, dyb, mul2(dxb, dxb)));
+            dv[h][0] = dA.x, dv[h][1] = dA.y, dv[h][2] = dB.x, dv[h][3] = dB.y;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            // cloud index of slot e of the group: FPS thread + 128 * fps_point_of_reg(4 q4 + e) = base + a constant per e
+            // (PG = 4: brev2(q4) + 4 e;  PG = 2: q4 + 2 (e >> 1) + 4 (e & 1))
+            const int q4 = static_cast<int>(quad[h] >> 7);
+            const int kbase = static_cast<int>(quad[h] & (PF_FPS_T - 1)) + PF_FPS_T * (PG == 4 ? ((q4 & 1) << 1 | (q4 >> 1)) : q4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool hit = act[h] && dv[h][e] <= tq;
+              const unsigned mk = __ballot_sync(FULL, hit);
+              const int pos = cnt + __popc(mk & lt_mask);
+              if (hit && pos < CAP)
+                qq[pos] = pack_key(dv[h][e], static_cast<uint32_t>(kbase + PF_FPS_T * (PG == 4 ? 4 * e : 2 * (e >> 1) + 4 * (e & 1))));
+              cnt += __popc(mk);
+            }
           }
         }
         __syncwarp();

@@ -165,6 +165,33 @@ def test_forward_corrupted_at_full_batch_equals_the_two_launch_form(tune):
         assert torch.equal(a_, b_)
 
 
+_RNG = np.random.default_rng(20261018)
+RANDOM_CASES = [(int(_RNG.integers(1, 4)), int(_RNG.integers(512, 2049)), int(_RNG.integers(1, 97)), int(_RNG.integers(1, 33)),
+                 bool(i % 2), int(_RNG.integers(0, 4))) for i in range(24)]
+
+
+@pytest.mark.parametrize("b,n,g,m,dup,t", RANDOM_CASES)
+def test_random_shapes_inside_the_fused_range(tune, b, n, g, m, dup, t):
+    """seeded sweep over cloud size, centre count, group size and matrix-chain length: plain and corrupting epilogue"""
+    xyz = synth.clouds(b, n, seed=7000 + n)
+    if dup:
+        xyz = synth.adversarial(xyz, seed=n, n_small=min(4, n // 8), n_dup=n // 4)
+    mats = _RNG.standard_normal((b, t, 3, 3)).astype(np.float32)
+    want_nb, want_c, want_tnb, want_tc, want_idx = oracle.group_affine(xyz, g, m, mats)
+    tune()
+    fps_idx, c, nb, tnb, tc, idx = ops.fps_group_affine(cu(xyz), g, m, torch.from_numpy(mats), want_idx=True)
+    f2, c2, nb2, idx2 = ops.fps_group(cu(xyz), g, m, want_idx=True)
+    np.testing.assert_array_equal(fps_idx.cpu().numpy(), oracle.fps(xyz, g))
+    np.testing.assert_array_equal(c.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+    np.testing.assert_array_equal(nb.cpu().numpy(), want_nb)
+    np.testing.assert_array_equal(tc.cpu().numpy(), want_tc)
+    np.testing.assert_array_equal(tnb.cpu().numpy(), want_tnb)
+    assert torch.equal(f2, fps_idx) and torch.equal(c2, c) and torch.equal(idx2, idx)
+    # the plain epilogue subtracts the centre once, the corrupting one re-adds and subtracts it (the reference's sequence)
+    np.testing.assert_array_equal(nb2.cpu().numpy(), oracle.group(xyz, g, m)[0])
+
+
 def test_invalid_arguments_are_rejected():
     X = cu(synth.clouds(1, 600, seed=1))
     with pytest.raises(RuntimeError):
