@@ -238,6 +238,10 @@ int pdae_tune_chamfer_split(int nc);
  * PDAE_CHAMFER_TC); eps_rel > 0 sets the filter's error bound relative to max|a - c|^2 + max|b - c|^2, eps_rel < 0 restores
  * the mode's default (2^-17 tf32, 2^-16 fp16; PDAE_CHAMFER_TC_EPS).  mode < 0 only queries.  Returns the previous mode.    */
 int pdae_tune_chamfer_tc(int mode, float eps_rel);
+/* host-only diagnostic: the cost-balanced shares of the tensor-core forward's persistent CTAs (a CTA pays for its
+ * 128-row blocks and for every operand image it builds) for b clouds of n against m points on `grid` CTAs.
+ * bounds_out[0..grid]: first unit of every CTA; returns grid + 1, or 0 when equal block counts are used.            */
+int pdae_chamfer_tc_shares(int b, int n, int m, int grid, long long *bounds_out, long long *units_out);
 /* probe: the tensor-core forward regardless of the mode, plus filter statistics in stats4 (4 x uint64, zeroed by the caller):
  * [0] float bits of the largest |approximate - exact| group minimum relative to the bound's scale, [1] rows decided by the
  * literal scan (list overflow / no finite candidate), [2] 32-column groups evaluated exactly, [3] rows written.

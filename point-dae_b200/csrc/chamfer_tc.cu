@@ -979,6 +979,27 @@ extern "C" int pdae_tune_chamfer_tc(int mode, float eps_rel) {
   return old;
 }
 
+// host-only diagnostic (no device work): the cost-balanced shares tcc_partition gives `grid` persistent CTAs for a
+// forward of b clouds of n against m points (256-column tiles).  bounds_out[0 .. grid] receives the first unit of every
+// CTA (units = 128-row blocks in (cloud, direction, chunk, block) order); returns grid + 1, or 0 when the launch would use
+// equal block counts (PDAE_TCC_BUILD_COST=0, too few units, or more CTAs than the parameter block holds), < 0 on bad arguments.
+extern "C" int pdae_chamfer_tc_shares(int b, int n, int m, int grid, long long *bounds_out, long long *units_out) {
+  if (b <= 0 || n <= 0 || m <= 0 || grid <= 0 || !bounds_out) return PDAE_E_INVALID;
+  pdae::TccArgs a;
+  a.nbounds = 0;
+  a.stats = nullptr;
+  a.trace = nullptr;
+  a.d[0] = pdae::TccDir{nullptr, nullptr, nullptr, nullptr, nullptr, n, m, (n + pdae::TCC_M - 1) / pdae::TCC_M, 1, pdae::TCC_MAXCOLS, 0};
+  a.d[1] = pdae::TccDir{nullptr, nullptr, nullptr, nullptr, nullptr, m, n, (m + pdae::TCC_M - 1) / pdae::TCC_M, 1, pdae::TCC_MAXCOLS, 0};
+  for (int d = 0; d < 2; ++d) pdae::tcc_chunks(a.d[d].nr, a.d[d].nch, a.d[d].chunk);
+  a.units = static_cast<long long>(b) * (static_cast<long long>(a.d[0].rbs) * a.d[0].nch + static_cast<long long>(a.d[1].rbs) * a.d[1].nch);
+  if (units_out) *units_out = a.units;
+  if (grid > a.units) grid = static_cast<int>(a.units);
+  pdae::tcc_partition<256>(a, b, grid);
+  for (int i = 0; i < a.nbounds; ++i) bounds_out[i] = a.bounds[i];
+  return a.nbounds;
+}
+
 // probe: the tensor-core forward regardless of the mode switch, plus filter statistics (4 x uint64, zeroed by the caller):
 // [0] float bits of the largest observed |approximate - exact| group minimum relative to max|a'|^2 + max|b'|^2,
 // [1] rows decided by the literal scan, [2] 32-column groups evaluated exactly, [3] rows written.

@@ -235,3 +235,39 @@ def test_corrupt_stack_keeps_level_bound_after_an_affine_r3_item():
         cut.corrupt_stack(3, ['rotate_z'])
     with pytest.raises(KeyError):
         cut.corrupt_stack(3, ['affine_r3', 'jitter'])
+
+
+def test_tensor_core_forward_shares_are_a_balanced_contiguous_partition():
+    """`tcc_partition` (csrc/chamfer_tc.cu, host side): the persistent CTAs' shares cover every 128-row block once, in
+    order, none empty, and their modelled cost (8 tiles per row block of a 2048-column chunk + 20 tiles per operand image a
+    CTA builds) has a smaller maximum than equal block counts give.  Checked through the host-only diagnostic entry."""
+    import ctypes
+    from pointdae_b200 import _native
+    L = _native.lib()
+
+    def shares(b, n, m, grid=148):
+        out = np.zeros(grid + 1, dtype=np.int64)
+        units = ctypes.c_longlong(0)
+        rc = L.pdae_chamfer_tc_shares(b, n, m, grid, out.ctypes.data, ctypes.addressof(units))
+        return rc, out, units.value
+
+    def cost(bounds, run_len, w=8.0, build=20.0):
+        worst = 0.0
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            runs = (hi - 1) // run_len - lo // run_len + 1
+            worst = max(worst, (hi - lo) * w + runs * build)
+        return worst
+
+    rc, got, units = shares(128, 2048, 2048)
+    assert rc == 149 and units == 128 * 32 and got[0] == 0 and got[-1] == units
+    assert (np.diff(got) > 0).all()
+    equal = np.array([i * units // 148 for i in range(149)])
+    assert cost(got, 16) < cost(equal, 16)
+    assert cost(got, 16) <= 276.0 + 1e-9  # 27 blocks + three builds, or 29 blocks + two
+    # scene scale, one rank's share of a sharded forward: long runs, every CTA still gets work and the spread stays small
+    rc, got, units = shares(1, 100000, 50000)
+    assert rc == 149 and got[-1] == units == 782 * 25 + 391 * 49 and (np.diff(got) > 0).all()
+    assert np.diff(got).max() <= 1.02 * units / 148 + 2
+    # fewer units than CTAs: equal shares (one unit each) are used
+    assert shares(1, 600, 600)[0] == 0
+    assert L.pdae_chamfer_tc_shares(0, 1, 1, 1, None, None) < 0
