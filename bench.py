@@ -308,10 +308,10 @@ def run_ours(args):
     side = torch.cuda.Stream(device=dev)
     aux = torch.cuda.Stream(device=dev)
 
-    def patchify(c):
+    def patchify(c, overlap_previous=False):
         """FPS + centre gather + kNN + gather + centre-subtract: one launch (csrc/patchify.cu) or the two-launch form"""
         if args.patchify == "fused":
-            return ops.fps_group(c, G, M, want_idx=False)[2]
+            return ops.fps_group(c, G, M, want_idx=False, overlap_previous=overlap_previous)[2]
         _, center = ops.fps_gather(c, G)
         return ops.group_points_knn(c, center, M, want_idx=False)[0]
 
@@ -324,6 +324,23 @@ def run_ours(args):
         main = torch.cuda.current_stream()
         br = side if overlap else main
         mode = args.patchifier if overlap else "first"
+        if mode == "pdl":
+            # the forward, then on the SAME stream the patchifier as a programmatic dependent (it reads only the cloud, the
+            # forward triggers its dependents at once: the patchifier's CTAs start as the forward's CTAs exit); loss and
+            # backward wait for the forward on the other two streams
+            d1, d2, i1, i2 = ops.chamfer_forward(p, c)
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(main)
+            nb = patchify(c, overlap_previous=True)
+            aux.wait_event(fwd_done)
+            with torch.cuda.stream(aux):
+                loss = ops.chamfer_mean_loss(d1, d2)[0]
+            side.wait_event(fwd_done)
+            with torch.cuda.stream(side):
+                gx1, gx2 = ops.chamfer_loss_backward(p, c, i1, i2, d1, d2, gone, 1.0, 1.0)
+            main.wait_stream(side)
+            main.wait_stream(aux)
+            return loss, nb, gx1
         if mode == "overlap" and args.patchify == "fused":  # both branches start together (priorities decide who gets the SMs)
             br.wait_stream(main)
             d1, d2, i1, i2 = ops.chamfer_forward(p, c)
@@ -382,7 +399,10 @@ def run_ours(args):
     # one CUDA graph per pool slot: the chain is launch-bound from Python (~30 us of host time per op),
     # so the resident-input measurement replays captured graphs; kernels and arguments are unchanged.
     graphs = []
-    if not args.no_graphs:
+    step_bufs = [ops.StepBuffers(B, N, G, M, dev) for _ in range(2)] if args.launch == "native" else None
+    if args.launch == "native":
+        pass  # the step is ONE native call (csrc/step.cu: six launches, a few us of host time): no graph needed
+    elif not args.no_graphs:
         for i in range(3):
             step_device(i)
         torch.cuda.synchronize()
@@ -393,7 +413,9 @@ def run_ours(args):
             graphs.append((g, out))
 
     def run_step(i):
-        if graphs:
+        if step_bufs is not None:
+            ops.hot_step(clouds_d[i % POOL], preds_d[i % POOL], G, M, gone, buffers=step_bufs[i % 2])
+        elif graphs:
             graphs[i % POOL][0].replay()
         else:
             step_device(i)
@@ -444,7 +466,7 @@ def run_ours(args):
             nb, center = grouper(c_in)
             loss = cd_l2(p_in, c_in)
             side.wait_stream(torch.cuda.current_stream())  # (keeps the join below valid inside a capture)
-        elif args.patchifier in ("tail", "split", "tail2"):  # (the Group module runs FPS and kNN back to back: no split here)
+        elif args.patchifier in ("tail", "pdl", "split", "tail2"):  # (the Group module runs FPS and kNN back to back: no split here)
             loss = cd_l2(p_in, c_in)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -610,6 +632,10 @@ def run_ours(args):
     e2e_checked = abs(e2e_loss - dev_loss) <= 1e-6 * abs(dev_loss)
     if not e2e_checked:
         raise RuntimeError("e2e loss %.9g != device-chain loss %.9g" % (e2e_loss, dev_loss))
+    if step_bufs is not None:  # ... and so does the native step call the resident arm timed
+        nat_loss = float(ops.hot_step(clouds_d[last % POOL], preds_d[last % POOL], G, M, gone, buffers=step_bufs[0]).loss3[0])
+        if abs(nat_loss - dev_loss) > 1e-6 * abs(dev_loss):
+            raise RuntimeError("native step loss %.9g != device-chain loss %.9g" % (nat_loss, dev_loss))
     clocks = sampler.stop() if rank == 0 else None
     # PCIe floor: the step's host -> device copy alone, every rank at once
     barrier()
@@ -711,7 +737,7 @@ def run_ours(args):
                 "share_of_step": cham_ms / ms_per_step, "fp32_pipe_forms": fp32_forms,
             }
         # patchifier (1 fused launch, or fps + knn), chamfer forward (1 or 3), loss x2, backward x2
-        fused_patchifier = args.patchify == "fused" and args.patchifier in ("tail", "first", "overlap")
+        fused_patchifier = args.patchify == "fused" and args.patchifier in ("tail", "pdl", "first", "overlap")
         launches_per_step = (7 if tc_mode > 0 else 9) - (1 if fused_patchifier else 0)
         try:
             others = other_kernels(dev, clouds_d, preds_d, peaks, props) if world == 1 else None
@@ -722,8 +748,11 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": config_dict(world),
-            "launch": ("eager, 3 streams" if args.no_graphs else "CUDA graph per pool slot, 3 streams") + {
+            "launch": "one native call per step (pdae_step_f32, csrc/step.cu: six launches issued from C++ on the caller's stream + "
+                      "two library-owned streams): Chamfer forward -> (FPS+Group as a programmatic dependent launch || loss || "
+                      "backward)" if args.launch == "native" else ("eager, 3 streams" if args.no_graphs else "CUDA graph per pool slot, 3 streams") + {
                 "tail": ": Chamfer forward -> (FPS+Group || loss || backward)",
+                "pdl": ": Chamfer forward -> (FPS+Group as a programmatic dependent launch || loss || backward)",
                 "split": ": FPS -> Chamfer forward -> (Group || loss || backward)",
                 "tail2": ": Chamfer forward -> FPS -> (Group || loss || backward)",
                 "first": ": FPS+Group -> Chamfer forward -> (loss || backward)",
@@ -1104,9 +1133,12 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA ops (oracle/_ref)")
     ap.add_argument("--sched", default="torch", choices=["torch", "priority"],
                     help="priority: graphs instantiated with per-node launch priorities (Chamfer branch first)")
+    ap.add_argument("--launch", default="native", choices=["graph", "native"],
+                    help="resident arm: graph = the step captured from the Python op layer and replayed as a CUDA graph; "
+                         "native = one pdae_step_f32 call per step (the same six launches issued from C++, no graph)")
     ap.add_argument("--patchify", default="fused", choices=["fused", "two"],
                     help="fused: FPS + Group as one launch (pdae_fps_group_f32); two: pdae_fps_gather_f32 + pdae_group_ws_f32")
-    ap.add_argument("--patchifier", default="tail", choices=["tail", "tail2", "split", "first", "overlap"],
+    ap.add_argument("--patchifier", default="tail", choices=["tail", "pdl", "tail2", "split", "first", "overlap"],
                     help="where FPS + Group run relative to the Chamfer forward: beside the loss / backward kernels after it "
                          "(default), before it (the model's order), or from the start on a second stream (round 1)")
     ap.add_argument("--knn-gate", default="none", choices=["scan", "none"],

@@ -105,11 +105,33 @@ int pdae_group_gather_f32(const float *xyz, const float *center, int b, int n, i
 size_t pdae_fps_group_workspace_bytes(int b, int n, int g, int m);
 int pdae_fps_group_f32(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx,
                        float *neighborhood, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
+/* same call with launch flags.  PDAE_LAUNCH_OVERLAP_PREVIOUS: the caller vouches that the kernel queued before this call on
+ * `stream` does not produce xyz (e.g. the Chamfer forward of the same training step); the single-launch form is then
+ * queued with programmatic stream serialization, so its CTAs start as the previous kernel's CTAs exit (that kernel must
+ * have triggered its dependents -- the tensor-core Chamfer forward does -- or the launch simply waits for it to end).
+ * Ignored by the two-launch form.                                                                                   */
+#define PDAE_LAUNCH_OVERLAP_PREVIOUS 1u
+int pdae_fps_group_ex_f32(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx,
+                          float *neighborhood, void *workspace, size_t workspace_bytes, unsigned flags, pdae_stream_t stream);
 int pdae_tune_patchify(int enabled, int qw, int ncw);
 /* diagnostics: while `device_buffer` (>= 1 + g + 8 * g int64, caller-zeroed) is set, CTA 0 of every single-launch
  * patchifier call stamps clock64 there: [0] start, [1 + j] centre j posted, [1 + g + 8 t + p] phases of search task t.
  * NULL switches the stamps off (the default).                                                                       */
 int pdae_patchify_trace(long long *device_buffer);
+
+/* ---- the hot path as one call ---------------------------------------------------------------------------------------
+ * One training step of the path (the model's order: models/PointCAE_transformer.py:1010-1066) enqueued natively with its
+ * launch choreography: on `stream` the Chamfer forward of `pred` against `cloud` (both (b,n,3)), then the patchifier of
+ * `cloud` (g centres, m neighbours; g = 0 skips it) as a programmatic dependent launch -- it reads only the cloud, so its
+ * CTAs start where a forward CTA exits; on two library-owned helper streams, after the forward only: the fused mean loss
+ * (loss3, see pdae_chamfer_loss_f32) and the gradients of that loss scaled by the device scalar *gloss (gpred, gcloud,
+ * see pdae_chamfer_loss_bwd_f32).  `stream` waits for both before the call returns; the call is capturable.
+ * Outputs as in pdae_fps_group_f32 / pdae_chamfer_fwd_f32 (dist1 / idx1 belong to pred's points); same bits.
+ * Six launches, a few microseconds of host time; workspace: pdae_step_workspace_bytes.                              */
+size_t pdae_step_workspace_bytes(int b, int n, int g, int m);
+int pdae_step_f32(const float *cloud, const float *pred, int b, int n, int g, int m, int *fps_idx, float *center,
+                  float *neighborhood, float *dist1, float *dist2, int *idx1, int *idx2, float *loss3, const float *gloss,
+                  float *gpred, float *gcloud, void *workspace, size_t workspace_bytes, pdae_stream_t stream);
 
 /* ---- DGCNN kNN + graph feature --------------------------------------------------------------
  * replaces: models/dgcnn_util.py:7-12 `knn(x, k)` and :15-36 `get_graph_feature`.

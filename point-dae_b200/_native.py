@@ -37,7 +37,10 @@ SIGNATURES = {
     "pdae_group_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pdae_fps_group_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "pdae_fps_group_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pdae_fps_group_ex_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_uint, _vp]),
     "pdae_tune_patchify": (_i, [_i, _i, _i]),
+    "pdae_step_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pdae_step_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_patchify_trace": (_i, [_vp]),
     "pdae_fps_group_affine_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pdae_group_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -224,6 +224,11 @@ __global__ void __launch_bounds__(TCC_THREADS, 1) chamfer_tc_kernel(const TccArg
   __syncthreads();
   tcc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // programmatic dependent launch: a kernel the caller has queued behind this one as INDEPENDENT of its results (the
+  // patchifier of a training step, pdae_fps_group_ex_f32 with PDAE_LAUNCH_OVERLAP_PREVIOUS) may be handed to the block
+  // scheduler now -- this grid is fully resident (one CTA per SM, all of shared and tensor memory), so the dependent's CTAs
+  // start exactly when and where a CTA of this grid exits instead of after the whole grid has drained.  No-op otherwise.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr uint32_t IDESC = F16 ? tcc::instr_desc_f16(TCC_M, TN) : tcc::instr_desc_tf32(TCC_M, TN);
 
   // this CTA's contiguous share of the row blocks

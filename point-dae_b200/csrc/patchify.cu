@@ -42,6 +42,7 @@ struct PatchArgs {
   int npb;   // ceil(n / 512): points per reference slot
   int nbuf;  // distance buffers in the ring (power of two, >= 2 QW)
   int lg_nbuf;
+  int overlap_previous;  // launch attribute only (not read by the kernel): programmatic stream serialization
   long long *trace;  // diagnostics (pdae_patchify_trace): clock64 stamps of CTA 0, else NULL
   int dbg;           // diagnostics (PDAE_PATCHIFY_DBG): 1 = consumers idle (outputs invalid), 2 = also no distance hand-over
 };
@@ -552,6 +553,22 @@ static int patch_launch(PatchArgs a, int b, cudaStream_t st) {
   for (a.lg_nbuf = 0; (1 << a.lg_nbuf) < a.nbuf; ++a.lg_nbuf) {}
   if (a.nbuf < 2 * QW || a.nbuf < 2 || smem > 220 * 1024) return PDAE_E_UNSUPPORTED;
   PDAE_CUDA_TRY(cudaFuncSetAttribute(fps_group_kernel<P, QW, NCW, AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (a.overlap_previous) {
+    // the caller vouches that the previous kernel on this stream does not produce this launch's inputs: the grid may be
+    // scheduled as soon as that kernel's CTAs have all started (it triggers `griddepcontrol.launch_dependents`) or exited
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(b), 1, 1);
+    cfg.blockDim = dim3(PF_FPS_T + NCW * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PDAE_CUDA_TRY(cudaLaunchKernelEx(&cfg, fps_group_kernel<P, QW, NCW, AFF>, a));
+    return 0;
+  }
   fps_group_kernel<P, QW, NCW, AFF><<<b, PF_FPS_T + NCW * 32, smem, st>>>(a);
   PDAE_RETURN_IF_LAUNCH_FAILED();
   return 0;
@@ -573,9 +590,9 @@ bool patchify_fused_applies(int b, int n, int g, int m) {
 }
 
 int patchify_fused(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx, float *neighborhood,
-                   int raw, const GroupAffine *affine, cudaStream_t st) {
+                   int raw, const GroupAffine *affine, cudaStream_t st, int overlap_previous = 0) {
   PatchArgs a{xyz, fps_idx, center, idx, neighborhood, raw, affine ? *affine : GroupAffine{nullptr, 0, nullptr, nullptr},
-              n, g, m, (n + 511) >> 9, 0, 0, patch_tune().trace, pf_env_int("PDAE_PATCHIFY_DBG", 0)};
+              n, g, m, (n + 511) >> 9, 0, 0, overlap_previous, patch_tune().trace, pf_env_int("PDAE_PATCHIFY_DBG", 0)};
   const PatchTune &t = patch_tune();
   if (affine) return n <= 1024 ? patch_launch_p<8, true>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, true>(a, b, t.qw, t.ncw, st);
   return n <= 1024 ? patch_launch_p<8, false>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, false>(a, b, t.qw, t.ncw, st);
@@ -602,17 +619,24 @@ extern "C" size_t pdae_fps_group_workspace_bytes(int b, int n, int g, int m) {
   return f > kq ? f : kq;
 }
 
-extern "C" int pdae_fps_group_f32(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx,
-                                  float *neighborhood, void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
-  if (b < 0 || n < 0 || g < 0 || m <= 0) return PDAE_E_INVALID;
+extern "C" int pdae_fps_group_ex_f32(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx,
+                                     float *neighborhood, void *workspace, size_t workspace_bytes, unsigned flags,
+                                     pdae_stream_t stream) {
+  if (b < 0 || n < 0 || g < 0 || m <= 0 || (flags & ~static_cast<unsigned>(PDAE_LAUNCH_OVERLAP_PREVIOUS))) return PDAE_E_INVALID;
   if (b == 0 || g == 0) return 0;
   if (n == 0 || m > n) return PDAE_E_INVALID;
   if (!xyz || !fps_idx || !center || !neighborhood) return PDAE_E_INVALID;
   if (patchify_fused_applies(b, n, g, m))
-    return patchify_fused(xyz, b, n, g, m, fps_idx, center, idx, neighborhood, 0, nullptr, static_cast<cudaStream_t>(stream));
+    return patchify_fused(xyz, b, n, g, m, fps_idx, center, idx, neighborhood, 0, nullptr, static_cast<cudaStream_t>(stream),
+                          (flags & PDAE_LAUNCH_OVERLAP_PREVIOUS) ? 1 : 0);
   const int rc = pdae_fps_gather_f32(xyz, b, n, 3, g, fps_idx, center, workspace, workspace_bytes, stream);
   if (rc) return rc;
   return pdae_group_ws_f32(xyz, center, b, n, g, m, idx, neighborhood, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pdae_fps_group_f32(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx,
+                                  float *neighborhood, void *workspace, size_t workspace_bytes, pdae_stream_t stream) {
+  return pdae_fps_group_ex_f32(xyz, b, n, g, m, fps_idx, center, idx, neighborhood, workspace, workspace_bytes, 0u, stream);
 }
 
 extern "C" int pdae_fps_group_affine_f32(const float *xyz, const float *mats, int b, int n, int g, int m, int t, int *fps_idx,

@@ -246,10 +246,13 @@ def group_points_knn(xyz, center, group_size, want_idx=True, subtract_center=Tru
     return nb, idx
 
 
-def fps_group(xyz, num_group, group_size, want_idx=False):
+def fps_group(xyz, num_group, group_size, want_idx=False, overlap_previous=False):
     """The whole patchifier of `Group.forward` (models/PointCAE_transformer.py:61-86) in one call / one launch:
     xyz (B,N,3) -> (fps_idx (B,G) int32, center (B,G,3), neighborhood (B,G,M,3) centre-subtracted, idx (B,G,M) int64|None).
-    Bit-identical with fps_gather + group_points_knn (the form shapes outside 512..2048 points / M <= 32 still take)."""
+    Bit-identical with fps_gather + group_points_knn (the form shapes outside 512..2048 points / M <= 32 still take).
+    overlap_previous=True: the caller vouches that the kernel queued before this call on the current stream does not
+    produce `xyz` (the Chamfer forward of the same step); the launch then uses programmatic stream serialization and its
+    CTAs start as that kernel's CTAs exit instead of after its whole grid has drained."""
     _require_cuda(xyz, "fps_group")
     _require_f32_contig(xyz, "xyz")
     if xyz.dim() != 3 or xyz.size(2) != 3:
@@ -266,11 +269,61 @@ def fps_group(xyz, num_group, group_size, want_idx=False):
         idx = torch.empty((b, g, m), dtype=torch.int64, device=xyz.device) if want_idx else None
         nbytes = int(L.pdae_fps_group_workspace_bytes(b, n, g, m))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device) if nbytes else None
-        rc = L.pdae_fps_group_f32(xyz.data_ptr(), b, n, g, m, fps_idx.data_ptr(), center.data_ptr(),
-                                  idx.data_ptr() if want_idx else None, nb.data_ptr(),
-                                  ws.data_ptr() if nbytes else None, nbytes, _stream())
-    _native.check(rc, "pdae_fps_group_f32")
+        rc = L.pdae_fps_group_ex_f32(xyz.data_ptr(), b, n, g, m, fps_idx.data_ptr(), center.data_ptr(),
+                                     idx.data_ptr() if want_idx else None, nb.data_ptr(),
+                                     ws.data_ptr() if nbytes else None, nbytes, 1 if overlap_previous else 0, _stream())
+    _native.check(rc, "pdae_fps_group_ex_f32")
     return fps_idx, center, nb, idx
+
+
+class StepBuffers:
+    """Outputs and workspace of `hot_step`, allocated once per shape (a training loop reuses them every step)."""
+
+    def __init__(self, b, n, g, m, device):
+        L = _native.lib()
+        f32, i32 = torch.float32, torch.int32
+        with _on(device):
+            self.fps_idx = torch.empty((b, g), dtype=i32, device=device)
+            self.center = torch.empty((b, g, 3), dtype=f32, device=device)
+            self.neighborhood = torch.empty((b, g, m, 3), dtype=f32, device=device)
+            self.dist1 = torch.empty((b, n), dtype=f32, device=device)
+            self.dist2 = torch.empty((b, n), dtype=f32, device=device)
+            self.idx1 = torch.empty((b, n), dtype=i32, device=device)
+            self.idx2 = torch.empty((b, n), dtype=i32, device=device)
+            self.loss3 = torch.empty(3, dtype=f32, device=device)
+            self.gpred = torch.empty((b, n, 3), dtype=f32, device=device)
+            self.gcloud = torch.empty((b, n, 3), dtype=f32, device=device)
+            self.ws_bytes = int(L.pdae_step_workspace_bytes(b, n, g, m))
+            self.ws = torch.empty(max(self.ws_bytes, 1), dtype=torch.uint8, device=device)
+        self.shape = (b, n, g, m)
+
+
+def hot_step(cloud, pred, num_group, group_size, gloss, buffers=None):
+    """One step of the hot path in ONE native call (csrc/step.cu): Chamfer forward of `pred` against `cloud`, the patchifier
+    of `cloud` as a programmatic dependent launch, the fused mean loss and the gradients of that loss scaled by the device
+    scalar `gloss`, on the current stream + two library-owned helper streams.  -> StepBuffers (neighborhood, center,
+    fps_idx, dist1/2, idx1/2, loss3 = [loss, mean1, mean2], gpred, gcloud); the values of fps_group + chamfer_forward +
+    chamfer_mean_loss + chamfer_loss_backward bit for bit."""
+    _require_cuda(cloud, "hot_step")
+    _require_f32_contig(cloud, "cloud")
+    _require_f32_contig(pred, "pred")
+    _same_device(cloud.device, pred=pred, gloss=gloss)
+    if cloud.dim() != 3 or cloud.size(2) != 3 or pred.shape != cloud.shape:
+        raise RuntimeError("cloud and pred must both have shape (B, N, 3)")
+    b, n, _ = cloud.shape
+    g, m = int(num_group), int(group_size)
+    if n < 1 or not (1 <= m <= n):
+        raise RuntimeError("group_size=%d must satisfy 1 <= group_size <= %d points" % (m, n))
+    if buffers is None or buffers.shape != (b, n, g, m) or buffers.loss3.device != cloud.device:
+        buffers = StepBuffers(b, n, g, m, cloud.device)
+    o = buffers
+    with _on(cloud.device):
+        rc = _native.lib().pdae_step_f32(cloud.data_ptr(), pred.data_ptr(), b, n, g, m, o.fps_idx.data_ptr(), o.center.data_ptr(),
+                                         o.neighborhood.data_ptr(), o.dist1.data_ptr(), o.dist2.data_ptr(), o.idx1.data_ptr(),
+                                         o.idx2.data_ptr(), o.loss3.data_ptr(), gloss.data_ptr(), o.gpred.data_ptr(),
+                                         o.gcloud.data_ptr(), o.ws.data_ptr(), o.ws_bytes, _stream())
+    _native.check(rc, "pdae_step_f32")
+    return o
 
 
 # -------------------------------------------------------------------- affine corruptions (SURVEY.md 8f row 3)
