@@ -79,6 +79,13 @@ extern "C" int pdae_step_f32(const float *cloud, const float *pred, int b, int n
   int rc = step_streams(&s);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the helper streams and events are shared by every caller on this device: a wait must see the record of its own call,
+  // so the enqueue sequence of a call is atomic with respect to other host threads (a wait captures the event's state
+  // when it is issued; the GPU work itself is not serialised by this)
+  static std::mutex enqueue_mu[STEP_MAX_DEVICES];
+  int dev = 0;
+  PDAE_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> enqueue_lock(enqueue_mu[dev]);
 
   rc = pdae_chamfer_fwd_f32(pred, cloud, b, n, n, dist1, dist2, idx1, idx2, w_fwd ? ws : nullptr, w_fwd, stream);
   if (rc) return rc;

@@ -89,6 +89,40 @@ def test_step_is_capturable_and_replays():
     _same(bufs, want)
 
 
+def test_two_host_threads_on_two_streams_share_the_helper_streams_safely():
+    """the library-owned streams / events are per device: calls from two host threads (the reference's nn.DataParallel
+    runs one thread per replica) must each wait on their own forward"""
+    import threading
+    b, n, g, m = 64, 2048, 64, 32
+    gone = torch.ones(1, device=DEV)
+    data, want, errs = [], [], []
+    for t in range(2):
+        xyz = synth.clouds(b, n, seed=40 + t)
+        c, p = cu(xyz), cu(synth.prediction(xyz, seed=t))
+        data.append((c, p))
+        want.append(_separate(c, p, g, m, gone))
+    torch.cuda.synchronize()
+
+    def work(t):
+        try:
+            st = torch.cuda.Stream()
+            bufs = ops.StepBuffers(b, n, g, m, torch.device(DEV))
+            with torch.cuda.stream(st):
+                for _ in range(20):
+                    ops.hot_step(data[t][0], data[t][1], g, m, gone, buffers=bufs)
+            st.synchronize()
+            _same(bufs, want[t])
+        except Exception as e:  # surfaced in the main thread
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+
+
 def test_step_rejects_bad_arguments():
     L = _native.lib()
     assert L.pdae_step_f32(None, None, 2, 600, 8, 4, *([None] * 11), None, 0, None) != 0
