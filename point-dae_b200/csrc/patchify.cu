@@ -528,9 +528,11 @@ static int pf_env_int(const char *name, int dflt) {
 struct PatchTune {
   int enabled, qw, ncw;
   long long *trace;
+  int dbg;  // PDAE_PATCHIFY_DBG (diagnostics, read once)
 };
 static PatchTune &patch_tune() {
-  static PatchTune t{pf_env_int("PDAE_PATCHIFY", 1), pf_env_int("PDAE_PATCHIFY_QW", 1), pf_env_int("PDAE_PATCHIFY_NCW", 8), nullptr};
+  static PatchTune t{pf_env_int("PDAE_PATCHIFY", 1), pf_env_int("PDAE_PATCHIFY_QW", 1), pf_env_int("PDAE_PATCHIFY_NCW", 8), nullptr,
+                     pf_env_int("PDAE_PATCHIFY_DBG", 0)};
   return t;
 }
 
@@ -592,7 +594,7 @@ bool patchify_fused_applies(int b, int n, int g, int m) {
 int patchify_fused(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx, float *neighborhood,
                    int raw, const GroupAffine *affine, cudaStream_t st, int overlap_previous = 0) {
   PatchArgs a{xyz, fps_idx, center, idx, neighborhood, raw, affine ? *affine : GroupAffine{nullptr, 0, nullptr, nullptr},
-              n, g, m, (n + 511) >> 9, 0, 0, overlap_previous, patch_tune().trace, pf_env_int("PDAE_PATCHIFY_DBG", 0)};
+              n, g, m, (n + 511) >> 9, 0, 0, overlap_previous, patch_tune().trace, patch_tune().dbg};
   const PatchTune &t = patch_tune();
   if (affine) return n <= 1024 ? patch_launch_p<8, true>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, true>(a, b, t.qw, t.ncw, st);
   return n <= 1024 ? patch_launch_p<8, false>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, false>(a, b, t.qw, t.ncw, st);
