@@ -920,8 +920,24 @@ def config_blocks(dev, peaks, world, max_over_ranks):
         "group k=32": entry(_median_ms(lambda: ops.group_points_knn(c, cen, 32, want_idx=False)), pairs=128 * 64 * 1024),
         "chamfer fwd 128x1024^2": entry(_median_ms(lambda: ops.chamfer_forward(p, c)), pairs=2.0 * 128 * 1024 * 1024),
         "chamfer fwd fine 5000x36x32": entry(_median_ms(lambda: ops.chamfer_forward(fa, fb)), pairs=2.0 * 5000 * 36 * 32),
+        "patchifier, one launch (fps + group k=32)": entry(_median_ms(lambda: ops.fps_group(c, 64, 32))),
     }
-    del c, cen, fa, fb, p
+    # the whole C2 step (patchifier + coarse ChamferL2 forward + loss + backward) as the native call, 200 steps back to back
+    gone = torch.ones(1, device=dev)
+    bufs = ops.StepBuffers(128, 1024, 64, 32, dev)
+    for _ in range(20):
+        ops.hot_step(c, p, 64, 32, gone, buffers=bufs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        ops.hot_step(c, p, 64, 32, gone, buffers=bufs)
+    e1.record()
+    torch.cuda.synchronize()
+    step_ms = max_over_ranks(e0.elapsed_time(e1) / 200)
+    out["C2 B=128 N=1024 G=64 M=32"]["step (pdae_step_f32: patchifier + ChamferL2 fwd + loss + bwd)"] = {
+        "ms": step_ms, "clouds_per_s_per_gpu": 128 / (step_ms * 1e-3)}
+    del c, cen, fa, fb, p, bufs
     # ---- C3: DGCNN k=20 at N=2048, batch-sharded: 128 clouds / world per rank (16 per GPU on 8)
     b3 = 16  # the per-GPU share of the 8-GPU configuration, whatever the world size of this run
     c3 = {"clouds_per_rank": b3, "note": "feature kNN: algorithmic work = C FMA-pipe lane-ops per point pair (the "
