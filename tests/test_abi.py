@@ -63,6 +63,16 @@ def test_argument_validation_needs_no_gpu():
     assert L.pdae_affine_points_f32(None, None, None, 0, 4, 4, 1, None, None, None) == 0
     assert L.pdae_group_affine_f32(None, None, None, 2, 64, 4, 8, 1, None, None, None, None, None) == -1
     assert L.pdae_group_affine_f32(None, None, None, 0, 64, 4, 8, 1, None, None, None, None, None) == 0
+    # the single-launch patchifier and the native step: null pointers, unknown launch flags, empty batch, workspace sizes
+    assert L.pdae_fps_group_f32(None, 2, 1024, 64, 32, None, None, None, None, None, 0, None) == -1
+    assert L.pdae_fps_group_ex_f32(None, 0, 1024, 64, 32, None, None, None, None, None, 0, 2, None) == -1  # flag 2 is not defined
+    assert L.pdae_fps_group_ex_f32(None, 0, 1024, 64, 32, None, None, None, None, None, 0, 1, None) == 0
+    assert L.pdae_fps_group_affine_f32(None, None, 2, 1024, 64, 32, 9, *([None] * 6), None, 0, None) == -1  # chain too long
+    assert L.pdae_fps_group_workspace_bytes(128, 2048, 64, 32) == 0      # one launch, state in shared memory
+    assert L.pdae_fps_group_workspace_bytes(1, 100000, 2048, 64) > 0     # two launches, chunked kNN merge
+    assert L.pdae_step_f32(None, None, 0, 2048, 64, 32, *([None] * 11), None, 0, None) == 0
+    assert L.pdae_step_f32(None, None, 2, 2048, 64, 32, *([None] * 11), None, 0, None) == -1
+    assert L.pdae_step_workspace_bytes(128, 2048, 64, 32) % 256 == 0
 
 
 def test_source_is_sm100a_only():
