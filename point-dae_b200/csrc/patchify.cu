@@ -44,7 +44,6 @@ struct PatchArgs {
   int lg_nbuf;
   int overlap_previous;  // launch attribute only (not read by the kernel): programmatic stream serialization
   long long *trace;  // diagnostics (pdae_patchify_trace): clock64 stamps of CTA 0, else NULL
-  int dbg;           // diagnostics (PDAE_PATCHIFY_DBG): 1 = consumers idle (outputs invalid), 2 = also no distance hand-over
 };
 
 __device__ __forceinline__ uint32_t pf_smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -157,8 +156,7 @@ __global__ void __launch_bounds__(PF_FPS_T + NCW * 32, 1) fps_group_kernel(const
     // given it back
     auto hand_over = [&](int c, const float (&dd)[P]) {
       const int buf = c & (nbuf - 1);
-      if (a.dbg == 2) return;
-      if (c >= nbuf && a.dbg != 1) {
+      if (c >= nbuf) {
         const uint32_t par = static_cast<uint32_t>((c >> a.lg_nbuf) - 1) & 1u;
         while (!pf_mbar_try_wait(empty + buf, par)) {}
       }
@@ -243,7 +241,6 @@ __global__ void __launch_bounds__(PF_FPS_T + NCW * 32, 1) fps_group_kernel(const
     planes[f] = x, planes[NP + f] = y, planes[2 * NP + f] = z;
   }
   named_barrier<2>(CNT);
-  if (a.dbg == 1 || a.dbg == 2) return;
 
   unsigned char *my_area = warp_area + static_cast<size_t>(cw) * (QW * PQ + PF_DENSE);
   uint32_t *dense = reinterpret_cast<uint32_t *>(my_area + static_cast<size_t>(QW) * PQ);  // [32 * LC]
@@ -528,11 +525,9 @@ static int pf_env_int(const char *name, int dflt) {
 struct PatchTune {
   int enabled, qw, ncw;
   long long *trace;
-  int dbg;  // PDAE_PATCHIFY_DBG (diagnostics, read once)
 };
 static PatchTune &patch_tune() {
-  static PatchTune t{pf_env_int("PDAE_PATCHIFY", 1), pf_env_int("PDAE_PATCHIFY_QW", 1), pf_env_int("PDAE_PATCHIFY_NCW", 8), nullptr,
-                     pf_env_int("PDAE_PATCHIFY_DBG", 0)};
+  static PatchTune t{pf_env_int("PDAE_PATCHIFY", 1), pf_env_int("PDAE_PATCHIFY_QW", 1), pf_env_int("PDAE_PATCHIFY_NCW", 8), nullptr};
   return t;
 }
 
@@ -594,7 +589,7 @@ bool patchify_fused_applies(int b, int n, int g, int m) {
 int patchify_fused(const float *xyz, int b, int n, int g, int m, int *fps_idx, float *center, int64_t *idx, float *neighborhood,
                    int raw, const GroupAffine *affine, cudaStream_t st, int overlap_previous = 0) {
   PatchArgs a{xyz, fps_idx, center, idx, neighborhood, raw, affine ? *affine : GroupAffine{nullptr, 0, nullptr, nullptr},
-              n, g, m, (n + 511) >> 9, 0, 0, overlap_previous, patch_tune().trace, patch_tune().dbg};
+              n, g, m, (n + 511) >> 9, 0, 0, overlap_previous, patch_tune().trace};
   const PatchTune &t = patch_tune();
   if (affine) return n <= 1024 ? patch_launch_p<8, true>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, true>(a, b, t.qw, t.ncw, st);
   return n <= 1024 ? patch_launch_p<8, false>(a, b, t.qw, t.ncw, st) : patch_launch_p<16, false>(a, b, t.qw, t.ncw, st);
