@@ -74,8 +74,6 @@ constexpr size_t PF_PQ = (PF_LC + 1) * 64 > PF_CAP * 8 ? (PF_LC + 1) * 64 : PF_C
 constexpr size_t PF_DENSE = static_cast<size_t>(PF_LC) * 32 * 4;
 constexpr int PF_FPS_T = 128;  // FPS threads (one warp per scheduler)
 
-__host__ __device__ constexpr size_t pf_align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
-
 }  // namespace
 
 // P = points per FPS thread (n <= 128 * P), QW = centres per consumer task, NCW = consumer warps, AFF = the epilogue
@@ -101,7 +99,7 @@ __global__ void __launch_bounds__(PF_FPS_T + NCW * 32, 1) fps_group_kernel(const
   float4 *cen_s = reinterpret_cast<float4 *>(ring + static_cast<size_t>(nbuf) * NP);     // [m] centres as selected
   uint64_t *full = reinterpret_cast<uint64_t *>(cen_s + m);                              // [ntask] centres + distances posted
   uint64_t *empty = full + ntask;                                                        // [nbuf] ring buffer given back
-  unsigned char *warp_area = reinterpret_cast<unsigned char *>(empty + nbuf);            // (16-byte aligned: host side)
+  unsigned char *warp_area = reinterpret_cast<unsigned char *>(empty + nbuf);            // (8-byte aligned: u64 key queues)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cloud_id = blockIdx.x;
   const float *__restrict__ cloud = a.data + static_cast<size_t>(cloud_id) * n * 3;
